@@ -1,0 +1,15 @@
+"""gnn-bfs-rans_b200 — B200-native (sm_100a) message-passing hot path of Caesar3142/GNN-BFS-RANS.
+
+Host side mirrors the reference's plugin surface:
+    nn.{GCNConv, GATConv, GINConv, TransformerConv, BatchNorm, MessagePassing, global_mean_pool}
+    data.{Data, Batch}
+    graph_constructor.GraphConstructor
+    dropin.install() / `python -m gnn_bfs_rans_b200.dropin <reference script>`
+All arithmetic goes through libb2g.so (C ABI in include/b2g.h, kernels in csrc/)."""
+from . import _lib  # noqa: F401
+from . import data, dropin, functional, graph, graph_constructor, nn, ops  # noqa: F401
+from .data import Batch, Data  # noqa: F401
+from .graph_constructor import GraphConstructor  # noqa: F401
+from .nn import BatchNorm, GATConv, GCNConv, GINConv, TransformerConv  # noqa: F401
+
+__version__ = "0.1.0"

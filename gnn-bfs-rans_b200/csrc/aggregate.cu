@@ -1,0 +1,315 @@
+// aggregate.cu — K2/K3: deterministic CSR segment-sum with fused normalisation, self term, bias and
+// ReLU.  Replaces PyG MessagePassing.propagate = x.index_select(0, edge_index[0]) (an [E,F]
+// temporary) + zeros(N,F).scatter_add_(0, edge_index[1], msg) for
+//   GCNConv  (gnn_model.py:63,166): out_i = sum_p dinv_i*dinv_j * xw_j + bias          
+//   GINConv  (gnn_model.py:75,166): h_i   = sum_p x_j + (1+eps) x_i                    
+// and, on the transposed CSR, their backward.  The [E,F] message tensor is never materialised.
+//
+// HBM-bound.  Algorithmic bytes per launch: 2*N*F*s + 4*nnz + 4*(N+1) (+4*N dinv).
+// Mapping: one group of LANES lanes per target row, each lane owns VPL 16-byte vectors of the row;
+// neighbour rows are read with 16-byte L1-bypassing loads, U rows in flight per lane, and re-used
+// across neighbouring targets through the 126 MB L2.  fp32 accumulation in CSR (= edge) order.
+#include "common.cuh"
+
+namespace b2g {
+
+template <int LANES>
+__device__ __forceinline__ unsigned group_mask() {
+  if (LANES >= 32) return 0xffffffffu;
+  const int g = (threadIdx.x & 31) / LANES;
+  return ((1u << (LANES & 31)) - 1u) << (g * LANES);
+}
+
+template <typename T, int LANES, int VPL, bool kScale>
+__global__ void __launch_bounds__(256)
+seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_self, int64_t ldxs,
+               T* __restrict__ out, int64_t ldo, int64_t n_rows, int nvec,
+               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+               const float* __restrict__ row_scale, const float* __restrict__ col_scale,
+               float self_coef, const float* __restrict__ bias, int relu) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int U = (VPL >= 4) ? 2 : 4;  // neighbour rows in flight per lane
+  const int gl = threadIdx.x % LANES;                       // lane within the row group
+  const unsigned gmask = group_mask<LANES>();
+  const int64_t groups_per_block = 256 / LANES;
+  const int64_t g0 = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / LANES;
+  const int64_t gstride = (int64_t)gridDim.x * groups_per_block;
+
+  for (int64_t i = g0; i < n_rows; i += gstride) {
+    const int b = __ldg(rowptr + i), e = __ldg(rowptr + i + 1);
+    const float rs = (kScale && row_scale) ? __ldg(row_scale + i) : 1.0f;
+    float acc[VPL][VN];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[v][k] = 0.f;
+
+    for (int base = b; base < e; base += LANES) {
+      const int n = min(LANES, e - base);
+      int c_l = 0;
+      float w_l = 0.f;
+      if (gl < n) {
+        c_l = __ldg(col + base + gl);
+        w_l = kScale ? ((col_scale ? __ldg(col_scale + c_l) : 1.0f) * rs) : 1.0f;
+      }
+      for (int j = 0; j < n; j += U) {
+        Vec<T> buf[U][VPL];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = __shfl_sync(gmask, c_l, j + u, LANES);
+          w[u] = kScale ? __shfl_sync(gmask, w_l, j + u, LANES) : 1.0f;
+          if (j + u < n) {
+            const T* __restrict__ row = x + (int64_t)c * ldx;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              const int vi = gl + v * LANES;
+              if (vi < nvec) buf[u][v] = ldg_vec<T>(row + vi * VN);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j + u < n) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              float f[VN];
+              buf[u][v].to_float(f);
+#pragma unroll
+              for (int k = 0; k < VN; ++k) acc[v][k] = kScale ? fmaf(w[u], f[k], acc[v][k]) : acc[v][k] + f[k];
+            }
+          }
+        }
+      }
+    }
+    // epilogue: self term, bias, relu, store
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int vi = gl + v * LANES;
+      if (vi < nvec) {
+        if (self_coef != 0.f) {
+          float f[VN];
+          ldg_vec<T>((x_self ? x_self + i * ldxs : x + i * ldx) + vi * VN).to_float(f);
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[v][k] = fmaf(self_coef, f[k], acc[v][k]);
+        }
+        if (bias) {
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[v][k] += __ldg(bias + vi * VN + k);
+        }
+        if (relu) {
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[v][k] = fmaxf(acc[v][k], 0.f);
+        }
+        Vec<T> o;
+        o.from_float(acc[v]);
+        stg_vec<T>(out + i * ldo + vi * VN, o);
+      }
+    }
+  }
+}
+
+template <typename T, int LANES, int VPL>
+static int launch_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                          int64_t ldo, int64_t n_rows, int nvec, const int32_t* rowptr,
+                          const int32_t* col, const float* row_scale, const float* col_scale,
+                          float self_coef, const float* bias, int relu, cudaStream_t st) {
+  const int64_t groups_per_block = 256 / LANES;
+  int64_t blocks = ceil_div(n_rows, groups_per_block);
+  const int64_t cap = (int64_t)B2G_NUM_SMS * 16;  // whole waves; grid-stride keeps a moving L2 window
+  if (blocks > cap) blocks = cap;
+  const bool scale = row_scale || col_scale;
+  if (scale)
+    seg_sum_kernel<T, LANES, VPL, true><<<(unsigned)blocks, 256, 0, st>>>(
+        (const T*)x, ldx, (const T*)x_self, ldxs, (T*)out, ldo, n_rows, nvec, rowptr, col, row_scale,
+        col_scale, self_coef, bias, relu);
+  else
+    seg_sum_kernel<T, LANES, VPL, false><<<(unsigned)blocks, 256, 0, st>>>(
+        (const T*)x, ldx, (const T*)x_self, ldxs, (T*)out, ldo, n_rows, nvec, rowptr, col, row_scale,
+        col_scale, self_coef, bias, relu);
+  count_launch();
+  return cuda_status();
+}
+
+template <typename T>
+static int dispatch_seg_sum(int nvec, const void* x, int64_t ldx, const void* x_self, int64_t ldxs,
+                            void* out, int64_t ldo, int64_t n_rows, const int32_t* rowptr,
+                            const int32_t* col, const float* rs, const float* cs, float self_coef,
+                            const float* bias, int relu, cudaStream_t st) {
+#define B2G_SS(L, V) \
+  return launch_seg_sum<T, L, V>(x, ldx, x_self, ldxs, out, ldo, n_rows, nvec, rowptr, col, rs, cs, self_coef, bias, relu, st)
+  if (nvec <= 8) B2G_SS(8, 1);
+  if (nvec <= 16) B2G_SS(16, 1);
+  if (nvec <= 32) B2G_SS(32, 1);
+  if (nvec <= 64) B2G_SS(32, 2);
+  if (nvec <= 128) B2G_SS(32, 4);
+  if (nvec <= 256) B2G_SS(32, 8);
+#undef B2G_SS
+  return B2G_E_SHAPE;
+}
+
+// ---------------------------------------------------------------- halo row gather / scatter-add
+template <typename T>
+__global__ void __launch_bounds__(256) rows_gather_kernel(const T* __restrict__ x, int64_t ldx,
+                                                          const int32_t* __restrict__ idx, int64_t n_idx,
+                                                          T* __restrict__ out, int64_t ldo, int nvec) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t total = n_idx * nvec;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / nvec;
+    const int v = (int)(t - r * nvec);
+    stg_vec<T>(out + r * ldo + v * VN, ldg_vec<T>(x + (int64_t)__ldg(idx + r) * ldx + v * VN));
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) rows_scatter_add_kernel(T* __restrict__ x, int64_t ldx,
+                                                               const int32_t* __restrict__ idx, int64_t n_idx,
+                                                               const T* __restrict__ in, int64_t ldi, int nvec) {
+  constexpr int VN = Vec<T>::N;
+  const int64_t total = n_idx * nvec;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / nvec;
+    const int v = (int)(t - r * nvec);
+    T* dst = x + (int64_t)__ldg(idx + r) * ldx + v * VN;
+    float a[VN], b[VN];
+    Vec<T> va = *reinterpret_cast<const Vec<T>*>(dst);
+    va.to_float(a);
+    ldg_vec<T>(in + r * ldi + v * VN).to_float(b);
+#pragma unroll
+    for (int k = 0; k < VN; ++k) a[k] += b[k];
+    va.from_float(a);
+    *reinterpret_cast<Vec<T>*>(dst) = va;
+  }
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+constexpr int COLSUM_BLOCKS = B2G_NUM_SMS * 4;
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, int64_t ldx, int64_t n_rows,
+                                                             int nvec, float* __restrict__ partial) {
+  constexpr int VN = Vec<T>::N;
+  __shared__ float red[256 * VN];
+  const int rows_per_iter = 256 / nvec;  // nvec <= 256
+  const int r_in = threadIdx.x / nvec, v = threadIdx.x % nvec;
+  float acc[VN];
+#pragma unroll
+  for (int k = 0; k < VN; ++k) acc[k] = 0.f;
+  if (r_in < rows_per_iter) {
+    for (int64_t row = (int64_t)blockIdx.x * rows_per_iter + r_in; row < n_rows;
+         row += (int64_t)gridDim.x * rows_per_iter) {
+      float f[VN];
+      ldg_vec<T>(x + row * ldx + v * VN).to_float(f);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[k] += f[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VN; ++k) red[threadIdx.x * VN + k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < nvec) {
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      float s = 0.f;
+      for (int r = 0; r < rows_per_iter; ++r) s += red[(r * nvec + threadIdx.x) * VN + k];  // fixed order
+      partial[(int64_t)blockIdx.x * nvec * VN + threadIdx.x * VN + k] = s;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int nb, int F,
+                                                           float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= F) return;
+  float s = 0.f;
+  for (int b = 0; b < nb; ++b) s += partial[(int64_t)b * F + c];
+  out[c] = s;
+}
+
+static inline unsigned grid_for(int64_t n, int threads, int per_sm = 8) {
+  int64_t b = ceil_div(n > 0 ? n : 1, threads);
+  const int64_t cap = (int64_t)B2G_NUM_SMS * per_sm;
+  return (unsigned)(b < cap ? b : cap);
+}
+
+}  // namespace b2g
+
+using namespace b2g;
+
+static inline int elem_size(int dt) { return dt == B2G_F32 ? 4 : 2; }
+static inline bool row_ok(const void* p, int64_t ld, int dt) {
+  return aligned16(p) && ((ld * elem_size(dt)) % 16 == 0);
+}
+
+extern "C" {
+
+int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                const int32_t* col, const float* row_scale, const float* col_scale,
+                float self_coef, const float* bias, int relu, void* stream) {
+  if (n_rows < 0 || F <= 0 || (dt != B2G_F32 && dt != B2G_BF16)) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (!x || !out || !rowptr) return B2G_E_ARG;
+  if ((F * elem_size(dt)) % 16 != 0) return B2G_E_SHAPE;
+  if (!row_ok(x, ldx, dt) || !row_ok(out, ldo, dt) || (x_self && !row_ok(x_self, ldxs, dt))) return B2G_E_ALIGN;
+  const int nvec = F * elem_size(dt) / 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == B2G_F32)
+    return dispatch_seg_sum<float>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);
+  return dispatch_seg_sum<__nv_bfloat16>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);
+}
+
+int64_t b2g_colsum_workspace_bytes(int F) { return F > 0 ? (int64_t)COLSUM_BLOCKS * F * 4 : B2G_E_ARG; }
+
+int b2g_colsum(const void* x, int64_t ldx, int64_t n_rows, int F, int dt, float* out, void* ws,
+               void* stream) {
+  if (n_rows < 0 || F <= 0 || (dt != B2G_F32 && dt != B2G_BF16) || !out || !ws) return B2G_E_ARG;
+  if ((F * elem_size(dt)) % 16 != 0) return B2G_E_SHAPE;
+  const int nvec = F * elem_size(dt) / 16;
+  if (nvec > 256) return B2G_E_SHAPE;
+  if (n_rows && !row_ok(x, ldx, dt)) return B2G_E_ALIGN;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == B2G_F32)
+    colsum_partial_kernel<float><<<COLSUM_BLOCKS, 256, 0, st>>>((const float*)x, ldx, n_rows, nvec, (float*)ws);
+  else
+    colsum_partial_kernel<__nv_bfloat16><<<COLSUM_BLOCKS, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, n_rows, nvec, (float*)ws);
+  colsum_final_kernel<<<(unsigned)ceil_div(F, 256), 256, 0, st>>>((const float*)ws, COLSUM_BLOCKS, F, out);
+  count_launch(2);
+  return cuda_status();
+}
+
+int b2g_rows_gather(const void* x, int64_t ldx, const int32_t* idx, int64_t n_idx, void* out,
+                    int64_t ldo, int F, int dt, void* stream) {
+  if (n_idx < 0 || F <= 0 || (dt != B2G_F32 && dt != B2G_BF16)) return B2G_E_ARG;
+  if (n_idx == 0) return B2G_OK;
+  if (!x || !idx || !out) return B2G_E_ARG;
+  if ((F * elem_size(dt)) % 16 != 0) return B2G_E_SHAPE;
+  if (!row_ok(x, ldx, dt) || !row_ok(out, ldo, dt)) return B2G_E_ALIGN;
+  const int nvec = F * elem_size(dt) / 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == B2G_F32)
+    rows_gather_kernel<float><<<grid_for(n_idx * nvec, 256), 256, 0, st>>>((const float*)x, ldx, idx, n_idx, (float*)out, ldo, nvec);
+  else
+    rows_gather_kernel<__nv_bfloat16><<<grid_for(n_idx * nvec, 256), 256, 0, st>>>((const __nv_bfloat16*)x, ldx, idx, n_idx, (__nv_bfloat16*)out, ldo, nvec);
+  count_launch();
+  return cuda_status();
+}
+
+int b2g_rows_scatter_add(void* x, int64_t ldx, const int32_t* idx, int64_t n_idx, const void* in,
+                         int64_t ldi, int F, int dt, void* stream) {
+  if (n_idx < 0 || F <= 0 || (dt != B2G_F32 && dt != B2G_BF16)) return B2G_E_ARG;
+  if (n_idx == 0) return B2G_OK;
+  if (!x || !idx || !in) return B2G_E_ARG;
+  if ((F * elem_size(dt)) % 16 != 0) return B2G_E_SHAPE;
+  if (!row_ok(x, ldx, dt) || !row_ok(in, ldi, dt)) return B2G_E_ALIGN;
+  const int nvec = F * elem_size(dt) / 16;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == B2G_F32)
+    rows_scatter_add_kernel<float><<<grid_for(n_idx * nvec, 256), 256, 0, st>>>((float*)x, ldx, idx, n_idx, (const float*)in, ldi, nvec);
+  else
+    rows_scatter_add_kernel<__nv_bfloat16><<<grid_for(n_idx * nvec, 256), 256, 0, st>>>((__nv_bfloat16*)x, ldx, idx, n_idx, (const __nv_bfloat16*)in, ldi, nvec);
+  count_launch();
+  return cuda_status();
+}
+
+}  // extern "C"

@@ -1,0 +1,853 @@
+// attention.cu — K4/K5: fused edge-score + segment-softmax + weighted aggregate (+ head mean,
+// bias / skip) for GATConv (gnn_model.py:65-68,168) and TransformerConv (gnn_model.py:77-80,170),
+// forward and backward.  Replaces, per layer call, PyG's
+//   x_j = index_select (an [E,H,C] temporary), softmax() (5 [E,H] temporaries: scatter amax, exp,
+//   scatter_add, gather, div), alpha * x_j, scatter_add_, mean(dim=1), + bias      (SURVEY §8a 5,7,8,9)
+// with ONE pass over the target-major CSR; nothing of size [E,*C] is ever materialised.
+//
+// HBM-bound.  Algorithmic bytes: GAT fwd  N*H*C*s + N*C*s + 2*4*N*H + 4*nnz + 4*(N+1)
+//                                            Tconv fwd 3*N*H*C*s + 2*N*C*s + 4*nnz + 4*(N+1).
+// Mapping: one warp per target row.  Within a head a lane owns CV 16-byte vectors; a neighbour
+// row costs H*CV coalesced 16-byte loads per lane (2 KB per warp at H=4, C=256, bf16).  Scores of
+// up to 32 edges live one-per-lane; the softmax is the online (running max / rescale) form so
+// rows of any degree take a single sweep, and for degree <= 32 it is exactly PyG's
+// max-subtracted two-pass softmax.  Deterministic: fp32 accumulation in CSR (= edge) order.
+#include "common.cuh"
+
+namespace b2g {
+
+enum { MODE_GAT = 0, MODE_TCONV = 1 };
+
+template <int H>
+__device__ __forceinline__ void warp_sum_heads(float* s) {
+  if (H == 4) {
+    warp_sum4(s[0], s[1], s[2], s[3]);
+  } else {
+#pragma unroll
+    for (int h = 0; h < H; ++h) s[h] = warp_sum(s[h]);
+  }
+}
+
+// Load the H*CV vectors of row `r` ([H*C] wide, head-major) this lane owns.
+template <typename T, int H, int CV>
+__device__ __forceinline__ void load_row(const T* __restrict__ base, int cvec, int lane, Vec<T> (&buf)[H][CV]) {
+  constexpr int VN = Vec<T>::N;
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int t = 0; t < CV; ++t) {
+      const int vi = lane + 32 * t;
+      if (vi < cvec) buf[h][t] = ldg_vec<T>(base + (h * cvec + vi) * VN);
+    }
+}
+// Load the CV vectors of a [C]-wide row this lane owns.
+template <typename T, int CV>
+__device__ __forceinline__ void load_row1(const T* __restrict__ base, int cvec, int lane, Vec<T> (&buf)[CV]) {
+  constexpr int VN = Vec<T>::N;
+#pragma unroll
+  for (int t = 0; t < CV; ++t) {
+    const int vi = lane + 32 * t;
+    if (vi < cvec) buf[t] = ldg_vec<T>(base + vi * VN);
+  }
+}
+
+template <typename T, int H, int CV>
+__device__ __forceinline__ void row_to_float(const Vec<T> (&buf)[H][CV], int cvec, int lane, float (&f)[H][CV][Vec<T>::N]) {
+  constexpr int VN = Vec<T>::N;
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int t = 0; t < CV; ++t) {
+      if (lane + 32 * t < cvec) buf[h][t].to_float(f[h][t]);
+      else {
+#pragma unroll
+        for (int k = 0; k < VN; ++k) f[h][t][k] = 0.f;
+      }
+    }
+}
+
+// partial[h] += <a[h], b[h]> over this lane's elements
+template <typename T, int H, int CV>
+__device__ __forceinline__ void dot_heads(const float (&a)[H][CV][Vec<T>::N], const Vec<T> (&b)[H][CV], int cvec, int lane, float* partial) {
+  constexpr int VN = Vec<T>::N;
+#pragma unroll
+  for (int h = 0; h < H; ++h)
+#pragma unroll
+    for (int t = 0; t < CV; ++t)
+      if (lane + 32 * t < cvec) {
+        float f[VN];
+        b[h][t].to_float(f);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) partial[h] = fmaf(a[h][t][k], f[k], partial[h]);
+      }
+}
+
+struct AttnArgs {
+  const void* val; int64_t ldv;        // GAT: xw [N,H*C];  TCONV: v [N,H*C]
+  const void* q; const void* k; int64_t ldqk;   // TCONV
+  const float* a_src; const float* a_dst; int64_t lda;   // GAT: fp32 [N,H] with row stride lda
+  const void* skip; int64_t lds;       // optional [N, out_w]
+  void* out; int64_t ldo;
+  const void* gout; int64_t ldg;       // backward
+  void* dq; int64_t lddq;              // TCONV backward
+  int64_t n_rows; int C; int concat; float slope; float qk_scale;
+  const int32_t* rowptr; const int32_t* col;
+  const float* bias; float* smax; float* ssum;
+  float p_drop; uint64_t seed;
+  float* alpha_e; float* ds_e; float* d_a_dst; int64_t ldda;
+};
+
+// ------------------------------------------------------------------------------------ forward
+template <typename T, int H, int CV, int MODE>
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int U = (H * CV >= 8) ? 1 : 2;  // neighbour rows in flight per lane
+  const int lane = threadIdx.x & 31;
+  const int cvec = a.C / VN;
+  const T* __restrict__ val = (const T*)a.val;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+
+  for (int64_t i = w0; i < a.n_rows; i += wstride) {
+    const int b = __ldg(a.rowptr + i), e = __ldg(a.rowptr + i + 1);
+    float ad[H];
+    float qf[MODE == MODE_TCONV ? H : 1][CV][VN];
+    if constexpr (MODE == MODE_GAT) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) ad[h] = __ldg(a.a_dst + i * a.lda + h);
+    } else {
+      Vec<T> qb[H][CV];
+      load_row<T, H, CV>((const T*)a.q + i * a.ldqk, cvec, lane, qb);
+      row_to_float<T, H, CV>(qb, cvec, lane, *reinterpret_cast<float(*)[H][CV][VN]>(&qf));
+    }
+    float m[H], z[H], acc[H][CV][VN];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      m[h] = -INFINITY;
+      z[h] = 0.f;
+#pragma unroll
+      for (int t = 0; t < CV; ++t)
+#pragma unroll
+        for (int k = 0; k < VN; ++k) acc[h][t][k] = 0.f;
+    }
+
+    for (int base = b; base < e; base += 32) {
+      const int n = min(32, e - base);
+      const int c_l = lane < n ? __ldg(a.col + base + lane) : 0;
+      float s_l[H];
+      // ---- scores, one edge per lane
+      if constexpr (MODE == MODE_GAT) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float s = -INFINITY;
+          if (lane < n) {
+            s = __ldg(a.a_src + (int64_t)c_l * a.lda + h) + ad[h];
+            s = s > 0.f ? s : s * a.slope;
+          }
+          s_l[h] = s;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) s_l[h] = -INFINITY;
+        for (int j = 0; j < n; j += U) {
+          Vec<T> kb[U][H][CV];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);
+            if (j + u < n) load_row<T, H, CV>((const T*)a.k + (int64_t)c * a.ldqk, cvec, lane, kb[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            if (j + u < n) {  // warp-uniform
+              float part[H];
+#pragma unroll
+              for (int h = 0; h < H; ++h) part[h] = 0.f;
+              dot_heads<T, H, CV>(*reinterpret_cast<const float(*)[H][CV][VN]>(&qf), kb[u], cvec, lane, part);
+              warp_sum_heads<H>(part);
+              if (lane == j + u) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) s_l[h] = part[h] * a.qk_scale;
+              }
+            }
+          }
+        }
+      }
+      // ---- online softmax update
+      float p_l[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float m_new = fmaxf(m[h], warp_max(s_l[h]));
+        const float scale = expf(m[h] - m_new);  // first chunk: exp(-inf) = 0
+        p_l[h] = lane < n ? expf(s_l[h] - m_new) : 0.f;
+        z[h] = z[h] * scale + warp_sum(p_l[h]);
+        m[h] = m_new;
+        if (base != b) {
+#pragma unroll
+          for (int t = 0; t < CV; ++t)
+#pragma unroll
+            for (int k = 0; k < VN; ++k) acc[h][t][k] *= scale;
+        }
+      }
+      if (a.p_drop > 0.f && lane < n) {
+        if (H == 4) {
+          float sc[4];
+          dropout_scale4(a.seed, (uint64_t)(base + lane), a.p_drop, sc);
+#pragma unroll
+          for (int h = 0; h < H; ++h) p_l[h] *= sc[h & 3];
+        } else {
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            float sc[4];
+            dropout_scale4(a.seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, sc);
+            p_l[h] *= sc[0];
+          }
+        }
+      }
+      // ---- weighted gather of the value rows
+      for (int j = 0; j < n; j += U) {
+        Vec<T> vb[U][H][CV];
+        float p[U][H];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);
+#pragma unroll
+          for (int h = 0; h < H; ++h) p[u][h] = __shfl_sync(0xffffffffu, p_l[h], (j + u) & 31);
+          if (j + u < n) load_row<T, H, CV>(val + (int64_t)c * a.ldv, cvec, lane, vb[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j + u < n) {
+#pragma unroll
+            for (int h = 0; h < H; ++h)
+#pragma unroll
+              for (int t = 0; t < CV; ++t)
+                if (lane + 32 * t < cvec) {
+                  float f[VN];
+                  vb[u][h][t].to_float(f);
+#pragma unroll
+                  for (int k = 0; k < VN; ++k) acc[h][t][k] = fmaf(p[u][h], f[k], acc[h][t][k]);
+                }
+          }
+        }
+      }
+    }
+
+    // ---- epilogue: normalise, head mean / concat, bias, skip, store; save softmax stats
+    float inv[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      z[h] += 1e-16f;
+      inv[h] = 1.0f / z[h];
+    }
+    if (a.smax && lane < H) {
+      float mm = 0.f, zz = 1.f;
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+        if (lane == h) { mm = (e > b) ? m[h] : 0.f; zz = z[h]; }
+      a.smax[i * H + lane] = mm;
+      a.ssum[i * H + lane] = zz;
+    }
+    T* __restrict__ orow = (T*)a.out + i * a.ldo;
+    const T* __restrict__ srow = a.skip ? (const T*)a.skip + i * a.lds : nullptr;
+    if (a.concat) {
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int t = 0; t < CV; ++t) {
+          const int vi = lane + 32 * t;
+          if (vi < cvec) {
+            const int off = (h * cvec + vi) * VN;
+            float o[VN];
+#pragma unroll
+            for (int k = 0; k < VN; ++k) o[k] = acc[h][t][k] * inv[h];
+            if (a.bias) {
+#pragma unroll
+              for (int k = 0; k < VN; ++k) o[k] += __ldg(a.bias + off + k);
+            }
+            if (srow) {
+              float f[VN];
+              ldg_vec<T>(srow + off).to_float(f);
+#pragma unroll
+              for (int k = 0; k < VN; ++k) o[k] += f[k];
+            }
+            Vec<T> ov;
+            ov.from_float(o);
+            stg_vec<T>(orow + off, ov);
+          }
+        }
+    } else {
+#pragma unroll
+      for (int t = 0; t < CV; ++t) {
+        const int vi = lane + 32 * t;
+        if (vi < cvec) {
+          float o[VN];
+#pragma unroll
+          for (int k = 0; k < VN; ++k) {
+            float s = 0.f;
+#pragma unroll
+            for (int h = 0; h < H; ++h) s += acc[h][t][k] * inv[h];
+            o[k] = s * (1.0f / H);
+          }
+          if (a.bias) {
+#pragma unroll
+            for (int k = 0; k < VN; ++k) o[k] += __ldg(a.bias + vi * VN + k);
+          }
+          if (srow) {
+            float f[VN];
+            ldg_vec<T>(srow + vi * VN).to_float(f);
+#pragma unroll
+            for (int k = 0; k < VN; ++k) o[k] += f[k];
+          }
+          Vec<T> ov;
+          ov.from_float(o);
+          stg_vec<T>(orow + vi * VN, ov);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- backward, target-major
+// Per target i (one warp): recompute alpha from the saved row max / sum, d_alpha_e = <g_i, val_j>,
+// D = sum_e alpha_e d_alpha_e, ds_e = alpha_e (d_alpha_e - D).  Writes alpha_e (with the dropout
+// mask folded in, as the source-major pass needs it) and ds_e (w.r.t. the pre-activation score)
+// in CSR order; GAT: d a_dst[i,h] = sum_e ds_e;  TCONV: dq[i] = scale * sum_e ds_e k_j.
+template <typename T, int H, int CV, int MODE>
+__global__ void __launch_bounds__(256) attn_bwd_dst_kernel(const AttnArgs a) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int U = (H * CV >= 8) ? 1 : 2;  // neighbour rows in flight per lane
+  const int lane = threadIdx.x & 31;
+  const int cvec = a.C / VN;
+  const T* __restrict__ val = (const T*)a.val;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  const float gscale = a.concat ? 1.0f : 1.0f / H;
+
+  for (int64_t i = w0; i < a.n_rows; i += wstride) {
+    const int b = __ldg(a.rowptr + i), e = __ldg(a.rowptr + i + 1);
+    // g_i per head (mean mode: the same [C] row scaled by 1/H for every head)
+    float gf[H][CV][VN];
+    {
+      const T* grow = (const T*)a.gout + i * a.ldg;
+      if (a.concat) {
+        Vec<T> gb[H][CV];
+        load_row<T, H, CV>(grow, cvec, lane, gb);
+        row_to_float<T, H, CV>(gb, cvec, lane, gf);
+      } else {
+        Vec<T> gb[CV];
+        load_row1<T, CV>(grow, cvec, lane, gb);
+#pragma unroll
+        for (int t = 0; t < CV; ++t) {
+          float f[VN];
+          if (lane + 32 * t < cvec) gb[t].to_float(f);
+          else {
+#pragma unroll
+            for (int k = 0; k < VN; ++k) f[k] = 0.f;
+          }
+#pragma unroll
+          for (int h = 0; h < H; ++h)
+#pragma unroll
+            for (int k = 0; k < VN; ++k) gf[h][t][k] = f[k] * gscale;
+        }
+      }
+    }
+    float ad[H], m[H], z[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      m[h] = __ldg(a.smax + i * H + h);
+      z[h] = __ldg(a.ssum + i * H + h);
+      ad[h] = MODE == MODE_GAT ? __ldg(a.a_dst + i * a.lda + h) : 0.f;
+    }
+    float qf[MODE == MODE_TCONV ? H : 1][CV][VN];
+    if constexpr (MODE == MODE_TCONV) {
+      Vec<T> qb[H][CV];
+      load_row<T, H, CV>((const T*)a.q + i * a.ldqk, cvec, lane, qb);
+      row_to_float<T, H, CV>(qb, cvec, lane, *reinterpret_cast<float(*)[H][CV][VN]>(&qf));
+    }
+
+    // ---- sweep 1: alpha_e, d_alpha_e per edge, D
+    float D[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) D[h] = 0.f;
+    float al_keep[H], da_keep[H], lr_keep[H];  // single-chunk rows keep their edge in registers
+    for (int base = b; base < e; base += 32) {
+      const int n = min(32, e - base);
+      const int c_l = lane < n ? __ldg(a.col + base + lane) : 0;
+      float s_l[H], da_l[H], lr_l[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) { s_l[h] = 0.f; da_l[h] = 0.f; lr_l[h] = 1.f; }
+      if (MODE == MODE_GAT && lane < n) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float s = __ldg(a.a_src + (int64_t)c_l * a.lda + h) + ad[h];
+          lr_l[h] = s > 0.f ? 1.f : a.slope;
+          s_l[h] = s * lr_l[h];
+        }
+      }
+      for (int j = 0; j < n; j += U) {
+        Vec<T> vb[U][H][CV];
+        Vec<T> kb[MODE == MODE_TCONV ? U : 1][H][CV];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);
+          if (j + u < n) {
+            load_row<T, H, CV>(val + (int64_t)c * a.ldv, cvec, lane, vb[u]);
+            if constexpr (MODE == MODE_TCONV) load_row<T, H, CV>((const T*)a.k + (int64_t)c * a.ldqk, cvec, lane, kb[MODE == MODE_TCONV ? u : 0]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j + u < n) {
+            float part[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) part[h] = 0.f;
+            dot_heads<T, H, CV>(gf, vb[u], cvec, lane, part);
+            warp_sum_heads<H>(part);
+            if (lane == j + u) {
+#pragma unroll
+              for (int h = 0; h < H; ++h) da_l[h] = part[h];
+            }
+            if constexpr (MODE == MODE_TCONV) {
+#pragma unroll
+              for (int h = 0; h < H; ++h) part[h] = 0.f;
+              dot_heads<T, H, CV>(*reinterpret_cast<const float(*)[H][CV][VN]>(&qf), kb[MODE == MODE_TCONV ? u : 0], cvec, lane, part);
+              warp_sum_heads<H>(part);
+              if (lane == j + u) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) s_l[h] = part[h] * a.qk_scale;
+              }
+            }
+          }
+        }
+      }
+      float al_l[H];
+      float sc[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) sc[h] = 1.f;
+      if (a.p_drop > 0.f && lane < n) {
+        if (H == 4) {
+          float s4[4];
+          dropout_scale4(a.seed, (uint64_t)(base + lane), a.p_drop, s4);
+#pragma unroll
+          for (int h = 0; h < H; ++h) sc[h] = s4[h & 3];
+        } else {
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            float s4[4];
+            dropout_scale4(a.seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, s4);
+            sc[h] = s4[0];
+          }
+        }
+      }
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        al_l[h] = lane < n ? expf(s_l[h] - m[h]) / z[h] : 0.f;
+        da_l[h] *= sc[h];                       // d(alpha) through the dropout mask
+        D[h] += warp_sum(al_l[h] * da_l[h]);
+      }
+      if (e - b <= 32) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) { al_keep[h] = al_l[h]; da_keep[h] = da_l[h]; lr_keep[h] = lr_l[h]; al_l[h] *= sc[h]; }
+        if (lane < n) {
+#pragma unroll
+          for (int h = 0; h < H; ++h) a.alpha_e[(int64_t)(base + lane) * H + h] = al_l[h];
+        }
+      } else if (lane < n) {  // park alpha (unmasked), d_alpha, and the mask/lrelu factor for sweep 2
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          a.alpha_e[(int64_t)(base + lane) * H + h] = al_l[h];
+          a.ds_e[(int64_t)(base + lane) * H + h] = da_l[h];
+        }
+      }
+    }
+
+    // ---- sweep 2: ds_e, per-target gradient
+    float dadst[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) dadst[h] = 0.f;
+    float dqa[MODE == MODE_TCONV ? H : 1][CV][VN];
+    if constexpr (MODE == MODE_TCONV) {
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int t = 0; t < CV; ++t)
+#pragma unroll
+          for (int k = 0; k < VN; ++k) dqa[MODE == MODE_TCONV ? h : 0][t][k] = 0.f;
+    }
+    for (int base = b; base < e; base += 32) {
+      const int n = min(32, e - base);
+      const int c_l = lane < n ? __ldg(a.col + base + lane) : 0;
+      float ds_l[H];
+      if (e - b <= 32) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) ds_l[h] = al_keep[h] * (da_keep[h] - D[h]) * lr_keep[h];
+      } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float al = 0.f, da = 0.f, lr = 1.f, scm = 1.f;
+          if (lane < n) {
+            al = a.alpha_e[(int64_t)(base + lane) * H + h];
+            da = a.ds_e[(int64_t)(base + lane) * H + h];
+            if constexpr (MODE == MODE_GAT) {
+              const float s = __ldg(a.a_src + (int64_t)c_l * a.lda + h) + ad[h];
+              lr = s > 0.f ? 1.f : a.slope;
+            }
+            if (a.p_drop > 0.f) {
+              float s4[4];
+              if (H == 4) { dropout_scale4(a.seed, (uint64_t)(base + lane), a.p_drop, s4); scm = s4[h & 3]; }
+              else { dropout_scale4(a.seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, s4); scm = s4[0]; }
+            }
+            a.alpha_e[(int64_t)(base + lane) * H + h] = al * scm;
+          }
+          ds_l[h] = al * (da - D[h]) * lr;
+        }
+      }
+      if (lane < n) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) a.ds_e[(int64_t)(base + lane) * H + h] = ds_l[h];
+      } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) ds_l[h] = 0.f;
+      }
+      if constexpr (MODE == MODE_GAT) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) dadst[h] += warp_sum(ds_l[h]);
+      } else {
+        for (int j = 0; j < n; j += U) {
+          Vec<T> kb[U][H][CV];
+          float dsj[U][H];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);
+#pragma unroll
+            for (int h = 0; h < H; ++h) dsj[u][h] = __shfl_sync(0xffffffffu, ds_l[h], (j + u) & 31);
+            if (j + u < n) load_row<T, H, CV>((const T*)a.k + (int64_t)c * a.ldqk, cvec, lane, kb[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (j + u < n) {
+#pragma unroll
+              for (int h = 0; h < H; ++h)
+#pragma unroll
+                for (int t = 0; t < CV; ++t)
+                  if (lane + 32 * t < cvec) {
+                    float f[VN];
+                    kb[u][h][t].to_float(f);
+#pragma unroll
+                    for (int k = 0; k < VN; ++k)
+                      dqa[MODE == MODE_TCONV ? h : 0][t][k] = fmaf(dsj[u][h], f[k], dqa[MODE == MODE_TCONV ? h : 0][t][k]);
+                  }
+            }
+        }
+      }
+    }
+    if constexpr (MODE == MODE_GAT) {
+      if (lane < H) {
+        float v = 0.f;
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+          if (lane == h) v = dadst[h];
+        a.d_a_dst[i * a.ldda + lane] = v;
+      }
+    } else {
+      T* dqrow = (T*)a.dq + i * a.lddq;
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+#pragma unroll
+        for (int t = 0; t < CV; ++t) {
+          const int vi = lane + 32 * t;
+          if (vi < cvec) {
+            float o[VN];
+#pragma unroll
+            for (int k = 0; k < VN; ++k) o[k] = dqa[MODE == MODE_TCONV ? h : 0][t][k] * a.qk_scale;
+            Vec<T> ov;
+            ov.from_float(o);
+            stg_vec<T>(dqrow + (h * cvec + vi) * VN, ov);
+          }
+        }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- backward, source-major
+// Over the transposed CSR (rows = sources j, col_t = targets i, perm -> position in the
+// target-major CSR where alpha_e / ds_e were written):
+//   d val[j,h,:] = sum_p alpha_p,h * g[i,(h),:] (/H if mean)
+//   GAT  : d a_src[j,h] = sum_p ds_p,h
+//   TCONV: d k[j,h,:]   = scale * sum_p ds_p,h * q[i,h,:]
+struct AttnSrcArgs {
+  const void* gout; int64_t ldg;
+  const void* q; int64_t ldq;
+  const float* alpha_e; const float* ds_e;
+  void* dval; void* dk; int64_t ldd;
+  float* d_a_src; int64_t ldda;
+  int64_t n_rows; int C; int concat; float qk_scale;
+  const int32_t* rowptr_t; const int32_t* col_t; const int32_t* perm;
+};
+
+template <typename T, int H, int CV, int MODE>
+__global__ void __launch_bounds__(256) attn_bwd_src_kernel(const AttnSrcArgs a) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int U = (H * CV >= 8) ? 1 : 2;  // neighbour rows in flight per lane
+  const int lane = threadIdx.x & 31;
+  const int cvec = a.C / VN;
+  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int64_t wstride = (int64_t)gridDim.x * 8;
+  const float gscale = a.concat ? 1.0f : 1.0f / H;
+
+  for (int64_t jn = w0; jn < a.n_rows; jn += wstride) {
+    const int b = __ldg(a.rowptr_t + jn), e = __ldg(a.rowptr_t + jn + 1);
+    float dv[H][CV][VN];
+    float dk[MODE == MODE_TCONV ? H : 1][CV][VN];
+    float das[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      das[h] = 0.f;
+#pragma unroll
+      for (int t = 0; t < CV; ++t)
+#pragma unroll
+        for (int k = 0; k < VN; ++k) {
+          dv[h][t][k] = 0.f;
+          if (MODE == MODE_TCONV) dk[MODE == MODE_TCONV ? h : 0][t][k] = 0.f;
+        }
+    }
+    for (int base = b; base < e; base += 32) {
+      const int n = min(32, e - base);
+      int c_l = 0;
+      float al_l[H], ds_l[H];
+#pragma unroll
+      for (int h = 0; h < H; ++h) { al_l[h] = 0.f; ds_l[h] = 0.f; }
+      if (lane < n) {
+        c_l = __ldg(a.col_t + base + lane);
+        const int64_t pp = __ldg(a.perm + base + lane);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          al_l[h] = __ldg(a.alpha_e + pp * H + h);
+          ds_l[h] = __ldg(a.ds_e + pp * H + h);
+        }
+      }
+      if constexpr (MODE == MODE_GAT) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) das[h] += warp_sum(ds_l[h]);
+      }
+      for (int j = 0; j < n; j += U) {
+        Vec<T> gbc[U][H][CV];                         // concat: per-head g
+        Vec<T> gbm[U][CV];                            // mean: one [C] row
+        Vec<T> qb[MODE == MODE_TCONV ? U : 1][H][CV];
+        float al[U][H], ds[U][H];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);
+#pragma unroll
+          for (int h = 0; h < H; ++h) {
+            al[u][h] = __shfl_sync(0xffffffffu, al_l[h], (j + u) & 31) * gscale;
+            if (MODE == MODE_TCONV) ds[u][h] = __shfl_sync(0xffffffffu, ds_l[h], (j + u) & 31);
+          }
+          if (j + u < n) {
+            const T* grow = (const T*)a.gout + (int64_t)c * a.ldg;
+            if (a.concat) load_row<T, H, CV>(grow, cvec, lane, gbc[u]);
+            else load_row1<T, CV>(grow, cvec, lane, gbm[u]);
+            if constexpr (MODE == MODE_TCONV) load_row<T, H, CV>((const T*)a.q + (int64_t)c * a.ldq, cvec, lane, qb[MODE == MODE_TCONV ? u : 0]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (j + u < n) {
+#pragma unroll
+            for (int t = 0; t < CV; ++t)
+              if (lane + 32 * t < cvec) {
+                float gm[VN];
+                if (!a.concat) gbm[u][t].to_float(gm);
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                  float g[VN];
+                  if (a.concat) gbc[u][h][t].to_float(g);
+#pragma unroll
+                  for (int k = 0; k < VN; ++k) dv[h][t][k] = fmaf(al[u][h], a.concat ? g[k] : gm[k], dv[h][t][k]);
+                  if constexpr (MODE == MODE_TCONV) {
+                    float qv[VN];
+                    qb[MODE == MODE_TCONV ? u : 0][h][t].to_float(qv);
+#pragma unroll
+                    for (int k = 0; k < VN; ++k)
+                      dk[MODE == MODE_TCONV ? h : 0][t][k] = fmaf(ds[u][h], qv[k], dk[MODE == MODE_TCONV ? h : 0][t][k]);
+                  }
+                }
+              }
+          }
+      }
+    }
+    T* dvrow = (T*)a.dval + jn * a.ldd;
+    T* dkrow = MODE == MODE_TCONV ? (T*)a.dk + jn * a.ldd : nullptr;
+#pragma unroll
+    for (int h = 0; h < H; ++h)
+#pragma unroll
+      for (int t = 0; t < CV; ++t) {
+        const int vi = lane + 32 * t;
+        if (vi < cvec) {
+          Vec<T> ov;
+          ov.from_float(dv[h][t]);
+          stg_vec<T>(dvrow + (h * cvec + vi) * VN, ov);
+          if constexpr (MODE == MODE_TCONV) {
+            float o[VN];
+#pragma unroll
+            for (int k = 0; k < VN; ++k) o[k] = dk[MODE == MODE_TCONV ? h : 0][t][k] * a.qk_scale;
+            ov.from_float(o);
+            stg_vec<T>(dkrow + (h * cvec + vi) * VN, ov);
+          }
+        }
+      }
+    if (MODE == MODE_GAT && lane < H) {
+      float v = 0.f;
+#pragma unroll
+      for (int h = 0; h < H; ++h)
+        if (lane == h) v = das[h];
+      a.d_a_src[jn * a.ldda + lane] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ dispatch
+static inline unsigned warp_grid(int64_t n_rows) {
+  int64_t blocks = ceil_div(n_rows > 0 ? n_rows : 1, 8);
+  const int64_t cap = (int64_t)B2G_NUM_SMS * 16;
+  return (unsigned)(blocks < cap ? blocks : cap);
+}
+
+template <typename T, int H, int CV, int MODE>
+static int launch3(int which, const AttnArgs& a, const AttnSrcArgs& s, cudaStream_t st) {
+  if (which == 0) attn_fwd_kernel<T, H, CV, MODE><<<warp_grid(a.n_rows), 256, 0, st>>>(a);
+  else if (which == 1) attn_bwd_dst_kernel<T, H, CV, MODE><<<warp_grid(a.n_rows), 256, 0, st>>>(a);
+  else attn_bwd_src_kernel<T, H, CV, MODE><<<warp_grid(s.n_rows), 256, 0, st>>>(s);
+  count_launch();
+  return cuda_status();
+}
+template <typename T, int MODE>
+static int dispatch(int which, int H, int C, const AttnArgs& a, const AttnSrcArgs& s, cudaStream_t st) {
+  constexpr int VN = Vec<T>::N;
+  if (C % VN) return B2G_E_SHAPE;
+  const int cvec = C / VN;
+  const int cv = cvec <= 32 ? 1 : (cvec <= 64 ? 2 : 0);
+  if (!cv) return B2G_E_SHAPE;
+#define B2G_AT(HH)                                                   \
+  if (H == HH) {                                                     \
+    if (cv == 1) return launch3<T, HH, 1, MODE>(which, a, s, st);    \
+    return launch3<T, HH, 2, MODE>(which, a, s, st);                 \
+  }
+  B2G_AT(1) B2G_AT(2) B2G_AT(4)
+  if (H == 8 && cv == 1) return launch3<T, 8, 1, MODE>(which, a, s, st);
+#undef B2G_AT
+  return B2G_E_SHAPE;
+}
+static int dispatch_dt(int mode, int which, int dt, int H, int C, const AttnArgs& a, const AttnSrcArgs& s, cudaStream_t st) {
+  if (dt == B2G_F32) return mode == MODE_GAT ? dispatch<float, MODE_GAT>(which, H, C, a, s, st) : dispatch<float, MODE_TCONV>(which, H, C, a, s, st);
+  if (dt == B2G_BF16) return mode == MODE_GAT ? dispatch<__nv_bfloat16, MODE_GAT>(which, H, C, a, s, st) : dispatch<__nv_bfloat16, MODE_TCONV>(which, H, C, a, s, st);
+  return B2G_E_ARG;
+}
+
+static inline int esz(int dt) { return dt == B2G_F32 ? 4 : 2; }
+static inline bool row_ok(const void* p, int64_t ld, int dt) { return p && aligned16(p) && ((ld * esz(dt)) % 16 == 0); }
+
+}  // namespace b2g
+
+using namespace b2g;
+
+extern "C" {
+
+int b2g_gat_fwd(const void* xw, int64_t ldxw, const float* a_src, const float* a_dst, int64_t lda, void* out,
+                int64_t ldo, int64_t n_rows, int H, int C, int dt, int concat, float slope,
+                const int32_t* rowptr, const int32_t* col, const float* bias, float* smax,
+                float* ssum, float p_drop, uint64_t seed, void* stream) {
+  if (n_rows < 0 || H <= 0 || C <= 0 || p_drop < 0.f || p_drop >= 1.f) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (!a_src || !a_dst || !rowptr || (smax && !ssum)) return B2G_E_ARG;
+  if (!row_ok(xw, ldxw, dt) || !row_ok(out, ldo, dt)) return B2G_E_ALIGN;
+  AttnArgs a{};
+  a.val = xw; a.ldv = ldxw; a.a_src = a_src; a.a_dst = a_dst; a.lda = lda; a.out = out; a.ldo = ldo;
+  a.n_rows = n_rows; a.C = C; a.concat = concat; a.slope = slope; a.rowptr = rowptr; a.col = col;
+  a.bias = bias; a.smax = smax; a.ssum = ssum; a.p_drop = p_drop; a.seed = seed;
+  return dispatch_dt(MODE_GAT, 0, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
+}
+
+int b2g_gat_bwd_dst(const void* xw, int64_t ldxw, const float* a_src, const float* a_dst, int64_t lda,
+                    const void* gout, int64_t ldg, int64_t n_rows, int H, int C, int dt, int concat,
+                    float slope, const int32_t* rowptr, const int32_t* col, const float* smax,
+                    const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* ds_e,
+                    float* d_a_dst, int64_t ldda, void* stream) {
+  if (n_rows < 0 || H <= 0 || C <= 0) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (!a_src || !a_dst || !rowptr || !smax || !ssum || !alpha_e || !ds_e || !d_a_dst) return B2G_E_ARG;
+  if (!row_ok(xw, ldxw, dt) || !row_ok(gout, ldg, dt)) return B2G_E_ALIGN;
+  AttnArgs a{};
+  a.val = xw; a.ldv = ldxw; a.a_src = a_src; a.a_dst = a_dst; a.lda = lda; a.gout = gout; a.ldg = ldg;
+  a.n_rows = n_rows; a.C = C; a.concat = concat; a.slope = slope; a.rowptr = rowptr; a.col = col;
+  a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum); a.p_drop = p_drop; a.seed = seed;
+  a.alpha_e = alpha_e; a.ds_e = ds_e; a.d_a_dst = d_a_dst; a.ldda = ldda;
+  return dispatch_dt(MODE_GAT, 1, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
+}
+
+int b2g_gat_bwd_src(const void* gout, int64_t ldg, const float* alpha_e, const float* ds_e,
+                    void* d_xw, int64_t ldd, float* d_a_src, int64_t ldda, int64_t n_rows, int H, int C, int dt,
+                    int concat, const int32_t* rowptr_t, const int32_t* col_t, const int32_t* perm,
+                    void* stream) {
+  if (n_rows < 0 || H <= 0 || C <= 0) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (!alpha_e || !ds_e || !d_a_src || !rowptr_t || !perm) return B2G_E_ARG;
+  if (!row_ok(gout, ldg, dt) || !row_ok(d_xw, ldd, dt)) return B2G_E_ALIGN;
+  AttnSrcArgs s{};
+  s.gout = gout; s.ldg = ldg; s.alpha_e = alpha_e; s.ds_e = ds_e; s.dval = d_xw; s.ldd = ldd;
+  s.d_a_src = d_a_src; s.ldda = ldda; s.n_rows = n_rows; s.C = C; s.concat = concat; s.qk_scale = 1.f;
+  s.rowptr_t = rowptr_t; s.col_t = col_t; s.perm = perm;
+  return dispatch_dt(MODE_GAT, 2, dt, H, C, AttnArgs{}, s, (cudaStream_t)stream);
+}
+
+int b2g_tconv_fwd(const void* q, const void* k, const void* v, int64_t ldqkv, const void* skip,
+                  int64_t lds, void* out, int64_t ldo, int64_t n_rows, int H, int C, int dt,
+                  int concat, const int32_t* rowptr, const int32_t* col, float* smax, float* ssum,
+                  float p_drop, uint64_t seed, void* stream) {
+  if (n_rows < 0 || H <= 0 || C <= 0 || p_drop < 0.f || p_drop >= 1.f) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (!rowptr || (smax && !ssum)) return B2G_E_ARG;
+  if (!row_ok(q, ldqkv, dt) || !row_ok(k, ldqkv, dt) || !row_ok(v, ldqkv, dt) || !row_ok(out, ldo, dt)) return B2G_E_ALIGN;
+  if (skip && !row_ok(skip, lds, dt)) return B2G_E_ALIGN;
+  AttnArgs a{};
+  a.val = v; a.ldv = ldqkv; a.q = q; a.k = k; a.ldqk = ldqkv; a.skip = skip; a.lds = lds;
+  a.out = out; a.ldo = ldo; a.n_rows = n_rows; a.C = C; a.concat = concat;
+  a.qk_scale = 1.0f / sqrtf((float)C); a.rowptr = rowptr; a.col = col; a.smax = smax; a.ssum = ssum;
+  a.p_drop = p_drop; a.seed = seed;
+  return dispatch_dt(MODE_TCONV, 0, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
+}
+
+int b2g_tconv_bwd_dst(const void* q, const void* k, const void* v, int64_t ldqkv, const void* gout,
+                      int64_t ldg, int64_t n_rows, int H, int C, int dt, int concat,
+                      const int32_t* rowptr, const int32_t* col, const float* smax,
+                      const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* ds_e,
+                      void* dq, int64_t lddq, void* stream) {
+  if (n_rows < 0 || H <= 0 || C <= 0) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (!rowptr || !smax || !ssum || !alpha_e || !ds_e) return B2G_E_ARG;
+  if (!row_ok(q, ldqkv, dt) || !row_ok(k, ldqkv, dt) || !row_ok(v, ldqkv, dt) || !row_ok(gout, ldg, dt) || !row_ok(dq, lddq, dt)) return B2G_E_ALIGN;
+  AttnArgs a{};
+  a.val = v; a.ldv = ldqkv; a.q = q; a.k = k; a.ldqk = ldqkv; a.gout = gout; a.ldg = ldg;
+  a.dq = dq; a.lddq = lddq; a.n_rows = n_rows; a.C = C; a.concat = concat;
+  a.qk_scale = 1.0f / sqrtf((float)C); a.rowptr = rowptr; a.col = col;
+  a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum); a.p_drop = p_drop; a.seed = seed;
+  a.alpha_e = alpha_e; a.ds_e = ds_e;
+  return dispatch_dt(MODE_TCONV, 1, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
+}
+
+int b2g_tconv_bwd_src(const void* q, int64_t ldq, const void* gout, int64_t ldg,
+                      const float* alpha_e, const float* ds_e, void* dk, void* dv, int64_t ldd,
+                      int64_t n_rows, int H, int C, int dt, int concat, const int32_t* rowptr_t,
+                      const int32_t* col_t, const int32_t* perm, void* stream) {
+  if (n_rows < 0 || H <= 0 || C <= 0) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (!alpha_e || !ds_e || !rowptr_t || !perm) return B2G_E_ARG;
+  if (!row_ok(q, ldq, dt) || !row_ok(gout, ldg, dt) || !row_ok(dk, ldd, dt) || !row_ok(dv, ldd, dt)) return B2G_E_ALIGN;
+  AttnSrcArgs s{};
+  s.gout = gout; s.ldg = ldg; s.q = q; s.ldq = ldq; s.alpha_e = alpha_e; s.ds_e = ds_e;
+  s.dval = dv; s.dk = dk; s.ldd = ldd; s.n_rows = n_rows; s.C = C; s.concat = concat;
+  s.qk_scale = 1.0f / sqrtf((float)C); s.rowptr_t = rowptr_t; s.col_t = col_t; s.perm = perm;
+  return dispatch_dt(MODE_TCONV, 2, dt, H, C, AttnArgs{}, s, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// common.cuh — shared device/host helpers for libb2g (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b2g.h"
+
+#define B2G_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+namespace b2g {
+
+extern int64_t g_launches;  // defined in api.cu
+inline void count_launch(int n = 1) { g_launches += n; }
+
+inline int cuda_status() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- 16-byte vector of features
+template <typename T>
+struct Vec;  // 16 bytes of T, convertible to/from fp32 lanes
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  float4 v;
+  __device__ __forceinline__ void to_float(float* f) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
+  __device__ __forceinline__ void from_float(const float* f) { v = make_float4(f[0], f[1], f[2], f[3]); }
+};
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  uint4 v;
+  __device__ __forceinline__ void to_float(float* f) const {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {  // bf16 -> fp32 is a 16-bit shift
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ __forceinline__ void from_float(const float* f) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 p = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    v = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// Gathered neighbour rows are re-used through L2 by adjacent targets: default caching, but keep
+// them out of L1 (no intra-SM reuse worth the pollution).  Streaming outputs bypass L1 too.
+template <typename T>
+__device__ __forceinline__ Vec<T> ldg_vec(const T* p) {
+  Vec<T> r;
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+               : "l"(p));
+  r.v = *reinterpret_cast<decltype(r.v)*>(&u);
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ void stg_vec(T* p, const Vec<T>& r) {
+  const uint4 u = *reinterpret_cast<const uint4*>(&r.v);
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y),
+               "r"(u.z), "r"(u.w)
+               : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Reduce four per-lane partials (one per attention head) across the warp with 9 shuffles instead
+// of 20: fold the lane space in halves while packing heads, then finish with a butterfly.
+// Returns, on every lane, the full sums {s0,s1,s2,s3}.
+__device__ __forceinline__ void warp_sum4(float& a, float& b, float& c, float& d) {
+  const int lane = threadIdx.x & 31;
+  // step 1: lanes <16 keep (a,b), lanes >=16 keep (c,d)
+  {
+    const bool hi = lane & 16;
+    float s0 = hi ? a : c, s1 = hi ? b : d;  // what we send away
+    float k0 = hi ? c : a, k1 = hi ? d : b;  // what we keep
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    a = k0; b = k1;  // lanes<16: (a,b)   lanes>=16: (c,d)
+  }
+  // step 2: within each half, lanes with bit3 clear keep first, set keep second
+  {
+    const bool hi = lane & 8;
+    float s = hi ? a : b, k = hi ? b : a;
+    k += __shfl_xor_sync(0xffffffffu, s, 8);
+    a = k;  // bit4,bit3 = 00:a 01:b 10:c 11:d
+  }
+  a += __shfl_xor_sync(0xffffffffu, a, 4);
+  a += __shfl_xor_sync(0xffffffffu, a, 2);
+  a += __shfl_xor_sync(0xffffffffu, a, 1);
+  // broadcast back: head h lives on lanes with (lane>>3)==h
+  const float r0 = __shfl_sync(0xffffffffu, a, 0);
+  const float r1 = __shfl_sync(0xffffffffu, a, 8);
+  const float r2 = __shfl_sync(0xffffffffu, a, 16);
+  const float r3 = __shfl_sync(0xffffffffu, a, 24);
+  a = r0; b = r1; c = r2; d = r3;
+}
+
+// ---------------------------------------------------------------- counter-based RNG for dropout
+// Philox-4x32-10 keyed by (seed), counter (element index).  One call -> 4 uniform floats in [0,1).
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+// keep-mask scale for attention dropout on edge position p (4 heads at once)
+__device__ __forceinline__ void dropout_scale4(uint64_t seed, uint64_t p, float p_drop, float* s) {
+  const uint4 r = philox4x32(seed, p);
+  const float inv = 1.0f / (1.0f - p_drop);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int h = 0; h < 4; ++h) s[h] = ((w[h] >> 8) * (1.0f / 16777216.0f) >= p_drop) ? inv : 0.0f;
+}
+
+}  // namespace b2g

@@ -1,0 +1,74 @@
+// linear.cu — C ABI of K6 (dense per-node Linear inside the conv layers) and the
+// choice between the tcgen05 tensor-core kernel (gemm_tc.cu) and the exact-fp32 SIMT kernel
+// (gemm_simt.cu).  impl: 0 = auto (tensor core when the shape/dtype is covered), 1 = SIMT, 2 = TC.
+#include "common.cuh"
+
+namespace b2g {
+int simt_linear_fwd(const void*, int64_t, const void*, int64_t, const float*, const float*, void*, int64_t, float*, int64_t, int64_t, int, int, int, int, int, cudaStream_t);
+int simt_linear_dgrad(const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int, int, int, cudaStream_t);
+int64_t simt_wgrad_ws_bytes(int64_t, int, int);
+int simt_linear_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_t, float*, int64_t, int, int, int, void*, cudaStream_t);
+// gemm_tc.cu
+bool tc_linear_supported(int64_t n, int m, int k, int dt, int which);
+int64_t tc_linear_ws_bytes(int64_t n, int m, int k, int dt, int which);
+int tc_linear_fwd(const void*, int64_t, const void*, int64_t, const float*, const float*, void*, int64_t, float*, int64_t, int64_t, int, int, int, int, int, void*, cudaStream_t);
+}  // namespace b2g
+
+using namespace b2g;
+
+static inline bool dt_ok(int dt) { return dt == B2G_F32 || dt == B2G_BF16; }
+
+extern "C" {
+
+int64_t b2g_linear_workspace_bytes(int64_t n, int m, int k, int dt, int which) {
+  if (n < 0 || m <= 0 || k <= 0 || !dt_ok(dt)) return B2G_E_ARG;
+  int64_t b = 256;
+  if (which == 2) b += simt_wgrad_ws_bytes(n, m, k);
+  if (tc_linear_supported(n, m, k, dt, which)) {
+    const int64_t t = tc_linear_ws_bytes(n, m, k, dt, which);
+    if (t > b) b = t;
+  }
+  return b;
+}
+
+int b2g_linear_impl(int64_t n, int m, int k, int dt, int which) {
+  if (n < 0 || m <= 0 || k <= 0 || !dt_ok(dt)) return B2G_E_ARG;
+  return tc_linear_supported(n, m, k, dt, which) ? 2 : 1;
+}
+
+int b2g_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                   const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n,
+                   int m, int m_main, int k, int dt, int act, int impl, void* ws, void* stream) {
+  if (n < 0 || m <= 0 || k <= 0 || !dt_ok(dt) || act < 0 || act > 1 || impl < 0 || impl > 2) return B2G_E_ARG;
+  if (m_main < 0 || m_main > m || (m_main < m && (!aux || (m_main % 8) != 0))) return B2G_E_ARG;
+  if (n == 0) return B2G_OK;
+  if (!X || !W || (m_main > 0 && !Y)) return B2G_E_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tc = tc_linear_supported(n, m, k, dt, 0);
+  if (impl == 2 && !tc) return B2G_E_UNSUPPORTED;
+  if (tc && impl != 1) return tc_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, ws, st);
+  return simt_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, st);
+}
+
+int b2g_linear_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dX,
+                     int64_t lddx, int64_t n, int m, int k, int dt, int impl, void* ws,
+                     void* stream) {
+  if (n < 0 || m <= 0 || k <= 0 || !dt_ok(dt) || impl < 0 || impl > 2) return B2G_E_ARG;
+  if (n == 0) return B2G_OK;
+  if (!dY || !W || !dX) return B2G_E_ARG;
+  if (impl == 2) return B2G_E_UNSUPPORTED;  // dgrad runs on the tensor cores through fwd with W^T (host side)
+  (void)ws;
+  return simt_linear_dgrad(dY, lddy, W, ldw, dX, lddx, n, m, k, dt, (cudaStream_t)stream);
+}
+
+int b2g_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
+                     int64_t lddw, float* db, int64_t n, int m, int k, int dt, int impl, void* ws,
+                     void* stream) {
+  if (n < 0 || m <= 0 || k <= 0 || !dt_ok(dt) || impl < 0 || impl > 2) return B2G_E_ARG;
+  if (!dW || !ws) return B2G_E_ARG;
+  if (n && (!dY || !X)) return B2G_E_ARG;
+  if (impl == 2) return B2G_E_UNSUPPORTED;
+  return simt_linear_wgrad(dY, lddy, X, ldx, dW, lddw, db, n, m, k, dt, ws, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+"""torch.autograd.Function wrappers that own the save-for-backward logic of the hot path.
+Each forward/backward is a short sequence of libb2g.so kernels (ops.py); no torch maths on
+[N,*]- or [E,*]-sized tensors happens here."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ops
+from .graph import Graph
+
+_SEED = [0x5DEECE66D]
+
+
+def _next_seed() -> int:
+    # dropout seeds come from torch's generator so torch.manual_seed() makes runs reproducible
+    return int(torch.randint(0, 2**62, (1,), device="cpu").item())
+
+
+def _cast_like(g32: torch.Tensor, ref: torch.Tensor):
+    return g32 if ref.dtype == torch.float32 else g32.to(ref.dtype)
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x @ W.T + b) (F.linear; PyG Linear) through K6."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act: int):
+        need_grad = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)
+        fuse_act = act if not need_grad else 0       # relu backward needs the pre-activation sign
+        y, _ = ops.linear_fwd(x, weight, bias, act=fuse_act)
+        if act and not fuse_act:
+            ctx.save_for_backward(x, weight, y)
+            ctx.act = act
+            ctx.has_bias = bias is not None
+            return torch.relu(y)
+        ctx.save_for_backward(x, weight, None)
+        ctx.act = 0
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight, pre = ctx.saved_tensors
+        if pre is not None:
+            gy = gy * (pre > 0).to(gy.dtype)
+        gy = gy.contiguous()
+        gx = ops.linear_dgrad(gy, weight) if ctx.needs_input_grad[0] else None
+        gw = gb = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.linear_wgrad(gy, x, want_bias=ctx.has_bias)
+            gw = _cast_like(dw, weight)
+            gb = db if ctx.has_bias else None
+        return gx, gw, gb, None
+
+
+class SegSumFn(torch.autograd.Function):
+    """out_i = rs_i * sum_{j->i} cs_j x_j + self_coef * x_i + bias over `variant` of the graph
+    (GCN: rs = cs = deg^-1/2 on the self-loop-replaced list; GIN: raw list, self_coef = 1+eps)."""
+
+    @staticmethod
+    def forward(ctx, x, bias, graph: Graph, variant: str, use_dinv: bool, self_coef: float):
+        csr = graph.csr(variant, False)
+        dinv = graph.dinv() if use_dinv else None
+        out = ops.seg_sum(x, csr.rowptr, csr.col, graph.N, dinv, dinv, self_coef, None,
+                          bias.float() if bias is not None else None)
+        ctx.graph, ctx.variant, ctx.use_dinv, ctx.self_coef = graph, variant, use_dinv, self_coef
+        ctx.has_bias = bias is not None
+        ctx.ei_keepalive = graph.edge_index
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        graph = ctx.graph
+        g = g.contiguous()
+        gx = gb = None
+        if ctx.needs_input_grad[0]:
+            csr_t = graph.csr(ctx.variant, True)
+            dinv = graph.dinv() if ctx.use_dinv else None
+            gx = ops.seg_sum(g, csr_t.rowptr, csr_t.col, graph.N, dinv, dinv, ctx.self_coef, None, None)
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            gb = ops.colsum(g)
+        return gx, gb, None, None, None, None
+
+
+class GATFn(torch.autograd.Function):
+    """GATConv core: [xw | a_src | a_dst] = x @ W_aug.T in one GEMM, then the fused
+    score/softmax/aggregate kernel.  W_aug = [W; att_src-folded rows; att_dst-folded rows] is
+    assembled (differentiably) by the module, so att_* and W get their gradients through it."""
+
+    @staticmethod
+    def forward(ctx, x, w_aug, bias, graph: Graph, H: int, C: int, concat: bool, slope: float, p_drop: float):
+        HC = H * C
+        xw, a = ops.linear_fwd(x, w_aug, None, m_main=HC)
+        csr = graph.csr("sl", False)
+        need_grad = x.requires_grad or w_aug.requires_grad
+        seed = _next_seed() if p_drop > 0 else 0
+        out, smax, ssum = ops.gat_fwd(xw, a, H, C, concat, slope, csr.rowptr, csr.col,
+                                      bias.float() if bias is not None else None, p_drop, seed, need_grad)
+        if need_grad:
+            recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"
+            ctx.save_for_backward(x, w_aug, None if recompute else xw, a, smax, ssum)
+            ctx.cfg = (graph, H, C, concat, slope, p_drop, seed, bias is not None)
+            ctx.ei_keepalive = graph.edge_index
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w_aug, xw, a, smax, ssum = ctx.saved_tensors
+        graph, H, C, concat, slope, p_drop, seed, has_bias = ctx.cfg
+        HC = H * C
+        g = g.contiguous()
+        if xw is None:
+            xw, _ = ops.linear_fwd(x, w_aug[:HC], None)
+        csr, csr_t, perm = graph.csr("sl", False), graph.csr("sl", True), graph.perm("sl")
+        N = x.shape[0]
+        # one [N, HC+2H] gradient matrix so dgrad / wgrad are single GEMMs over W_aug
+        pad = (-(HC + 2 * H)) % (16 // x.element_size())
+        d_aug = torch.empty((N, HC + 2 * H + pad), dtype=x.dtype, device=x.device)
+        d_a = ops.gat_bwd(xw, a, g, H, C, concat, slope, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
+                          d_aug[:, :HC])
+        d_aug[:, HC:HC + 2 * H] = d_a
+        if pad:
+            d_aug[:, HC + 2 * H:] = 0
+        dy = d_aug[:, :HC + 2 * H] if not pad else d_aug
+        w_eff = w_aug if not pad else torch.cat([w_aug, w_aug.new_zeros((pad, w_aug.shape[1]))], 0)
+        gx = ops.linear_dgrad(dy, w_eff) if ctx.needs_input_grad[0] else None
+        gw = None
+        if ctx.needs_input_grad[1]:
+            dw, _ = ops.linear_wgrad(dy, x, want_bias=False)
+            gw = _cast_like(dw[:HC + 2 * H], w_aug)
+        gb = ops.colsum(g) if (has_bias and ctx.needs_input_grad[2]) else None
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+class TConvFn(torch.autograd.Function):
+    """TransformerConv core: [q | k | v | skip] = x @ W_cat.T + b_cat in one GEMM, then the fused
+    q.k score / softmax / aggregate / head-mean / +skip kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w_cat, b_cat, graph: Graph, H: int, C: int, concat: bool, p_drop: float, has_skip: bool):
+        HC = H * C
+        y, _ = ops.linear_fwd(x, w_cat, b_cat)
+        q, k, v = y[:, :HC], y[:, HC:2 * HC], y[:, 2 * HC:3 * HC]
+        skip = y[:, 3 * HC:] if has_skip else None
+        csr = graph.csr("raw", False)
+        need_grad = x.requires_grad or w_cat.requires_grad
+        seed = _next_seed() if p_drop > 0 else 0
+        out, smax, ssum = ops.tconv_fwd(q, k, v, skip, H, C, concat, csr.rowptr, csr.col, p_drop, seed, need_grad)
+        if need_grad:
+            recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"
+            ctx.save_for_backward(x, w_cat, b_cat, None if recompute else y, smax, ssum)
+            ctx.cfg = (graph, H, C, concat, p_drop, seed, has_skip)
+            ctx.ei_keepalive = graph.edge_index
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w_cat, b_cat, y, smax, ssum = ctx.saved_tensors
+        graph, H, C, concat, p_drop, seed, has_skip = ctx.cfg
+        HC = H * C
+        g = g.contiguous()
+        if y is None:
+            y, _ = ops.linear_fwd(x, w_cat, b_cat)
+        q, k, v = y[:, :HC], y[:, HC:2 * HC], y[:, 2 * HC:3 * HC]
+        csr, csr_t, perm = graph.csr("raw", False), graph.csr("raw", True), graph.perm("raw")
+        d_y = torch.empty_like(y)
+        ops.tconv_bwd(q, k, v, g, H, C, concat, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
+                      d_y[:, :HC], d_y[:, HC:2 * HC], d_y[:, 2 * HC:3 * HC])
+        if has_skip:
+            d_y[:, 3 * HC:] = g
+        gx = ops.linear_dgrad(d_y, w_cat) if ctx.needs_input_grad[0] else None
+        gw = gb = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = ops.linear_wgrad(d_y, x, want_bias=True)
+            gw = _cast_like(dw, w_cat)
+            gb = _cast_like(db, b_cat) if b_cat is not None else None
+        return gx, gw, gb, None, None, None, None, None, None
+
+
+def linear(x, weight, bias=None, act: int = 0):
+    return LinearFn.apply(x, weight, bias, act)

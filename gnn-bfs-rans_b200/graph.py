@@ -1,0 +1,103 @@
+"""Device CSR cache.  PyG has no counterpart: GCNConv re-derives gcn_norm and GATConv re-does
+remove/add self loops on EVERY forward of EVERY layer (cached=False at /root/reference/gnn_model.py:63).
+Here the CSR of an `edge_index` is built once per distinct tensor (identity + version + shape) and
+shared by all L layers of a forward (gnn_model.py:162-172 passes the same tensor to each layer) and
+by the backward pass.  `batch.to(device)` (train.py:167) creates a fresh tensor each step, so in the
+reference's loop the CSR is rebuilt once per step, not once per layer."""
+from __future__ import annotations
+
+import weakref
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+
+
+class CSR:
+    """One orientation of one variant: rowptr/col/eid (+dinv)."""
+    __slots__ = ("rowptr", "col", "eid", "dinv", "nnz")
+
+    def __init__(self, rowptr, col, eid, dinv):
+        self.rowptr, self.col, self.eid, self.dinv = rowptr, col, eid, dinv
+        self.nnz = col.numel()
+
+    def pair(self):
+        return (self.rowptr, self.col)
+
+
+class Graph:
+    """All CSRs derived from one edge_index [2,E] over N nodes (built lazily, cached).
+    variant 'sl'  : self loops removed then one per node appended (GCNConv / GATConv)
+    variant 'raw' : the list as given (GINConv / TransformerConv)."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int):
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError(f"edge_index must have shape [2, num_edges], got {tuple(edge_index.shape)}")
+        ei = edge_index if edge_index.dtype == torch.int64 else edge_index.long()
+        ei = ei.contiguous()
+        # hold the caller's tensor weakly (a cached Graph must not pin a 1 GB edge_index of a finished
+        # step); keep a strong reference only to a private contiguous/int64 copy
+        self._ei_ref = weakref.ref(edge_index)
+        self._ei_own = None if ei is edge_index else ei
+        self.N = int(num_nodes)
+        self.E = int(edge_index.shape[1])
+        self._csr = {}
+        self._perm = {}
+
+    @property
+    def edge_index(self) -> torch.Tensor:
+        ei = self._ei_own if self._ei_own is not None else self._ei_ref()
+        if ei is None:
+            raise RuntimeError("b2g: the edge_index tensor of this cached graph was freed")
+        return ei
+
+    def csr(self, variant: str, by_source: bool = False) -> CSR:
+        key = (variant, by_source)
+        c = self._csr.get(key)
+        if c is None:
+            sl = variant == "sl"
+            c = CSR(*ops.csr_build(self.edge_index, self.N, sl, by_source, want_dinv=(sl and not by_source)))
+            self._csr[key] = c
+        return c
+
+    def dinv(self) -> torch.Tensor:
+        """GCN deg^-1/2 over the self-loop-replaced list (in-degree by target)."""
+        return self.csr("sl", False).dinv
+
+    def perm(self, variant: str) -> torch.Tensor:
+        """Position in the target-major CSR of each entry of the source-major CSR."""
+        p = self._perm.get(variant)
+        if p is None:
+            a, b = self.csr(variant, False), self.csr(variant, True)
+            p = ops.csr_perm(a.eid, b.eid, self.E + self.N)
+            self._perm[variant] = p
+        return p
+
+
+_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+_CACHE_MAX = 8
+
+
+def graph_of(edge_index: torch.Tensor, num_nodes: int) -> Graph:
+    """Cached Graph for this edge_index tensor (keyed on storage identity, version, shape, N)."""
+    key = (edge_index.data_ptr(), edge_index._version, tuple(edge_index.shape), tuple(edge_index.stride()),
+           int(num_nodes), edge_index.device.index)
+    for k in [k for k, (r, _) in _CACHE.items() if r() is None]:   # drop graphs of freed tensors
+        del _CACHE[k]
+    hit = _CACHE.get(key)
+    if hit is not None:
+        ref, g = hit
+        if ref() is edge_index:          # same live tensor object -> same content (version matched)
+            _CACHE.move_to_end(key)
+            return g
+        del _CACHE[key]
+    g = Graph(edge_index, num_nodes)
+    _CACHE[key] = (weakref.ref(edge_index), g)
+    while len(_CACHE) > _CACHE_MAX:
+        _CACHE.popitem(last=False)
+    return g
+
+
+def clear_cache():
+    _CACHE.clear()

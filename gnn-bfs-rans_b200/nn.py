@@ -1,0 +1,326 @@
+"""Drop-in `torch_geometric.nn` surface for the reference's model code
+(/root/reference/gnn_model.py:8-10 imports; :62-80 constructors; :165-172 forward calls).
+
+Same class names, constructor arguments, forward(x, edge_index) signatures, parameter names /
+shapes (so PyG-trained checkpoints load through inference.py:48) and initialisers as PyG >= 2.3;
+the arithmetic is libb2g.so (hand-written sm_100a CUDA) instead of index_select + scatter_add_.
+Only the argument combinations the reference uses have kernels; other PyG flags raise
+NotImplementedError.  There is no CPU path: a non-CUDA input raises RuntimeError."""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Optional
+
+import torch
+import torch.nn as tnn
+
+from . import functional as Fn
+from .graph import graph_of
+
+
+# ---- torch_geometric.nn.inits ----------------------------------------------------------------------
+def glorot(t: Optional[torch.Tensor]):
+    if t is not None:
+        a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+        with torch.no_grad():
+            t.uniform_(-a, a)
+
+
+def zeros(t: Optional[torch.Tensor]):
+    if t is not None:
+        with torch.no_grad():
+            t.zero_()
+
+
+class Linear(tnn.Module):
+    """torch_geometric.nn.dense.linear.Linear: weight [out,in], optional bias; glorot or
+    kaiming_uniform(a=sqrt(5)) init.  forward = K6 GEMM."""
+
+    def __init__(self, in_channels: int, out_channels: int, bias: bool = True,
+                 weight_initializer: Optional[str] = None, bias_initializer: Optional[str] = None):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight_initializer, self.bias_initializer = weight_initializer, bias_initializer
+        self.weight = tnn.Parameter(torch.empty(out_channels, in_channels))
+        if bias:
+            self.bias = tnn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        if self.weight_initializer == 'glorot':
+            glorot(self.weight)
+        else:  # PyG default: kaiming_uniform(fan=in_channels, a=sqrt(5)) == U(+-1/sqrt(in))
+            bound = 1.0 / math.sqrt(self.in_channels) if self.in_channels > 0 else 0.0
+            with torch.no_grad():
+                self.weight.uniform_(-bound, bound)
+        if self.bias is not None:
+            if self.bias_initializer == 'zeros':
+                zeros(self.bias)
+            else:
+                bound = 1.0 / math.sqrt(self.in_channels) if self.in_channels > 0 else 0.0
+                with torch.no_grad():
+                    self.bias.uniform_(-bound, bound)
+
+    def forward(self, x):
+        return Fn.linear(x, self.weight, self.bias)
+
+    def extra_repr(self):
+        return f'{self.in_channels}, {self.out_channels}, bias={self.bias is not None}'
+
+
+def _check_x(x, edge_index):
+    if not isinstance(x, torch.Tensor):
+        raise NotImplementedError("b2g: bipartite (x_src, x_dst) inputs are not supported")
+    if x.dim() != 2:
+        raise RuntimeError(f"b2g: x must be [num_nodes, channels], got {tuple(x.shape)}")
+    if not x.is_cuda or not edge_index.is_cuda:
+        raise RuntimeError("b2g: message passing needs CUDA tensors (B200 path, no CPU fallback)")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"b2g: x dtype {x.dtype} not supported (float32 / bfloat16)")
+
+
+class MessagePassing(tnn.Module):
+    """Name-only base class (gnn_model.py:8 imports it; nothing in the reference subclasses it)."""
+
+    def __init__(self, aggr: str = 'add', **kwargs):
+        super().__init__()
+        self.aggr = aggr
+
+    def reset_parameters(self):
+        pass
+
+
+class GCNConv(MessagePassing):
+    """GCNConv(in, out) — gnn_model.py:63; forward(x, edge_index) at :166.
+    out = D^-1/2 (A_noloop + I) D^-1/2 (x W^T) + b   (gcn_norm)."""
+
+    def __init__(self, in_channels: int, out_channels: int, improved: bool = False, cached: bool = False,
+                 add_self_loops: bool = True, normalize: bool = True, bias: bool = True, **kwargs):
+        super().__init__(aggr='add')
+        if improved or not add_self_loops or not normalize:
+            raise NotImplementedError("b2g GCNConv: only improved=False, add_self_loops=True, normalize=True")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.improved, self.cached, self.add_self_loops, self.normalize = improved, cached, add_self_loops, normalize
+        self.lin = Linear(in_channels, out_channels, bias=False, weight_initializer='glorot')
+        if bias:
+            self.bias = tnn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+        zeros(self.bias)
+
+    def forward(self, x, edge_index, edge_weight=None):
+        if edge_weight is not None:
+            raise NotImplementedError("b2g GCNConv: edge_weight is not supported")
+        _check_x(x, edge_index)
+        g = graph_of(edge_index, x.shape[0])
+        xw = Fn.LinearFn.apply(x, self.lin.weight, None, 0)
+        return Fn.SegSumFn.apply(xw, self.bias, g, "sl", True, 0.0)
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels})'
+
+
+class GATConv(MessagePassing):
+    """GATConv(in, out, heads=4, concat=False, dropout=p) — gnn_model.py:65-68; forward at :168."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
+                 negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
+                 edge_dim: Optional[int] = None, fill_value='mean', bias: bool = True, **kwargs):
+        super().__init__(aggr='add')
+        if not add_self_loops or edge_dim is not None:
+            raise NotImplementedError("b2g GATConv: only add_self_loops=True, edge_dim=None")
+        if not isinstance(in_channels, int):
+            raise NotImplementedError("b2g GATConv: bipartite in_channels are not supported")
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.negative_slope, self.dropout, self.add_self_loops = negative_slope, dropout, add_self_loops
+        self.edge_dim, self.fill_value = edge_dim, fill_value
+        self.lin = Linear(in_channels, heads * out_channels, bias=False, weight_initializer='glorot')
+        self.att_src = tnn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = tnn.Parameter(torch.empty(1, heads, out_channels))
+        if bias:
+            self.bias = tnn.Parameter(torch.empty(heads * out_channels if concat else out_channels))
+        else:
+            self.register_parameter('bias', None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+        glorot(self.att_src)
+        glorot(self.att_dst)
+        zeros(self.bias)
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # PyG <= 2.5 checkpoints spell the shared projection lin_src / lin_dst (same tensor)
+        src, dst, new = prefix + 'lin_src.weight', prefix + 'lin_dst.weight', prefix + 'lin.weight'
+        if new not in state_dict and src in state_dict:
+            state_dict[new] = state_dict[src]
+        state_dict.pop(src, None)
+        state_dict.pop(dst, None)
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def _w_aug(self, dtype):
+        H, C = self.heads, self.out_channels
+        W = self.lin.weight
+        Wv = W.view(H, C, self.in_channels)
+        vs = torch.einsum('hc,hcf->hf', self.att_src[0], Wv)     # a_src = x @ vs^T == (xW^T * att_src).sum(-1)
+        vd = torch.einsum('hc,hcf->hf', self.att_dst[0], Wv)
+        return torch.cat([W, vs, vd], dim=0).to(dtype)
+
+    def forward(self, x, edge_index, edge_attr=None, size=None, return_attention_weights=None):
+        if return_attention_weights:
+            raise NotImplementedError("b2g GATConv: return_attention_weights is not supported")
+        if edge_attr is not None:
+            raise NotImplementedError("b2g GATConv: edge_attr needs edge_dim (not supported)")
+        _check_x(x, edge_index)
+        g = graph_of(edge_index, x.shape[0])
+        p = self.dropout if self.training else 0.0
+        return Fn.GATFn.apply(x, self._w_aug(x.dtype), self.bias, g, self.heads, self.out_channels, self.concat,
+                              self.negative_slope, p)
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})'
+
+
+class GINConv(MessagePassing):
+    """GINConv(nn) — gnn_model.py:70-75; forward at :166.  out = nn(sum_j x_j + (1+eps) x_i)."""
+
+    def __init__(self, nn, eps: float = 0.0, train_eps: bool = False, **kwargs):
+        super().__init__(aggr='add')
+        self.nn = nn
+        self.initial_eps = eps
+        if train_eps:
+            self.eps = tnn.Parameter(torch.empty(1))
+        else:
+            self.register_buffer('eps', torch.empty(1))
+        self._train_eps = train_eps
+        self._eps_host, self._eps_key = None, None
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for m in self.nn.modules() if isinstance(self.nn, tnn.Module) else []:
+            if m is not self.nn and hasattr(m, 'reset_parameters'):
+                m.reset_parameters()
+        with torch.no_grad():
+            self.eps.fill_(self.initial_eps)
+
+    def _mlp(self, h):
+        n = self.nn
+        if (isinstance(n, tnn.Sequential) and len(n) == 3 and isinstance(n[0], tnn.Linear)
+                and isinstance(n[1], tnn.ReLU) and isinstance(n[2], tnn.Linear)):
+            h = Fn.linear(h, n[0].weight, n[0].bias, act=1)       # Linear + ReLU fused epilogue
+            return Fn.linear(h, n[2].weight, n[2].bias)
+        return n(h)
+
+    def forward(self, x, edge_index, size=None):
+        _check_x(x, edge_index)
+        g = graph_of(edge_index, x.shape[0])
+        if self._train_eps:
+            h = Fn.SegSumFn.apply(x, None, g, "raw", False, 0.0) + (1 + self.eps).to(x.dtype) * x
+        else:
+            key = (self.eps.data_ptr(), self.eps._version)
+            if self._eps_key != key:                       # eps is a buffer: one host read per change
+                self._eps_host, self._eps_key = float(self.eps.item()), key
+            h = Fn.SegSumFn.apply(x, None, g, "raw", False, 1.0 + self._eps_host)
+        return self._mlp(h)
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}(nn={self.nn})'
+
+
+class TransformerConv(MessagePassing):
+    """TransformerConv(in, out, heads=4, concat=False, dropout=p) — gnn_model.py:77-80; forward at :170
+    (called with edge_attr=..., which PyG cannot consume without edge_dim: see forward)."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
+                 beta: bool = False, dropout: float = 0.0, edge_dim: Optional[int] = None, bias: bool = True,
+                 root_weight: bool = True, **kwargs):
+        super().__init__(aggr='add')
+        if beta or edge_dim is not None:
+            raise NotImplementedError("b2g TransformerConv: only beta=False, edge_dim=None")
+        if not isinstance(in_channels, int):
+            raise NotImplementedError("b2g TransformerConv: bipartite in_channels are not supported")
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.beta, self.dropout, self.edge_dim, self.root_weight = beta, dropout, edge_dim, root_weight
+        self.lin_key = Linear(in_channels, heads * out_channels)
+        self.lin_query = Linear(in_channels, heads * out_channels)
+        self.lin_value = Linear(in_channels, heads * out_channels)
+        self.lin_edge = None
+        if root_weight:
+            self.lin_skip = Linear(in_channels, heads * out_channels if concat else out_channels, bias=bias)
+        else:
+            self.lin_skip = None
+        self.lin_beta = None
+        self._warned_edge_attr = False
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        self.lin_key.reset_parameters()
+        self.lin_query.reset_parameters()
+        self.lin_value.reset_parameters()
+        if self.root_weight:
+            self.lin_skip.reset_parameters()
+
+    def forward(self, x, edge_index, edge_attr=None, return_attention_weights=None):
+        if return_attention_weights:
+            raise NotImplementedError("b2g TransformerConv: return_attention_weights is not supported")
+        if edge_attr is not None and not self._warned_edge_attr:
+            # edge_dim=None => PyG has no lin_edge; its message() would add [E,4] to [E,H,C] and raise
+            # (SURVEY §8a row 7).  Parity target = forward(x, edge_index); the attribute is ignored.
+            warnings.warn("b2g TransformerConv: edge_attr ignored because edge_dim=None")
+            self._warned_edge_attr = True
+        _check_x(x, edge_index)
+        g = graph_of(edge_index, x.shape[0])
+        ws = [self.lin_query.weight, self.lin_key.weight, self.lin_value.weight]
+        bs = [self.lin_query.bias, self.lin_key.bias, self.lin_value.bias]
+        if self.root_weight:
+            ws.append(self.lin_skip.weight)
+            sb = self.lin_skip.bias
+            bs.append(sb if sb is not None else torch.zeros(self.lin_skip.out_channels, device=x.device))
+        w_cat = torch.cat(ws, 0).to(x.dtype)
+        b_cat = torch.cat(bs, 0).float()
+        p = self.dropout if self.training else 0.0
+        return Fn.TConvFn.apply(x, w_cat, b_cat, g, self.heads, self.out_channels, self.concat, p, self.root_weight)
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})'
+
+
+class BatchNorm(tnn.Module):
+    """torch_geometric.nn.BatchNorm — gnn_model.py:87,188: a BatchNorm1d held as `.module`
+    (state_dict keys module.weight / module.running_mean / ...)."""
+
+    def __init__(self, in_channels: int, eps: float = 1e-5, momentum: Optional[float] = 0.1, affine: bool = True,
+                 track_running_stats: bool = True, allow_single_element: bool = False):
+        super().__init__()
+        self.module = tnn.BatchNorm1d(in_channels, eps, momentum, affine, track_running_stats)
+        self.in_channels = in_channels
+        self.allow_single_element = allow_single_element
+
+    def reset_running_stats(self):
+        self.module.reset_running_stats()
+
+    def reset_parameters(self):
+        self.module.reset_parameters()
+
+    def forward(self, x):
+        return self.module(x)
+
+    def __repr__(self):
+        return f'{self.__class__.__name__}({self.module.num_features})'
+
+
+def global_mean_pool(x, batch=None, size=None):
+    """Imported but never called by the reference (gnn_model.py:8).  Mean of node rows per graph."""
+    if batch is None:
+        return x.mean(dim=0, keepdim=True)
+    size = int(batch.max().item()) + 1 if size is None else size
+    out = x.new_zeros((size, x.shape[1])).index_add_(0, batch, x)
+    cnt = torch.bincount(batch, minlength=size).clamp(min=1).to(x.dtype)
+    return out / cnt.unsqueeze(1)

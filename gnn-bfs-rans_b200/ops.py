@@ -1,0 +1,326 @@
+"""Thin torch-tensor wrappers over the C ABI (include/b2g.h).  PyTorch is plumbing here: it owns
+device memory and the stream; every computation is a libb2g.so kernel.  No CPU fallback: a
+non-CUDA tensor raises RuntimeError."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"b2g: unsupported feature dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("b2g: CUDA tensor required (this is the B200 path; there is no CPU fallback)")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: torch.Tensor) -> torch.Tensor:
+    """2-D, unit stride in the last dim, 16-byte aligned rows; copy only if the view is not."""
+    if t.dim() != 2:
+        raise RuntimeError("b2g: expected a 2-D feature matrix")
+    es = t.element_size()
+    if t.stride(1) != 1 or (t.stride(0) * es) % 16 or t.data_ptr() % 16 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+        if (t.shape[1] * es) % 16:
+            raise RuntimeError(f"b2g: feature width {t.shape[1]} x {es} B is not a multiple of 16 bytes")
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------ K0
+def build_edge_index(owner: torch.Tensor, neighbour: torch.Tensor) -> torch.Tensor:
+    """graph_constructor.py:28-56 on device.  owner/neighbour: int32 CUDA."""
+    _cuda(owner, neighbour)
+    lib = _lib.load()
+    n_o, n_n = owner.numel(), neighbour.numel()
+    if n_n > n_o:
+        raise IndexError("index out of bounds: neighbour is longer than owner")  # reference: owner[i], :40
+    E = n_o + n_n
+    out = torch.empty((2, E), dtype=torch.int64, device=owner.device)
+    if E:
+        _lib.check(lib.b2g_build_edge_index(_p(owner), _p(neighbour), n_o, n_n, _p(out), _stream()), "build_edge_index")
+    return out
+
+
+def mask_to_map(mask_u8: torch.Tensor):
+    _cuda(mask_u8)
+    lib = _lib.load()
+    n = mask_u8.numel()
+    o2n = torch.empty(n, dtype=torch.int32, device=mask_u8.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=mask_u8.device)
+    ws = _ws(lib.b2g_mask_to_map_workspace_bytes(n), mask_u8.device)
+    _lib.check(lib.b2g_mask_to_map(_p(mask_u8), n, _p(o2n), _p(cnt), _p(ws), _stream()), "mask_to_map")
+    return o2n, int(cnt.item())
+
+
+def build_graph_edges(owner, neighbour, mode: int, old_to_new, n_cells: int, n_nodes: int) -> torch.Tensor:
+    """Edge part of GraphConstructor.build_graph (graph_constructor.py:109-187, 220-227)."""
+    _cuda(owner, neighbour, old_to_new)
+    lib = _lib.load()
+    dev = owner.device
+    n_o, n_n = owner.numel(), neighbour.numel()
+    if n_n > n_o:
+        raise IndexError("index out of bounds: neighbour is longer than owner")
+    ws = _ws(lib.b2g_build_graph_workspace_bytes(n_o, n_n, n_nodes), dev)
+    counts = torch.zeros(3, dtype=torch.int64, device=dev)
+    st = _stream()
+    _lib.check(lib.b2g_build_graph_count(_p(owner), _p(neighbour), n_o, n_n, mode, _p(old_to_new), n_cells,
+                                         n_nodes, _p(ws), _p(counts), st), "build_graph_count")
+    e_kept, n_iso, n_bad = (int(v) for v in counts.tolist())      # the one host sync of the builder
+    if n_bad:
+        raise IndexError(f"index out of bounds: {n_bad} internal faces reference cells outside [0, {n_cells})")
+    E = e_kept + n_iso
+    out = torch.empty((2, E), dtype=torch.int64, device=dev)
+    if E:
+        _lib.check(lib.b2g_build_graph_fill(_p(owner), _p(neighbour), n_o, n_n, mode, _p(old_to_new), n_cells,
+                                            n_nodes, _p(ws), E, _p(out), st), "build_graph_fill")
+    return out
+
+
+def edge_attr(cell_centers_f64: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+    """graph_constructor.py:58-90 / :190-219 on device.  fp64 [n,3] centres -> fp32 [E,4]."""
+    _cuda(cell_centers_f64, edge_index)
+    lib = _lib.load()
+    cc = cell_centers_f64.contiguous()
+    ei = edge_index.contiguous()
+    E = ei.shape[1]
+    out = torch.empty((E, 4), dtype=torch.float32, device=ei.device)
+    if E:
+        _lib.check(lib.b2g_edge_attr(_p(cc), cc.shape[0], _p(ei), E, _p(out), _stream()), "edge_attr")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K1
+def csr_build(edge_index: torch.Tensor, N: int, self_loops: bool, by_source: bool, want_dinv: bool):
+    """-> (rowptr int32[N+1], col int32[nnz], eid int32[nnz], dinv fp32[N] | None)."""
+    _cuda(edge_index)
+    lib = _lib.load()
+    ei = edge_index.contiguous()
+    dev = ei.device
+    E = ei.shape[1]
+    ws = _ws(lib.b2g_csr_workspace_bytes(E, N), dev)
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    nnz_d = torch.zeros(2, dtype=torch.int64, device=dev)
+    st = _stream()
+    _lib.check(lib.b2g_csr_count(_p(ei), E, N, int(self_loops), int(by_source), _p(rowptr), _p(nnz_d), _p(ws), st), "csr_count")
+    nnz, bad = (int(v) for v in nnz_d.tolist())                   # one host sync per distinct edge_index
+    if bad:
+        raise RuntimeError(f"b2g: edge_index has {bad} edges with an endpoint outside [0, {N})")
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    eid = torch.empty(nnz, dtype=torch.int32, device=dev)
+    dinv = torch.empty(N, dtype=torch.float32, device=dev) if want_dinv else None
+    _lib.check(lib.b2g_csr_fill(_p(ei), E, N, int(self_loops), int(by_source), _p(rowptr), nnz, _p(col), _p(eid),
+                                _p(dinv), _p(ws), st), "csr_fill")
+    return rowptr, col, eid, dinv
+
+
+def csr_perm(eid_a, eid_b, id_space: int):
+    lib = _lib.load()
+    nnz = eid_a.numel()
+    scratch = torch.empty(max(id_space, 1), dtype=torch.int32, device=eid_a.device)
+    perm = torch.empty(nnz, dtype=torch.int32, device=eid_a.device)
+    _lib.check(lib.b2g_csr_perm(_p(eid_a), _p(eid_b), nnz, _p(scratch), _p(perm), _stream()), "csr_perm")
+    return perm
+
+
+# ------------------------------------------------------------------------------------------ K2/K3
+def seg_sum(x, rowptr, col, n_rows, row_scale=None, col_scale=None, self_coef=0.0, x_self=None, bias=None,
+            relu=False, out=None):
+    _cuda(x)
+    lib = _lib.load()
+    x = _rows(x)
+    xs = _rows(x_self) if x_self is not None else None
+    F = x.shape[1]
+    if out is None:
+        out = torch.empty((n_rows, F), dtype=x.dtype, device=x.device)
+    _lib.check(lib.b2g_seg_sum(_p(x), _ld(x), _p(xs), _ld(xs) if xs is not None else 0, _p(out), _ld(out), n_rows, F,
+                               _dt(x), _p(rowptr), _p(col), _p(row_scale), _p(col_scale), float(self_coef),
+                               _p(bias), int(relu), _stream()), "seg_sum")
+    return out
+
+
+def colsum(x) -> torch.Tensor:
+    _cuda(x)
+    lib = _lib.load()
+    x = _rows(x)
+    F = x.shape[1]
+    out = torch.empty(F, dtype=torch.float32, device=x.device)
+    ws = _ws(lib.b2g_colsum_workspace_bytes(F), x.device)
+    _lib.check(lib.b2g_colsum(_p(x), _ld(x), x.shape[0], F, _dt(x), _p(out), _p(ws), _stream()), "colsum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K6
+GEMM_IMPL = 0  # 0 auto, 1 SIMT, 2 tcgen05 (tests force one or the other)
+
+
+def linear_fwd(x, w, bias=None, row_scale=None, act=0, m_main=None, out=None):
+    """y = act(row_scale * (x @ w.T) + bias).  Returns (y [n,m_main], aux fp32 [n,m-m_main] | None)."""
+    _cuda(x, w)
+    lib = _lib.load()
+    x = _rows(x)
+    w = _rows(w)
+    if w.dtype != x.dtype:
+        w = w.to(x.dtype)
+    n, k = x.shape
+    m = w.shape[0]
+    if w.shape[1] != k:
+        raise RuntimeError(f"b2g linear: weight [{m},{w.shape[1]}] does not match input width {k}")
+    m_main = m if m_main is None else m_main
+    y = out if out is not None else torch.empty((n, m_main), dtype=x.dtype, device=x.device)
+    aux = torch.empty((n, m - m_main), dtype=torch.float32, device=x.device) if m_main < m else None
+    b = bias.float().contiguous() if bias is not None else None
+    ws = _ws(lib.b2g_linear_workspace_bytes(n, m, k, _dt(x), 0), x.device)
+    _lib.check(lib.b2g_linear_fwd(_p(x), _ld(x), _p(w), _ld(w), _p(b), _p(row_scale), _p(y), _ld(y), _p(aux),
+                                  (m - m_main) if aux is not None else 0, n, m, m_main, k, _dt(x), int(act),
+                                  GEMM_IMPL, _p(ws), _stream()), "linear_fwd")
+    return y, aux
+
+
+def linear_dgrad(dy, w, out=None):
+    """dx[n,k] = dy[n,m] @ w[m,k]."""
+    _cuda(dy, w)
+    lib = _lib.load()
+    dy = _rows(dy)
+    w = _rows(w)
+    if w.dtype != dy.dtype:
+        w = w.to(dy.dtype)
+    n, m = dy.shape
+    k = w.shape[1]
+    dx = out if out is not None else torch.empty((n, k), dtype=dy.dtype, device=dy.device)
+    if GEMM_IMPL != 1 and lib.b2g_linear_impl(n, k, m, _dt(dy), 0) == 2:
+        # tensor-core path: dgrad is a forward GEMM against W^T (a [k,m] copy of a few hundred KB)
+        y, _ = linear_fwd(dy, w.t().contiguous(), out=dx)
+        return y
+    ws = _ws(256, dy.device)
+    _lib.check(lib.b2g_linear_dgrad(_p(dy), _ld(dy), _p(w), _ld(w), _p(dx), _ld(dx), n, m, k, _dt(dy), 1,
+                                    _p(ws), _stream()), "linear_dgrad")
+    return dx
+
+
+def linear_wgrad(dy, x, want_bias=True):
+    """dW[m,k] = dy.T @ x (fp32), db[m] = dy.sum(0) (fp32)."""
+    _cuda(dy, x)
+    lib = _lib.load()
+    dy = _rows(dy)
+    x = _rows(x)
+    n, m = dy.shape
+    k = x.shape[1]
+    dw = torch.empty((m, k), dtype=torch.float32, device=dy.device)
+    db = torch.empty(m, dtype=torch.float32, device=dy.device) if want_bias else None
+    ws = _ws(lib.b2g_linear_workspace_bytes(n, m, k, _dt(dy), 2), dy.device)
+    _lib.check(lib.b2g_linear_wgrad(_p(dy), _ld(dy), _p(x), _ld(x), _p(dw), k, _p(db), n, m, k, _dt(dy), 0,
+                                    _p(ws), _stream()), "linear_wgrad")
+    return dw, db
+
+
+# ------------------------------------------------------------------------------------------ K4
+def gat_fwd(xw, a, H, C, concat, slope, rowptr, col, bias, p_drop, seed, save_stats):
+    """xw [N,H*C]; a fp32 [N,2H] = [a_src | a_dst].  -> out, smax, ssum."""
+    lib = _lib.load()
+    N = xw.shape[0]
+    out = torch.empty((N, H * C if concat else C), dtype=xw.dtype, device=xw.device)
+    smax = torch.empty((N, H), dtype=torch.float32, device=xw.device) if save_stats else None
+    ssum = torch.empty((N, H), dtype=torch.float32, device=xw.device) if save_stats else None
+    _lib.check(lib.b2g_gat_fwd(_p(xw), _ld(xw), _p(a), a.data_ptr() + 4 * H, a.stride(0), _p(out), _ld(out), N, H, C,
+                               _dt(xw), int(concat), float(slope), _p(rowptr), _p(col), _p(bias), _p(smax), _p(ssum),
+                               float(p_drop), int(seed), _stream()), "gat_fwd")
+    return out, smax, ssum
+
+
+def gat_bwd(xw, a, gout, H, C, concat, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, d_xw_out):
+    """-> d_a fp32 [N,2H]; writes d_xw into d_xw_out (a [N,H*C] view, any row stride)."""
+    lib = _lib.load()
+    N = xw.shape[0]
+    dev = xw.device
+    nnz = csr[1].numel()
+    alpha_e = torch.empty((nnz, H), dtype=torch.float32, device=dev)
+    ds_e = torch.empty((nnz, H), dtype=torch.float32, device=dev)
+    d_a = torch.empty((N, 2 * H), dtype=torch.float32, device=dev)
+    gout = _rows(gout)
+    st = _stream()
+    _lib.check(lib.b2g_gat_bwd_dst(_p(xw), _ld(xw), _p(a), a.data_ptr() + 4 * H, a.stride(0), _p(gout), _ld(gout), N,
+                                   H, C, _dt(xw), int(concat), float(slope), _p(csr[0]), _p(csr[1]), _p(smax),
+                                   _p(ssum), float(p_drop), int(seed), _p(alpha_e), _p(ds_e),
+                                   d_a.data_ptr() + 4 * H, 2 * H, st), "gat_bwd_dst")
+    _lib.check(lib.b2g_gat_bwd_src(_p(gout), _ld(gout), _p(alpha_e), _p(ds_e), _p(d_xw_out), _ld(d_xw_out),
+                                   _p(d_a), 2 * H, N, H, C, _dt(xw), int(concat), _p(csr_t[0]), _p(csr_t[1]),
+                                   _p(perm), st), "gat_bwd_src")
+    return d_a
+
+
+# ------------------------------------------------------------------------------------------ K5
+def tconv_fwd(q, k, v, skip, H, C, concat, rowptr, col, p_drop, seed, save_stats):
+    lib = _lib.load()
+    N = q.shape[0]
+    out = torch.empty((N, H * C if concat else C), dtype=q.dtype, device=q.device)
+    smax = torch.empty((N, H), dtype=torch.float32, device=q.device) if save_stats else None
+    ssum = torch.empty((N, H), dtype=torch.float32, device=q.device) if save_stats else None
+    assert q.stride(0) == k.stride(0) == v.stride(0)
+    _lib.check(lib.b2g_tconv_fwd(_p(q), _p(k), _p(v), _ld(q), _p(skip), _ld(skip) if skip is not None else 0, _p(out),
+                                 _ld(out), N, H, C, _dt(q), int(concat), _p(rowptr), _p(col), _p(smax), _p(ssum),
+                                 float(p_drop), int(seed), _stream()), "tconv_fwd")
+    return out, smax, ssum
+
+
+def tconv_bwd(q, k, v, gout, H, C, concat, csr, csr_t, perm, smax, ssum, p_drop, seed, dq, dk, dv):
+    """Writes dq, dk, dv (views [N,H*C] sharing one row stride)."""
+    lib = _lib.load()
+    N = q.shape[0]
+    dev = q.device
+    nnz = csr[1].numel()
+    alpha_e = torch.empty((nnz, H), dtype=torch.float32, device=dev)
+    ds_e = torch.empty((nnz, H), dtype=torch.float32, device=dev)
+    gout = _rows(gout)
+    st = _stream()
+    assert dk.stride(0) == dv.stride(0)
+    _lib.check(lib.b2g_tconv_bwd_dst(_p(q), _p(k), _p(v), _ld(q), _p(gout), _ld(gout), N, H, C, _dt(q), int(concat),
+                                     _p(csr[0]), _p(csr[1]), _p(smax), _p(ssum), float(p_drop), int(seed),
+                                     _p(alpha_e), _p(ds_e), _p(dq), _ld(dq), st), "tconv_bwd_dst")
+    _lib.check(lib.b2g_tconv_bwd_src(_p(q), _ld(q), _p(gout), _ld(gout), _p(alpha_e), _p(ds_e), _p(dk), _p(dv),
+                                     _ld(dk), N, H, C, _dt(q), int(concat), _p(csr_t[0]), _p(csr_t[1]), _p(perm),
+                                     st), "tconv_bwd_src")
+
+
+# ------------------------------------------------------------------------------------------ halo
+def rows_gather(x, idx, out=None):
+    lib = _lib.load()
+    x = _rows(x)
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n, x.shape[1]), dtype=x.dtype, device=x.device)
+    _lib.check(lib.b2g_rows_gather(_p(x), _ld(x), _p(idx), n, _p(out), _ld(out), x.shape[1], _dt(x), _stream()), "rows_gather")
+    return out
+
+
+def rows_scatter_add(x, idx, src):
+    lib = _lib.load()
+    src = _rows(src)
+    _lib.check(lib.b2g_rows_scatter_add(_p(x), _ld(x), _p(idx), idx.numel(), _p(src), _ld(src), x.shape[1], _dt(x),
+                                        _stream()), "rows_scatter_add")
+    return x

@@ -1,0 +1,52 @@
+"""Synthetic meshes of BASELINE.json's configs, emitted the way OpenFOAM stores them: owner/neighbour
+face lists with owner < neighbour, internal faces sorted by owner (upper-triangular order), boundary
+faces after them."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def hex_mesh_faces(nx: int, ny: int, nz: int, device="cpu", boundary: bool = False):
+    """Structured hex block, lexicographic cell ids (x fastest).  Returns int32 (owner, neighbour):
+    internal faces only unless boundary=True (then owner also lists one entry per boundary face)."""
+    dev = torch.device(device)
+    N = nx * ny * nz
+    ids = torch.arange(N, dtype=torch.int64, device=dev)
+    ix = ids % nx
+    iy = (ids // nx) % ny
+    iz = ids // (nx * ny)
+    # per cell up to three "upper" faces (+x, +y, +z), interleaved per owner so the list is sorted by owner
+    has = torch.stack([ix < nx - 1, iy < ny - 1, iz < nz - 1], dim=1)
+    nb = torch.stack([ids + 1, ids + nx, ids + nx * ny], dim=1)
+    own = ids.unsqueeze(1).expand(-1, 3)
+    owner = own[has].to(torch.int32)
+    nei = nb[has].to(torch.int32)
+    if boundary:
+        nbnd = (ix == 0).int() + (ix == nx - 1).int() + (iy == 0).int() + (iy == ny - 1).int() + \
+               (iz == 0).int() + (iz == nz - 1).int()
+        owner = torch.cat([owner, torch.repeat_interleave(ids, nbnd.long()).to(torch.int32)])
+    return owner.contiguous(), nei.contiguous()
+
+
+def hex_cell_centers(nx: int, ny: int, nz: int) -> np.ndarray:
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    return np.stack([x.ravel() + 0.5, y.ravel() + 0.5, z.ravel() + 0.5], axis=1).astype(np.float64)
+
+
+def delaunay_dual_faces(n_points: int, seed: int = 1):
+    """cfg3: cells = triangles of a Delaunay triangulation of uniform points in the unit square;
+    faces = shared triangle edges.  Returns (owner, neighbour int32 numpy, centres float64 [N,3])."""
+    from scipy.spatial import Delaunay
+    pts = np.random.default_rng(seed).random((n_points, 2))
+    tri = Delaunay(pts)
+    nbr = tri.neighbors                       # [N,3], -1 at the hull
+    N = len(nbr)
+    own = np.repeat(np.arange(N), 3)
+    nb = nbr.ravel()
+    keep = (nb >= 0) & (own < nb)             # each shared edge once, owner < neighbour
+    own, nb = own[keep], nb[keep]
+    order = np.lexsort((nb, own))
+    c = pts[tri.simplices].mean(axis=1)
+    centres = np.concatenate([c, np.zeros((N, 1))], axis=1)
+    return own[order].astype(np.int32), nb[order].astype(np.int32), centres

@@ -1,0 +1,210 @@
+/*
+ * b2g.h — C ABI of libb2g.so: the B200-native (sm_100a) message-passing hot path that replaces,
+ * behind the reference's own Python API, what Caesar3142/GNN-BFS-RANS executes through
+ * torch-geometric and Python loops.  Every entry point cites the reference interface it replaces
+ * (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain `extern "C"`, plain pointers and sizes, no torch types.
+ *   - every pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`.
+ *     Outputs and workspaces are pre-allocated by the caller (`*_workspace_bytes` queries).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*).
+ *   - return value: 0 = ok, <0 = invalid argument (B2G_E_*), >0 = a cudaError_t.
+ *   - feature matrices are row-major [rows, width] with an explicit row stride `ld` in ELEMENTS;
+ *     rows must be 16-byte aligned (ld*sizeof(elem) % 16 == 0, base 16-byte aligned).
+ *   - index arrays of the CSR are int32 (E < 2^31); edge_index stays int64 as in PyG.
+ *   - no global mutable state except lazily initialised per-device attributes.
+ */
+#ifndef B2G_H_
+#define B2G_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2G_VERSION 100
+
+typedef enum { B2G_F32 = 0, B2G_BF16 = 1 } b2g_dtype;
+
+enum {
+  B2G_OK = 0,
+  B2G_E_ARG = -1,        /* null pointer / negative size / bad enum                         */
+  B2G_E_ALIGN = -2,      /* pointer or row stride not 16-byte aligned                       */
+  B2G_E_SHAPE = -3,      /* unsupported width / heads combination                           */
+  B2G_E_RANGE = -4,      /* size does not fit the int32 CSR index type                      */
+  B2G_E_UNSUPPORTED = -5 /* this build has no kernel for the request                        */
+};
+
+int b2g_version(void);
+const char* b2g_error_string(int code);
+/* Number of kernels this library has launched in this process (bench.py's `gpu_launches`). */
+int64_t b2g_launch_count(void);
+void b2g_launch_count_reset(void);
+
+/* ===================================================================================== K0
+ * Graph builder.  Replaces GraphConstructor.build_edge_index (graph_constructor.py:28-56) and the
+ * edge part of GraphConstructor.build_graph (graph_constructor.py:109-187, 220-227).
+ * Bit-exact int64 [2,E] row-major output. */
+
+/* build_edge_index(): E = 2*n_nei + (n_owner - n_nei); out_ei is int64 [2,E]. */
+int b2g_build_edge_index(const int32_t* owner, const int32_t* neighbour, int64_t n_owner,
+                         int64_t n_nei, int64_t* out_ei, void* stream);
+
+/* internal_mask (uint8 [n_cells]) -> old_to_new (int32 [n_cells], rank among set entries or -1)
+ * (graph_constructor.py:116-129).  n_set_out: device int64[1]. */
+int64_t b2g_mask_to_map_workspace_bytes(int64_t n_cells);
+int b2g_mask_to_map(const uint8_t* mask, int64_t n_cells, int32_t* old_to_new, int64_t* n_set_out,
+                    void* ws, void* stream);
+
+/* build_graph edge list in two phases (output size is data dependent).
+ *   mode 0 ("C", graph_constructor.py:156,168-173): build_edge_index() then drop edges with an
+ *          endpoint >= n_nodes.  old_to_new must be NULL.
+ *   mode 1 ("A"/"B", graph_constructor.py:137-154): keep internal faces whose two cells both map
+ *          to >= 0 through old_to_new[n_cells]; endpoints are remapped.  For mode A
+ *          (n_internal_cells = n) pass old_to_new = NULL and n_nodes = n (identity map on [0,n)).
+ * Then (graph_constructor.py:176-187, 220-227) one (v,v) per node v in [0,n_nodes) that appears in
+ * no kept edge, ascending, appended after the kept edges.
+ * counts_out: device int64[3] = {E_kept, n_isolated, n_bad} (n_bad = cell ids outside
+ * [0,n_cells) met in mode 1: the reference raises IndexError there).
+ * Phase 2 needs E_total = E_kept + n_isolated known on the host; out_ei is int64 [2,E_total]. */
+int64_t b2g_build_graph_workspace_bytes(int64_t n_owner, int64_t n_nei, int64_t n_nodes);
+int b2g_build_graph_count(const int32_t* owner, const int32_t* neighbour, int64_t n_owner,
+                          int64_t n_nei, int mode, const int32_t* old_to_new, int64_t n_cells,
+                          int64_t n_nodes, void* ws, int64_t* counts_out, void* stream);
+int b2g_build_graph_fill(const int32_t* owner, const int32_t* neighbour, int64_t n_owner,
+                         int64_t n_nei, int mode, const int32_t* old_to_new, int64_t n_cells,
+                         int64_t n_nodes, const void* ws, int64_t E_total, int64_t* out_ei,
+                         void* stream);
+
+/* Edge attributes [dir_x,dir_y,dir_z,dist]: float64 arithmetic, fp32 output, zeros for self loops
+ * and out-of-range endpoints.  Replaces graph_constructor.py:58-90 and :190-219.
+ * cell_centers: float64 [n_centers,3]; edge_index int64 [2,E]; out fp32 [E,4]. */
+int b2g_edge_attr(const double* cell_centers, int64_t n_centers, const int64_t* edge_index,
+                  int64_t E, float* out, void* stream);
+
+/* ===================================================================================== K1
+ * CSR of the edge list a layer aggregates over.  No reference counterpart (PyG rebuilds gcn_norm /
+ * self loops on every forward and scatters by edge); defined as the STABLE sort of the effective
+ * edge list by the grouping endpoint.
+ *   self_loops: 0 = raw list (GINConv, TransformerConv);
+ *               1 = remove_self_loops + add_self_loops appended at the end (GCNConv gcn_norm,
+ *                   GATConv; torch_geometric.utils.loop).
+ *   by_source : 0 = rows are targets (edge_index[1]), col = source   (forward aggregation)
+ *               1 = rows are sources (edge_index[0]), col = target   (backward / transposed)
+ * Outputs: rowptr int32 [N+1]; col int32 [nnz]; eid int32 [nnz] (edge id: the position e in
+ * edge_index for a kept edge, E+v for the appended loop of node v); dinv fp32 [N] = deg^-1/2 (0 if deg==0), may be
+ * NULL.  nnz = b2g_csr_nnz result: E for self_loops=0, (E - #loops) + N for self_loops=1; the
+ * #loops count needs a device pass: b2g_csr_count writes {nnz} to nnz_out (device int64[1]).
+ * Edges with an endpoint outside [0,N) are an error (counted in nnz_out[1]). */
+int64_t b2g_csr_workspace_bytes(int64_t E, int64_t N);
+int b2g_csr_count(const int64_t* edge_index, int64_t E, int64_t N, int self_loops, int by_source,
+                  int32_t* rowptr, int64_t* nnz_out, void* ws, void* stream);
+int b2g_csr_fill(const int64_t* edge_index, int64_t E, int64_t N, int self_loops, int by_source,
+                 const int32_t* rowptr, int64_t nnz, int32_t* col, int32_t* eid, float* dinv,
+                 void* ws, void* stream);
+/* perm[q] = position in `csr_a` of the edge stored at position q of `csr_b` (two CSRs of the same
+ * effective edge list).  scratch: int32 [E+N] (edge-id space). */
+int b2g_csr_perm(const int32_t* eid_a, const int32_t* eid_b, int64_t nnz, int32_t* scratch,
+                 int32_t* perm, void* stream);
+
+/* ===================================================================================== K2/K3
+ * Deterministic CSR segment-sum.  Replaces MessagePassing.propagate's index_select + scatter_add_
+ *  for GCNConv (gnn_model.py:63,166) and GINConv (gnn_model.py:75,166):
+ *   out[i,:] = row_scale[i] * sum_{p in row i} col_scale[col[p]] * x[col[p],:]
+ *              + self_coef * x[i,:] + bias[:]
+ * row_scale / col_scale / bias may be NULL (=1 / =1 / =0); accumulation in fp32 in CSR order.
+ * x: [*, F] dtype `dt`, row stride ldx; out: [n_rows, F] dtype `dt`, row stride ldo.
+ * `x_self` (may be NULL -> x) is the matrix the self term reads (rows indexed by i).
+ * relu != 0 applies max(.,0) last. */
+int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                const int32_t* col, const float* row_scale, const float* col_scale,
+                float self_coef, const float* bias, int relu, void* stream);
+
+/* ===================================================================================== K4
+ * GATConv (gnn_model.py:65-68,168) fused edge-score + segment-softmax + aggregate + head-mean +
+ * bias.  xw: [N, H*C] (= lin(x)); a_src/a_dst: fp32 [N,H] with row stride
+ * lda (they are the two halves of the aux output of b2g_linear_fwd, see K6).
+ *   s_p = leaky_relu(a_src[col[p],h] + a_dst[i,h], slope); alpha = softmax over row i;
+ *   out[i,c] = (concat ? per head : mean over h) sum_p alpha_{p,h} xw[col[p],h,c] + bias
+ * smax/ssum: fp32 [N,H] saved row max and sum(exp)+1e-16 (may be NULL in inference).
+ * dropout: p_drop in [0,1) with Philox seed/offset (0 -> no dropout); mask regenerated in bwd. */
+int b2g_gat_fwd(const void* xw, int64_t ldxw, const float* a_src, const float* a_dst, int64_t lda,
+                void* out, int64_t ldo, int64_t n_rows, int H, int C, int dt, int concat, float slope,
+                const int32_t* rowptr, const int32_t* col, const float* bias, float* smax,
+                float* ssum, float p_drop, uint64_t seed, void* stream);
+/* Backward, target-major pass: recomputes alpha, produces per-edge alpha_e / dscore_e (fp32
+ * [nnz,H], CSR order) and d a_dst [N,H].  gout: [N, concat?H*C:C]. */
+int b2g_gat_bwd_dst(const void* xw, int64_t ldxw, const float* a_src, const float* a_dst, int64_t lda,
+                    const void* gout, int64_t ldg, int64_t n_rows, int H, int C, int dt, int concat,
+                    float slope, const int32_t* rowptr, const int32_t* col, const float* smax,
+                    const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* ds_e,
+                    float* d_a_dst, int64_t ldda, void* stream);
+/* Backward, source-major pass over the transposed CSR (perm maps its positions to CSR positions):
+ *   d xw[j,h,:] = sum_p alpha_{p,h} * gout[col_t[p], (h,):] (/H if mean);  d a_src[j,h] = sum_p ds_{p,h} */
+int b2g_gat_bwd_src(const void* gout, int64_t ldg, const float* alpha_e, const float* ds_e,
+                    void* d_xw, int64_t ldd, float* d_a_src, int64_t ldda, int64_t n_rows, int H, int C, int dt,
+                    int concat, const int32_t* rowptr_t, const int32_t* col_t, const int32_t* perm,
+                    void* stream);
+
+/* ===================================================================================== K5
+ * TransformerConv (gnn_model.py:77-80,170) fused q.k score + segment-softmax + aggregate +
+ * head-mean + skip.  q,k,v: [N,H*C]; skip: [N, concat?H*C:C] or NULL.
+ *   alpha = softmax_row( <q[i,h,:], k[col[p],h,:]> / sqrt(C) );  out = mean_h sum alpha v + skip */
+int b2g_tconv_fwd(const void* q, const void* k, const void* v, int64_t ldqkv, const void* skip,
+                  int64_t lds, void* out, int64_t ldo, int64_t n_rows, int H, int C, int dt,
+                  int concat, const int32_t* rowptr, const int32_t* col, float* smax, float* ssum,
+                  float p_drop, uint64_t seed, void* stream);
+int b2g_tconv_bwd_dst(const void* q, const void* k, const void* v, int64_t ldqkv, const void* gout,
+                      int64_t ldg, int64_t n_rows, int H, int C, int dt, int concat,
+                      const int32_t* rowptr, const int32_t* col, const float* smax,
+                      const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* ds_e,
+                      void* dq, int64_t lddq, void* stream);
+int b2g_tconv_bwd_src(const void* q, int64_t ldq, const void* gout, int64_t ldg,
+                      const float* alpha_e, const float* ds_e, void* dk, void* dv, int64_t ldd,
+                      int64_t n_rows, int H, int C, int dt, int concat, const int32_t* rowptr_t,
+                      const int32_t* col_t, const int32_t* perm, void* stream);
+
+/* ===================================================================================== K6
+ * Dense per-node Linear (PyG Linear / torch nn.Linear inside the conv layers).
+ *   fwd  : Y[n,m] = act( row_scale[n] * (sum_k X[n,k] W[m,k]) + bias[m] )        (F.linear)
+ *          columns [0,m_main) go to Y (dtype dt); columns [m_main,m) go to `aux` as fp32 with row
+ *          stride ldaux (GATConv's per-head attention logits ride along as extra columns of the
+ *          same GEMM); m_main == m and aux == NULL for a plain Linear.
+ *   dgrad: dX[n,k] = sum_m dY[n,m] W[m,k]
+ *   wgrad: dW[m,k] = sum_n dY[n,m] X[n,k];  db[m] = sum_n dY[n,m]   (fp32 outputs)
+ * X,Y,dX,dY dtype `dt`; W dtype `dt` for fwd/dgrad; accumulate fp32.  act: 0 none, 1 relu.
+ * impl: 0 = auto, 1 = SIMT (FFMA) kernel, 2 = tcgen05 tensor-core kernel. */
+int64_t b2g_linear_workspace_bytes(int64_t n, int m, int k, int dt, int which /*0 fwd 1 dgrad 2 wgrad*/);
+/* Which kernel impl=0 (auto) picks for this shape: 1 = SIMT, 2 = tcgen05. */
+int b2g_linear_impl(int64_t n, int m, int k, int dt, int which);
+int b2g_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                   const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n,
+                   int m, int m_main, int k, int dt, int act, int impl, void* ws, void* stream);
+int b2g_linear_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dX,
+                     int64_t lddx, int64_t n, int m, int k, int dt, int impl, void* ws,
+                     void* stream);
+int b2g_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
+                     int64_t lddw, float* db, int64_t n, int m, int k, int dt, int impl, void* ws,
+                     void* stream);
+
+/* Column sums: out[c] = sum_r x[r,c] (fp32, fixed order -> deterministic): bias gradients.
+ * ws: fp32 [b2g_colsum_workspace_bytes(F)/4]. */
+int64_t b2g_colsum_workspace_bytes(int F);
+int b2g_colsum(const void* x, int64_t ldx, int64_t n_rows, int F, int dt, float* out, void* ws,
+               void* stream);
+
+/* ===================================================================================== halo
+ * Multi-GPU halo plumbing (no reference counterpart).  pack: out[r,:] = x[idx[r],:];
+ * unpack_add: x[idx[r],:] += in[r,:] (idx unique within one call). */
+int b2g_rows_gather(const void* x, int64_t ldx, const int32_t* idx, int64_t n_idx, void* out,
+                    int64_t ldo, int F, int dt, void* stream);
+int b2g_rows_scatter_add(void* x, int64_t ldx, const int32_t* idx, int64_t n_idx, const void* in,
+                         int64_t ldi, int F, int dt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2G_H_ */

@@ -1,0 +1,95 @@
+"""The hot path behind its caller: FlowGNN (mirror of gnn_model.py:14-220) forward / gradients vs the
+fp64 oracle for every layer type, the drop-in module registration, and a short training run."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    b = b.double().cpu()
+    return float((a.double().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def grid_graph(nx, ny):
+    ids = np.arange(nx * ny).reshape(ny, nx)
+    o = np.concatenate([ids[:, :-1].ravel(), ids[:-1, :].ravel()])
+    n = np.concatenate([ids[:, 1:].ravel(), ids[1:, :].ravel()])
+    order = np.lexsort((n, o))
+    return o[order].astype(np.int32), n[order].astype(np.int32)
+
+
+@pytest.mark.parametrize("layer_type", ["GCN", "GAT", "GIN", "Transformer"])
+@pytest.mark.parametrize("training", [False, True])
+def test_flowgnn_matches_oracle(layer_type, training):
+    from gnn_bfs_rans_b200.flow_model import FlowGNN
+    from gnn_bfs_rans_b200 import GraphConstructor
+    from oracle import layers_oracle as lo
+    nx, ny = 40, 30
+    o, n = grid_graph(nx, ny)
+    cc = np.random.default_rng(0).standard_normal((nx * ny, 3))
+    g = GraphConstructor(dict(owner=o, neighbour=n, cell_centers=cc, n_cells=nx * ny)).build_graph(
+        filter_internal=True, n_internal_cells=nx * ny)
+    torch.manual_seed(0)
+    model = FlowGNN(3, 64, 7, 3, layer_type, dropout=0.0).cuda()
+    model.train(training)
+    x = g.x.cuda().requires_grad_(True)
+    out = model(x, g.edge_index.cuda(), g.edge_attr.cuda())
+    out.square().mean().backward()
+    p = {k: v.detach().double().cpu().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    x64 = g.x.double().requires_grad_(True)
+    ref = lo.flow_gnn_forward(x64, g.edge_index, p, layer_type, training=training)
+    ref.square().mean().backward()
+    assert rel(out.detach(), ref.detach()) < 2e-5
+    assert rel(x.grad, x64.grad) < 5e-5
+    for name, par in model.named_parameters():
+        if par.grad is not None and p[name].grad is not None and float(p[name].grad.abs().max()) > 1e-12:
+            assert rel(par.grad, p[name].grad) < 1e-4, name
+
+
+def test_dropin_registers_reference_import_names():
+    import importlib
+    import sys
+    from gnn_bfs_rans_b200 import dropin
+    saved = {k: sys.modules.get(k) for k in ("torch_geometric", "torch_geometric.nn", "torch_geometric.data", "graph_constructor")}
+    try:
+        dropin.install()
+        nn = importlib.import_module("torch_geometric.nn")
+        from torch_geometric.nn import MessagePassing, global_mean_pool, GCNConv, GATConv, GINConv, TransformerConv, BatchNorm  # noqa
+        from torch_geometric.data import Data, Batch  # noqa
+        from graph_constructor import GraphConstructor  # noqa
+        assert nn.GCNConv.__module__.endswith("nn")
+        d1 = Data(x=torch.randn(3, 2), edge_index=torch.tensor([[0, 1], [1, 2]]), num_nodes=3)
+        d2 = Data(x=torch.randn(2, 2), edge_index=torch.tensor([[0], [1]]), num_nodes=2)
+        b = Batch.from_data_list([d1, d2]).to('cuda')
+        assert b.edge_index.tolist() == [[0, 1, 3], [1, 2, 4]] and b.batch.tolist() == [0, 0, 0, 1, 1]
+        assert b.x.is_cuda and b.num_nodes == 5
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def test_short_training_run_reduces_loss():
+    from gnn_bfs_rans_b200.flow_model import FlowGNN
+    o, n = grid_graph(50, 40)
+    N = 2000
+    ei = torch.cat([torch.tensor(np.stack([o, n])), torch.tensor(np.stack([n, o]))], 1).long().cuda()
+    torch.manual_seed(0)
+    x = torch.rand(N, 3, device='cuda')
+    y = torch.stack([torch.sin(3 * x[:, 0]), torch.cos(2 * x[:, 1]), x[:, 0] * x[:, 1], x[:, 2], x.sum(1), x[:, 0] ** 2, x[:, 1]], 1)
+    for lt in ("GCN", "GAT"):
+        model = FlowGNN(3, 64, 7, 3, lt, dropout=0.1).cuda()
+        opt = torch.optim.Adam(model.parameters(), lr=3e-3)
+        losses = []
+        for _ in range(60):
+            opt.zero_grad()
+            loss = (model(x, ei) - y).square().mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            losses.append(float(loss))
+        assert losses[-1] < 0.5 * losses[0], (lt, losses[0], losses[-1])
