@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json's metric on BASELINE.json's config.
+
+metric   : message-passing edges/sec (whole job) = edges one GCNConv layer aggregates / step time
+workload : cfg4 — synthetic 3-D hex mesh 250x200x200 = 10 M cells PER GPU (lexicographic ids,
+           OpenFOAM owner/neighbour face list -> device builder mode A -> edge_index), GCNConv(256,256)
+           layer forward = K6 Linear + K2 fused-normalisation CSR segment-sum + bias.  E_sl = 69.72 M
+           aggregated edges per 10 M cells.  Inputs are > 5 GB, far larger than the 126 MB L2.
+step     : one pass of the hot path = `GCNConv.forward(x, edge_index)` over the whole mesh.
+value    : device-resident inputs, CSR cached (static mesh), CUDA-event timed, max over ranks.
+e2e      : the same layer call from HOST buffers: pinned x and edge_index are copied host->device, the
+           CSR is rebuilt (a new edge_index tensor every step, as `batch.to(device)` does at
+           train.py:167), the layer runs, the output is copied device->host; all inside the timed region.
+roofline : the dominant kernel (seg_sum, K2), algorithmic bytes 2*N*F*s + 4*nnz + 4*(N+1) + 4*N
+            / its own CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline / --impl reference : the reference's CPU path for this layer = the fp32 pure-torch
+           restatement of PyG's GCNConv (oracle/layers_oracle.py; PyG itself is not installable here),
+           all host threads, on a bounded sample of the same workload (a smaller hex block).
+N > 1    : weak scaling — every rank owns a 250x200x200 block of a 250x200x(200 N) mesh (what RCB gives
+           on this domain), with a real per-layer halo exchange of boundary rows over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NX, NY, NZ = 250, 200, 200
+F = 256
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b2g", choices=["b2g", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--layer", default="GCN", choices=["GCN", "GAT", "GIN", "Transformer"])
+    ap.add_argument("--small", action="store_true", help="64^3 mesh: for ncu captures and CPU-side debugging")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-layer-type / train-step extras")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            p = [t.strip() for t in s.split(",")]
+            if len(p) < 6:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU reference
+def cpu_reference(layer, steps, warmup, sample=(80, 80, 80)):
+    """The reference's CPU path for one layer forward: fp32 pure-torch restatement of PyG (oracle port)."""
+    import torch
+    from oracle import builder_oracle as bo
+    from oracle import layers_oracle as lo
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nx, ny, nz = sample
+    o, n = hex_mesh_faces(nx, ny, nz)
+    N = nx * ny * nz
+    ei = torch.from_numpy(bo.build_graph(dict(owner=o.numpy(), neighbour=n.numpy(), cell_centers=torch.zeros(N, 3).numpy(),
+                                              n_cells=N), filter_internal=True, n_internal_cells=N)['edge_index'])
+    torch.manual_seed(0)
+    x = torch.randn(N, F)
+    H = 4
+    g = lambda *s: lo.glorot_(torch.empty(*s))
+    if layer == "GCN":
+        W, b = g(F, F), torch.zeros(F)
+        fn = lambda: lo.gcn_conv(x, ei, W, b)
+        e_agg = int((ei[0] != ei[1]).sum()) + N
+    elif layer == "GAT":
+        W, a_s, a_d, b = g(H * F, F), g(1, H, F), g(1, H, F), torch.zeros(F)
+        fn = lambda: lo.gat_conv(x, ei, W, a_s, a_d, b, heads=H)
+        e_agg = int((ei[0] != ei[1]).sum()) + N
+    elif layer == "GIN":
+        w1, w2, b1, b2 = g(F, F), g(F, F), torch.zeros(F), torch.zeros(F)
+        fn = lambda: lo.gin_conv(x, ei, lo.gin_mlp(w1, b1, w2, b2))
+        e_agg = ei.shape[1]
+    else:
+        ws = [g(H * F, F) for _ in range(3)] + [g(F, F)]
+        bs = [torch.zeros(H * F) for _ in range(3)] + [torch.zeros(F)]
+        fn = lambda: lo.transformer_conv(x, ei, ws[0], bs[0], ws[1], bs[1], ws[2], bs[2], ws[3], bs[3], heads=H)
+        e_agg = ei.shape[1]
+    with torch.no_grad():
+        for _ in range(warmup):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dict(value=e_agg / dt, unit="edges/s", cores=cores, kind="port",
+                sample=f"hex {nx}x{ny}x{nz} ({N} cells, {e_agg} aggregated edges) {layer}Conv F={F} fp32 forward, "
+                       f"{steps} timed steps, torch CPU ops PyG dispatches to (oracle/layers_oracle.py)"), dt * 1e3, e_agg
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, ms, e_agg = cpu_reference(args.layer, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": "message_passing_edges_per_sec", "value": cb["value"], "unit": "edges/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg4 hex mesh GCNConv({F},{F}) layer forward; CPU arm timed on a bounded sample: "
+                                   + cb["sample"]},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import gnn_bfs_rans_b200 as b2g
+    from gnn_bfs_rans_b200 import _lib, ops
+    from gnn_bfs_rans_b200.graph import Graph
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    _lib.load()  # fail loudly if the CUDA extension is missing
+
+    nx, ny, nz = (64, 64, 64) if args.small else (NX, NY, NZ)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    s = 2 if args.dtype == "bf16" else 4
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    # ---- mesh -> edge_index through the device builder (mode A), per rank block + halo plan
+    from gnn_bfs_rans_b200.distributed import slab_partition_hex
+    part = slab_partition_hex(nx, ny, nz, world, rank, dev)      # owned block + ghost planes + exchange plan
+    N = part.n_owned
+    ei = part.edge_index                                           # local ids, ghosts >= N
+    torch.manual_seed(1234 + rank)
+    x = torch.randn(N, F, device=dev).to(dtype)
+    layer = {"GCN": lambda: b2g.nn.GCNConv(F, F),
+             "GAT": lambda: b2g.nn.GATConv(F, F, heads=4, concat=False),
+             "GIN": lambda: b2g.nn.GINConv(torch.nn.Sequential(torch.nn.Linear(F, F), torch.nn.ReLU(), torch.nn.Linear(F, F))),
+             "Transformer": lambda: b2g.nn.TransformerConv(F, F, heads=4, concat=False)}[args.layer]()
+    torch.manual_seed(0)
+    layer.reset_parameters()
+    layer = layer.to(dev).to(dtype).eval()
+
+    fwd = part.wrap_forward(layer)                                 # adds the halo exchange when world > 1
+    e_agg_local = part.aggregated_edges(args.layer)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        with torch.no_grad():
+            for _ in range(warmup):
+                fn()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---- value: device-resident, CSR cached
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    _lib.launch_count_reset()
+    ms = timed(lambda: fwd(x, ei), args.steps, max(args.warmup, 3))
+    launches = _lib.launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    launches_per_step = launches / (args.steps + max(args.warmup, 3))
+    e_total = e_agg_local
+    if world > 1:
+        t = torch.tensor([e_agg_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        e_total = int(t)
+    value = e_total / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (K2 seg_sum for GCN/GIN; fused attention for GAT/Transformer)
+    g = b2g.graph.graph_of(ei, part.n_local)
+    roof = None
+    with torch.no_grad():
+        if args.layer in ("GCN", "GIN"):
+            variant = "sl" if args.layer == "GCN" else "raw"
+            csr = g.csr(variant, False)
+            dinv = g.dinv() if args.layer == "GCN" else None
+            xin = torch.randn(part.n_local, F, device=dev).to(dtype)
+            out = torch.empty(N, F, device=dev, dtype=dtype)
+            kfn = lambda: ops.seg_sum(xin, csr.rowptr, csr.col, N, dinv, dinv, 0.0 if args.layer == "GCN" else 1.0, None,
+                                      None, out=out)
+            kms = timed(kfn, args.steps, 3)
+            alg = 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1) + (4 * N if dinv is not None else 0)
+            kname = "seg_sum_kernel (K2/K3)"
+        else:
+            H = 4
+            kms, alg, kname = None, None, "attn_fwd_kernel (K4/K5)"
+            if args.layer == "GAT":
+                csr = g.csr("sl", False)
+                xw = torch.randn(part.n_local, H * F, device=dev).to(dtype)
+                a = torch.randn(part.n_local, 2 * H, device=dev)
+                kfn = lambda: ops.gat_fwd(xw, a, H, F, False, 0.2, csr.rowptr, csr.col, None, 0.0, 0, False)
+                alg = N * H * F * s + N * F * s + 2 * 4 * N * H + 4 * csr.nnz + 4 * (N + 1)
+            else:
+                csr = g.csr("raw", False)
+                y = torch.randn(part.n_local, 3 * H * F + F, device=dev).to(dtype)
+                q, k, v, sk = y[:, :H * F], y[:, H * F:2 * H * F], y[:, 2 * H * F:3 * H * F], y[:, 3 * H * F:]
+                kfn = lambda: ops.tconv_fwd(q, k, v, sk, H, F, False, csr.rowptr, csr.col, 0.0, 0, False)
+                alg = 3 * N * H * F * s + 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1)
+            kms = timed(kfn, args.steps, 3)
+        ach = alg / (kms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes": alg, "kernel_ms": kms,
+                "kernel_edges_per_sec": e_agg_local / (kms * 1e-3), "peak_source": peak_src}
+        tfile = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tfile):
+            try:
+                roof["traffic"] = json.load(open(tfile)).get(f"{args.layer}_{args.dtype}")
+            except Exception:
+                pass
+
+    # ---- e2e: host buffers in, host buffer out, CSR rebuilt each step (fresh edge_index tensor)
+    e2e = None
+    if world == 1:
+        with torch.no_grad():
+            hx = x.cpu().pin_memory()
+            hei = ei.cpu().pin_memory()
+            hout = torch.empty((N, F), dtype=dtype).pin_memory()
+
+            def e2e_step():
+                dx = hx.to(dev, non_blocking=True)
+                dei = hei.to(dev, non_blocking=True)
+                o = layer(dx, dei)
+                hout.copy_(o, non_blocking=True)
+
+            steps_e = max(3, min(args.steps, 5))
+            for _ in range(2):
+                e2e_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps_e):
+                e2e_step()
+            e1.record()
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) / steps_e
+            ems = max(e0.elapsed_time(e1) / steps_e, wall * 1e3)
+            e2e = {"value": e_total / (ems * 1e-3), "unit": "edges/s", "ms_per_step": ems,
+                   "h2d_bytes_per_step": hx.numel() * hx.element_size() + hei.numel() * 8,
+                   "d2h_bytes_per_step": hout.numel() * hout.element_size(), "steps": steps_e,
+                   "includes": "H2D x + edge_index, CSR rebuild, layer forward, D2H output"}
+            del hx, hei, hout
+    else:
+        e2e = {"value": None, "unit": "edges/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "note": "measured at N=1 only"}
+
+    # ---- extras: other layer types / fp32 / fwd+bwd / FlowGNN train step (not the headline)
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = run_extras(b2g, ops, part, dev, timed)
+
+    # ---- CPU baseline (rank 0, N=1, bounded sample)
+    cb = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb, _, _ = cpu_reference(args.layer, 3, 1, sample=(100, 100, 100))
+
+    if rank == 0:
+        line = {"metric": "message_passing_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+                "config": {"workload": f"cfg4: 3-D hex mesh {nx}x{ny}x{nz} = {N} cells per GPU "
+                                       f"({nx}x{ny}x{nz * world} total), {args.layer}Conv({F},{F}) layer forward, "
+                                       f"{e_total} aggregated edges/step",
+                           "cells_per_gpu": N, "edges_per_step": e_total, "hidden": F, "layer": args.layer,
+                           "partition": "none" if world == 1 else f"RCB slabs x{world}, 1-ring halo exchange per layer (NCCL)",
+                           "cache_policy": "inputs (>5 GB) larger than the 126 MB L2; CSR cached across steps in `value`"},
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
+                "gpu_launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cb, "extras": extras}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_extras(b2g, ops, part, dev, timed):
+    """Per-layer-type forward and forward+backward throughput (bf16 and fp32), kept short."""
+    import torch
+    out = {}
+    N, ei = part.n_owned, part.edge_index
+    for dt_name, dtype in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
+        for lt in ("GCN", "GAT", "GIN", "Transformer"):
+            try:
+                torch.manual_seed(0)
+                layer = {"GCN": lambda: b2g.nn.GCNConv(F, F),
+                         "GAT": lambda: b2g.nn.GATConv(F, F, heads=4, concat=False),
+                         "GIN": lambda: b2g.nn.GINConv(torch.nn.Sequential(torch.nn.Linear(F, F), torch.nn.ReLU(), torch.nn.Linear(F, F))),
+                         "Transformer": lambda: b2g.nn.TransformerConv(F, F, heads=4, concat=False)}[lt]().to(dev).to(dtype).eval()
+                x = torch.randn(N, F, device=dev).to(dtype)
+                ms = timed(lambda: layer(x, ei), 5, 2)
+                e_agg = part.aggregated_edges(lt)
+                out[f"{lt}_{dt_name}_fwd"] = {"ms": ms, "edges_per_sec": e_agg / (ms * 1e-3)}
+                del layer, x
+                torch.cuda.empty_cache()
+            except Exception as e:  # an extra must never take the headline down
+                out[f"{lt}_{dt_name}_fwd"] = {"error": str(e)[:200]}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,8 @@
 
 namespace b2g {
 
+constexpr int SEG_ITERS = 4;  // rows per row-group per CTA chunk
+
 template <int LANES>
 __device__ __forceinline__ unsigned group_mask() {
   if (LANES >= 32) return 0xffffffffu;
@@ -31,11 +33,17 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
   constexpr int U = (VPL >= 4) ? 2 : 4;  // neighbour rows in flight per lane
   const int gl = threadIdx.x % LANES;                       // lane within the row group
   const unsigned gmask = group_mask<LANES>();
-  const int64_t groups_per_block = 256 / LANES;
-  const int64_t g0 = (int64_t)blockIdx.x * groups_per_block + threadIdx.x / LANES;
-  const int64_t gstride = (int64_t)gridDim.x * groups_per_block;
+  constexpr int GPB = 256 / LANES;                          // row groups per CTA
+  constexpr int64_t CHUNK = (int64_t)GPB * SEG_ITERS;       // consecutive rows a CTA owns per grid stride
+  const int gi = threadIdx.x / LANES;
 
-  for (int64_t i = g0; i < n_rows; i += gstride) {
+  // A CTA walks CHUNK consecutive rows (adjacent rows share neighbours -> L1 hits), then strides by the
+  // whole (co-resident) grid, so at any time the chip works on one compact window of rows whose
+  // neighbour rows are still in L2.
+  for (int64_t c0 = (int64_t)blockIdx.x * CHUNK; c0 < n_rows; c0 += (int64_t)gridDim.x * CHUNK)
+  for (int it = 0; it < SEG_ITERS; ++it) {
+    const int64_t i = c0 + (int64_t)it * GPB + gi;
+    if (i >= n_rows) break;
     const int b = __ldg(rowptr + i), e = __ldg(rowptr + i + 1);
     const float rs = (kScale && row_scale) ? __ldg(row_scale + i) : 1.0f;
     float acc[VPL][VN];
@@ -64,7 +72,7 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
 #pragma unroll
             for (int v = 0; v < VPL; ++v) {
               const int vi = gl + v * LANES;
-              if (vi < nvec) buf[u][v] = ldg_vec<T>(row + vi * VN);
+              if (vi < nvec) buf[u][v] = ldg_vec_l1<T>(row + vi * VN);
             }
           }
         }
@@ -114,11 +122,12 @@ static int launch_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_
                           int64_t ldo, int64_t n_rows, int nvec, const int32_t* rowptr,
                           const int32_t* col, const float* row_scale, const float* col_scale,
                           float self_coef, const float* bias, int relu, cudaStream_t st) {
-  const int64_t groups_per_block = 256 / LANES;
-  int64_t blocks = ceil_div(n_rows, groups_per_block);
-  const int64_t cap = (int64_t)B2G_NUM_SMS * 16;  // whole waves; grid-stride keeps a moving L2 window
-  if (blocks > cap) blocks = cap;
+  const int64_t chunk = (int64_t)(256 / LANES) * SEG_ITERS;
+  int64_t blocks = ceil_div(n_rows, chunk);
   const bool scale = row_scale || col_scale;
+  const int64_t cap = scale ? resident_ctas(seg_sum_kernel<T, LANES, VPL, true>, 256)
+                            : resident_ctas(seg_sum_kernel<T, LANES, VPL, false>, 256);
+  if (blocks > cap) blocks = cap;
   if (scale)
     seg_sum_kernel<T, LANES, VPL, true><<<(unsigned)blocks, 256, 0, st>>>(
         (const T*)x, ldx, (const T*)x_self, ldxs, (T*)out, ldo, n_rows, nvec, rowptr, col, row_scale,

@@ -17,6 +17,8 @@
 namespace b2g {
 
 enum { MODE_GAT = 0, MODE_TCONV = 1 };
+constexpr int ATT_ITERS = 4;               // rows per warp per CTA chunk
+constexpr int ATT_CHUNK = 8 * ATT_ITERS;   // consecutive rows a CTA owns per grid stride (see aggregate.cu)
 
 template <int H>
 __device__ __forceinline__ void warp_sum_heads(float* s) {
@@ -37,7 +39,7 @@ __device__ __forceinline__ void load_row(const T* __restrict__ base, int cvec, i
 #pragma unroll
     for (int t = 0; t < CV; ++t) {
       const int vi = lane + 32 * t;
-      if (vi < cvec) buf[h][t] = ldg_vec<T>(base + (h * cvec + vi) * VN);
+      if (vi < cvec) buf[h][t] = ldg_vec_l1<T>(base + (h * cvec + vi) * VN);
     }
 }
 // Load the CV vectors of a [C]-wide row this lane owns.
@@ -47,7 +49,7 @@ __device__ __forceinline__ void load_row1(const T* __restrict__ base, int cvec, 
 #pragma unroll
   for (int t = 0; t < CV; ++t) {
     const int vi = lane + 32 * t;
-    if (vi < cvec) buf[t] = ldg_vec<T>(base + vi * VN);
+    if (vi < cvec) buf[t] = ldg_vec_l1<T>(base + vi * VN);
   }
 }
 
@@ -105,10 +107,12 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
   const int lane = threadIdx.x & 31;
   const int cvec = a.C / VN;
   const T* __restrict__ val = (const T*)a.val;
-  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int64_t wstride = (int64_t)gridDim.x * 8;
+  const int wi = threadIdx.x >> 5;
 
-  for (int64_t i = w0; i < a.n_rows; i += wstride) {
+  for (int64_t c0 = (int64_t)blockIdx.x * ATT_CHUNK; c0 < a.n_rows; c0 += (int64_t)gridDim.x * ATT_CHUNK)
+  for (int it = 0; it < ATT_ITERS; ++it) {
+    const int64_t i = c0 + it * 8 + wi;
+    if (i >= a.n_rows) break;
     const int b = __ldg(a.rowptr + i), e = __ldg(a.rowptr + i + 1);
     float ad[H];
     float qf[MODE == MODE_TCONV ? H : 1][CV][VN];
@@ -319,11 +323,13 @@ __global__ void __launch_bounds__(256) attn_bwd_dst_kernel(const AttnArgs a) {
   const int lane = threadIdx.x & 31;
   const int cvec = a.C / VN;
   const T* __restrict__ val = (const T*)a.val;
-  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int64_t wstride = (int64_t)gridDim.x * 8;
+  const int wi = threadIdx.x >> 5;
   const float gscale = a.concat ? 1.0f : 1.0f / H;
 
-  for (int64_t i = w0; i < a.n_rows; i += wstride) {
+  for (int64_t c0 = (int64_t)blockIdx.x * ATT_CHUNK; c0 < a.n_rows; c0 += (int64_t)gridDim.x * ATT_CHUNK)
+  for (int it = 0; it < ATT_ITERS; ++it) {
+    const int64_t i = c0 + it * 8 + wi;
+    if (i >= a.n_rows) break;
     const int b = __ldg(a.rowptr + i), e = __ldg(a.rowptr + i + 1);
     // g_i per head (mean mode: the same [C] row scaled by 1/H for every head)
     float gf[H][CV][VN];
@@ -591,11 +597,13 @@ __global__ void __launch_bounds__(256) attn_bwd_src_kernel(const AttnSrcArgs a) 
   constexpr int U = (H * CV >= 8) ? 1 : 2;  // neighbour rows in flight per lane
   const int lane = threadIdx.x & 31;
   const int cvec = a.C / VN;
-  const int64_t w0 = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int64_t wstride = (int64_t)gridDim.x * 8;
+  const int wi = threadIdx.x >> 5;
   const float gscale = a.concat ? 1.0f : 1.0f / H;
 
-  for (int64_t jn = w0; jn < a.n_rows; jn += wstride) {
+  for (int64_t c0 = (int64_t)blockIdx.x * ATT_CHUNK; c0 < a.n_rows; c0 += (int64_t)gridDim.x * ATT_CHUNK)
+  for (int it = 0; it < ATT_ITERS; ++it) {
+    const int64_t jn = c0 + it * 8 + wi;
+    if (jn >= a.n_rows) break;
     const int b = __ldg(a.rowptr_t + jn), e = __ldg(a.rowptr_t + jn + 1);
     float dv[H][CV][VN];
     float dk[MODE == MODE_TCONV ? H : 1][CV][VN];
@@ -707,17 +715,18 @@ __global__ void __launch_bounds__(256) attn_bwd_src_kernel(const AttnSrcArgs a) 
 }
 
 // ------------------------------------------------------------------------------------ dispatch
-static inline unsigned warp_grid(int64_t n_rows) {
-  int64_t blocks = ceil_div(n_rows > 0 ? n_rows : 1, 8);
-  const int64_t cap = (int64_t)B2G_NUM_SMS * 16;
+template <typename K>
+static inline unsigned warp_grid(K kernel, int64_t n_rows) {
+  const int64_t blocks = ceil_div(n_rows > 0 ? n_rows : 1, ATT_CHUNK);
+  const int64_t cap = resident_ctas(kernel, 256);   // all CTAs co-resident: one compact L2 window
   return (unsigned)(blocks < cap ? blocks : cap);
 }
 
 template <typename T, int H, int CV, int MODE>
 static int launch3(int which, const AttnArgs& a, const AttnSrcArgs& s, cudaStream_t st) {
-  if (which == 0) attn_fwd_kernel<T, H, CV, MODE><<<warp_grid(a.n_rows), 256, 0, st>>>(a);
-  else if (which == 1) attn_bwd_dst_kernel<T, H, CV, MODE><<<warp_grid(a.n_rows), 256, 0, st>>>(a);
-  else attn_bwd_src_kernel<T, H, CV, MODE><<<warp_grid(s.n_rows), 256, 0, st>>>(s);
+  if (which == 0) attn_fwd_kernel<T, H, CV, MODE><<<warp_grid(attn_fwd_kernel<T, H, CV, MODE>, a.n_rows), 256, 0, st>>>(a);
+  else if (which == 1) attn_bwd_dst_kernel<T, H, CV, MODE><<<warp_grid(attn_bwd_dst_kernel<T, H, CV, MODE>, a.n_rows), 256, 0, st>>>(a);
+  else attn_bwd_src_kernel<T, H, CV, MODE><<<warp_grid(attn_bwd_src_kernel<T, H, CV, MODE>, s.n_rows), 256, 0, st>>>(s);
   count_launch();
   return cuda_status();
 }

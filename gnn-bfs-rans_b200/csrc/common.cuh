@@ -22,6 +22,19 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Grid for a grid-stride kernel whose CTAs must ALL be co-resident: 148 SMs x (CTAs that fit per SM).
+// A larger grid would run in waves, each wave sweeping the whole matrix on its own, and the
+// neighbour-row reuse the gather kernels get from L2 would be lost (measured: 3.5x DRAM re-reads).
+template <typename Kernel>
+inline int64_t resident_ctas(Kernel kernel, int threads, size_t dyn_smem = 0) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, dyn_smem) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  return (int64_t)per_sm * B2G_NUM_SMS;
+}
+
 // ---------------------------------------------------------------- 16-byte vector of features
 template <typename T>
 struct Vec;  // 16 bytes of T, convertible to/from fp32 lanes
@@ -62,6 +75,17 @@ __device__ __forceinline__ Vec<T> ldg_vec(const T* p) {
   Vec<T> r;
   uint4 u;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+               : "l"(p));
+  r.v = *reinterpret_cast<decltype(r.v)*>(&u);
+  return r;
+}
+// Gathered neighbour rows: adjacent targets (same CTA) share x+-1 / self rows, so let them allocate in L1.
+template <typename T>
+__device__ __forceinline__ Vec<T> ldg_vec_l1(const T* p) {
+  Vec<T> r;
+  uint4 u;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
                : "l"(p));
   r.v = *reinterpret_cast<decltype(r.v)*>(&u);

@@ -1,12 +1,342 @@
-// gemm_tc.cu — K6 (tensor-core path): tcgen05 / TMEM / TMA GEMM for the per-node Linear.
-// Placeholder until the tcgen05 kernel lands: reports "not supported" so linear.cu uses the SIMT path.
+// gemm_tc.cu — K6 (tensor-core path): the per-node Linear  Y[n,m] = act(rs[n] * X[n,k] W[m,k]^T + b[m])
+// as a hand-written sm_100a kernel: TMA (cp.async.bulk.tensor, 128B swizzle) stages bf16 operand
+// tiles in shared memory, ONE elected thread issues tcgen05.mma (kind::f16, 128 x 256 x 16, fp32
+// accumulate) into TMEM, tcgen05.commit hands completion to mbarriers, four epilogue warps read the
+// accumulator back with tcgen05.ld and apply row-scale / bias / ReLU / the fp32 aux split.
+// Replaces F.linear inside GCNConv / GATConv / GINConv / TransformerConv.
+//
+// Shape of the problem: n = 10^6..10^8 rows, k = m = 256 (..3328 fused outputs): arithmetic
+// intensity at bf16 is ~k/2 flop/B < the B200 ridge (~210), so the kernel is HBM-bound and is laid
+// out to stream X once and Y once: persistent CTAs (one per SM), a 4-stage TMA ring, two TMEM
+// accumulators (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1; W (<= 1.7 MB)
+// stays L2-resident.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace b2g {
-bool tc_linear_supported(int64_t, int, int, int, int) { return false; }
-int64_t tc_linear_ws_bytes(int64_t, int, int, int, int) { return 0; }
-int tc_linear_fwd(const void*, int64_t, const void*, int64_t, const float*, const float*, void*, int64_t,
-                  float*, int64_t, int64_t, int, int, int, int, int, void*, cudaStream_t) {
-  return B2G_E_UNSUPPORTED;
+
+constexpr int TC_BM = 128;        // rows of X per tile == UMMA_M (cta_group::1)
+constexpr int TC_BN = 256;        // output columns per tile == UMMA_N
+constexpr int TC_BK = 64;         // bf16 elements per k-block = 128 bytes = one swizzle atom row
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;   // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TC_TMEM_COLS = 512; // two 256-column fp32 accumulators
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   bits [0,14) start address >> 4; [16,30) leading byte offset >> 4 (unused for swizzled K-major);
+//   [32,46) stride byte offset >> 4 = 1024 B between 8-row groups; [46,48) version = 1 (Blackwell);
+//   [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                       // LBO = 1 (ignored for swizzled K-major; CUTLASS convention)
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D = fp32 (bits 4-5 = 1), A = B = bf16
+// (bits 7-9 = 1, 10-12 = 1), both K-major (bits 15, 16 = 0), N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+  int64_t n;
+  int m, m_main, k;
+  const float* bias;
+  const float* row_scale;
+  __nv_bfloat16* Y;
+  int64_t ldy;
+  float* aux;
+  int64_t ldaux;
+  int act;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B needs 1024-byte alignment
+  const uint32_t bars = smem_base + TC_STAGES * TC_STAGE_BYTES;
+  // barrier slots (8 bytes each): full[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (TC_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * TC_STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row_tiles = (p.n + TC_BM - 1) / TC_BM;
+  const int col_tiles = (p.m + TC_BN - 1) / TC_BN;
+  const int64_t tiles = row_tiles * col_tiles;
+  const int kblocks = (p.k + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);   // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer (one elected lane)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t rt = t / col_tiles;
+        const int ct = (int)(t - rt * col_tiles);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          const uint32_t sb = sa + TC_A_BYTES;
+          mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+          tma_load_2d(sa, &map_a, full_bar(stage), kb * TC_BK, (int)(rt * TC_BM));
+          tma_load_2d(sb, &map_b, full_bar(stage), kb * TC_BK, ct * TC_BN);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one elected lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, TC_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);                 // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
+          const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 16; ++ks) {          // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
+            const uint64_t ad = make_smem_desc(sa + ks * 32);
+            const uint64_t bd = make_smem_desc(sb + ks * 32);
+            tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));                       // frees the smem slot when these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));                           // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps 2..5
+    const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int64_t rt = t / col_tiles;
+      const int ct = (int)(t - rt * col_tiles);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t row = rt * TC_BM + q * 32 + lane;
+      const bool row_ok = row < p.n;
+      const float rs = (p.row_scale && row_ok) ? __ldg(p.row_scale + row) : 1.0f;
+      const int col0 = ct * TC_BN;
+      const int ncols = min(TC_BN, p.m - col0);
+#pragma unroll 1
+      for (int c = 0; c < ncols; c += 32) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c), r);
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.row_scale) x *= rs;
+            const int cg = col0 + c + j;
+            if (p.bias && cg < p.m) x += __ldg(p.bias + cg);
+            if (p.act == 1) x = fmaxf(x, 0.f);
+            v[j] = x;
+          }
+          const int cg0 = col0 + c;
+          if (cg0 + 32 <= p.m_main) {                         // whole chunk -> bf16 Y, four 16-byte stores
+            __nv_bfloat16* dst = p.Y + row * p.ldy + cg0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              Vec<__nv_bfloat16> o;
+              o.from_float(v + j);
+              *reinterpret_cast<uint4*>(dst + j) = o.v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int cg = cg0 + j;
+              if (cg < p.m_main) p.Y[row * p.ldy + cg] = __float2bfloat16_rn(v[j]);
+              else if (cg < p.m) p.aux[row * p.ldaux + (cg - p.m_main)] = v[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle, zero OOB fill
+static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tc_linear_supported(int64_t n, int m, int k, int dt, int which) {
+  if (which != 0 || dt != B2G_BF16) return false;
+  if (n < 1 || k < 8 || (k % 8) != 0 || m < 1) return false;
+  return get_encode() != nullptr;
+}
+
+int64_t tc_linear_ws_bytes(int64_t, int, int, int, int) { return 256; }
+
+int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                  const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n, int m,
+                  int m_main, int k, int dt, int act, void* ws, cudaStream_t st) {
+  (void)ws;
+  if (dt != B2G_BF16) return B2G_E_UNSUPPORTED;
+  if (!aligned16(X) || !aligned16(W) || (ldx * 2) % 16 || (ldw * 2) % 16) return B2G_E_ALIGN;
+  if (m_main > 0 && (!aligned16(Y) || (ldy * 2) % 16)) return B2G_E_ALIGN;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, X, n, k, ldx, TC_BM) || !make_map(&map_b, W, m, k, ldw, TC_BN)) return B2G_E_UNSUPPORTED;
+  TcParams p;
+  p.n = n; p.m = m; p.m_main = m_main; p.k = k; p.bias = bias; p.row_scale = row_scale;
+  p.Y = static_cast<__nv_bfloat16*>(Y); p.ldy = ldy; p.aux = aux; p.ldaux = ldaux; p.act = act;
+  const int64_t tiles = ceil_div(n, TC_BM) * ceil_div(m, TC_BN);
+  int sms = B2G_NUM_SMS;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, p);
+  count_launch();
+  return cuda_status();
+}
+
 }  // namespace b2g

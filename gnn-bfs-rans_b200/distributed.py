@@ -1,0 +1,269 @@
+"""Multi-GPU message passing (the reference has no counterpart — it is single-process).
+
+One process per GPU.  Cells are partitioned by recursive coordinate bisection (RCB) of the cell
+centres; each rank owns its cells plus a 1-ring halo (ghost cells = sources of edges whose target it
+owns).  Local node ids are [owned | ghosts grouped by owning rank, ascending global id]; the local
+CSR only has rows for owned targets.  One exchange step per layer: the rows a peer needs are packed
+by a libb2g.so gather kernel and shipped with NCCL send/recv over NVLink; the backward is the
+reverse exchange with a scatter-add into the owners.  Global reductions (BatchNorm statistics, loss
+means, the flat gradient all-reduce) keep single-GPU parity.
+
+The plan (who sends which rows to whom) is computed WITHOUT communication: every rank derives both
+sides from the same global partition vector, so send and receive orders agree by construction."""
+from __future__ import annotations
+
+from typing import Callable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------------------ RCB
+def rcb_partition(centers: torch.Tensor, parts: int) -> torch.Tensor:
+    """Recursive coordinate bisection.  centers [N,3] -> part id int64 [N] in [0, parts); parts = 2^k.
+    Each split cuts the longest extent of the current box at the median (ties by cell id, so the two
+    halves differ by at most one cell)."""
+    if parts & (parts - 1):
+        raise ValueError("rcb_partition: parts must be a power of two")
+    N = centers.shape[0]
+    part = torch.zeros(N, dtype=torch.int64, device=centers.device)
+    groups = [torch.arange(N, device=centers.device)]
+    p = 1
+    while p < parts:
+        nxt = []
+        for gi, idx in enumerate(groups):
+            c = centers[idx]
+            ext = c.max(0).values - c.min(0).values if idx.numel() else torch.zeros(3, device=centers.device)
+            ax = int(torch.argmax(ext))
+            order = torch.argsort(c[:, ax], stable=True)
+            half = (idx.numel() + 1) // 2
+            lo, hi = idx[order[:half]], idx[order[half:]]
+            lo, hi = lo.sort().values, hi.sort().values
+            nxt += [lo, hi]
+        groups = nxt
+        p *= 2
+    for gi, idx in enumerate(groups):
+        part[idx] = gi
+    return part
+
+
+# ------------------------------------------------------------------------------------------ plan
+class Partition:
+    """One rank's share of a partitioned graph + its halo exchange plan."""
+
+    def __init__(self, rank: int, world: int, n_owned: int, owned_global: Optional[torch.Tensor],
+                 edge_index: torch.Tensor, send_idx: List[torch.Tensor], recv_counts: List[int],
+                 ghost_global: Optional[torch.Tensor], n_edges_raw_owned: int, n_loops_owned: int):
+        self.rank, self.world = rank, world
+        self.n_owned = int(n_owned)
+        self.recv_counts = [int(c) for c in recv_counts]
+        self.n_ghost = sum(self.recv_counts)
+        self.n_local = self.n_owned + self.n_ghost
+        self.owned_global, self.ghost_global = owned_global, ghost_global
+        self.edge_index = edge_index                      # local ids; every target < n_owned
+        self.send_idx = send_idx                          # per peer: int32 local (owned) rows to send
+        self.send_counts = [int(t.numel()) for t in send_idx]
+        self._send_all = torch.cat(send_idx) if any(self.send_counts) else None
+        self._e_raw, self._loops = int(n_edges_raw_owned), int(n_loops_owned)
+        self._dinv_ready = False
+
+    # edges a layer aggregates for the OWNED targets (the unit of the throughput metric)
+    def aggregated_edges(self, layer_type: str) -> int:
+        if layer_type in ("GCN", "GAT"):
+            return self._e_raw - self._loops + self.n_owned       # self loops replaced: E_sl
+        return self._e_raw
+
+    # ---------------------------------------------------------------- exchange
+    def exchange(self, x_full: torch.Tensor, gather: Optional[Callable] = None) -> torch.Tensor:
+        """Fill the ghost rows x_full[n_owned:] with the owners' rows (in place).  `gather(x, idx)` packs
+        rows; the default is the libb2g.so kernel (CUDA only)."""
+        if self.world == 1 or (self.n_ghost == 0 and not any(self.send_counts)):
+            return x_full
+        if gather is None:
+            from . import ops
+            gather = ops.rows_gather
+        pack = gather(x_full, self._send_all) if self._send_all is not None else x_full[:0]
+        reqs, off_s, off_r = [], 0, self.n_owned
+        ops_list = []
+        for peer in range(self.world):
+            ns, nr = self.send_counts[peer], self.recv_counts[peer]
+            if ns:
+                ops_list.append(dist.P2POp(dist.isend, pack[off_s:off_s + ns], peer))
+            if nr:
+                ops_list.append(dist.P2POp(dist.irecv, x_full[off_r:off_r + nr], peer))
+            off_s += ns
+            off_r += nr
+        if ops_list:
+            reqs = dist.batch_isend_irecv(ops_list)
+            for r in reqs:
+                r.wait()
+        return x_full
+
+    def exchange_reverse_add(self, g_full: torch.Tensor, scatter_add: Optional[Callable] = None) -> torch.Tensor:
+        """Backward of `exchange`: ghost-row gradients travel back and are added into the owners' rows."""
+        if self.world == 1 or (self.n_ghost == 0 and not any(self.send_counts)):
+            return g_full
+        if scatter_add is None:
+            from . import ops
+            scatter_add = ops.rows_scatter_add
+        n_send = sum(self.send_counts)
+        back = g_full.new_empty((n_send, g_full.shape[1]))
+        ops_list, off_s, off_r = [], 0, self.n_owned
+        for peer in range(self.world):
+            ns, nr = self.send_counts[peer], self.recv_counts[peer]
+            if nr:
+                ops_list.append(dist.P2POp(dist.isend, g_full[off_r:off_r + nr].contiguous(), peer))
+            if ns:
+                ops_list.append(dist.P2POp(dist.irecv, back[off_s:off_s + ns], peer))
+            off_s += ns
+            off_r += nr
+        if ops_list:
+            for r in dist.batch_isend_irecv(ops_list):
+                r.wait()
+        # a row may be needed by several peers: add peer by peer so each call sees unique indices
+        off = 0
+        for peer in range(self.world):
+            ns = self.send_counts[peer]
+            if ns:
+                scatter_add(g_full, self.send_idx[peer], back[off:off + ns])
+            off += ns
+        return g_full
+
+    # ---------------------------------------------------------------- graph glue
+    def prepare_graph(self):
+        """Build the cached Graph of the local edge list and patch the GCN deg^-1/2 of the ghost rows
+        with their owners' values (a ghost's local row has no incoming edges)."""
+        from .graph import graph_of
+        g = graph_of(self.edge_index, self.n_local)
+        if not self._dinv_ready and self.world > 1:
+            dinv = g.dinv()
+            buf = torch.zeros((self.n_local, 4), dtype=torch.float32, device=dinv.device)
+            buf[:, 0] = dinv
+            self.exchange(buf)
+            dinv[self.n_owned:] = buf[self.n_owned:, 0]
+        self._dinv_ready = True
+        return g
+
+    def wrap_forward(self, layer):
+        """fn(x_owned_or_full, edge_index) -> out for the owned rows, with the halo exchange in front.
+        Ghost projections are recomputed locally (exchange x, width F) rather than shipping H*C-wide rows."""
+        self.prepare_graph()
+        if self.world == 1:
+            return lambda x, ei: layer(x, ei)
+        holder = {}
+
+        def fwd(x, ei):
+            if x.shape[0] == self.n_local:
+                xf = x
+            else:
+                xf = holder.get("buf")
+                if xf is None or xf.shape[1] != x.shape[1] or xf.dtype != x.dtype:
+                    xf = holder["buf"] = x.new_empty((self.n_local, x.shape[1]))
+                xf[:self.n_owned] = x
+            self.exchange(xf)
+            return layer(xf, ei)[:self.n_owned]
+
+        return fwd
+
+
+class HaloFn(torch.autograd.Function):
+    """Differentiable halo exchange: x_owned [n_owned,F] -> x_full [n_local,F]."""
+
+    @staticmethod
+    def forward(ctx, x_owned, part: Partition):
+        xf = x_owned.new_empty((part.n_local, x_owned.shape[1]))
+        xf[:part.n_owned] = x_owned
+        part.exchange(xf)
+        ctx.part = part
+        return xf
+
+    @staticmethod
+    def backward(ctx, g_full):
+        part = ctx.part
+        g = g_full.contiguous().clone()
+        part.exchange_reverse_add(g)
+        return g[:part.n_owned], None
+
+
+def build_partition(edge_index: torch.Tensor, part: torch.Tensor, rank: int, world: int,
+                    device=None) -> Partition:
+    """General (unstructured) case: every rank holds the global edge_index [2,E] and the partition
+    vector [N] (e.g. from rcb_partition) and cuts out its share.  Local edge order = global edge order."""
+    src, dst = edge_index[0], edge_index[1]
+    N = part.numel()
+    mine = part[dst] == rank
+    src_m, dst_m = src[mine], dst[mine]
+    owned = torch.nonzero(part == rank).squeeze(1)                       # ascending global ids
+    n_owned = owned.numel()
+    ghost_mask = part[src_m] != rank
+    ghosts = torch.unique(src_m[ghost_mask])                              # ascending
+    gp = part[ghosts]
+    order = torch.argsort(gp, stable=True)                                # group by owner, keep id order
+    ghosts = ghosts[order]
+    recv_counts = torch.bincount(part[ghosts], minlength=world).tolist() if ghosts.numel() else [0] * world
+    g2l = torch.full((N,), -1, dtype=torch.int64, device=edge_index.device)
+    g2l[owned] = torch.arange(n_owned, device=edge_index.device)
+    g2l[ghosts] = n_owned + torch.arange(ghosts.numel(), device=edge_index.device)
+    ei_local = torch.stack([g2l[src_m], g2l[dst_m]])
+    # what I must send to peer q: my owned cells that are sources of edges whose target q owns
+    send_idx = []
+    for q in range(world):
+        if q == rank:
+            send_idx.append(torch.zeros(0, dtype=torch.int32, device=edge_index.device))
+            continue
+        sel = (part[dst] == q) & (part[src] == rank)
+        need = torch.unique(src[sel])                                     # ascending global == q's recv order
+        send_idx.append(g2l[need].to(torch.int32))
+    n_loops = int((src_m == dst_m).sum())
+    dev = device if device is not None else edge_index.device
+    return Partition(rank, world, n_owned, owned.to(dev), ei_local.contiguous().to(dev),
+                     [s.to(dev) for s in send_idx], recv_counts, ghosts.to(dev), int(src_m.numel()), n_loops)
+
+
+def slab_partition_hex(nx: int, ny: int, nz: int, world: int, rank: int, device) -> Partition:
+    """Weak-scaling bench mesh: a hex block nx x ny x (nz*world), which RCB cuts into `world` slabs of
+    nz planes along z.  Each rank generates only its own slab (OpenFOAM-style faces -> device builder
+    mode A) plus the edges arriving from the neighbouring slabs' boundary planes."""
+    from . import ops
+    from .synthetic import hex_mesh_faces
+    dev = torch.device(device)
+    owner, nei = hex_mesh_faces(nx, ny, nz, device=dev)
+    N = nx * ny * nz
+    ei = ops.build_graph_edges(owner, nei, 1, None, N, N)                 # [2, E_block], bit-exact builder
+    del owner, nei
+    plane = nx * ny
+    pid = torch.arange(plane, dtype=torch.int64, device=dev)
+    send_idx = [torch.zeros(0, dtype=torch.int32, device=dev) for _ in range(world)]
+    recv_counts = [0] * world
+    extra, goff = [], N
+    if rank > 0:                                                           # ghosts from the slab below
+        extra.append(torch.stack([goff + pid, pid]))                       # ghost(below c) -> c, z_local = 0
+        send_idx[rank - 1] = pid.to(torch.int32)                           # my bottom plane goes down
+        recv_counts[rank - 1] = plane
+        goff += plane
+    if rank < world - 1:                                                   # ghosts from the slab above
+        top = (nz - 1) * plane + pid
+        extra.append(torch.stack([goff + pid, top]))
+        send_idx[rank + 1] = top.to(torch.int32)
+        recv_counts[rank + 1] = plane
+        goff += plane
+    n_raw = ei.shape[1] + sum(e.shape[1] for e in extra)
+    if extra:
+        ei = torch.cat([ei] + extra, dim=1).contiguous()
+    return Partition(rank, world, N, None, ei, send_idx, recv_counts, None, n_raw, 0)
+
+
+# ------------------------------------------------------------------------------------------ training glue
+def allreduce_gradients(params, world: int):
+    """One flat all-reduce (SUM) over every parameter gradient (~0.4-2 M parameters -> a
+    single bucket), then scatter back.  Loss terms must already be normalised by GLOBAL counts."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if world == 1 or not grads:
+        return
+    flat = torch.cat([g.reshape(-1).float() for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n

@@ -37,15 +37,26 @@ def test_flowgnn_matches_oracle(layer_type, training):
     x = g.x.cuda().requires_grad_(True)
     out = model(x, g.edge_index.cuda(), g.edge_attr.cuda())
     out.square().mean().backward()
-    p = {k: v.detach().double().cpu().requires_grad_(v.is_floating_point()) for k, v in model.state_dict().items()}
+    pnames = {k for k, _ in model.named_parameters()}
+    p = {k: v.detach().double().cpu().requires_grad_(k in pnames) for k, v in model.state_dict().items()}
     x64 = g.x.double().requires_grad_(True)
     ref = lo.flow_gnn_forward(x64, g.edge_index, p, layer_type, training=training)
     ref.square().mean().backward()
+    # whole-model gate: L layers + BatchNorm + head in fp32 (torch ops of the caller included), so the
+    # per-layer 1e-5 compounds; gradients are gauged against the largest gradient of the model because
+    # several (biases in front of a BatchNorm) are zero in exact arithmetic.
     assert rel(out.detach(), ref.detach()) < 2e-5
-    assert rel(x.grad, x64.grad) < 5e-5
+    gx, gr = x.grad.double().cpu(), x64.grad
+    assert float((gx - gr).norm() / gr.norm()) < 1e-4
+    # max-norm: a ReLU whose fp32 pre-activation lands within rounding of 0 flips against fp64 and moves
+    # that node's gradient row by O(1); allow at most two such rows, everything else within 1e-4.
+    bad_rows = ((gx - gr).abs().max(1).values > 1e-4 * gr.abs().max()).sum()
+    assert int(bad_rows) <= 2, int(bad_rows)
+    scale = max(float(p[n].grad.abs().max()) for n in pnames if p[n].grad is not None)
     for name, par in model.named_parameters():
-        if par.grad is not None and p[name].grad is not None and float(p[name].grad.abs().max()) > 1e-12:
-            assert rel(par.grad, p[name].grad) < 1e-4, name
+        if par.grad is not None and p[name].grad is not None:
+            err = float((par.grad.double().cpu() - p[name].grad).abs().max())
+            assert err / max(float(p[name].grad.abs().max()), 1e-4 * scale) < 1e-4, name
 
 
 def test_dropin_registers_reference_import_names():
