@@ -22,7 +22,9 @@ __device__ __forceinline__ unsigned group_mask() {
   return ((1u << (LANES & 31)) - 1u) << (g * LANES);
 }
 
-template <typename T, int LANES, int VPL, bool kScale>
+// kScale: 0 = plain sum, 1 = per-row scale only (applied once at the end), 2 = per-edge weight rs_i * cs_j
+// kFull : the row is exactly LANES*VPL vectors wide (no per-vector bounds checks)
+template <typename T, int LANES, int VPL, int kScale, bool kFull>
 __global__ void __launch_bounds__(256)
 seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_self, int64_t ldxs,
                T* __restrict__ out, int64_t ldo, int64_t n_rows, int nvec,
@@ -30,89 +32,97 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
                const float* __restrict__ row_scale, const float* __restrict__ col_scale,
                float self_coef, const float* __restrict__ bias, int relu) {
   constexpr int VN = Vec<T>::N;
-  constexpr int U = (VPL >= 4) ? 2 : 4;  // neighbour rows in flight per lane
+  constexpr int U = (VPL == 1) ? 8 : (VPL == 2 ? 4 : 2);   // neighbour rows in flight per lane (mesh rows: 7)
   const int gl = threadIdx.x % LANES;                       // lane within the row group
-  const unsigned gmask = group_mask<LANES>();
   constexpr int GPB = 256 / LANES;                          // row groups per CTA
   constexpr int64_t CHUNK = (int64_t)GPB * SEG_ITERS;       // consecutive rows a CTA owns per grid stride
   const int gi = threadIdx.x / LANES;
+  const uint64_t pol_stream = l2_policy_evict_first();      // outputs are written once: do not let them push x rows out of L2
+
+  float bias_r[VPL][VN];                                    // this lane's bias columns, loaded once
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      const int vi = gl + v * LANES;
+      bias_r[v][k] = (bias && (kFull || vi < nvec)) ? __ldg(bias + vi * VN + k) : 0.f;
+    }
 
   // A CTA walks CHUNK consecutive rows (adjacent rows share neighbours -> L1 hits), then strides by the
   // whole (co-resident) grid, so at any time the chip works on one compact window of rows whose
   // neighbour rows are still in L2.
-  for (int64_t c0 = (int64_t)blockIdx.x * CHUNK; c0 < n_rows; c0 += (int64_t)gridDim.x * CHUNK)
-  for (int it = 0; it < SEG_ITERS; ++it) {
-    const int64_t i = c0 + (int64_t)it * GPB + gi;
-    if (i >= n_rows) break;
-    const int b = __ldg(rowptr + i), e = __ldg(rowptr + i + 1);
-    const float rs = (kScale && row_scale) ? __ldg(row_scale + i) : 1.0f;
-    float acc[VPL][VN];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v)
-#pragma unroll
-      for (int k = 0; k < VN; ++k) acc[v][k] = 0.f;
-
-    for (int base = b; base < e; base += LANES) {
-      const int n = min(LANES, e - base);
-      int c_l = 0;
-      float w_l = 0.f;
-      if (gl < n) {
-        c_l = __ldg(col + base + gl);
-        w_l = kScale ? ((col_scale ? __ldg(col_scale + c_l) : 1.0f) * rs) : 1.0f;
+  for (int64_t c0 = (int64_t)blockIdx.x * CHUNK; c0 < n_rows; c0 += (int64_t)gridDim.x * CHUNK) {
+    int64_t i = c0 + gi;
+    int b = 0, e = 0;
+    if (i < n_rows) {
+      b = __ldg(rowptr + i);
+      e = __ldg(rowptr + i + 1);
+    }
+    for (int it = 0; it < SEG_ITERS; ++it, i += GPB) {
+      if (i >= n_rows) break;
+      const int64_t i2 = i + GPB;
+      int b2 = 0, e2 = 0;
+      if (it + 1 < SEG_ITERS && i2 < n_rows) {                // next row's extent: off the critical path
+        b2 = __ldg(rowptr + i2);
+        e2 = __ldg(rowptr + i2 + 1);
       }
-      for (int j = 0; j < n; j += U) {
+      const float rs = (kScale && row_scale) ? __ldg(row_scale + i) : 1.0f;
+      float acc[VPL][VN];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int k = 0; k < VN; ++k) acc[v][k] = 0.f;
+
+      // Branch-free gather, U neighbour rows in flight.  Every lane of the group reads the same col[] entry
+      // (one broadcast transaction, no shuffles); slots past the end of the row re-read its last neighbour
+      // with weight 0 (an L1 hit), so the unrolled body carries no predicates, and w = 1 reproduces a plain
+      // fp32 add bit for bit.
+      for (int j = b; j < e; j += U) {
         Vec<T> buf[U][VPL];
         float w[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int c = __shfl_sync(gmask, c_l, j + u, LANES);
-          w[u] = kScale ? __shfl_sync(gmask, w_l, j + u, LANES) : 1.0f;
-          if (j + u < n) {
-            const T* __restrict__ row = x + (int64_t)c * ldx;
+          const int c = __ldg(col + min(j + u, e - 1));
+          if (kScale == 2) w[u] = (j + u < e) ? (col_scale ? __ldg(col_scale + c) : 1.0f) * rs : 0.f;
+          else w[u] = (j + u < e) ? 1.0f : 0.f;
+          const T* __restrict__ row = x + (int64_t)c * ldx;
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-              const int vi = gl + v * LANES;
-              if (vi < nvec) buf[u][v] = ldg_vec_l1<T>(row + vi * VN);
-            }
+          for (int v = 0; v < VPL; ++v) {
+            const int vi = gl + v * LANES;
+            if (kFull || vi < nvec) buf[u][v] = ldg_vec_l1<T>(row + vi * VN);
           }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j + u < n) {
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-              float f[VN];
-              buf[u][v].to_float(f);
+          for (int v = 0; v < VPL; ++v)
+            if (kFull || gl + v * LANES < nvec) fma_vec(acc[v], w[u], buf[u][v]);
+      }
+      // epilogue: row scale, self term, bias, relu, store
 #pragma unroll
-              for (int k = 0; k < VN; ++k) acc[v][k] = kScale ? fmaf(w[u], f[k], acc[v][k]) : acc[v][k] + f[k];
-            }
+      for (int v = 0; v < VPL; ++v) {
+        const int vi = gl + v * LANES;
+        if (kFull || vi < nvec) {
+          if (kScale == 1) {
+#pragma unroll
+            for (int k = 0; k < VN; ++k) acc[v][k] *= rs;
           }
+          if (self_coef != 0.f) {
+            const Vec<T> sv = ldg_vec_l1<T>((x_self ? x_self + i * ldxs : x + i * ldx) + vi * VN);
+            fma_vec(acc[v], self_coef, sv);
+          }
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[v][k] += bias_r[v][k];
+          if (relu) {
+#pragma unroll
+            for (int k = 0; k < VN; ++k) acc[v][k] = fmaxf(acc[v][k], 0.f);
+          }
+          Vec<T> o;
+          o.from_float(acc[v]);
+          stg_vec_hint<T>(out + i * ldo + vi * VN, o, pol_stream);
         }
       }
-    }
-    // epilogue: self term, bias, relu, store
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      const int vi = gl + v * LANES;
-      if (vi < nvec) {
-        if (self_coef != 0.f) {
-          float f[VN];
-          ldg_vec<T>((x_self ? x_self + i * ldxs : x + i * ldx) + vi * VN).to_float(f);
-#pragma unroll
-          for (int k = 0; k < VN; ++k) acc[v][k] = fmaf(self_coef, f[k], acc[v][k]);
-        }
-        if (bias) {
-#pragma unroll
-          for (int k = 0; k < VN; ++k) acc[v][k] += __ldg(bias + vi * VN + k);
-        }
-        if (relu) {
-#pragma unroll
-          for (int k = 0; k < VN; ++k) acc[v][k] = fmaxf(acc[v][k], 0.f);
-        }
-        Vec<T> o;
-        o.from_float(acc[v]);
-        stg_vec<T>(out + i * ldo + vi * VN, o);
-      }
+      b = b2; e = e2;
     }
   }
 }
@@ -124,18 +134,22 @@ static int launch_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_
                           float self_coef, const float* bias, int relu, cudaStream_t st) {
   const int64_t chunk = (int64_t)(256 / LANES) * SEG_ITERS;
   int64_t blocks = ceil_div(n_rows, chunk);
-  const bool scale = row_scale || col_scale;
-  const int64_t cap = scale ? resident_ctas(seg_sum_kernel<T, LANES, VPL, true>, 256)
-                            : resident_ctas(seg_sum_kernel<T, LANES, VPL, false>, 256);
-  if (blocks > cap) blocks = cap;
-  if (scale)
-    seg_sum_kernel<T, LANES, VPL, true><<<(unsigned)blocks, 256, 0, st>>>(
-        (const T*)x, ldx, (const T*)x_self, ldxs, (T*)out, ldo, n_rows, nvec, rowptr, col, row_scale,
-        col_scale, self_coef, bias, relu);
-  else
-    seg_sum_kernel<T, LANES, VPL, false><<<(unsigned)blocks, 256, 0, st>>>(
-        (const T*)x, ldx, (const T*)x_self, ldxs, (T*)out, ldo, n_rows, nvec, rowptr, col, row_scale,
-        col_scale, self_coef, bias, relu);
+  const int mode = col_scale ? 2 : (row_scale ? 1 : 0);
+  const bool full = nvec == LANES * VPL;
+#define B2G_LAUNCH(MODE, FULL)                                                                            \
+  {                                                                                                       \
+    const int64_t cap = resident_ctas(seg_sum_kernel<T, LANES, VPL, MODE, FULL>, 256);                    \
+    if (blocks > cap) blocks = cap;                                                                       \
+    seg_sum_kernel<T, LANES, VPL, MODE, FULL><<<(unsigned)blocks, 256, 0, st>>>(                          \
+        (const T*)x, ldx, (const T*)x_self, ldxs, (T*)out, ldo, n_rows, nvec, rowptr, col, row_scale,     \
+        col_scale, self_coef, bias, relu);                                                                \
+  }
+  if (full) {
+    if (mode == 2) B2G_LAUNCH(2, true) else if (mode == 1) B2G_LAUNCH(1, true) else B2G_LAUNCH(0, true)
+  } else {
+    if (mode == 2) B2G_LAUNCH(2, false) else if (mode == 1) B2G_LAUNCH(1, false) else B2G_LAUNCH(0, false)
+  }
+#undef B2G_LAUNCH
   count_launch();
   return cuda_status();
 }

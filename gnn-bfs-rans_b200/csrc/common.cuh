@@ -99,6 +99,45 @@ __device__ __forceinline__ void stg_vec(T* p, const Vec<T>& r) {
                : "memory");
 }
 
+// Packed fp32 FMA (sm_100 fma.rn.f32x2): (a0,a1) += w * (f0,f1) in one issue slot.  Same rounding as two FFMAs.
+__device__ __forceinline__ void ffma2(float& a0, float& a1, float w, float f0, float f1) {
+  asm("{\n"
+      ".reg .b64 ra, rw, rf;\n"
+      "mov.b64 ra, {%0, %1};\n"
+      "mov.b64 rw, {%2, %2};\n"
+      "mov.b64 rf, {%3, %4};\n"
+      "fma.rn.f32x2 ra, rw, rf, ra;\n"
+      "mov.b64 {%0, %1}, ra;\n"
+      "}\n"
+      : "+f"(a0), "+f"(a1)
+      : "f"(w), "f"(f0), "f"(f1));
+}
+// acc[0..N) += w * (16-byte vector of T), fp32 accumulation
+__device__ __forceinline__ void fma_vec(float* acc, float w, const Vec<float>& v) {
+  ffma2(acc[0], acc[1], w, v.v.x, v.v.y);
+  ffma2(acc[2], acc[3], w, v.v.z, v.v.w);
+}
+__device__ __forceinline__ void fma_vec(float* acc, float w, const Vec<__nv_bfloat16>& v) {
+  const uint32_t u[4] = {v.v.x, v.v.y, v.v.z, v.v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)   // bf16 pair -> fp32 pair: low half shifted up, high half masked
+    ffma2(acc[2 * i], acc[2 * i + 1], w, __uint_as_float(u[i] << 16), __uint_as_float(u[i] & 0xffff0000u));
+}
+
+// L2 eviction-priority policies (createpolicy) for streaming traffic.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+template <typename T>
+__device__ __forceinline__ void stg_vec_hint(T* p, const Vec<T>& r, uint64_t pol) {
+  const uint4 u = *reinterpret_cast<const uint4*>(&r.v);
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(u.x),
+               "r"(u.y), "r"(u.z), "r"(u.w), "l"(pol)
+               : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,8 +11,10 @@
 // accumulators (2 x 256 columns) so the epilogue of tile t overlaps the MMAs of tile t+1; W (<= 1.7 MB)
 // stays L2-resident.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = epilogue (TMEM lane quadrant = warp_idx % 4; the two warps of a quadrant take alternate
+// 64-column chunks).  The epilogue is instruction-bound with one warp per scheduler, hence eight warps
+// and a specialised chunk body per (row-scale, bias, ReLU) combination.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -22,13 +24,24 @@ namespace b2g {
 constexpr int TC_BM = 128;        // rows of X per tile == UMMA_M (cta_group::1)
 constexpr int TC_BN = 256;        // output columns per tile == UMMA_N
 constexpr int TC_BK = 64;         // bf16 elements per k-block = 128 bytes = one swizzle atom row
-constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
+constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;   // 32 KB
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int TC_TMEM_COLS = 512; // two 256-column fp32 accumulators
+constexpr int TC_STG_PITCH = 128; // epilogue staging: 32 rows x 128 B per warp, 16-byte pieces XOR-swizzled by row
+constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * TC_STG_PITCH;   // 32 KB: a private 32-row x 128-byte buffer per epilogue warp
+constexpr int TC_BAR_BYTES = 128;                     // (2*5 + 6) x 8 bytes
+// Two shared-memory plans (227 KB = 232448 B per CTA on sm_100):
+//  kBRes = true  (m <= 256, k <= 256: GCNConv / GINConv / plain Linear): W is loaded ONCE per CTA and stays
+//                resident (k/64 x 32 KB); only X tiles stream through a 4-deep ring of 16 KB stages.
+//  kBRes = false (wide fused outputs: GAT 4F+8, Transformer 13F): a 4-deep ring of (X 16 KB + W 32 KB) stages.
+constexpr int TC_RES_STAGES = 4;
+constexpr int TC_STR_STAGES = 4;
+constexpr int TC_RES_KB_MAX = 4;
+constexpr int TC_SMEM_RES = TC_RES_KB_MAX * TC_B_BYTES + TC_RES_STAGES * TC_A_BYTES + TC_STG_BYTES + TC_BAR_BYTES;   // 229504
+constexpr int TC_SMEM_STR = TC_STR_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_STG_BYTES + TC_BAR_BYTES;                  // 213120
+static_assert(TC_SMEM_RES + 1024 <= 232448 && TC_SMEM_STR + 1024 <= 232448, "shared-memory plan exceeds 227 KB (1 KB is charged for the 1024-byte alignment)");
 
 // ---------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -107,6 +120,36 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// One 32-column slice of the accumulator row held by this lane: fused row-scale / bias / ReLU, pack to
+// bf16 and park it in the warp's staging buffer (16-byte pieces XOR-swizzled by row: conflict-free).
+template <bool kRS, bool kBias, bool kRelu>
+__device__ __forceinline__ void epi_pack(const uint32_t (&r)[32], float rs, const float* __restrict__ bias, int cg0,
+                                         uint8_t* stg, int lane, int hlf) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[j + k]);
+    if (kRS) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] *= rs;
+    }
+    if (kBias) {   // same address on every lane: two broadcast 16-byte loads
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + cg0 + j));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cg0 + j + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    if (kRelu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+    }
+    Vec<__nv_bfloat16> o;
+    o.from_float(v);
+    *reinterpret_cast<uint4*>(stg + lane * TC_STG_PITCH + (((hlf * 4 + (j >> 3)) ^ (lane & 7)) << 4)) = o.v;
+  }
+}
+
 struct TcParams {
   int64_t n;
   int m, m_main, k;
@@ -119,18 +162,26 @@ struct TcParams {
   int act;
 };
 
+template <bool kBRes>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;            // SWIZZLE_128B needs 1024-byte alignment
-  const uint32_t bars = smem_base + TC_STAGES * TC_STAGE_BYTES;
-  // barrier slots (8 bytes each): full[S], empty[S], tmem_full[2], tmem_empty[2]; then the TMEM base address word
+  constexpr int STAGES = kBRes ? TC_RES_STAGES : TC_STR_STAGES;
+  constexpr int STAGE_BYTES = kBRes ? TC_A_BYTES : (TC_A_BYTES + TC_B_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();                          // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t bres = smem_base;                          // resident W (kBRes only)
+  const uint32_t ring = smem_base + (kBRes ? TC_RES_KB_MAX * TC_B_BYTES : 0);
+  const uint32_t stg = ring + STAGES * STAGE_BYTES;
+  const uint32_t bars = stg + TC_STG_BYTES;
+  // barrier slots (8 bytes each): full[S], empty[S], tmem_full[2], tmem_empty[2], b_full; then the TMEM base word
   auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (TC_STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * TC_STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * TC_STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * TC_STAGES + 4);
-  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t bfull_bar = bars + 8u * (2 * STAGES + 4);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 5);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_tiles = (p.n + TC_BM - 1) / TC_BM;
@@ -141,14 +192,15 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-    for (int s = 0; s < TC_STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), TC_EPI_WARPS);   // one arrive per epilogue warp
     }
+    mbar_init(bfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
@@ -163,6 +215,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0) {
     // ===================================================== TMA producer (one elected lane)
     if (lane == 0) {
+      if (kBRes) {                                           // W: loaded once, resident for every tile of this CTA
+        mbar_expect_tx(bfull_bar, (uint32_t)kblocks * TC_B_BYTES);
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(bres + kb * TC_B_BYTES, &map_b, bfull_bar, kb * TC_BK, 0);
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -170,12 +226,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int ct = (int)(t - rt * col_tiles);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-          const uint32_t sb = sa + TC_A_BYTES;
-          mbar_expect_tx(full_bar(stage), TC_STAGE_BYTES);
+          const uint32_t sa = ring + stage * STAGE_BYTES;
+          mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           tma_load_2d(sa, &map_a, full_bar(stage), kb * TC_BK, (int)(rt * TC_BM));
-          tma_load_2d(sb, &map_b, full_bar(stage), kb * TC_BK, ct * TC_BN);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (!kBRes) tma_load_2d(sa + TC_A_BYTES, &map_b, full_bar(stage), kb * TC_BK, ct * TC_BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -187,6 +242,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      if (kBRes) {
+        mbar_wait(bfull_bar, 0);
+        tc_fence_after();
+      }
       for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
@@ -194,8 +253,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);                 // TMA bytes have landed
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * TC_STAGE_BYTES;
-          const uint32_t sb = sa + TC_A_BYTES;
+          const uint32_t sa = ring + stage * STAGE_BYTES;
+          const uint32_t sb = kBRes ? (bres + kb * TC_B_BYTES) : (sa + TC_A_BYTES);
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 16; ++ks) {          // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
             const uint64_t ad = make_smem_desc(sa + ks * 32);
@@ -203,15 +262,19 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
           }
           tc_commit(empty_bar(stage));                       // frees the smem slot when these MMAs retire
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar(acc));                           // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================================================== epilogue warps 2..5
+    // ===================================================== epilogue warps 2..9
     const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;                         // which of the quadrant's two warps
+    uint8_t* my_stg = smem_raw + (stg - smem_base) + (warp - 2) * 32 * TC_STG_PITCH;
+    const bool vec_ok = (p.m_main % 8) == 0;                  // 16-byte pieces never straddle the Y / aux split
+    const int flags = (p.row_scale ? 1 : 0) | (p.bias ? 2 : 0) | (p.act == 1 ? 4 : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -219,41 +282,67 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int ct = (int)(t - rt * col_tiles);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int64_t row = rt * TC_BM + q * 32 + lane;
+      const int64_t row0 = rt * TC_BM + q * 32;
+      const int64_t row = row0 + lane;
       const bool row_ok = row < p.n;
       const float rs = (p.row_scale && row_ok) ? __ldg(p.row_scale + row) : 1.0f;
       const int col0 = ct * TC_BN;
       const int ncols = min(TC_BN, p.m - col0);
 #pragma unroll 1
-      for (int c = 0; c < ncols; c += 32) {
-        uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c), r);
-        if (row_ok) {
-          float v[32];
+      for (int c = half * 64; c < ncols; c += 128) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c);
+        const int cg0 = col0 + c;
+        if (vec_ok && cg0 + 64 <= p.m_main) {
+          // ---- fast path: 64 full columns -> bf16 -> swizzled staging -> 128-byte row stores
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (p.row_scale) x *= rs;
-            const int cg = col0 + c + j;
-            if (p.bias && cg < p.m) x += __ldg(p.bias + cg);
-            if (p.act == 1) x = fmaxf(x, 0.f);
-            v[j] = x;
-          }
-          const int cg0 = col0 + c;
-          if (cg0 + 32 <= p.m_main) {                         // whole chunk -> bf16 Y, four 16-byte stores
-            __nv_bfloat16* dst = p.Y + row * p.ldy + cg0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              Vec<__nv_bfloat16> o;
-              o.from_float(v + j);
-              *reinterpret_cast<uint4*>(dst + j) = o.v;
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t r[32];
+            tc_ld32(taddr + hlf * 32, r);
+            switch (flags) {   // warp-uniform; each case is a straight-line body without per-element predicates
+              case 0: epi_pack<false, false, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
+              case 1: epi_pack<true, false, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
+              case 2: epi_pack<false, true, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
+              case 3: epi_pack<true, true, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
+              case 4: epi_pack<false, false, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
+              case 5: epi_pack<true, false, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
+              case 6: epi_pack<false, true, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
+              default: epi_pack<true, true, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
             }
-          } else {
+          }
+          __syncwarp();
+          const int piece = lane & 7;                         // 16-byte piece inside the 128-byte row segment
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int cg = cg0 + j;
-              if (cg < p.m_main) p.Y[row * p.ldy + cg] = __float2bfloat16_rn(v[j]);
-              else if (cg < p.m) p.aux[row * p.ldaux + (cg - p.m_main)] = v[j];
+          for (int r4 = 0; r4 < 32; r4 += 4) {
+            const int rr = r4 + (lane >> 3);
+            if (row0 + rr < p.n) {
+              const uint4 val = *reinterpret_cast<const uint4*>(my_stg + rr * TC_STG_PITCH + ((piece ^ (rr & 7)) << 4));
+              __nv_bfloat16* dst = p.Y + (row0 + rr) * p.ldy + cg0 + piece * 8;
+              asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(val.x), "r"(val.y),
+                           "r"(val.z), "r"(val.w)
+                           : "memory");
+            }
+          }
+          __syncwarp();
+        } else {
+          // ---- ragged / split chunk (tail columns, fp32 aux columns): element-wise
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            const int cc = c + hlf * 32;
+            if (cc >= ncols) break;                           // warp-uniform
+            uint32_t r[32];
+            tc_ld32(taddr + hlf * 32, r);
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {                    // static indices keep r[] in registers
+                const int cg = col0 + cc + j;
+                if (cg < p.m) {
+                  float x = __uint_as_float(r[j]);
+                  if (p.row_scale) x *= rs;
+                  if (p.bias) x += __ldg(p.bias + cg);
+                  if (p.act == 1) x = fmaxf(x, 0.f);
+                  if (cg < p.m_main) p.Y[row * p.ldy + cg] = __float2bfloat16_rn(x);
+                  else p.aux[row * p.ldaux + (cg - p.m_main)] = x;
+                }
+              }
             }
           }
         }
@@ -322,7 +411,8 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   if (m_main > 0 && (!aligned16(Y) || (ldy * 2) % 16)) return B2G_E_ALIGN;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_STR);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
@@ -334,7 +424,10 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   const int64_t tiles = ceil_div(n, TC_BM) * ceil_div(m, TC_BN);
   int sms = B2G_NUM_SMS;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  tc_linear_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(map_a, map_b, p);
+  if (m <= TC_BN && k <= TC_RES_KB_MAX * TC_BK)
+    tc_linear_kernel<true><<<grid, TC_THREADS, TC_SMEM_RES, st>>>(map_a, map_b, p);
+  else
+    tc_linear_kernel<false><<<grid, TC_THREADS, TC_SMEM_STR, st>>>(map_a, map_b, p);
   count_launch();
   return cuda_status();
 }

@@ -84,6 +84,42 @@ class SegSumFn(torch.autograd.Function):
         return gx, gb, None, None, None, None
 
 
+class GCNFn(torch.autograd.Function):
+    """GCNConv core: out = D^-1/2 A_hat D^-1/2 (x W^T) + b.  The source-side D^-1/2 is fused into the GEMM
+    epilogue (xs = dinv * (x W^T)), so the aggregation kernel gathers plain rows and applies the
+    target-side D^-1/2 once per row: no per-edge weight lookups on the forward path."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, graph: Graph):
+        csr = graph.csr("sl", False)
+        dinv = graph.dinv()
+        xs, _ = ops.linear_fwd(x, weight, None, row_scale=dinv)
+        out = ops.seg_sum(xs, csr.rowptr, csr.col, graph.N, dinv, None, 0.0, None,
+                          bias.float() if bias is not None else None)
+        ctx.save_for_backward(x, weight)
+        ctx.graph, ctx.has_bias = graph, bias is not None
+        ctx.ei_keepalive = graph.edge_index
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        graph = ctx.graph
+        g = g.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            csr_t, dinv = graph.csr("sl", True), graph.dinv()
+            d_xw = ops.seg_sum(g, csr_t.rowptr, csr_t.col, graph.N, dinv, dinv, 0.0, None, None)   # D A^T D g
+            if ctx.needs_input_grad[0]:
+                gx = ops.linear_dgrad(d_xw, weight)
+            if ctx.needs_input_grad[1]:
+                dw, _ = ops.linear_wgrad(d_xw, x, want_bias=False)
+                gw = _cast_like(dw, weight)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(g)
+        return gx, gw, gb, None
+
+
 class GATFn(torch.autograd.Function):
     """GATConv core: [xw | a_src | a_dst] = x @ W_aug.T in one GEMM, then the fused
     score/softmax/aggregate kernel.  W_aug = [W; att_src-folded rows; att_dst-folded rows] is

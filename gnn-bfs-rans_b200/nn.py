@@ -120,8 +120,7 @@ class GCNConv(MessagePassing):
             raise NotImplementedError("b2g GCNConv: edge_weight is not supported")
         _check_x(x, edge_index)
         g = graph_of(edge_index, x.shape[0])
-        xw = Fn.LinearFn.apply(x, self.lin.weight, None, 0)
-        return Fn.SegSumFn.apply(xw, self.bias, g, "sl", True, 0.0)
+        return Fn.GCNFn.apply(x, self.lin.weight, self.bias, g)
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels})'

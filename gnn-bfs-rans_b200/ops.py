@@ -143,7 +143,7 @@ def csr_perm(eid_a, eid_b, id_space: int):
     lib = _lib.load()
     nnz = eid_a.numel()
     scratch = torch.empty(max(id_space, 1), dtype=torch.int32, device=eid_a.device)
-    perm = torch.empty(nnz, dtype=torch.int32, device=eid_a.device)
+    perm = torch.empty(max(nnz, 1), dtype=torch.int32, device=eid_a.device)
     _lib.check(lib.b2g_csr_perm(_p(eid_a), _p(eid_b), nnz, _p(scratch), _p(perm), _stream()), "csr_perm")
     return perm
 
@@ -259,8 +259,8 @@ def gat_bwd(xw, a, gout, H, C, concat, slope, csr, csr_t, perm, smax, ssum, p_dr
     N = xw.shape[0]
     dev = xw.device
     nnz = csr[1].numel()
-    alpha_e = torch.empty((nnz, H), dtype=torch.float32, device=dev)
-    ds_e = torch.empty((nnz, H), dtype=torch.float32, device=dev)
+    alpha_e = torch.empty((max(nnz, 1), H), dtype=torch.float32, device=dev)
+    ds_e = torch.empty((max(nnz, 1), H), dtype=torch.float32, device=dev)
     d_a = torch.empty((N, 2 * H), dtype=torch.float32, device=dev)
     gout = _rows(gout)
     st = _stream()
@@ -294,8 +294,8 @@ def tconv_bwd(q, k, v, gout, H, C, concat, csr, csr_t, perm, smax, ssum, p_drop,
     N = q.shape[0]
     dev = q.device
     nnz = csr[1].numel()
-    alpha_e = torch.empty((nnz, H), dtype=torch.float32, device=dev)
-    ds_e = torch.empty((nnz, H), dtype=torch.float32, device=dev)
+    alpha_e = torch.empty((max(nnz, 1), H), dtype=torch.float32, device=dev)
+    ds_e = torch.empty((max(nnz, 1), H), dtype=torch.float32, device=dev)
     gout = _rows(gout)
     st = _stream()
     assert dk.stride(0) == dv.stride(0)

@@ -18,7 +18,7 @@ for dtype, s in ((torch.bfloat16, 2), (torch.float32, 4)):
         for variant, use_dinv in (("sl", True), ("raw", False)):
             csr = g.csr(variant, False)
             dinv = g.dinv() if use_dinv else None
-            fn = lambda: ops.seg_sum(x, csr.rowptr, csr.col, N, dinv, dinv, 0.0 if use_dinv else 1.0, None, None, out=out)
+            fn = lambda: ops.seg_sum(x, csr.rowptr, csr.col, N, dinv, None, 0.0 if use_dinv else 1.0, None, None, out=out)
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
