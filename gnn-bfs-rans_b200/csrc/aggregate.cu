@@ -13,7 +13,7 @@
 
 namespace b2g {
 
-constexpr int SEG_ITERS = 4;  // rows per row-group per CTA chunk
+constexpr int SEG_ITERS = 16;  // rows per row-group per CTA chunk (128 consecutive rows per CTA step at 8 groups)
 
 template <int LANES>
 __device__ __forceinline__ unsigned group_mask() {
@@ -74,24 +74,46 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
         for (int k = 0; k < VN; ++k) acc[v][k] = 0.f;
 
       // Branch-free gather, U neighbour rows in flight.  Every lane of the group reads the same col[] entry
-      // (one broadcast transaction, no shuffles); slots past the end of the row re-read its last neighbour
-      // with weight 0 (an L1 hit), so the unrolled body carries no predicates, and w = 1 reproduces a plain
-      // fp32 add bit for bit.
-      for (int j = b; j < e; j += U) {
+      // (one broadcast transaction, no shuffles); slots past the end of the row re-read row i itself with
+      // weight 0, so the unrolled body carries no predicates, and w = 1 reproduces a plain fp32 add bit for bit.
+      // The self term (GIN: (1+eps) x_i) rides along as a virtual first neighbour of the same batch.
+      const int ns = (self_coef != 0.f && !x_self && kScale != 1) ? 1 : 0;
+      for (int j = b - ns; j < e; j += U) {
         Vec<T> buf[U][VPL];
         float w[U];
+        int c[U];
+        // phase 1: all U column indices; phase 2: all U row loads; phase 3: the FMAs.
+#pragma unroll
+        for (int u = 0; u < U; ++u) c[u] = (j + u < b || j + u >= e) ? (int)i : ldg_i32_ordered(col + j + u);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int c = __ldg(col + min(j + u, e - 1));
-          if (kScale == 2) w[u] = (j + u < e) ? (col_scale ? __ldg(col_scale + c) : 1.0f) * rs : 0.f;
-          else w[u] = (j + u < e) ? 1.0f : 0.f;
-          const T* __restrict__ row = x + (int64_t)c * ldx;
+          const T* __restrict__ row = x + (int64_t)c[u] * ldx;
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             const int vi = gl + v * LANES;
             if (kFull || vi < nvec) buf[u][v] = ldg_vec_l1<T>(row + vi * VN);
           }
         }
+        if (j == b && e2 > b2 && gl == 0) prefetch_l1(col + b2);   // next row's indices land in L1 meanwhile
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (kScale == 2) w[u] = (j + u < e) ? (col_scale ? __ldg(col_scale + c[u]) : 1.0f) * rs : 0.f;
+          else w[u] = (j + u < e) ? 1.0f : 0.f;
+          if (j + u < b) w[u] = self_coef;
+        }
+        // ptxas otherwise sinks each FMA group next to its load (load -> use -> load -> use: ONE row in flight
+        // per warp; ncu showed a long-scoreboard stall on every buffer).  Make every FMA depend on all U loads
+        // through a value ptxas cannot fold: XOR one word of each buffer, XOR it with its own identity shuffle
+        // (always 0, but opaque), and OR that zero into the weights.
+        uint32_t dep = 0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+            if (kFull || gl + v * LANES < nvec) dep ^= first_word(buf[u][v]);
+        dep ^= __shfl_sync(group_mask<LANES>(), dep, threadIdx.x & 31);
+#pragma unroll
+        for (int u = 0; u < U; ++u) w[u] = __uint_as_float(__float_as_uint(w[u]) | dep);
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
@@ -107,7 +129,7 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
 #pragma unroll
             for (int k = 0; k < VN; ++k) acc[v][k] *= rs;
           }
-          if (self_coef != 0.f) {
+          if (self_coef != 0.f && !ns) {
             const Vec<T> sv = ldg_vec_l1<T>((x_self ? x_self + i * ldxs : x + i * ldx) + vi * VN);
             fma_vec(acc[v], self_coef, sv);
           }
@@ -257,6 +279,13 @@ static inline unsigned grid_for(int64_t n, int threads, int per_sm = 8) {
 
 }  // namespace b2g
 
+namespace b2g {
+bool bulk_seg_sum_supported(int nvec, int64_t n_rows);
+int bulk_seg_sum(int, const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int, int, const int32_t*,
+                 const int32_t*, const float*, const float*, float, const float*, int, cudaStream_t);
+int g_seg_impl = 0;   // 0 = auto, 1 = register gather (LDG), 2 = cp.async.bulk ring, 3 = cp.async (LDGSTS) ring
+}  // namespace b2g
+
 using namespace b2g;
 
 static inline int elem_size(int dt) { return dt == B2G_F32 ? 4 : 2; }
@@ -265,6 +294,12 @@ static inline bool row_ok(const void* p, int64_t ld, int dt) {
 }
 
 extern "C" {
+
+int b2g_set_seg_impl(int impl) {
+  if (impl < 0 || impl > 3) return B2G_E_ARG;
+  g_seg_impl = impl;
+  return B2G_OK;
+}
 
 int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
                 int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
@@ -277,6 +312,11 @@ int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, vo
   if (!row_ok(x, ldx, dt) || !row_ok(out, ldo, dt) || (x_self && !row_ok(x_self, ldxs, dt))) return B2G_E_ALIGN;
   const int nvec = F * elem_size(dt) / 16;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool bulk_ok = bulk_seg_sum_supported(nvec, n_rows);
+  if (g_seg_impl >= 2 && !bulk_ok) return B2G_E_UNSUPPORTED;
+  if (bulk_ok && g_seg_impl >= 2)
+    return bulk_seg_sum(g_seg_impl, x, ldx, x_self, ldxs, out, ldo, n_rows, nvec, dt, rowptr, col, row_scale, col_scale, self_coef,
+                        bias, relu, st);
   if (dt == B2G_F32)
     return dispatch_seg_sum<float>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);
   return dispatch_seg_sum<__nv_bfloat16>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);

@@ -68,8 +68,12 @@ struct Vec<__nv_bfloat16> {
   }
 };
 
-// Gathered neighbour rows are re-used through L2 by adjacent targets: default caching, but keep
-// them out of L1 (no intra-SM reuse worth the pollution).  Streaming outputs bypass L1 too.
+// Gather loads and their consumers (fma_vec) are BOTH `asm volatile`: volatile asm statements keep their
+// relative order, so a kernel that writes "U loads, then U fma_vec" really gets U rows in flight per lane.
+// (With plain C++ consumers the optimiser sank each load next to its use: load -> use -> load -> use, one
+// row in flight per warp — measured with ncu as long-scoreboard stalls on every buffer and a 3x slowdown.)
+// ldg_vec   : streaming data, read once (bypass L1 allocation)
+// ldg_vec_l1: gathered neighbour rows; adjacent targets of a CTA share x+-1 / self rows -> allocate in L1
 template <typename T>
 __device__ __forceinline__ Vec<T> ldg_vec(const T* p) {
   Vec<T> r;
@@ -80,7 +84,6 @@ __device__ __forceinline__ Vec<T> ldg_vec(const T* p) {
   r.v = *reinterpret_cast<decltype(r.v)*>(&u);
   return r;
 }
-// Gathered neighbour rows: adjacent targets (same CTA) share x+-1 / self rows, so let them allocate in L1.
 template <typename T>
 __device__ __forceinline__ Vec<T> ldg_vec_l1(const T* p) {
   Vec<T> r;
@@ -90,6 +93,13 @@ __device__ __forceinline__ Vec<T> ldg_vec_l1(const T* p) {
                : "l"(p));
   r.v = *reinterpret_cast<decltype(r.v)*>(&u);
   return r;
+}
+__device__ __forceinline__ uint32_t first_word(const Vec<float>& v) { return __float_as_uint(v.v.x); }
+__device__ __forceinline__ uint32_t first_word(const Vec<__nv_bfloat16>& v) { return v.v.x; }
+__device__ __forceinline__ int ldg_i32_ordered(const int32_t* p) {   // index load that stays in program order
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 template <typename T>
 __device__ __forceinline__ void stg_vec(T* p, const Vec<T>& r) {
@@ -112,17 +122,79 @@ __device__ __forceinline__ void ffma2(float& a0, float& a1, float w, float f0, f
       : "+f"(a0), "+f"(a1)
       : "f"(w), "f"(f0), "f"(f1));
 }
-// acc[0..N) += w * (16-byte vector of T), fp32 accumulation
+// acc[0..N) += w * (16-byte vector of T), fp32 accumulation, packed fma.rn.f32x2.  One volatile asm block
+// (conversion included) so it cannot be hoisted in between the gather loads that precede it.
 __device__ __forceinline__ void fma_vec(float* acc, float w, const Vec<float>& v) {
-  ffma2(acc[0], acc[1], w, v.v.x, v.v.y);
-  ffma2(acc[2], acc[3], w, v.v.z, v.v.w);
+  asm volatile(
+      "{\n"
+      ".reg .b64 ww, f0, f1, a0, a1;\n"
+      "mov.b64 ww, {%4, %4};\n"
+      "mov.b64 f0, {%5, %6};\n"
+      "mov.b64 f1, {%7, %8};\n"
+      "mov.b64 a0, {%0, %1};\n"
+      "mov.b64 a1, {%2, %3};\n"
+      "fma.rn.f32x2 a0, ww, f0, a0;\n"
+      "fma.rn.f32x2 a1, ww, f1, a1;\n"
+      "mov.b64 {%0, %1}, a0;\n"
+      "mov.b64 {%2, %3}, a1;\n"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+      : "f"(w), "f"(v.v.x), "f"(v.v.y), "f"(v.v.z), "f"(v.v.w));
 }
 __device__ __forceinline__ void fma_vec(float* acc, float w, const Vec<__nv_bfloat16>& v) {
-  const uint32_t u[4] = {v.v.x, v.v.y, v.v.z, v.v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i)   // bf16 pair -> fp32 pair: low half shifted up, high half masked
-    ffma2(acc[2 * i], acc[2 * i + 1], w, __uint_as_float(u[i] << 16), __uint_as_float(u[i] & 0xffff0000u));
+  // bf16 pair -> fp32 pair: low half shifted up, high half masked
+  asm volatile(
+      "{\n"
+      ".reg .b32 l0, h0, l1, h1, l2, h2, l3, h3;\n"
+      ".reg .b64 ww, f0, f1, f2, f3, a0, a1, a2, a3;\n"
+      "shl.b32 l0, %9, 16;\n  and.b32 h0, %9, 0xffff0000;\n"
+      "shl.b32 l1, %10, 16;\n and.b32 h1, %10, 0xffff0000;\n"
+      "shl.b32 l2, %11, 16;\n and.b32 h2, %11, 0xffff0000;\n"
+      "shl.b32 l3, %12, 16;\n and.b32 h3, %12, 0xffff0000;\n"
+      "mov.b64 ww, {%8, %8};\n"
+      "mov.b64 f0, {l0, h0};\n mov.b64 f1, {l1, h1};\n mov.b64 f2, {l2, h2};\n mov.b64 f3, {l3, h3};\n"
+      "mov.b64 a0, {%0, %1};\n mov.b64 a1, {%2, %3};\n mov.b64 a2, {%4, %5};\n mov.b64 a3, {%6, %7};\n"
+      "fma.rn.f32x2 a0, ww, f0, a0;\n"
+      "fma.rn.f32x2 a1, ww, f1, a1;\n"
+      "fma.rn.f32x2 a2, ww, f2, a2;\n"
+      "fma.rn.f32x2 a3, ww, f3, a3;\n"
+      "mov.b64 {%0, %1}, a0;\n mov.b64 {%2, %3}, a1;\n mov.b64 {%4, %5}, a2;\n mov.b64 {%6, %7}, a3;\n"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
+      : "f"(w), "r"(v.v.x), "r"(v.v.y), "r"(v.v.z), "r"(v.v.w));
 }
+
+// acc += v (no weight): packed add.rn.f32x2, same volatile-asm ordering contract as fma_vec.
+__device__ __forceinline__ void add_vec(float* acc, const Vec<float>& v) {
+  asm volatile(
+      "{\n"
+      ".reg .b64 f0, f1, a0, a1;\n"
+      "mov.b64 f0, {%4, %5};\n mov.b64 f1, {%6, %7};\n"
+      "mov.b64 a0, {%0, %1};\n mov.b64 a1, {%2, %3};\n"
+      "add.rn.f32x2 a0, a0, f0;\n add.rn.f32x2 a1, a1, f1;\n"
+      "mov.b64 {%0, %1}, a0;\n mov.b64 {%2, %3}, a1;\n"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+      : "f"(v.v.x), "f"(v.v.y), "f"(v.v.z), "f"(v.v.w));
+}
+__device__ __forceinline__ void add_vec(float* acc, const Vec<__nv_bfloat16>& v) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 l0, h0, l1, h1, l2, h2, l3, h3;\n"
+      ".reg .b64 f0, f1, f2, f3, a0, a1, a2, a3;\n"
+      "shl.b32 l0, %8, 16;\n  and.b32 h0, %8, 0xffff0000;\n"
+      "shl.b32 l1, %9, 16;\n  and.b32 h1, %9, 0xffff0000;\n"
+      "shl.b32 l2, %10, 16;\n and.b32 h2, %10, 0xffff0000;\n"
+      "shl.b32 l3, %11, 16;\n and.b32 h3, %11, 0xffff0000;\n"
+      "mov.b64 f0, {l0, h0};\n mov.b64 f1, {l1, h1};\n mov.b64 f2, {l2, h2};\n mov.b64 f3, {l3, h3};\n"
+      "mov.b64 a0, {%0, %1};\n mov.b64 a1, {%2, %3};\n mov.b64 a2, {%4, %5};\n mov.b64 a3, {%6, %7};\n"
+      "add.rn.f32x2 a0, a0, f0;\n add.rn.f32x2 a1, a1, f1;\n add.rn.f32x2 a2, a2, f2;\n add.rn.f32x2 a3, a3, f3;\n"
+      "mov.b64 {%0, %1}, a0;\n mov.b64 {%2, %3}, a1;\n mov.b64 {%4, %5}, a2;\n mov.b64 {%6, %7}, a3;\n"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
+      : "r"(v.v.x), "r"(v.v.y), "r"(v.v.z), "r"(v.v.w));
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // L2 eviction-priority policies (createpolicy) for streaming traffic.
 __device__ __forceinline__ uint64_t l2_policy_evict_first() {

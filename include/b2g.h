@@ -118,6 +118,9 @@ int b2g_csr_perm(const int32_t* eid_a, const int32_t* eid_b, int64_t nnz, int32_
  * x: [*, F] dtype `dt`, row stride ldx; out: [n_rows, F] dtype `dt`, row stride ldo.
  * `x_self` (may be NULL -> x) is the matrix the self term reads (rows indexed by i).
  * relu != 0 applies max(.,0) last. */
+/* Kernel choice for b2g_seg_sum: 0 = auto, 1 = register gather (LDG.128 per lane), 2 = bulk-async gather
+ * (one cp.async.bulk per neighbour row into shared memory).  Results are bit-identical. */
+int b2g_set_seg_impl(int impl);
 int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
                 int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
                 const int32_t* col, const float* row_scale, const float* col_scale,

@@ -7,6 +7,8 @@ from gnn_bfs_rans_b200.graph import Graph
 from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
 
 what = sys.argv[1]
+from gnn_bfs_rans_b200 import _lib
+_lib.load().b2g_set_seg_impl(int(os.environ.get("SEG_IMPL", "1")))
 dtype = torch.float32 if (len(sys.argv) > 2 and sys.argv[2] == "fp32") else torch.bfloat16
 reps = 3
 if what == "gemm":

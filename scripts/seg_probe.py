@@ -11,7 +11,9 @@ N = nx * ny * nz
 o, n = hex_mesh_faces(nx, ny, nz, device='cuda')
 ei = ops.build_graph_edges(o, n, 1, None, N, N)
 g = Graph(ei, N)
-for dtype, s in ((torch.bfloat16, 2), (torch.float32, 4)):
+from gnn_bfs_rans_b200 import _lib
+for impl, dtype, s in ((1, torch.bfloat16, 2), (3, torch.bfloat16, 2), (1, torch.float32, 4), (3, torch.float32, 4)):
+    _lib.load().b2g_set_seg_impl(impl)
     for F in (256, 128):
         x = torch.randn(N, F, device='cuda').to(dtype)
         out = torch.empty_like(x)
@@ -22,6 +24,13 @@ for dtype, s in ((torch.bfloat16, 2), (torch.float32, 4)):
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
+            if impl >= 2:   # bit-identical to the register-gather kernel
+                ref = torch.empty_like(out)
+                _lib.load().b2g_set_seg_impl(1)
+                ops.seg_sum(x, csr.rowptr, csr.col, N, dinv, None, 0.0 if use_dinv else 1.0, None, None, out=ref)
+                _lib.load().b2g_set_seg_impl(impl)
+                torch.cuda.synchronize()
+                assert torch.equal(ref, out), "bulk kernel differs from LDG kernel"
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(10):
@@ -30,7 +39,7 @@ for dtype, s in ((torch.bfloat16, 2), (torch.float32, 4)):
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 10
             alg = 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1) + (4 * N if use_dinv else 0)
-            print(f"{str(dtype):15s} F={F} {variant}: {ms:.3f} ms  {alg/ms/1e6:.0f} GB/s algorithmic  ({alg/ms/1e6/6553:.2%} of measured HBM)  gather-model {csr.nnz*F*s/ms/1e6:.0f} GB/s", flush=True)
+            print(f"impl{impl} {str(dtype):15s} F={F} {variant}: {ms:.3f} ms  {alg/ms/1e6:.0f} GB/s algorithmic  ({alg/ms/1e6/6553:.2%} of measured HBM)  gather-model {csr.nnz*F*s/ms/1e6:.0f} GB/s", flush=True)
 # pure streaming reference: copy N x 256 bf16
 x = torch.randn(N, 256, device='cuda').bfloat16(); y = torch.empty_like(x)
 for _ in range(3): y.copy_(x)
