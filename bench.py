@@ -201,7 +201,7 @@ def main():
     N = part.n_owned
     ei = part.edge_index                                           # local ids, ghosts >= N
     torch.manual_seed(1234 + rank)
-    x = torch.randn(N, F, device=dev).to(dtype)
+    x = torch.randn(part.n_local, F, device=dev).to(dtype)      # owned rows first, ghost rows (filled by the halo exchange) after
     layer = {"GCN": lambda: b2g.nn.GCNConv(F, F),
              "GAT": lambda: b2g.nn.GATConv(F, F, heads=4, concat=False),
              "GIN": lambda: b2g.nn.GINConv(torch.nn.Sequential(torch.nn.Linear(F, F), torch.nn.ReLU(), torch.nn.Linear(F, F))),
@@ -298,7 +298,7 @@ def main():
     e2e = None
     if world == 1:
         with torch.no_grad():
-            hx = x.cpu().pin_memory()
+            hx = x[:N].cpu().pin_memory()
             hei = ei.cpu().pin_memory()
             hout = torch.empty((N, F), dtype=dtype).pin_memory()
 

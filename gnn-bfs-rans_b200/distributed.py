@@ -130,18 +130,20 @@ class Partition:
         return g_full
 
     # ---------------------------------------------------------------- graph glue
-    def prepare_graph(self):
+    def prepare_graph(self, exchange: Optional[Callable] = None):
         """Build the cached Graph of the local edge list and patch the GCN deg^-1/2 of the ghost rows
-        with their owners' values (a ghost's local row has no incoming edges)."""
+        with their owners' values (a ghost's local row has no incoming edges).  `exchange(buf)` fills the
+        ghost rows of a [n_local, 4] fp32 buffer in place (default: self.exchange over NCCL)."""
         from .graph import graph_of
         g = graph_of(self.edge_index, self.n_local)
         if not self._dinv_ready and self.world > 1:
             dinv = g.dinv()
             buf = torch.zeros((self.n_local, 4), dtype=torch.float32, device=dinv.device)
             buf[:, 0] = dinv
-            self.exchange(buf)
+            (exchange or self.exchange)(buf)
             dinv[self.n_owned:] = buf[self.n_owned:, 0]
         self._dinv_ready = True
+        self._graph = g          # keep the patched Graph alive (the cache only holds it while edge_index lives)
         return g
 
     def wrap_forward(self, layer):

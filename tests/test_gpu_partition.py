@@ -1,0 +1,136 @@
+"""Multi-GPU path: partitioned == monolithic.
+ * virtual ranks on ONE GPU: every rank's Partition is built in this process and the halo exchange is
+   emulated by index copies between the ranks' tensors (what the driver's 1-GPU run can execute);
+ * real NCCL with 2 processes when >= 2 GPUs are visible (gpurun --gpus 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def make_layer(kind, F):
+    import gnn_bfs_rans_b200 as b2g
+    torch.manual_seed(11)
+    m = {"GCN": lambda: b2g.nn.GCNConv(F, F), "GAT": lambda: b2g.nn.GATConv(F, F, heads=4, concat=False),
+         "GIN": lambda: b2g.nn.GINConv(torch.nn.Sequential(torch.nn.Linear(F, F), torch.nn.ReLU(), torch.nn.Linear(F, F))),
+         "Transformer": lambda: b2g.nn.TransformerConv(F, F, heads=4, concat=False)}[kind]()
+    with torch.no_grad():
+        for p in m.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.5, 0.5)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("kind", ["GCN", "GAT", "GIN", "Transformer"])
+def test_virtual_ranks_slab_partition(kind, world):
+    from gnn_bfs_rans_b200 import ops
+    from gnn_bfs_rans_b200.distributed import slab_partition_hex
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    nx, ny, nz, F = 12, 10, 6, 64
+    # monolithic graph of the whole nx x ny x (nz*world) block
+    o, n = hex_mesh_faces(nx, ny, nz * world, device='cuda')
+    N = nx * ny * nz * world
+    ei = ops.build_graph_edges(o, n, 1, None, N, N)
+    layer = make_layer(kind, F)
+    torch.manual_seed(3)
+    x = torch.randn(N, F, device='cuda')
+    with torch.no_grad():
+        ref = layer(x, ei)
+    parts = [slab_partition_hex(nx, ny, nz, world, r, 'cuda') for r in range(world)]
+    nb = nx * ny * nz
+    owned = [x[r * nb:(r + 1) * nb] for r in range(world)]
+
+    def emulate_exchange(r, rows_of):
+        """fill rank r's ghost rows from the owners' tensors using the PEERS' send lists"""
+        def fn(buf):
+            off = parts[r].n_owned
+            for p in range(world):
+                cnt = parts[r].recv_counts[p]
+                if cnt:
+                    buf[off:off + cnt] = rows_of(p)[parts[p].send_idx[r].long()]
+                    off += cnt
+            return buf
+        return fn
+
+    dinvs = {}
+    from gnn_bfs_rans_b200.graph import graph_of
+    for r in range(world):                       # local deg^-1/2 of the owned rows (complete: all in-edges present)
+        dinvs[r] = graph_of(parts[r].edge_index, parts[r].n_local).dinv()[:parts[r].n_owned].clone()
+    for r in range(world):
+        pr = parts[r]
+        pr.prepare_graph(exchange=emulate_exchange(r, lambda p: torch.stack([dinvs[p]] + [torch.zeros_like(dinvs[p])] * 3, 1)))
+        xf = torch.empty(pr.n_local, F, device='cuda')
+        xf[:pr.n_owned] = owned[r]
+        emulate_exchange(r, lambda p: owned[p])(xf)
+        with torch.no_grad():
+            out = layer(xf, pr.edge_index)[:pr.n_owned]
+        assert rel(out, ref[r * nb:(r + 1) * nb]) < 1e-5, (kind, world, r)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from gnn_bfs_rans_b200 import ops
+    from gnn_bfs_rans_b200.distributed import HaloFn, allreduce_gradients, slab_partition_hex
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        nx, ny, nz, F = 16, 12, 8, 64
+        nb = nx * ny * nz
+        part = slab_partition_hex(nx, ny, nz, world, rank, f"cuda:{rank}")
+        part.prepare_graph()
+        layer = make_layer("GCN", F).to(f"cuda:{rank}").train()
+        torch.manual_seed(3)
+        x_all = torch.randn(nb * world, F, device=f"cuda:{rank}")
+        xo = x_all[rank * nb:(rank + 1) * nb].clone().requires_grad_(True)
+        out = layer(HaloFn.apply(xo, part), part.edge_index)[:part.n_owned]
+        loss = out.square().sum()
+        loss.backward()
+        allreduce_gradients(list(layer.parameters()), world)
+        # monolithic reference on every rank
+        o, n = hex_mesh_faces(nx, ny, nz * world, device=f"cuda:{rank}")
+        ei = ops.build_graph_edges(o, n, 1, None, nb * world, nb * world)
+        ref_layer = make_layer("GCN", F).to(f"cuda:{rank}").train()
+        xr = x_all.clone().requires_grad_(True)
+        ref = ref_layer(xr, ei)
+        ref.square().sum().backward()
+        e_out = rel(out.detach(), ref.detach()[rank * nb:(rank + 1) * nb])
+        e_gx = rel(xo.grad, xr.grad[rank * nb:(rank + 1) * nb])
+        e_gw = rel(layer.lin.weight.grad, ref_layer.lin.weight.grad)
+        q.put((rank, e_out, e_gx, e_gw))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_nccl_halo_forward_backward():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, e_out, e_gx, e_gw in res:
+        assert e_out < 1e-5 and e_gx < 1e-5 and e_gw < 1e-5, res
