@@ -39,15 +39,6 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
   const int gi = threadIdx.x / LANES;
   const uint64_t pol_stream = l2_policy_evict_first();      // outputs are written once: do not let them push x rows out of L2
 
-  float bias_r[VPL][VN];                                    // this lane's bias columns, loaded once
-#pragma unroll
-  for (int v = 0; v < VPL; ++v)
-#pragma unroll
-    for (int k = 0; k < VN; ++k) {
-      const int vi = gl + v * LANES;
-      bias_r[v][k] = (bias && (kFull || vi < nvec)) ? __ldg(bias + vi * VN + k) : 0.f;
-    }
-
   // A CTA walks CHUNK consecutive rows (adjacent rows share neighbours -> L1 hits), then strides by the
   // whole (co-resident) grid, so at any time the chip works on one compact window of rows whose
   // neighbour rows are still in L2.
@@ -80,7 +71,6 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
       const int ns = (self_coef != 0.f && !x_self && kScale != 1) ? 1 : 0;
       for (int j = b - ns; j < e; j += U) {
         Vec<T> buf[U][VPL];
-        float w[U];
         int c[U];
         // phase 1: all U column indices; phase 2: all U row loads; phase 3: the FMAs.
 #pragma unroll
@@ -95,16 +85,10 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
           }
         }
         if (j == b && e2 > b2 && gl == 0) prefetch_l1(col + b2);   // next row's indices land in L1 meanwhile
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (kScale == 2) w[u] = (j + u < e) ? (col_scale ? __ldg(col_scale + c[u]) : 1.0f) * rs : 0.f;
-          else w[u] = (j + u < e) ? 1.0f : 0.f;
-          if (j + u < b) w[u] = self_coef;
-        }
         // ptxas otherwise sinks each FMA group next to its load (load -> use -> load -> use: ONE row in flight
-        // per warp; ncu showed a long-scoreboard stall on every buffer).  Make every FMA depend on all U loads
+        // per warp; ncu showed a long-scoreboard stall on every buffer).  Make every add depend on all U loads
         // through a value ptxas cannot fold: XOR one word of each buffer, XOR it with its own identity shuffle
-        // (always 0, but opaque), and OR that zero into the weights.
+        // (always 0, but opaque), and OR that zero into the weight / predicate of every slot.
         uint32_t dep = 0;
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -113,12 +97,22 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
             if (kFull || gl + v * LANES < nvec) dep ^= first_word(buf[u][v]);
         dep ^= __shfl_sync(group_mask<LANES>(), dep, threadIdx.x & 31);
 #pragma unroll
-        for (int u = 0; u < U; ++u) w[u] = __uint_as_float(__float_as_uint(w[u]) | dep);
+        for (int u = 0; u < U; ++u) {
+          if (kScale == 2 || ns) {
+            float w = (j + u < e) ? 1.0f : 0.f;
+            if (kScale == 2 && j + u >= b && j + u < e) w = (col_scale ? __ldg(col_scale + c[u]) : 1.0f) * rs;
+            if (j + u < b) w = self_coef;
+            w = __uint_as_float(__float_as_uint(w) | dep);
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+            for (int v = 0; v < VPL; ++v)
+              if (kFull || gl + v * LANES < nvec) fma_vec(acc[v], w, buf[u][v]);
+          } else {
+            const uint32_t pred = (uint32_t)(j + u < e) | dep;      // plain sum: predicated packed adds, no weights
 #pragma unroll
-          for (int v = 0; v < VPL; ++v)
-            if (kFull || gl + v * LANES < nvec) fma_vec(acc[v], w[u], buf[u][v]);
+            for (int v = 0; v < VPL; ++v)
+              if (kFull || gl + v * LANES < nvec) add_vec_if(acc[v], buf[u][v], pred);
+          }
+        }
       }
       // epilogue: row scale, self term, bias, relu, store
 #pragma unroll
@@ -133,8 +127,13 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
             const Vec<T> sv = ldg_vec_l1<T>((x_self ? x_self + i * ldxs : x + i * ldx) + vi * VN);
             fma_vec(acc[v], self_coef, sv);
           }
+          if (bias) {   // per-row reload from L1 (registers are reserved for rows in flight)
 #pragma unroll
-          for (int k = 0; k < VN; ++k) acc[v][k] += bias_r[v][k];
+            for (int k = 0; k < VN; k += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + vi * VN + k));
+              acc[v][k] += bb.x; acc[v][k + 1] += bb.y; acc[v][k + 2] += bb.z; acc[v][k + 3] += bb.w;
+            }
+          }
           if (relu) {
 #pragma unroll
             for (int k = 0; k < VN; ++k) acc[v][k] = fmaxf(acc[v][k], 0.f);
@@ -147,6 +146,119 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
       b = b2; e = e2;
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path for rows that are whole multiples of 512 bytes (F = 256 bf16, F = 128/256 fp32, ...): one warp per
+// target row, VPL 16-byte vectors per lane, the first U (= 8 at VPL 1) neighbour rows handled by STRAIGHT-LINE code.
+// What makes it faster than seg_sum_kernel (each point measured, see DESIGN.md §4 and scripts/micro/):
+//  * `__launch_bounds__(256, minBlocks)`: without a min-blocks hint ptxas schedules for minimum registers and
+//    sinks every load next to its use (LDG; FFMA2 x4; LDG; ... = one row in flight per warp); with the hint it
+//    issues all U loads back to back (8 x LDG.128, then 32 x FFMA2) at 60-72 registers;
+//  * no loop around the common case: rows longer than U fall into a cold loop;
+//  * the self term and the padding slots are ordinary entries of the batch (weight self_coef / 0).
+constexpr int ST_CHUNK = 128;               // consecutive rows per CTA step (16 per warp): x+-1 / self rows hit L1
+
+template <typename T, int VPL, int kScale>
+__global__ void __launch_bounds__(256, (VPL == 1 ? 4 : (VPL == 2 ? 3 : 2)))
+seg_sum_rows_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_t ldo, int64_t n_rows,
+                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                      const float* __restrict__ row_scale, const float* __restrict__ col_scale,
+                      float self_coef, const float* __restrict__ bias, int relu) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int U = (VPL == 1) ? 8 : (VPL == 2 ? 4 : 2);
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const uint4* __restrict__ xv = reinterpret_cast<const uint4*>(x);
+  const int64_t ldv = ldx / VN;                                // row stride in 16-byte vectors
+  const int ns = (self_coef != 0.f) ? 1 : 0;
+  for (int64_t c0 = (int64_t)blockIdx.x * ST_CHUNK; c0 < n_rows; c0 += (int64_t)gridDim.x * ST_CHUNK)
+    for (int it = 0; it * 8 < ST_CHUNK; ++it) {
+      const int64_t i = c0 + it * 8 + wi;
+      if (i >= n_rows) break;
+      const int b = __ldg(rowptr + i), e = __ldg(rowptr + i + 1);
+      const float rs = (kScale && row_scale) ? __ldg(row_scale + i) : 1.0f;
+      float acc[VPL][VN];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int k = 0; k < VN; ++k) acc[v][k] = 0.f;
+      // One batch of U neighbour rows as straight-line code (mesh rows: <= 7 + self), then a cold loop for the
+      // rest of longer rows.  ptxas batches the U loads of the straight-line copy; inside a loop it sinks every
+      // load next to its use (one row in flight per warp).
+      auto batch = [&](int j) {
+        int c[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int t = j + u;
+          c[u] = (t >= b && t < e) ? __ldg(col + t) : (int)i;
+          w[u] = (t < e) ? 1.f : 0.f;
+          if (t < b) w[u] = self_coef;
+        }
+        if (kScale == 2) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (j + u >= b && j + u < e) w[u] = (col_scale ? __ldg(col_scale + c[u]) : 1.0f) * rs;
+        }
+        uint4 buf[U][VPL];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) buf[u][v] = __ldg(xv + (int64_t)c[u] * ldv + lane + 32 * v);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            Vec<T> t;
+            t.v = *reinterpret_cast<decltype(t.v)*>(&buf[u][v]);
+            fma_vec(acc[v], w[u], t);
+          }
+      };
+      batch(b - ns);
+      if (e - (b - ns) > U)
+        for (int j = b - ns + U; j < e; j += U) batch(j);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        const int vi = lane + 32 * v;
+        if (kScale == 1) {
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[v][k] *= rs;
+        }
+        if (bias) {
+#pragma unroll
+          for (int k = 0; k < VN; k += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + vi * VN + k));
+            acc[v][k] += bb.x; acc[v][k + 1] += bb.y; acc[v][k + 2] += bb.z; acc[v][k + 3] += bb.w;
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[v][k] = fmaxf(acc[v][k], 0.f);
+        }
+        Vec<T> o;
+        o.from_float(acc[v]);
+        __stcs(reinterpret_cast<uint4*>(out + i * ldo + vi * VN), *reinterpret_cast<uint4*>(&o.v));
+      }
+    }
+}
+
+template <typename T, int VPL>
+static int launch_rows(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t n_rows, const int32_t* rowptr,
+                         const int32_t* col, const float* rs, const float* cs, float self_coef, const float* bias,
+                         int relu, cudaStream_t st) {
+  int64_t blocks = ceil_div(n_rows, ST_CHUNK);
+  const int mode = cs ? 2 : (rs ? 1 : 0);
+#define B2G_ST(MODE)                                                                                   \
+  {                                                                                                    \
+    const int64_t cap = resident_ctas(seg_sum_rows_kernel<T, VPL, MODE>, 256);                       \
+    if (blocks > cap) blocks = cap;                                                                    \
+    seg_sum_rows_kernel<T, VPL, MODE><<<(unsigned)blocks, 256, 0, st>>>(                             \
+        (const T*)x, ldx, (T*)out, ldo, n_rows, rowptr, col, rs, cs, self_coef, bias, relu);           \
+  }
+  if (mode == 2) B2G_ST(2) else if (mode == 1) B2G_ST(1) else B2G_ST(0)
+#undef B2G_ST
+  count_launch();
+  return cuda_status();
 }
 
 template <typename T, int LANES, int VPL>
@@ -317,6 +429,15 @@ int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, vo
   if (bulk_ok && g_seg_impl >= 2)
     return bulk_seg_sum(g_seg_impl, x, ldx, x_self, ldxs, out, ldo, n_rows, nvec, dt, rowptr, col, row_scale, col_scale, self_coef,
                         bias, relu, st);
+  // rows of whole 512-byte multiples (F = 256 bf16, F = 128/256 fp32, ...): warp-per-row fast path
+  if (g_seg_impl != 1 && !x_self && nvec % 32 == 0 && nvec <= 128 && n_rows >= 1024) {
+#define B2G_STD(T)                                                                                                         \
+    if (nvec == 32) return launch_rows<T, 1>(x, ldx, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st); \
+    if (nvec == 64) return launch_rows<T, 2>(x, ldx, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st); \
+    if (nvec == 128) return launch_rows<T, 4>(x, ldx, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);
+    if (dt == B2G_F32) { B2G_STD(float) } else { B2G_STD(__nv_bfloat16) }
+#undef B2G_STD
+  }
   if (dt == B2G_F32)
     return dispatch_seg_sum<float>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);
   return dispatch_seg_sum<__nv_bfloat16>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);

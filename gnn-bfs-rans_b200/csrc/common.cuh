@@ -194,6 +194,60 @@ __device__ __forceinline__ void add_vec(float* acc, const Vec<__nv_bfloat16>& v)
       : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
       : "r"(v.v.x), "r"(v.v.y), "r"(v.v.z), "r"(v.v.w));
 }
+// Predicated packed add: acc += v iff pred != 0.  The predicate lives inside the asm block, so the unrolled
+// gather body has no branches (no BSSY/BSYNC) and needs no per-slot weight registers.
+__device__ __forceinline__ void add_vec_if(float* acc, const Vec<float>& v, uint32_t pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 f0, f1, a0, a1;\n"
+      "setp.ne.b32 p, %8, 0;\n"
+      "mov.b64 f0, {%4, %5};\n mov.b64 f1, {%6, %7};\n"
+      "mov.b64 a0, {%0, %1};\n mov.b64 a1, {%2, %3};\n"
+      "@p add.rn.f32x2 a0, a0, f0;\n @p add.rn.f32x2 a1, a1, f1;\n"
+      "mov.b64 {%0, %1}, a0;\n mov.b64 {%2, %3}, a1;\n"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3])
+      : "f"(v.v.x), "f"(v.v.y), "f"(v.v.z), "f"(v.v.w), "r"(pred));
+}
+__device__ __forceinline__ void add_vec_if(float* acc, const Vec<__nv_bfloat16>& v, uint32_t pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b32 l0, h0, l1, h1, l2, h2, l3, h3;\n"
+      ".reg .b64 f0, f1, f2, f3, a0, a1, a2, a3;\n"
+      "setp.ne.b32 p, %12, 0;\n"
+      "shl.b32 l0, %8, 16;\n  and.b32 h0, %8, 0xffff0000;\n"
+      "shl.b32 l1, %9, 16;\n  and.b32 h1, %9, 0xffff0000;\n"
+      "shl.b32 l2, %10, 16;\n and.b32 h2, %10, 0xffff0000;\n"
+      "shl.b32 l3, %11, 16;\n and.b32 h3, %11, 0xffff0000;\n"
+      "mov.b64 f0, {l0, h0};\n mov.b64 f1, {l1, h1};\n mov.b64 f2, {l2, h2};\n mov.b64 f3, {l3, h3};\n"
+      "mov.b64 a0, {%0, %1};\n mov.b64 a1, {%2, %3};\n mov.b64 a2, {%4, %5};\n mov.b64 a3, {%6, %7};\n"
+      "@p add.rn.f32x2 a0, a0, f0;\n @p add.rn.f32x2 a1, a1, f1;\n @p add.rn.f32x2 a2, a2, f2;\n @p add.rn.f32x2 a3, a3, f3;\n"
+      "mov.b64 {%0, %1}, a0;\n mov.b64 {%2, %3}, a1;\n mov.b64 {%4, %5}, a2;\n mov.b64 {%6, %7}, a3;\n"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
+      : "r"(v.v.x), "r"(v.v.y), "r"(v.v.z), "r"(v.v.w), "r"(pred));
+}
+// bf16 rows, unweighted: sm_100 mixed-precision add (add.rn.f32.bf16 -> SASS FHADD.BF16 Rd, Ra.H0|H1, Rc) adds a
+// bf16 half straight into an fp32 accumulator: 8 instructions per 16 bytes, no unpacking.  Exact (bf16 -> fp32 is
+// exact, one fp32 rounding per add), i.e. bit-identical to convert-then-add.
+__device__ __forceinline__ void add_vec_mixed_if(float* acc, const Vec<__nv_bfloat16>& v, uint32_t pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b16 l0, h0, l1, h1, l2, h2, l3, h3;\n"
+      "setp.ne.b32 p, %12, 0;\n"
+      "mov.b32 {l0, h0}, %8;\n mov.b32 {l1, h1}, %9;\n mov.b32 {l2, h2}, %10;\n mov.b32 {l3, h3}, %11;\n"
+      "@p add.rn.f32.bf16 %0, l0, %0;\n @p add.rn.f32.bf16 %1, h0, %1;\n"
+      "@p add.rn.f32.bf16 %2, l1, %2;\n @p add.rn.f32.bf16 %3, h1, %3;\n"
+      "@p add.rn.f32.bf16 %4, l2, %4;\n @p add.rn.f32.bf16 %5, h2, %5;\n"
+      "@p add.rn.f32.bf16 %6, l3, %6;\n @p add.rn.f32.bf16 %7, h3, %7;\n"
+      "}\n"
+      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
+      : "r"(v.v.x), "r"(v.v.y), "r"(v.v.z), "r"(v.v.w), "r"(pred));
+}
+__device__ __forceinline__ void add_vec_mixed_if(float* acc, const Vec<float>& v, uint32_t pred) { add_vec_if(acc, v, pred); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // L2 eviction-priority policies (createpolicy) for streaming traffic.
