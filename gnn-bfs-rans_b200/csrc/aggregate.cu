@@ -25,7 +25,7 @@ __device__ __forceinline__ unsigned group_mask() {
 // kScale: 0 = plain sum, 1 = per-row scale only (applied once at the end), 2 = per-edge weight rs_i * cs_j
 // kFull : the row is exactly LANES*VPL vectors wide (no per-vector bounds checks)
 template <typename T, int LANES, int VPL, int kScale, bool kFull>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (VPL <= 2 ? 3 : (VPL == 4 ? 2 : 1)))
 seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_self, int64_t ldxs,
                T* __restrict__ out, int64_t ldo, int64_t n_rows, int nvec,
                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,

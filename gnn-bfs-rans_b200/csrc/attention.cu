@@ -100,8 +100,9 @@ struct AttnArgs {
 };
 
 // ------------------------------------------------------------------------------------ forward
+// min-blocks hint: without it ptxas schedules for minimum registers and serialises the gathers (aggregate.cu)
 template <typename T, int H, int CV, int MODE>
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(256, (H * CV <= 4 && MODE == MODE_GAT) ? 2 : 1) attn_fwd_kernel(const AttnArgs a) {
   constexpr int VN = Vec<T>::N;
   constexpr int U = (H * CV >= 8) ? 1 : 2;  // neighbour rows in flight per lane
   const int lane = threadIdx.x & 31;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const AttnArgs a) {
 // mask folded in, as the source-major pass needs it) and ds_e (w.r.t. the pre-activation score)
 // in CSR order; GAT: d a_dst[i,h] = sum_e ds_e;  TCONV: dq[i] = scale * sum_e ds_e k_j.
 template <typename T, int H, int CV, int MODE>
-__global__ void __launch_bounds__(256) attn_bwd_dst_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(256, 1) attn_bwd_dst_kernel(const AttnArgs a) {
   constexpr int VN = Vec<T>::N;
   constexpr int U = (H * CV >= 8) ? 1 : 2;  // neighbour rows in flight per lane
   const int lane = threadIdx.x & 31;
@@ -602,7 +603,7 @@ struct AttnSrcArgs {
 };
 
 template <typename T, int H, int CV, int MODE>
-__global__ void __launch_bounds__(256) attn_bwd_src_kernel(const AttnSrcArgs a) {
+__global__ void __launch_bounds__(256, 1) attn_bwd_src_kernel(const AttnSrcArgs a) {
   constexpr int VN = Vec<T>::N;
   constexpr int U = (H * CV >= 8) ? 1 : 2;  // neighbour rows in flight per lane
   const int lane = threadIdx.x & 31;

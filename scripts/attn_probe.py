@@ -27,16 +27,16 @@ def timeit(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-for dtype, s in ((torch.bfloat16, 2), (torch.float32, 4)):
+for dtype, s in ((torch.bfloat16, 2),):
     csr = g.csr("sl", False)
-    xw = torch.randn(N, H * F, device='cuda').to(dtype)
+    xw = torch.empty(N, H * F, device='cuda', dtype=dtype).normal_()
     a = torch.randn(N, 2 * H, device='cuda')
     ms = timeit(lambda: ops.gat_fwd(xw, a, H, F, False, 0.2, csr.rowptr, csr.col, None, 0.0, 0, False))
     alg = N * H * F * s + N * F * s + 2 * 4 * N * H + 4 * csr.nnz + 4 * (N + 1)
     print(f"GAT fwd  {str(dtype):15s}: {ms:7.3f} ms  {alg/ms/1e6:6.0f} GB/s alg ({alg/ms/1e6/6553:.1%})  {csr.nnz/ms/1e6:.2f} G edges/s", flush=True)
     del xw, a
     csr = g.csr("raw", False)
-    y = torch.randn(N, 3 * H * F + F, device='cuda').to(dtype)
+    y = torch.empty(N, 3 * H * F + F, device='cuda', dtype=dtype).normal_()
     q, k, v, sk = y[:, :H * F], y[:, H * F:2 * H * F], y[:, 2 * H * F:3 * H * F], y[:, 3 * H * F:]
     ms = timeit(lambda: ops.tconv_fwd(q, k, v, sk, H, F, False, csr.rowptr, csr.col, 0.0, 0, False))
     alg = 3 * N * H * F * s + 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1)
