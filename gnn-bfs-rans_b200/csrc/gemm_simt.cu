@@ -250,6 +250,14 @@ wgrad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__
   }
 }
 
+void wgrad_reduce_launch(const float* partial, int splits, int m, int k, float* dW, int64_t lddw, cudaStream_t st) {
+  const int64_t total = (int64_t)m * k;
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > B2G_NUM_SMS * 8) blocks = B2G_NUM_SMS * 8;
+  wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, nullptr, splits, m, k, dW, lddw, nullptr);
+  count_launch();
+}
+
 int wgrad_splits(int64_t n, int m, int k) {
   const int64_t tiles = ceil_div(m, BM) * ceil_div(k, BN);
   int64_t s = (B2G_NUM_SMS * 4) / tiles;

@@ -362,6 +362,149 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   }
 }
 
+// =====================================================================================================
+// wgrad on the tensor cores:  dW[m,k] = sum_n dY[n,m] X[n,k]   (bf16 in, fp32 out)
+// Both operands are "MN-major" for tcgen05: the reduction index n is the SLOW index of dY [n,m] and X [n,k].
+// TMA boxes of {64 contiguous columns (128 B), 64 rows of n} land in shared memory as 64 rows x 128 B with the
+// 128-byte swizzle = the canonical MN-major SW128 layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)) with SBO = 1024 B
+// (8 n-rows) and LBO = 8192 B (the next 64-column block).  One UMMA (K = 16 n-rows) advances the start address
+// by 2 x SBO.  A CTA owns one 256(m) x 256(k) output tile for a contiguous n-range: two 128 x 256 fp32
+// accumulators fill all 512 TMEM columns; partial tiles go to a workspace and are summed in a fixed order.
+constexpr int WG_BN = 64;                          // n rows (reduction) per stage
+constexpr int WG_SUB = 64 * WG_BN * 2;             // one {64 cols x 64 rows} bf16 box = 8 KB
+constexpr int WG_OPER = 4 * WG_SUB;                // 256 columns of one operand = 32 KB
+constexpr int WG_STAGE = 2 * WG_OPER;              // dY block + X block = 64 KB
+constexpr int WG_STAGES = 3;
+constexpr int WG_SMEM = WG_STAGES * WG_STAGE + 128;
+static_assert(WG_SMEM + 1024 <= 232448, "wgrad shared-memory plan exceeds 227 KB");
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(WG_SUB >> 4) << 16;            // LBO: next 64-element block along M/N
+  d |= (uint64_t)(1024 >> 4) << 32;              // SBO: next group of 8 rows along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct WgParams {
+  int64_t n;
+  int m, k, m_chunks, k_chunks, splits;
+  int64_t rows_per_split;                         // multiple of WG_BN
+  float* partial;                                 // [splits][m][k]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  const uint32_t bars = smem_base + WG_STAGES * WG_STAGE;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (WG_STAGES + s); };
+  const uint32_t tfull_bar = bars + 8u * (2 * WG_STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * WG_STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // work item of this CTA: (m chunk, k chunk, split of n)
+  const int tile = blockIdx.x / p.splits, split = blockIdx.x % p.splits;
+  const int mc = tile / p.k_chunks, kc = tile % p.k_chunks;
+  const int64_t n0 = (int64_t)split * p.rows_per_split;
+  const int64_t n1 = min(p.n, n0 + p.rows_per_split);
+  const int nblocks = n1 > n0 ? (int)((n1 - n0 + WG_BN - 1) / WG_BN) : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_dy) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    for (int s = 0; s < WG_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tfull_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nb = 0; nb < nblocks; ++nb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sa = smem_base + stage * WG_STAGE;
+        mbar_expect_tx(full_bar(stage), WG_STAGE);
+        const int row = (int)(n0 + (int64_t)nb * WG_BN);
+        // rows past n1 but inside the tensor belong to the next split: they must not be counted twice, so the
+        // split boundaries are multiples of WG_BN (rows_per_split) and only the global tail is zero-filled.
+#pragma unroll
+        for (int sub = 0; sub < 4; ++sub) {
+          tma_load_2d(sa + sub * WG_SUB, &map_dy, full_bar(stage), mc * 256 + sub * 64, row);
+          tma_load_2d(sa + WG_OPER + sub * WG_SUB, &map_x, full_bar(stage), kc * 256 + sub * 64, row);
+        }
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16_mn(128, 256);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int nb = 0; nb < nblocks; ++nb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * WG_STAGE;
+        const uint32_t sb = sa + WG_OPER;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {                      // two 128-row halves of the 256 m rows
+#pragma unroll
+          for (int ks = 0; ks < WG_BN / 16; ++ks) {           // K = 16 n-rows per UMMA = 2 x SBO
+            const uint64_t ad = make_smem_desc_mn(sa + mt * 2 * WG_SUB + ks * 2048);
+            const uint64_t bd = make_smem_desc_mn(sb + ks * 2048);
+            tc_mma_bf16(tmem_base + (uint32_t)(mt * 256), ad, bd, idesc, (nb | ks) ? 1u : 0u);
+          }
+        }
+        tc_commit(empty_bar(stage));
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tc_commit(tfull_bar);
+    }
+  } else {
+    // epilogue (once): TMEM -> fp32 partial tile
+    const int q = warp & 3, half = (warp - 2) >> 2;           // half = which 128-row accumulator
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    const int mrow = mc * 256 + half * 128 + q * 32 + lane;
+    float* dst = p.partial + ((int64_t)split * p.m + mrow) * p.k + kc * 256;
+#pragma unroll 1
+    for (int c = 0; c < 256; c += 32) {
+      uint32_t r[32];
+      if (nblocks > 0) tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 256 + c), r);
+      if (mrow < p.m) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int kk = kc * 256 + c + j;
+          if (kk < p.k) dst[c + j] = nblocks > 0 ? __uint_as_float(r[j]) : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -383,6 +526,7 @@ static PFN_encodeTiled get_encode() {
 
 // 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle, zero OOB fill
 static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  if (rows >= ((int64_t)1 << 31)) return false;
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -394,8 +538,54 @@ static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t co
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+void wgrad_reduce_launch(const float* partial, int splits, int m, int k, float* dW, int64_t lddw, cudaStream_t st);
+
+static void wg_plan(int64_t n, int m, int k, WgParams& p) {
+  p.n = n; p.m = m; p.k = k;
+  p.m_chunks = (int)ceil_div(m, 256);
+  p.k_chunks = (int)ceil_div(k, 256);
+  const int tiles = p.m_chunks * p.k_chunks;
+  int splits = B2G_NUM_SMS / tiles;
+  if (splits < 1) splits = 1;
+  const int64_t blocks = ceil_div(n, WG_BN);
+  if (splits > blocks) splits = (int)(blocks > 0 ? blocks : 1);
+  p.splits = splits;
+  p.rows_per_split = ceil_div(blocks, splits) * WG_BN;
+}
+
+int64_t tc_wgrad_ws_bytes(int64_t n, int m, int k) {
+  WgParams p;
+  wg_plan(n, m, k, p);
+  return (int64_t)p.splits * m * k * 4 + 256;
+}
+
+int tc_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw, int64_t n,
+                    int m, int k, void* ws, cudaStream_t st) {
+  if (!aligned16(dY) || !aligned16(X) || (lddy * 2) % 16 || (ldx * 2) % 16) return B2G_E_ALIGN;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  WgParams p;
+  wg_plan(n, m, k, p);
+  p.partial = static_cast<float*>(ws);
+  CUtensorMap map_dy, map_x;
+  if (!make_map(&map_dy, dY, n, m, lddy, WG_BN) || !make_map(&map_x, X, n, k, ldx, WG_BN)) return B2G_E_UNSUPPORTED;
+  const unsigned grid = (unsigned)(p.m_chunks * p.k_chunks * p.splits);
+  tc_wgrad_kernel<<<grid, TC_THREADS, WG_SMEM, st>>>(map_dy, map_x, p);
+  count_launch();
+  int rc = cuda_status();
+  if (rc) return rc;
+  wgrad_reduce_launch(p.partial, p.splits, m, k, dW, lddw, st);
+  return cuda_status();
+}
+
 bool tc_linear_supported(int64_t n, int m, int k, int dt, int which) {
-  if (which != 0 || dt != B2G_BF16) return false;
+  if (dt != B2G_BF16) return false;
+  if (which == 2) return n >= 1 && m % 8 == 0 && k % 8 == 0 && m >= 8 && k >= 8 && get_encode() != nullptr;
+  if (which != 0) return false;
   if (n < 1 || k < 8 || (k % 8) != 0 || m < 1) return false;
   return get_encode() != nullptr;
 }

@@ -12,6 +12,8 @@ int simt_linear_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_
 bool tc_linear_supported(int64_t n, int m, int k, int dt, int which);
 int64_t tc_linear_ws_bytes(int64_t n, int m, int k, int dt, int which);
 int tc_linear_fwd(const void*, int64_t, const void*, int64_t, const float*, const float*, void*, int64_t, float*, int64_t, int64_t, int, int, int, int, int, void*, cudaStream_t);
+int64_t tc_wgrad_ws_bytes(int64_t n, int m, int k);
+int tc_linear_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int, int, void*, cudaStream_t);
 }  // namespace b2g
 
 using namespace b2g;
@@ -25,7 +27,7 @@ int64_t b2g_linear_workspace_bytes(int64_t n, int m, int k, int dt, int which) {
   int64_t b = 256;
   if (which == 2) b += simt_wgrad_ws_bytes(n, m, k);
   if (tc_linear_supported(n, m, k, dt, which)) {
-    const int64_t t = tc_linear_ws_bytes(n, m, k, dt, which);
+    const int64_t t = which == 2 ? tc_wgrad_ws_bytes(n, m, k) : tc_linear_ws_bytes(n, m, k, dt, which);
     if (t > b) b = t;
   }
   return b;
@@ -67,7 +69,12 @@ int b2g_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, f
   if (n < 0 || m <= 0 || k <= 0 || !dt_ok(dt) || impl < 0 || impl > 2) return B2G_E_ARG;
   if (!dW || !ws) return B2G_E_ARG;
   if (n && (!dY || !X)) return B2G_E_ARG;
-  if (impl == 2) return B2G_E_UNSUPPORTED;
+  const bool tc = n > 0 && tc_linear_supported(n, m, k, dt, 2);
+  if (impl == 2 && !tc) return B2G_E_UNSUPPORTED;
+  if (tc && impl != 1) {
+    if (db) return B2G_E_ARG;   // the tensor-core wgrad leaves the bias gradient to b2g_colsum (host side)
+    return tc_linear_wgrad(dY, lddy, X, ldx, dW, lddw, n, m, k, ws, (cudaStream_t)stream);
+  }
   return simt_linear_wgrad(dY, lddy, X, ldx, dW, lddw, db, n, m, k, dt, ws, (cudaStream_t)stream);
 }
 

@@ -64,7 +64,7 @@ class SegSumFn(torch.autograd.Function):
         csr = graph.csr(variant, False)
         dinv = graph.dinv() if use_dinv else None
         out = ops.seg_sum(x, csr.rowptr, csr.col, graph.N, dinv, dinv, self_coef, None,
-                          bias.float() if bias is not None else None)
+                          bias.float() if bias is not None else None, band=graph.band())
         ctx.graph, ctx.variant, ctx.use_dinv, ctx.self_coef = graph, variant, use_dinv, self_coef
         ctx.has_bias = bias is not None
         ctx.ei_keepalive = graph.edge_index
@@ -78,7 +78,8 @@ class SegSumFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             csr_t = graph.csr(ctx.variant, True)
             dinv = graph.dinv() if ctx.use_dinv else None
-            gx = ops.seg_sum(g, csr_t.rowptr, csr_t.col, graph.N, dinv, dinv, ctx.self_coef, None, None)
+            gx = ops.seg_sum(g, csr_t.rowptr, csr_t.col, graph.N, dinv, dinv, ctx.self_coef, None, None,
+                             band=graph.band())
         if ctx.has_bias and ctx.needs_input_grad[1]:
             gb = ops.colsum(g)
         return gx, gb, None, None, None, None
@@ -95,7 +96,7 @@ class GCNFn(torch.autograd.Function):
         dinv = graph.dinv()
         xs, _ = ops.linear_fwd(x, weight, None, row_scale=dinv)
         out = ops.seg_sum(xs, csr.rowptr, csr.col, graph.N, dinv, None, 0.0, None,
-                          bias.float() if bias is not None else None)
+                          bias.float() if bias is not None else None, band=graph.band())
         ctx.save_for_backward(x, weight)
         ctx.graph, ctx.has_bias = graph, bias is not None
         ctx.ei_keepalive = graph.edge_index
@@ -109,7 +110,8 @@ class GCNFn(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             csr_t, dinv = graph.csr("sl", True), graph.dinv()
-            d_xw = ops.seg_sum(g, csr_t.rowptr, csr_t.col, graph.N, dinv, dinv, 0.0, None, None)   # D A^T D g
+            d_xw = ops.seg_sum(g, csr_t.rowptr, csr_t.col, graph.N, dinv, dinv, 0.0, None, None,
+                               band=graph.band())                                                  # D A^T D g
             if ctx.needs_input_grad[0]:
                 gx = ops.linear_dgrad(d_xw, weight)
             if ctx.needs_input_grad[1]:

@@ -150,7 +150,7 @@ def csr_perm(eid_a, eid_b, id_space: int):
 
 # ------------------------------------------------------------------------------------------ K2/K3
 def seg_sum(x, rowptr, col, n_rows, row_scale=None, col_scale=None, self_coef=0.0, x_self=None, bias=None,
-            relu=False, out=None):
+            relu=False, out=None, band=0):
     _cuda(x)
     lib = _lib.load()
     x = _rows(x)
@@ -158,9 +158,9 @@ def seg_sum(x, rowptr, col, n_rows, row_scale=None, col_scale=None, self_coef=0.
     F = x.shape[1]
     if out is None:
         out = torch.empty((n_rows, F), dtype=x.dtype, device=x.device)
-    _lib.check(lib.b2g_seg_sum(_p(x), _ld(x), _p(xs), _ld(xs) if xs is not None else 0, _p(out), _ld(out), n_rows, F,
-                               _dt(x), _p(rowptr), _p(col), _p(row_scale), _p(col_scale), float(self_coef),
-                               _p(bias), int(relu), _stream()), "seg_sum")
+    _lib.check(lib.b2g_seg_sum_banded(_p(x), _ld(x), _p(xs), _ld(xs) if xs is not None else 0, _p(out), _ld(out),
+                                      n_rows, F, _dt(x), _p(rowptr), _p(col), _p(row_scale), _p(col_scale),
+                                      float(self_coef), _p(bias), int(relu), int(band), _stream()), "seg_sum")
     return out
 
 
@@ -232,9 +232,14 @@ def linear_wgrad(dy, x, want_bias=True):
     n, m = dy.shape
     k = x.shape[1]
     dw = torch.empty((m, k), dtype=torch.float32, device=dy.device)
-    db = torch.empty(m, dtype=torch.float32, device=dy.device) if want_bias else None
     ws = _ws(lib.b2g_linear_workspace_bytes(n, m, k, _dt(dy), 2), dy.device)
-    _lib.check(lib.b2g_linear_wgrad(_p(dy), _ld(dy), _p(x), _ld(x), _p(dw), k, _p(db), n, m, k, _dt(dy), 0,
+    if GEMM_IMPL != 1 and n > 0 and lib.b2g_linear_impl(n, m, k, _dt(dy), 2) == 2:
+        # tcgen05 wgrad; the bias gradient is a separate column-sum kernel
+        _lib.check(lib.b2g_linear_wgrad(_p(dy), _ld(dy), _p(x), _ld(x), _p(dw), k, None, n, m, k, _dt(dy), 2,
+                                        _p(ws), _stream()), "linear_wgrad(tc)")
+        return dw, (colsum(dy) if want_bias else None)
+    db = torch.empty(m, dtype=torch.float32, device=dy.device) if want_bias else None
+    _lib.check(lib.b2g_linear_wgrad(_p(dy), _ld(dy), _p(x), _ld(x), _p(dw), k, _p(db), n, m, k, _dt(dy), 1,
                                     _p(ws), _stream()), "linear_wgrad")
     return dw, db
 

@@ -126,6 +126,15 @@ int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, vo
                 const int32_t* col, const float* row_scale, const float* col_scale,
                 float self_coef, const float* bias, int relu, void* stream);
 
+/* Same, with the graph's index band (max |col - row| over all entries) as a hint: for band-structured meshes the
+ * rows are processed panel by panel so the +-band neighbours stay L2-resident (see aggregate.cu RowOrder).
+ * band <= 0 = linear order.  Results are independent of the hint (every row is computed exactly once, in the
+ * same per-row summation order). */
+int b2g_seg_sum_banded(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                       int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                       const int32_t* col, const float* row_scale, const float* col_scale,
+                       float self_coef, const float* bias, int relu, int64_t band, void* stream);
+
 /* ===================================================================================== K4
  * GATConv (gnn_model.py:65-68,168) fused edge-score + segment-softmax + aggregate + head-mean +
  * bias.  xw: [N, H*C] (= lin(x)); a_src/a_dst: fp32 [N,H] with row stride

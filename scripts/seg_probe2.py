@@ -24,7 +24,9 @@ for name, x in (("randn", torch.randn(N, F, device='cuda').bfloat16()), ("const"
                 ("zeros", torch.zeros(N, F, device='cuda', dtype=torch.bfloat16))):
     for mode, rs in (("rowscale", g.dinv()), ("plain", None)):
         ms = t(lambda: ops.seg_sum(x, csr.rowptr, csr.col, N, rs, None, 0.0, None, None, out=out))
-        print(f"{name:6s} {mode:8s}: {ms:.3f} ms")
+        ref = out.clone()
+        ms2 = t(lambda: ops.seg_sum(x, csr.rowptr, csr.col, N, rs, None, 0.0, None, None, out=out, band=g.band()))
+        print(f"{name:6s} {mode:8s}: linear {ms:.3f} ms   panel order (band {g.band()}) {ms2:.3f} ms   identical={torch.equal(ref, out)}")
 # sorted-col CSR like the micro-benchmark
 col_sorted = csr.col.clone()
 x = torch.randn(N, F, device='cuda').bfloat16()
