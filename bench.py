@@ -11,7 +11,7 @@ value    : device-resident inputs, CSR cached (static mesh), CUDA-event timed, m
 e2e      : the same layer call from HOST buffers: pinned x and edge_index are copied host->device, the
            CSR is rebuilt (a new edge_index tensor every step, as `batch.to(device)` does at
            train.py:167), the layer runs, the output is copied device->host; all inside the timed region.
-roofline : the dominant kernel (seg_sum, K2), algorithmic bytes 2*N*F*s + 4*nnz + 4*(N+1) + 4*N
+roofline : the dominant kernel (seg_sum_rows_kernel, K2), algorithmic bytes 2*N*F*s + 4*nnz + 4*(N+1) + 4*N
             / its own CUDA-event time, against MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline / --impl reference : the reference's CPU path for this layer = the fp32 pure-torch
            restatement of PyG's GCNConv (oracle/layers_oracle.py; PyG itself is not installable here),
@@ -266,7 +266,7 @@ def main():
                                       None, out=out)       # exactly the launch the layer forward makes
             kms = timed(kfn, args.steps, 3)
             alg = 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1) + (4 * N if dinv is not None else 0)
-            kname = "seg_sum_kernel (K2/K3)"
+            kname = "seg_sum_rows_kernel (K2/K3)"
         else:
             H = 4
             kms, alg, kname = None, None, "attn_fwd_kernel (K4/K5)"
@@ -358,26 +358,89 @@ def main():
 
 
 def run_extras(b2g, ops, part, dev, timed):
-    """Per-layer-type forward and forward+backward throughput (bf16 and fp32), kept short."""
+    """Not the headline: per-layer-type forward and forward+backward throughput, and the reference's train step
+    (FlowGNN forward + MSE loss + backward + clip_grad_norm_ + Adam, train.py:170-189) on the same mesh."""
     import torch
+    from gnn_bfs_rans_b200.flow_model import FlowGNN
     out = {}
     N, ei = part.n_owned, part.edge_index
+
+    def mk(lt):
+        return {"GCN": lambda: b2g.nn.GCNConv(F, F),
+                "GAT": lambda: b2g.nn.GATConv(F, F, heads=4, concat=False),
+                "GIN": lambda: b2g.nn.GINConv(torch.nn.Sequential(torch.nn.Linear(F, F), torch.nn.ReLU(), torch.nn.Linear(F, F))),
+                "Transformer": lambda: b2g.nn.TransformerConv(F, F, heads=4, concat=False)}[lt]()
+
+    def timed_grad(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
     for dt_name, dtype in (("bf16", torch.bfloat16), ("fp32", torch.float32)):
         for lt in ("GCN", "GAT", "GIN", "Transformer"):
+            key = f"{lt}_{dt_name}"
             try:
                 torch.manual_seed(0)
-                layer = {"GCN": lambda: b2g.nn.GCNConv(F, F),
-                         "GAT": lambda: b2g.nn.GATConv(F, F, heads=4, concat=False),
-                         "GIN": lambda: b2g.nn.GINConv(torch.nn.Sequential(torch.nn.Linear(F, F), torch.nn.ReLU(), torch.nn.Linear(F, F))),
-                         "Transformer": lambda: b2g.nn.TransformerConv(F, F, heads=4, concat=False)}[lt]().to(dev).to(dtype).eval()
-                x = torch.randn(N, F, device=dev).to(dtype)
+                layer = mk(lt).to(dev).to(dtype).eval()
+                x = torch.empty(N, F, device=dev, dtype=dtype).normal_()
                 ms = timed(lambda: layer(x, ei), 5, 2)
                 e_agg = part.aggregated_edges(lt)
-                out[f"{lt}_{dt_name}_fwd"] = {"ms": ms, "edges_per_sec": e_agg / (ms * 1e-3)}
+                out[key + "_fwd"] = {"ms": ms, "edges_per_sec": e_agg / (ms * 1e-3)}
+                if dt_name == "bf16":
+                    xg = x.requires_grad_(True)
+
+                    def fb():
+                        xg.grad = None
+                        layer.zero_grad(set_to_none=True)
+                        layer(xg, ei).backward(gout)
+                    gout = torch.empty(N, F, device=dev, dtype=dtype).normal_()
+                    ms = timed_grad(fb, 3, 2)
+                    out[key + "_fwd_bwd"] = {"ms": ms, "edges_per_sec": e_agg / (ms * 1e-3)}
+                    del xg, gout
                 del layer, x
-                torch.cuda.empty_cache()
             except Exception as e:  # an extra must never take the headline down
-                out[f"{lt}_{dt_name}_fwd"] = {"error": str(e)[:200]}
+                out[key] = {"error": str(e)[:200]}
+            torch.cuda.empty_cache()
+
+    # FlowGNN train step (hidden 256, 4 layers, bf16) on the largest of these meshes that fits
+    for lt in ("GCN", "GAT"):
+        for frac in (4,):     # 2.5 M cells: the caller's own torch ops keep ~17 [N,256] tensors per layer alive
+            n_sub = N // frac
+            try:
+                torch.manual_seed(0)
+                sub_ei = ei if frac == 1 else None
+                if frac != 1:
+                    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+                    o, nb = hex_mesh_faces(NX, NY, NZ // frac, device=dev)
+                    sub_ei = ops.build_graph_edges(o, nb, 1, None, n_sub, n_sub)
+                torch.cuda.reset_peak_memory_stats()
+                model = FlowGNN(3, F, 7, 4, lt, dropout=0.1).to(dev).to(torch.bfloat16).train()
+                opt = torch.optim.Adam(model.parameters(), lr=3e-4, weight_decay=1e-5)
+                xin = torch.rand(n_sub, 3, device=dev, dtype=torch.bfloat16)
+                y = torch.rand(n_sub, 7, device=dev, dtype=torch.bfloat16)
+
+                def step():
+                    opt.zero_grad(set_to_none=True)
+                    loss = (model(xin, sub_ei) - y).float().square().mean()
+                    loss.backward()
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+                    opt.step()
+                ms = timed_grad(step, 3, 2)
+                out[f"train_step_FlowGNN_{lt}_L4_F256_bf16"] = {"ms": ms, "cells": n_sub, "edges": int(sub_ei.shape[1]),
+                                                             "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+                del model, opt, xin, y
+                torch.cuda.empty_cache()
+                break
+            except Exception as e:
+                out[f"train_step_FlowGNN_{lt}_cells{n_sub}"] = {"error": str(e)[:160]}
+                torch.cuda.empty_cache()
     return out
 
 
