@@ -250,14 +250,25 @@ seg_sum_rows_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, i
         for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int v = 0; v < VPL; ++v) buf[u][v] = __ldg(xv + (int64_t)c[u] * ldv + lane + 32 * v);
+        if (kScale == 2 || ns || sizeof(T) == 4) {
 #pragma unroll
-        for (int u = 0; u < U; ++u)
+          for (int u = 0; u < U; ++u)
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) {
-            Vec<T> t;
-            t.v = *reinterpret_cast<decltype(t.v)*>(&buf[u][v]);
-            fma_vec(acc[v], w[u], t);
-          }
+            for (int v = 0; v < VPL; ++v) {
+              Vec<T> t;
+              t.v = *reinterpret_cast<decltype(t.v)*>(&buf[u][v]);
+              fma_vec(acc[v], w[u], t);
+            }
+        } else {   // unweighted: predicated adds (bf16: FHADD.BF16 mixed-precision add, no unpacking)
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              Vec<T> t;
+              t.v = *reinterpret_cast<decltype(t.v)*>(&buf[u][v]);
+              add_vec_mixed_if(acc[v], t, (uint32_t)(j + u < e));
+            }
+        }
       };
       batch(b - ns);
       if (e - (b - ns) > U)
