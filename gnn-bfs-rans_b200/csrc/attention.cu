@@ -322,6 +322,110 @@ __global__ void __launch_bounds__(256, (H * CV <= 4 && MODE == MODE_GAT) ? 2 : 1
   }
 }
 
+// ------------------------------------------------------------------------- GAT forward, small-degree fast path
+// Mesh graphs: every row has <= 32 entries, heads are averaged (concat = False).  All scores of a row sit one per
+// lane, so the softmax is exact two-pass (PyG's max-subtracted form) BEFORE any feature row is touched, the head
+// average 1/H and the 1/z normalisation are folded into the per-edge weights, and ONE [C]-wide accumulator replaces
+// the H per-head accumulators of the general kernel.  The registers that frees hold twice as many neighbour rows in
+// flight (U = 4 rows x H*C*s = 8 KB per warp at H = 4, C = 256, bf16) — the gather is latency-bound.
+template <typename T, int H, int CV>
+__global__ void __launch_bounds__(256, 2) gat_fwd_small_kernel(const AttnArgs a) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int U = (H * CV <= 4) ? 4 : 2;
+  const int lane = threadIdx.x & 31;
+  const int wi = threadIdx.x >> 5;
+  const int cvec = a.C / VN;
+  const T* __restrict__ val = (const T*)a.val;
+  for (int64_t c0 = (int64_t)blockIdx.x * ATT_CHUNK; c0 < a.n_rows; c0 += (int64_t)gridDim.x * ATT_CHUNK)
+  for (int it = 0; it < ATT_ITERS; ++it) {
+    const int64_t i = c0 + it * 8 + wi;
+    if (i >= a.n_rows) break;
+    const int b = __ldg(a.rowptr + i), e = __ldg(a.rowptr + i + 1);
+    const int n = e - b;                                        // <= 32 (checked on the host)
+    const int c_l = lane < n ? __ldg(a.col + b + lane) : (int)i;
+    float al[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+      float sc = -INFINITY;
+      if (lane < n) {
+        sc = __ldg(a.a_src + (int64_t)c_l * a.lda + h) + __ldg(a.a_dst + i * a.lda + h);
+        sc = sc > 0.f ? sc : sc * a.slope;
+      }
+      const float m = warp_max(sc);
+      const float p = lane < n ? expf(sc - m) : 0.f;
+      const float z = warp_sum(p) + 1e-16f;
+      al[h] = (p / z) * (1.0f / H);                             // alpha / H; 0 on padding lanes
+      if (a.smax && lane == 0) {
+        a.smax[i * H + h] = n > 0 ? m : 0.f;
+        a.ssum[i * H + h] = z;
+      }
+    }
+    if (a.p_drop > 0.f && lane < n) {
+      if (H == 4) {
+        float s4[4];
+        dropout_scale4(a.seed, (uint64_t)(b + lane), a.p_drop, s4);
+#pragma unroll
+        for (int h = 0; h < H; ++h) al[h] *= s4[h & 3];
+      } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          float s4[4];
+          dropout_scale4(a.seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(b + lane), a.p_drop, s4);
+          al[h] *= s4[0];
+        }
+      }
+    }
+    float acc[CV][VN];
+#pragma unroll
+    for (int t = 0; t < CV; ++t)
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[t][k] = 0.f;
+    for (int j = 0; j < n; j += U) {
+      Vec<T> vb[U][H][CV];
+      float w[U][H];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int c = __shfl_sync(0xffffffffu, c_l, (j + u) & 31);   // padding lanes hold row i itself, weight 0
+#pragma unroll
+        for (int h = 0; h < H; ++h) w[u][h] = __shfl_sync(0xffffffffu, al[h], (j + u) & 31);
+        load_row<T, H, CV>(val + (int64_t)c * a.ldv, cvec, lane, vb[u]);
+      }
+      uint32_t dep = 0;                                            // all loads before the first FMA (aggregate.cu)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int t = 0; t < CV; ++t)
+            if (lane + 32 * t < cvec) dep ^= first_word(vb[u][h][t]);
+      dep ^= __shfl_sync(0xffffffffu, dep, lane);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float pw = __uint_as_float(__float_as_uint(w[u][h]) | dep);
+#pragma unroll
+          for (int t = 0; t < CV; ++t)
+            if (lane + 32 * t < cvec) fma_vec(acc[t], pw, vb[u][h][t]);
+        }
+    }
+    T* __restrict__ orow = (T*)a.out + i * a.ldo;
+#pragma unroll
+    for (int t = 0; t < CV; ++t) {
+      const int vi = lane + 32 * t;
+      if (vi < cvec) {
+        if (a.bias) {
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[t][k] += __ldg(a.bias + vi * VN + k);
+        }
+        Vec<T> ov;
+        ov.from_float(acc[t]);
+        stg_vec<T>(orow + vi * VN, ov);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------- backward, target-major
 // Per target i (one warp): recompute alpha from the saved row max / sum, d_alpha_e = <g_i, val_j>,
 // D = sum_e alpha_e d_alpha_e, ds_e = alpha_e (d_alpha_e - D).  Writes alpha_e (with the dropout
@@ -735,7 +839,9 @@ static inline unsigned warp_grid(K kernel, int64_t n_rows) {
 
 template <typename T, int H, int CV, int MODE>
 static int launch3(int which, const AttnArgs& a, const AttnSrcArgs& s, cudaStream_t st) {
-  if (which == 0) attn_fwd_kernel<T, H, CV, MODE><<<warp_grid(attn_fwd_kernel<T, H, CV, MODE>, a.n_rows), 256, 0, st>>>(a);
+  if (which == 3) {
+    if constexpr (MODE == MODE_GAT) gat_fwd_small_kernel<T, H, CV><<<warp_grid(gat_fwd_small_kernel<T, H, CV>, a.n_rows), 256, 0, st>>>(a);
+  } else if (which == 0) attn_fwd_kernel<T, H, CV, MODE><<<warp_grid(attn_fwd_kernel<T, H, CV, MODE>, a.n_rows), 256, 0, st>>>(a);
   else if (which == 1) attn_bwd_dst_kernel<T, H, CV, MODE><<<warp_grid(attn_bwd_dst_kernel<T, H, CV, MODE>, a.n_rows), 256, 0, st>>>(a);
   else attn_bwd_src_kernel<T, H, CV, MODE><<<warp_grid(attn_bwd_src_kernel<T, H, CV, MODE>, s.n_rows), 256, 0, st>>>(s);
   count_launch();
@@ -776,7 +882,7 @@ extern "C" {
 int b2g_gat_fwd(const void* xw, int64_t ldxw, const float* a_src, const float* a_dst, int64_t lda, void* out,
                 int64_t ldo, int64_t n_rows, int H, int C, int dt, int concat, float slope,
                 const int32_t* rowptr, const int32_t* col, const float* bias, float* smax,
-                float* ssum, float p_drop, uint64_t seed, void* stream) {
+                float* ssum, float p_drop, uint64_t seed, int max_degree, void* stream) {
   if (n_rows < 0 || H <= 0 || C <= 0 || p_drop < 0.f || p_drop >= 1.f) return B2G_E_ARG;
   if (n_rows == 0) return B2G_OK;
   if (!a_src || !a_dst || !rowptr || (smax && !ssum)) return B2G_E_ARG;
@@ -785,7 +891,9 @@ int b2g_gat_fwd(const void* xw, int64_t ldxw, const float* a_src, const float* a
   a.val = xw; a.ldv = ldxw; a.a_src = a_src; a.a_dst = a_dst; a.lda = lda; a.out = out; a.ldo = ldo;
   a.n_rows = n_rows; a.C = C; a.concat = concat; a.slope = slope; a.rowptr = rowptr; a.col = col;
   a.bias = bias; a.smax = smax; a.ssum = ssum; a.p_drop = p_drop; a.seed = seed;
-  return dispatch_dt(MODE_GAT, 0, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
+  // every row fits one lane-per-edge chunk and heads are averaged: single-accumulator fast path
+  const int which = (max_degree > 0 && max_degree <= 32 && !concat) ? 3 : 0;
+  return dispatch_dt(MODE_GAT, which, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
 }
 
 int b2g_gat_bwd_dst(const void* xw, int64_t ldxw, const float* a_src, const float* a_dst, int64_t lda,

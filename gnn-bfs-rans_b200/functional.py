@@ -135,7 +135,8 @@ class GATFn(torch.autograd.Function):
         need_grad = x.requires_grad or w_aug.requires_grad
         seed = _next_seed() if p_drop > 0 else 0
         out, smax, ssum = ops.gat_fwd(xw, a, H, C, concat, slope, csr.rowptr, csr.col,
-                                      bias.float() if bias is not None else None, p_drop, seed, need_grad)
+                                      bias.float() if bias is not None else None, p_drop, seed, need_grad,
+                                      max_degree=graph.max_degree("sl"))
         if need_grad:
             recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"
             ctx.save_for_backward(x, w_aug, None if recompute else xw, a, smax, ssum)

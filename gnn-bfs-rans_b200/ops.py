@@ -245,7 +245,7 @@ def linear_wgrad(dy, x, want_bias=True):
 
 
 # ------------------------------------------------------------------------------------------ K4
-def gat_fwd(xw, a, H, C, concat, slope, rowptr, col, bias, p_drop, seed, save_stats):
+def gat_fwd(xw, a, H, C, concat, slope, rowptr, col, bias, p_drop, seed, save_stats, max_degree=0):
     """xw [N,H*C]; a fp32 [N,2H] = [a_src | a_dst].  -> out, smax, ssum."""
     lib = _lib.load()
     N = xw.shape[0]
@@ -254,7 +254,7 @@ def gat_fwd(xw, a, H, C, concat, slope, rowptr, col, bias, p_drop, seed, save_st
     ssum = torch.empty((N, H), dtype=torch.float32, device=xw.device) if save_stats else None
     _lib.check(lib.b2g_gat_fwd(_p(xw), _ld(xw), _p(a), a.data_ptr() + 4 * H, a.stride(0), _p(out), _ld(out), N, H, C,
                                _dt(xw), int(concat), float(slope), _p(rowptr), _p(col), _p(bias), _p(smax), _p(ssum),
-                               float(p_drop), int(seed), _stream()), "gat_fwd")
+                               float(p_drop), int(seed), int(max_degree), _stream()), "gat_fwd")
     return out, smax, ssum
 
 

@@ -142,11 +142,13 @@ int b2g_seg_sum_banded(const void* x, int64_t ldx, const void* x_self, int64_t l
  *   s_p = leaky_relu(a_src[col[p],h] + a_dst[i,h], slope); alpha = softmax over row i;
  *   out[i,c] = (concat ? per head : mean over h) sum_p alpha_{p,h} xw[col[p],h,c] + bias
  * smax/ssum: fp32 [N,H] saved row max and sum(exp)+1e-16 (may be NULL in inference).
- * dropout: p_drop in [0,1) with Philox seed/offset (0 -> no dropout); mask regenerated in bwd. */
+ * dropout: p_drop in [0,1) with Philox seed/offset (0 -> no dropout); mask regenerated in bwd.
+ * max_degree: largest row length of the CSR if the caller knows it (0 = unknown); <= 32 with concat == 0 selects
+ * the single-accumulator small-degree kernel (same result up to fp32 rounding order). */
 int b2g_gat_fwd(const void* xw, int64_t ldxw, const float* a_src, const float* a_dst, int64_t lda,
                 void* out, int64_t ldo, int64_t n_rows, int H, int C, int dt, int concat, float slope,
                 const int32_t* rowptr, const int32_t* col, const float* bias, float* smax,
-                float* ssum, float p_drop, uint64_t seed, void* stream);
+                float* ssum, float p_drop, uint64_t seed, int max_degree, void* stream);
 /* Backward, target-major pass: recomputes alpha, produces per-edge alpha_e / dscore_e (fp32
  * [nnz,H], CSR order) and d a_dst [N,H].  gout: [N, concat?H*C:C]. */
 int b2g_gat_bwd_dst(const void* xw, int64_t ldxw, const float* a_src, const float* a_dst, int64_t lda,

@@ -32,10 +32,10 @@ else:
             ops.seg_sum(x, csr.rowptr, csr.col, N, g.dinv(), None, 0.0, None, None, out=out)
     elif what == "gat":
         csr = g.csr("sl", False)
-        xw = torch.randn(N, H * F, device='cuda').to(dtype)
+        xw = torch.empty(N, H * F, device='cuda', dtype=dtype).normal_()
         a = torch.randn(N, 2 * H, device='cuda')
         for _ in range(reps):
-            ops.gat_fwd(xw, a, H, F, False, 0.2, csr.rowptr, csr.col, None, 0.0, 0, False)
+            ops.gat_fwd(xw, a, H, F, False, 0.2, csr.rowptr, csr.col, None, 0.0, 0, False, max_degree=int(os.environ.get('MAXDEG', '7')))
     elif what == "tconv":
         csr = g.csr("raw", False)
         y = torch.randn(N, 3 * H * F + F, device='cuda').to(dtype)
