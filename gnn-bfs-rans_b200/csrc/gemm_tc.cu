@@ -363,6 +363,249 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 // =====================================================================================================
+// fp32 Linear on the tensor cores: 3 x TF32 split ("3xTF32").  The parity gate for fp32 is 1e-5, which a single
+// TF32 pass (10-bit mantissa, ~1e-3) cannot meet and which costs 35 ms per cfg4 layer on the FP32 pipe.  Every fp32
+// operand is split exactly into hi = the TF32-representable head (low 13 mantissa bits cleared) and lo = x - hi
+// (exact in fp32), and D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo with fp32 accumulation in TMEM; the dropped term
+// A_lo*B_lo and the truncation of lo to TF32 are ~2^-22 relative (tests: <= 1e-6 of the max-abs reference).
+// X tiles are split in shared memory by four converter warps between the TMA load and the MMAs (in place for hi,
+// a second buffer for lo, then fence.proxy.async so the tensor core's async proxy sees the generic-proxy writes);
+// W is split once per call by a small kernel into a [2m, k] workspace and streamed through TMA like X.
+constexpr int T3_BK = 32;                               // fp32 elements per k-block = 128 bytes
+constexpr int T3_A = TC_BM * T3_BK * 4;                 // 16 KB
+constexpr int T3_B = TC_BN * T3_BK * 4;                 // 32 KB
+constexpr int T3_STAGE = 2 * T3_A + 2 * T3_B;           // A_hi, A_lo, B_hi, B_lo = 96 KB
+constexpr int T3_STAGES = 2;
+constexpr int T3_SMEM = T3_STAGES * T3_STAGE + 128;
+static_assert(T3_SMEM + 1024 <= 232448, "3xTF32 shared-memory plan exceeds 227 KB");
+
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, int64_t ldw, int m, int k,
+                                                         float* __restrict__ out /*[2m,k]*/) {
+  const int64_t total = (int64_t)m * k;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / k), c = (int)(t - (int64_t)r * k);
+    const float v = w[(int64_t)r * ldw + c];
+    const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    out[t] = hi;
+    out[total + t] = v - hi;
+  }
+}
+
+struct T3Params {
+  int64_t n;
+  int m, m_main, k;
+  const float* bias;
+  const float* row_scale;
+  float* Y;
+  int64_t ldy;
+  float* aux;
+  int64_t ldaux;
+  int act;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const T3Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  const uint32_t bars = smem_base + T3_STAGES * T3_STAGE;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto conv_bar = [&](int s) { return bars + 8u * (T3_STAGES + s); };
+  auto empty_bar = [&](int s) { return bars + 8u * (2 * T3_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (3 * T3_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (3 * T3_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (3 * T3_STAGES + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row_tiles = (p.n + TC_BM - 1) / TC_BM;
+  const int col_tiles = (p.m + TC_BN - 1) / TC_BN;
+  const int64_t tiles = row_tiles * col_tiles;
+  const int kblocks = (p.k + T3_BK - 1) / T3_BK;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    for (int s = 0; s < T3_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(conv_bar(s), 4);      // one arrive per converter warp
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);    // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer: A (raw fp32), B_hi, B_lo
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int64_t rt = t / col_tiles;
+        const int ct = (int)(t - rt * col_tiles);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * T3_STAGE;
+          mbar_expect_tx(full_bar(stage), T3_A + 2 * T3_B);
+          tma_load_2d(sa, &map_a, full_bar(stage), kb * T3_BK, (int)(rt * TC_BM));
+          tma_load_2d(sa + 2 * T3_A, &map_b, full_bar(stage), kb * T3_BK, ct * TC_BN);                 // W_hi rows
+          tma_load_2d(sa + 2 * T3_A + T3_B, &map_b, full_bar(stage), kb * T3_BK, p.m + ct * TC_BN);   // W_lo rows
+          if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer: 3 products per k-block
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TC_BM, TC_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(conv_bar(stage), phase);                 // X tile split into hi / lo by the converter warps
+          tc_fence_after();
+          const uint32_t a_hi = smem_base + stage * T3_STAGE, a_lo = a_hi + T3_A;
+          const uint32_t b_hi = a_hi + 2 * T3_A, b_lo = b_hi + T3_B;
+#pragma unroll
+          for (int ks = 0; ks < T3_BK / 8; ++ks) {           // UMMA_K = 8 tf32 = 32 bytes
+            const uint64_t dah = make_smem_desc(a_hi + ks * 32), dal = make_smem_desc(a_lo + ks * 32);
+            const uint64_t dbh = make_smem_desc(b_hi + ks * 32), dbl = make_smem_desc(b_lo + ks * 32);
+            tc_mma_tf32(d_tmem, dal, dbh, idesc, (kb | ks) ? 1u : 0u);   // small terms first
+            tc_mma_tf32(d_tmem, dah, dbl, idesc, 1u);
+            tc_mma_tf32(d_tmem, dah, dbh, idesc, 1u);
+          }
+          tc_commit(empty_bar(stage));
+          if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================================================== converter warps 2..5: X -> (hi in place, lo)
+    const int tid = threadIdx.x - 64;                        // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        float4* hi = reinterpret_cast<float4*>(smem_raw + (size_t)stage * T3_STAGE);
+        float4* lo = reinterpret_cast<float4*>(smem_raw + (size_t)stage * T3_STAGE + T3_A);
+#pragma unroll
+        for (int i = 0; i < T3_A / 16 / 128; ++i) {          // 8 float4 per thread; elementwise, layout-agnostic
+          const int idx = i * 128 + tid;
+          const float4 v = hi[idx];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(conv_bar(stage));
+        if (++stage == T3_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================== epilogue warps 6..9 (TMEM lane quadrant = warp % 4)
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int64_t rt = t / col_tiles;
+      const int ct = (int)(t - rt * col_tiles);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int64_t row = rt * TC_BM + q * 32 + lane;
+      const bool row_ok = row < p.n;
+      const float rs = (p.row_scale && row_ok) ? __ldg(p.row_scale + row) : 1.0f;
+      const int col0 = ct * TC_BN;
+      const int ncols = min(TC_BN, p.m - col0);
+#pragma unroll 1
+      for (int c = 0; c < ncols; c += 32) {
+        uint32_t r[32];
+        tc_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c), r);
+        if (row_ok) {
+          const int cg0 = col0 + c;
+          if (cg0 + 32 <= p.m_main) {                          // a full 128-byte line of this row
+            float* dst = p.Y + row * p.ldy + cg0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              float* of = reinterpret_cast<float*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = __uint_as_float(r[j + e]);
+                if (p.row_scale) x *= rs;
+                if (p.bias) x += __ldg(p.bias + cg0 + j + e);
+                if (p.act == 1) x = fmaxf(x, 0.f);
+                of[e] = x;
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int cg = cg0 + j;
+              if (cg < p.m) {
+                float x = __uint_as_float(r[j]);
+                if (p.row_scale) x *= rs;
+                if (p.bias) x += __ldg(p.bias + cg);
+                if (p.act == 1) x = fmaxf(x, 0.f);
+                if (cg < p.m_main) p.Y[row * p.ldy + cg] = x;
+                else p.aux[row * p.ldaux + (cg - p.m_main)] = x;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// =====================================================================================================
 // wgrad on the tensor cores:  dW[m,k] = sum_n dY[n,m] X[n,k]   (bf16 in, fp32 out)
 // Both operands are "MN-major" for tcgen05: the reduction index n is the SLOW index of dY [n,m] and X [n,k].
 // TMA boxes of {64 contiguous columns (128 B), 64 rows of n} land in shared memory as 64 rows x 128 B with the
@@ -525,15 +768,16 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2-D bf16 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 64 cols], 128B swizzle, zero OOB fill
-static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                     bool f32 = false) {
   if (rows >= ((int64_t)1 << 31)) return false;
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {(cuuint32_t)(f32 ? T3_BK : TC_BK), (cuuint32_t)box_rows};     // 128 bytes wide either way
   cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+  return enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -582,7 +826,13 @@ int tc_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, fl
   return cuda_status();
 }
 
+static int g_tf32x3 = 1;   // fp32 Linear on tensor cores via the 3xTF32 split (0 = exact-fp32 SIMT only)
+void tc_set_tf32x3(int on) { g_tf32x3 = on ? 1 : 0; }
+
 bool tc_linear_supported(int64_t n, int m, int k, int dt, int which) {
+  // fp32: the TMEM accumulation truncates, so the error grows ~linearly with the reduction length (measured: 3e-6 at
+  // k = 256, 2.6e-5 at k = 3328 against the 1e-5 gate) -> longer reductions stay on the exact-fp32 SIMT kernel.
+  if (dt == B2G_F32) return g_tf32x3 && which == 0 && n >= 1 && k >= 4 && k <= 512 && (k % 4) == 0 && m >= 1 && get_encode() != nullptr;
   if (dt != B2G_BF16) return false;
   if (which == 2) return n >= 1 && m % 8 == 0 && k % 8 == 0 && m >= 8 && k >= 8 && get_encode() != nullptr;
   if (which != 0) return false;
@@ -590,12 +840,43 @@ bool tc_linear_supported(int64_t n, int m, int k, int dt, int which) {
   return get_encode() != nullptr;
 }
 
-int64_t tc_linear_ws_bytes(int64_t, int, int, int, int) { return 256; }
+int64_t tc_linear_ws_bytes(int64_t, int m, int k, int dt, int) { return dt == B2G_F32 ? (int64_t)2 * m * k * 4 + 256 : 256; }
+
+static int tc_linear_fwd_tf32x3(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                                const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n,
+                                int m, int m_main, int k, int act, void* ws, cudaStream_t st) {
+  if (!ws) return B2G_E_ARG;
+  if (!aligned16(X) || (ldx * 4) % 16) return B2G_E_ALIGN;
+  if (m_main > 0 && (!aligned16(Y) || (ldy * 4) % 16)) return B2G_E_ALIGN;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  float* wsplit = static_cast<float*>(ws);                     // [2m, k]: rows 0..m-1 = hi, m..2m-1 = lo
+  const int64_t total = (int64_t)m * k;
+  int64_t blocks = ceil_div(total, 256);
+  if (blocks > B2G_NUM_SMS * 4) blocks = B2G_NUM_SMS * 4;
+  split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(W), ldw, m, k, wsplit);
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, X, n, k, ldx, TC_BM, true) || !make_map(&map_b, wsplit, 2 * (int64_t)m, k, k, TC_BN, true))
+    return B2G_E_UNSUPPORTED;
+  T3Params p;
+  p.n = n; p.m = m; p.m_main = m_main; p.k = k; p.bias = bias; p.row_scale = row_scale;
+  p.Y = static_cast<float*>(Y); p.ldy = ldy; p.aux = aux; p.ldaux = ldaux; p.act = act;
+  const int64_t tiles = ceil_div(n, TC_BM) * ceil_div(m, TC_BN);
+  const unsigned grid = (unsigned)(tiles < B2G_NUM_SMS ? tiles : B2G_NUM_SMS);
+  tc_linear_tf32x3_kernel<<<grid, TC_THREADS, T3_SMEM, st>>>(map_a, map_b, p);
+  count_launch(2);
+  return cuda_status();
+}
 
 int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                   const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n, int m,
                   int m_main, int k, int dt, int act, void* ws, cudaStream_t st) {
-  (void)ws;
+  if (dt == B2G_F32)
+    return tc_linear_fwd_tf32x3(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, act, ws, st);
   if (dt != B2G_BF16) return B2G_E_UNSUPPORTED;
   if (!aligned16(X) || !aligned16(W) || (ldx * 2) % 16 || (ldw * 2) % 16) return B2G_E_ALIGN;
   if (m_main > 0 && (!aligned16(Y) || (ldy * 2) % 16)) return B2G_E_ALIGN;
