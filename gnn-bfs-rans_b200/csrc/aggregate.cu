@@ -148,177 +148,6 @@ seg_sum_kernel(const T* __restrict__ x, int64_t ldx, const T* __restrict__ x_sel
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Fast path for rows that are whole multiples of 512 bytes (F = 256 bf16, F = 128/256 fp32, ...): one warp per
-// target row, VPL 16-byte vectors per lane, the first U (= 8 at VPL 1) neighbour rows handled by STRAIGHT-LINE code.
-// What makes it faster than seg_sum_kernel (each point measured, see DESIGN.md §4 and scripts/micro/):
-//  * `__launch_bounds__(256, minBlocks)`: without a min-blocks hint ptxas schedules for minimum registers and
-//    sinks every load next to its use (LDG; FFMA2 x4; LDG; ... = one row in flight per warp); with the hint it
-//    issues all U loads back to back (8 x LDG.128, then 32 x FFMA2) at 60-72 registers;
-//  * no loop around the common case: rows longer than U fall into a cold loop;
-//  * the self term and the padding slots are ordinary entries of the batch (weight self_coef / 0).
-constexpr int ST_CHUNK = 128;               // consecutive rows per CTA step (16 per warp): x+-1 / self rows hit L1
-
-// Row processing order.  A mesh numbered plane by plane has neighbours at index distance ~B (the "band": 50 000
-// rows = 25.6 MB of bf16 features at cfg4), so a linear sweep needs two planes (+ the streamed output) to stay in
-// L2 between the first and the last use of a row; ncu measured 14.3 GB of DRAM reads for 5.1 GB of features.
-// Panel order: split every band-sized block [kB, (k+1)B) into panels of S rows and sweep panel p of ALL blocks
-// before panel p+1.  The +-B neighbours of a row then sit S rows (a few MB) away in processing order instead of B.
-// The mapping is arithmetic (no permutation array); band = 0 selects the linear order.
-struct RowOrder {
-  int64_t n_chunks, band, panel;            // band, panel: multiples of ST_CHUNK (0 = linear)
-  int64_t n_blocks, chunks_per_panel;
-  __device__ __forceinline__ int64_t chunk(int64_t q, int64_t n_rows, int& rows) const {
-    if (band == 0) {
-      const int64_t c0 = q * ST_CHUNK;
-      rows = (int)min((int64_t)ST_CHUNK, n_rows - c0);
-      return c0;
-    }
-    const int64_t per_panel = n_blocks * chunks_per_panel;
-    const int64_t p = q / per_panel, rem = q - p * per_panel;
-    const int64_t k = rem / chunks_per_panel, tc = rem - k * chunks_per_panel;
-    const int64_t off = p * panel + tc * ST_CHUNK;          // offset inside the block
-    const int64_t c0 = k * band + off;
-    int64_t r = min((int64_t)ST_CHUNK, band - off);
-    r = min(r, n_rows - c0);
-    rows = (int)max(r, (int64_t)0);
-    return c0;
-  }
-};
-static RowOrder make_row_order(int64_t n_rows, int64_t band) {
-  RowOrder o{};
-  const int64_t panel = 64 * ST_CHUNK;                       // 8192 rows: 4 MB of bf16 F=256 rows per block
-  if (band < 4 * panel || band * 2 > n_rows) {               // narrow band (already L2 friendly) or no band structure
-    o.band = 0;
-    o.n_chunks = ceil_div(n_rows, ST_CHUNK);
-    return o;
-  }
-  o.band = ceil_div(band, ST_CHUNK) * ST_CHUNK;              // block size >= band keeps +-band neighbours in adjacent blocks
-  o.panel = panel;
-  o.n_blocks = ceil_div(n_rows, o.band);
-  o.chunks_per_panel = panel / ST_CHUNK;
-  o.n_chunks = ceil_div(o.band, panel) * o.n_blocks * o.chunks_per_panel;
-  return o;
-}
-
-template <typename T, int VPL, int kScale>
-__global__ void __launch_bounds__(256, (VPL == 1 ? 4 : (VPL == 2 ? 3 : 2)))
-seg_sum_rows_kernel(const T* __restrict__ x, int64_t ldx, T* __restrict__ out, int64_t ldo, int64_t n_rows,
-                      const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                      const float* __restrict__ row_scale, const float* __restrict__ col_scale,
-                      float self_coef, const float* __restrict__ bias, int relu, RowOrder ord) {
-  constexpr int VN = Vec<T>::N;
-  constexpr int U = (VPL == 1) ? 8 : (VPL == 2 ? 4 : 2);
-  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
-  const uint4* __restrict__ xv = reinterpret_cast<const uint4*>(x);
-  const int64_t ldv = ldx / VN;                                // row stride in 16-byte vectors
-  const int ns = (self_coef != 0.f) ? 1 : 0;
-  for (int64_t q = blockIdx.x; q < ord.n_chunks; q += gridDim.x) {
-    int rows;
-    const int64_t c0 = ord.chunk(q, n_rows, rows);
-    for (int it = 0; it * 8 < ST_CHUNK; ++it) {
-      const int r = it * 8 + wi;
-      if (r >= rows) break;
-      const int64_t i = c0 + r;
-      const int b = __ldg(rowptr + i), e = __ldg(rowptr + i + 1);
-      const float rs = (kScale && row_scale) ? __ldg(row_scale + i) : 1.0f;
-      float acc[VPL][VN];
-#pragma unroll
-      for (int v = 0; v < VPL; ++v)
-#pragma unroll
-        for (int k = 0; k < VN; ++k) acc[v][k] = 0.f;
-      // One batch of U neighbour rows as straight-line code (mesh rows: <= 7 + self), then a cold loop for the
-      // rest of longer rows.  ptxas batches the U loads of the straight-line copy; inside a loop it sinks every
-      // load next to its use (one row in flight per warp).
-      auto batch = [&](int j) {
-        int c[U];
-        float w[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int t = j + u;
-          c[u] = (t >= b && t < e) ? __ldg(col + t) : (int)i;
-          w[u] = (t < e) ? 1.f : 0.f;
-          if (t < b) w[u] = self_coef;
-        }
-        if (kScale == 2) {
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (j + u >= b && j + u < e) w[u] = (col_scale ? __ldg(col_scale + c[u]) : 1.0f) * rs;
-        }
-        uint4 buf[U][VPL];
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-          for (int v = 0; v < VPL; ++v) buf[u][v] = __ldg(xv + (int64_t)c[u] * ldv + lane + 32 * v);
-        if (kScale == 2 || ns || sizeof(T) == 4) {
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-              Vec<T> t;
-              t.v = *reinterpret_cast<decltype(t.v)*>(&buf[u][v]);
-              fma_vec(acc[v], w[u], t);
-            }
-        } else {   // unweighted: predicated adds (bf16: FHADD.BF16 mixed-precision add, no unpacking)
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int v = 0; v < VPL; ++v) {
-              Vec<T> t;
-              t.v = *reinterpret_cast<decltype(t.v)*>(&buf[u][v]);
-              add_vec_mixed_if(acc[v], t, (uint32_t)(j + u < e));
-            }
-        }
-      };
-      batch(b - ns);
-      if (e - (b - ns) > U)
-        for (int j = b - ns + U; j < e; j += U) batch(j);
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int vi = lane + 32 * v;
-        if (kScale == 1) {
-#pragma unroll
-          for (int k = 0; k < VN; ++k) acc[v][k] *= rs;
-        }
-        if (bias) {
-#pragma unroll
-          for (int k = 0; k < VN; k += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + vi * VN + k));
-            acc[v][k] += bb.x; acc[v][k + 1] += bb.y; acc[v][k + 2] += bb.z; acc[v][k + 3] += bb.w;
-          }
-        }
-        if (relu) {
-#pragma unroll
-          for (int k = 0; k < VN; ++k) acc[v][k] = fmaxf(acc[v][k], 0.f);
-        }
-        Vec<T> o;
-        o.from_float(acc[v]);
-        __stcs(reinterpret_cast<uint4*>(out + i * ldo + vi * VN), *reinterpret_cast<uint4*>(&o.v));
-      }
-    }
-  }
-}
-
-template <typename T, int VPL>
-static int launch_rows(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t n_rows, const int32_t* rowptr,
-                         const int32_t* col, const float* rs, const float* cs, float self_coef, const float* bias,
-                         int relu, int64_t band, cudaStream_t st) {
-  const RowOrder ord = make_row_order(n_rows, band);
-  int64_t blocks = ord.n_chunks;
-  const int mode = cs ? 2 : (rs ? 1 : 0);
-#define B2G_ST(MODE)                                                                                   \
-  {                                                                                                    \
-    const int64_t cap = resident_ctas(seg_sum_rows_kernel<T, VPL, MODE>, 256);                       \
-    if (blocks > cap) blocks = cap;                                                                    \
-    seg_sum_rows_kernel<T, VPL, MODE><<<(unsigned)blocks, 256, 0, st>>>(                             \
-        (const T*)x, ldx, (T*)out, ldo, n_rows, rowptr, col, rs, cs, self_coef, bias, relu, ord);      \
-  }
-  if (mode == 2) B2G_ST(2) else if (mode == 1) B2G_ST(1) else B2G_ST(0)
-#undef B2G_ST
-  count_launch();
-  return cuda_status();
-}
-
 template <typename T, int LANES, int VPL>
 static int launch_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
                           int64_t ldo, int64_t n_rows, int nvec, const int32_t* rowptr,
@@ -453,6 +282,10 @@ namespace b2g {
 bool bulk_seg_sum_supported(int nvec, int64_t n_rows);
 int bulk_seg_sum(int, const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int, int, const int32_t*,
                  const int32_t*, const float*, const float*, float, const float*, int, cudaStream_t);
+int rows_seg_sum(const void*, int64_t, void*, int64_t, int64_t, int, int, const int32_t*, const int32_t*, const float*,
+                 const float*, float, const float*, int, int64_t, int64_t, cudaStream_t);
+int rows_set_sched(int chunk_rows, int panel_rows);
+int64_t g_maxlen_hint = 0;
 int g_seg_impl = 0;   // 0 = auto, 1 = register gather (LDG), 2 = cp.async.bulk ring, 3 = cp.async (LDGSTS) ring
 int64_t g_band_hint = 0;
 }  // namespace b2g
@@ -470,6 +303,13 @@ int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, vo
                 int F, int dt, const int32_t* rowptr, const int32_t* col, const float* row_scale,
                 const float* col_scale, float self_coef, const float* bias, int relu, void* stream);
 
+int b2g_set_seg_sched(int chunk_rows, int panel_rows) { return rows_set_sched(chunk_rows, panel_rows); }
+
+int b2g_seg_sum_hinted(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                       int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                       const int32_t* col, const float* row_scale, const float* col_scale,
+                       float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, void* stream);
+
 int b2g_set_seg_impl(int impl) {
   if (impl < 0 || impl > 3) return B2G_E_ARG;
   g_seg_impl = impl;
@@ -480,10 +320,20 @@ int b2g_seg_sum_banded(const void* x, int64_t ldx, const void* x_self, int64_t l
                        int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
                        const int32_t* col, const float* row_scale, const float* col_scale,
                        float self_coef, const float* bias, int relu, int64_t band, void* stream) {
+  return b2g_seg_sum_hinted(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale, self_coef,
+                            bias, relu, band, 0, stream);
+}
+
+int b2g_seg_sum_hinted(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                       int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                       const int32_t* col, const float* row_scale, const float* col_scale,
+                       float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, void* stream) {
   g_band_hint = band > 0 ? band : 0;
+  g_maxlen_hint = max_row_len > 0 ? max_row_len : 0;
   const int rc = b2g_seg_sum(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale,
                              self_coef, bias, relu, stream);
   g_band_hint = 0;
+  g_maxlen_hint = 0;
   return rc;
 }
 
@@ -503,14 +353,11 @@ int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, vo
   if (bulk_ok && g_seg_impl >= 2)
     return bulk_seg_sum(g_seg_impl, x, ldx, x_self, ldxs, out, ldo, n_rows, nvec, dt, rowptr, col, row_scale, col_scale, self_coef,
                         bias, relu, st);
-  // rows of whole 512-byte multiples (F = 256 bf16, F = 128/256 fp32, ...): warp-per-row fast path
-  if (g_seg_impl != 1 && !x_self && nvec % 32 == 0 && nvec <= 128 && n_rows >= 1024) {
-#define B2G_STD(T)                                                                                                         \
-    if (nvec == 32) return launch_rows<T, 1>(x, ldx, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, g_band_hint, st); \
-    if (nvec == 64) return launch_rows<T, 2>(x, ldx, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, g_band_hint, st); \
-    if (nvec == 128) return launch_rows<T, 4>(x, ldx, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, g_band_hint, st);
-    if (dt == B2G_F32) { B2G_STD(float) } else { B2G_STD(__nv_bfloat16) }
-#undef B2G_STD
+  // rows of whole 512-byte multiples (F = 256 bf16, F = 128/256 fp32, ...): warp-per-row fast path (aggregate_rows.cu)
+  if (g_seg_impl != 1 && !x_self) {
+    const int rc = rows_seg_sum(x, ldx, out, ldo, n_rows, nvec, dt, rowptr, col, row_scale, col_scale, self_coef, bias, relu,
+                                g_band_hint, g_maxlen_hint, st);
+    if (rc != B2G_E_UNSUPPORTED) return rc;
   }
   if (dt == B2G_F32)
     return dispatch_seg_sum<float>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);

@@ -2,7 +2,7 @@
 # Runs each GPU test file in its own process (a CUDA fault in one must not poison the rest) and keeps logs.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-for f in tests/test_gpu_builder.py tests/test_gpu_csr.py tests/test_gpu_linear.py tests/test_gpu_layers.py tests/test_gpu_model.py tests/test_gpu_partition.py; do
+for f in tests/test_gpu_*.py; do
   n=$(basename $f .py)
   timeout 900 python -m pytest $f -m gpu -q --tb=short --maxfail=8 -p no:cacheprovider > gpurun_out/$n.log 2>&1
   echo "== $n exit $?"; tail -n 25 gpurun_out/$n.log
