@@ -263,10 +263,10 @@ def main():
             xin = torch.randn(part.n_local, F, device=dev).to(dtype)
             out = torch.empty(N, F, device=dev, dtype=dtype)
             kfn = lambda: ops.seg_sum(xin, csr.rowptr, csr.col, N, dinv, None, 0.0 if args.layer == "GCN" else 1.0, None,
-                                      None, out=out)       # exactly the launch the layer forward makes
+                                      None, out=out, band=g.band())   # exactly the launch the layer forward makes
             kms = timed(kfn, args.steps, 3)
             alg = 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1) + (4 * N if dinv is not None else 0)
-            kname = "seg_sum_rows_kernel (K2/K3)"
+            kname = "seg_rows_kernel (K2/K3, aggregate_rows.cu)"
         else:
             H = 4
             kms, alg, kname = None, None, "attn_fwd_kernel (K4/K5)"
@@ -302,11 +302,17 @@ def main():
             hei = ei.cpu().pin_memory()
             hout = torch.empty((N, F), dtype=dtype).pin_memory()
 
-            def e2e_step():
-                dx = hx.to(dev, non_blocking=True)
-                dei = hei.to(dev, non_blocking=True)
-                o = layer(dx, dei)
-                hout.copy_(o, non_blocking=True)
+            if args.layer == "GCN":     # public host-buffer entry: copies pipelined with the kernels (streaming.py)
+                def e2e_step():
+                    b2g.streaming.gcn_forward_host(layer, hx, hei, hout)
+                e2e_api = "gnn_bfs_rans_b200.streaming.gcn_forward_host(layer, x_host, edge_index_host, out_host)"
+            else:
+                def e2e_step():
+                    dx = hx.to(dev, non_blocking=True)
+                    dei = hei.to(dev, non_blocking=True)
+                    o = layer(dx, dei)
+                    hout.copy_(o, non_blocking=True)
+                e2e_api = "layer(x.to(dev), edge_index.to(dev)) -> pinned host copy"
 
             steps_e = max(3, min(args.steps, 5))
             for _ in range(2):
@@ -324,7 +330,7 @@ def main():
             e2e = {"value": e_total / (ems * 1e-3), "unit": "edges/s", "ms_per_step": ems,
                    "h2d_bytes_per_step": hx.numel() * hx.element_size() + hei.numel() * 8,
                    "d2h_bytes_per_step": hout.numel() * hout.element_size(), "steps": steps_e,
-                   "includes": "H2D x + edge_index, CSR rebuild, layer forward, D2H output"}
+                   "includes": "H2D x + edge_index, CSR rebuild, layer forward, D2H output", "api": e2e_api}
             del hx, hei, hout
     else:
         e2e = {"value": None, "unit": "edges/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,

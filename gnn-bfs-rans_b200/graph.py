@@ -77,6 +77,10 @@ class Graph:
         # B2G_PANEL_ORDER=0 switches the hint off (linear sweep) for A/B runs.
         if os.environ.get("B2G_PANEL_ORDER", "1") == "0":
             return 0
+        return self.band_raw()
+
+    def band_raw(self) -> int:
+        """max |source - target| (cached): rows [r0, r1) only read rows [r0 - band, r1 + band)."""
         if not hasattr(self, "_band"):
             ei = self.edge_index
             self._band = int((ei[0] - ei[1]).abs().max()) if ei.shape[1] else 0
