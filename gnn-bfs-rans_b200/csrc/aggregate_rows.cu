@@ -17,37 +17,12 @@
 //    prefetch is issued ahead of the gathers with its address operands long arrived;
 //  * a linear sweep re-read every feature row 2.3x from DRAM (fp32: 3x): the co-resident CTAs must work on one
 //    narrow front and, on band-structured meshes, panel by panel (RowSched below): 14.3 -> 5.9 GB of reads.
-#include "common.cuh"
+#include "rows.cuh"
 
 namespace b2g {
 
-// Row schedule.  The co-resident CTAs take chunks of `chunk_rows` consecutive rows round-robin, so the chip works on
-// ONE front of grid x chunk_rows rows.  A mesh numbered plane by plane has neighbours at index distance ~B (the
-// "band": 50 000 rows = 25.6 MB of bf16 features at cfg4); in a linear sweep the three uses of a row are 2B rows apart
-// and - with the streamed output and the far-die copies - do not meet in L2.  Panel order: split every band-sized
-// block [kB, (k+1)B) into panels of `panel` rows and sweep panel p of ALL blocks before panel p+1; the +-B
-// neighbours of a row are then `panel` rows away in processing order.  band = 0 selects the linear order.
-struct RowSched {
-  uint32_t n_chunks, chunk_rows;
-  uint32_t band, panel, per_panel, cpp_shift;        // band, panel: multiples of chunk_rows; per_panel = blocks << cpp_shift
-  // first row and row count of chunk q; n_rows < 2^32 - 2^25 (checked by the launcher) keeps everything in 32 bits
-  __device__ __forceinline__ uint32_t chunk(uint32_t q, uint32_t n_rows, uint32_t& rows) const {
-    if (band == 0) {
-      const uint32_t c0 = q * chunk_rows;
-      rows = min(chunk_rows, n_rows - c0);
-      return c0;
-    }
-    const uint32_t p = q / per_panel, rem = q - p * per_panel;
-    const uint32_t k = rem >> cpp_shift, tc = rem & ((1u << cpp_shift) - 1u);
-    const uint32_t off = p * panel + tc * chunk_rows;          // offset inside the block
-    const uint32_t c0 = k * band + off;
-    rows = 0;
-    if (off < band && c0 < n_rows) rows = min(min(chunk_rows, band - off), n_rows - c0);
-    return c0;
-  }
-};
-static int g_seg_chunk = 32;                 // rows per CTA step (b2g_set_seg_sched)
-static int g_seg_panel = 8192;               // rows per panel of the band order (power-of-two multiple of the chunk)
+int g_seg_chunk = 32;
+int g_seg_panel = 8192;
 
 int rows_set_sched(int chunk_rows, int panel_rows) {
   if (chunk_rows < 8 || (chunk_rows & (chunk_rows - 1)) || chunk_rows > 4096) return B2G_E_ARG;
@@ -55,63 +30,6 @@ int rows_set_sched(int chunk_rows, int panel_rows) {
   g_seg_chunk = chunk_rows;
   g_seg_panel = panel_rows;
   return B2G_OK;
-}
-
-static bool make_row_sched(int64_t n_rows, int64_t band, RowSched& o) {
-  o = RowSched{};
-  o.chunk_rows = (uint32_t)g_seg_chunk;
-  const int64_t panel = g_seg_panel;
-  if (band < 4 * panel || band * 2 > n_rows) {               // narrow band (already L2 friendly) or no band structure
-    const int64_t nc = ceil_div(n_rows, o.chunk_rows);
-    if (nc >= (1ll << 31)) return false;
-    o.n_chunks = (uint32_t)nc;
-    return true;
-  }
-  const int64_t bandr = ceil_div(band, o.chunk_rows) * o.chunk_rows;   // block >= band keeps +-band neighbours in adjacent blocks
-  const int64_t blocks = ceil_div(n_rows, bandr);
-  uint32_t sh = 0;
-  while (((int64_t)o.chunk_rows << sh) < panel) ++sh;
-  const int64_t per_panel = blocks << sh;
-  const int64_t nc = ceil_div(bandr, panel) * per_panel;
-  if (nc >= (1ll << 31) || bandr >= (1ll << 31)) return false;
-  o.band = (uint32_t)bandr;
-  o.panel = (uint32_t)panel;
-  o.cpp_shift = sh;
-  o.per_panel = (uint32_t)per_panel;
-  o.n_chunks = (uint32_t)nc;
-  return true;
-}
-
-__device__ __forceinline__ uint4 ldg_row16(const char* p) {   // gathered rows: allocate in L1 (x+-1 / self reuse inside a CTA)
-  uint4 u;
-  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
-  return u;
-}
-// acc += v, unweighted: bf16 -> sm_100 mixed-precision add (SASS FHADD.BF16; exact: bf16 -> fp32 is exact, one fp32
-// rounding per add), fp32 -> packed add.rn.f32x2
-__device__ __forceinline__ void add_row16(float* acc, const uint4& u, __nv_bfloat16) {
-  asm volatile(
-      "{\n"
-      ".reg .b16 l0, h0, l1, h1, l2, h2, l3, h3;\n"
-      "mov.b32 {l0, h0}, %8;\n mov.b32 {l1, h1}, %9;\n mov.b32 {l2, h2}, %10;\n mov.b32 {l3, h3}, %11;\n"
-      "add.rn.f32.bf16 %0, l0, %0;\n add.rn.f32.bf16 %1, h0, %1;\n"
-      "add.rn.f32.bf16 %2, l1, %2;\n add.rn.f32.bf16 %3, h1, %3;\n"
-      "add.rn.f32.bf16 %4, l2, %4;\n add.rn.f32.bf16 %5, h2, %5;\n"
-      "add.rn.f32.bf16 %6, l3, %6;\n add.rn.f32.bf16 %7, h3, %7;\n"
-      "}\n"
-      : "+f"(acc[0]), "+f"(acc[1]), "+f"(acc[2]), "+f"(acc[3]), "+f"(acc[4]), "+f"(acc[5]), "+f"(acc[6]), "+f"(acc[7])
-      : "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w));
-}
-__device__ __forceinline__ void add_row16(float* acc, const uint4& u, float) {
-  Vec<float> t;
-  t.v = *reinterpret_cast<const float4*>(&u);
-  add_vec(acc, t);
-}
-template <typename T>
-__device__ __forceinline__ void fma_row16(float* acc, float w, const uint4& u) {
-  Vec<T> t;
-  t.v = *reinterpret_cast<const decltype(t.v)*>(&u);
-  fma_vec(acc, w, t);
 }
 
 struct RowsArgs {

@@ -1,0 +1,716 @@
+// gat_rows.cu — K4 "aggregate first" path of GATConv(heads = 4, concat = False) (gnn_model.py:65-68,168;
+// SURVEY §8a rows 5, 8) for feature rows of 512 / 1024 bytes (F = 256 bf16, F = 128 / 256 fp32).
+//
+// PyG computes  out_i = 1/H sum_h sum_j alpha_ijh (W_h x_j) + b  by projecting first (an [N, H*C] matrix) and
+// gathering H*C-wide rows per edge (2 KB per edge at H = 4, C = 256, bf16: 143 GB through L2 at cfg4, measured
+// 24 ms, 17 % of the HBM roofline).  The sum over j is linear, so
+//      out_i = 1/H sum_h W_h (sum_j alpha_ijh x_j) + b = z_i Wc^T + b,   z_i = [sum_j alpha_ij1 x_j | ... | sum_j alpha_ijH x_j]
+// and the scores only need  a_src[j,h] = x_j . (W_h^T att_src_h),  a_dst[i,h] = x_i . (W_h^T att_dst_h):
+//   b2g_rowdot        a[N, 2H] = x V^T                          (one pass over x, 8 dot products per row)
+//   b2g_gatz_fwd      z[N, H*F]: per target row the exact max-subtracted segment softmax (one entry per lane) and
+//                     ONE gather of the F-wide neighbour rows shared by all heads (4x fewer gathered bytes)
+//   K6 GEMM           out = z Wc^T + b                           (gemm_tc.cu, k = H*F)
+// Backward, by the same linearity (g = d out):  dz = g Wc (GEMM);
+//   b2g_gatz_bwd_dst  d alpha_ijh = dz_ih . x_j (x rows gathered once per edge), softmax / LeakyReLU backward,
+//                     per-edge alpha and d e in target-major order, d a_dst
+//   b2g_gatz_bwd_src  y_j = [sum_i alpha_ij1 g_i | ...] over the transposed CSR (F-wide rows of g), d a_src
+//   K6 GEMM           dx = [y | d a] [W/H ; V]                   (one GEMM, k = H*C + 2H)
+// Deterministic: fp32 accumulation in CSR (= edge) order; attention dropout is the same counter-based Philox stream as
+// attention.cu (keyed by the target-major edge position), regenerated in backward.
+#include "rows.cuh"
+
+namespace b2g {
+
+constexpr uint32_t ROW_END = 0xffffffffu;
+constexpr int GH = 4;                         // heads (the reference's GATConv: heads = 4)
+
+// This warp's rows (wi, wi + 8, ... of chunk q, then of chunk q + grid, ...) with the rowptr pair fetched two rows ahead
+// (see aggregate_rows.cu: every prefetch is issued with its address operands long arrived).
+struct WarpRows {
+  uint32_t q, iend, n_rows;
+  uint32_t i, i2, i2c, i3, i3c;
+  int b, e, b2, e2, b3, e3;
+  __device__ __forceinline__ uint32_t next_chunk_first(const RowSched& ord, int wi) {
+    while (q < ord.n_chunks) {
+      uint32_t rows;
+      const uint32_t c0 = ord.chunk(q, n_rows, rows);
+      q += gridDim.x;
+      if ((uint32_t)wi < rows) {
+        iend = c0 + rows;
+        return c0 + wi;
+      }
+    }
+    return ROW_END;
+  }
+  __device__ __forceinline__ uint32_t advance(uint32_t i_, const RowSched& ord, int wi) {
+    if (i_ == ROW_END) return ROW_END;
+    const uint32_t n = i_ + 8u;
+    return n < iend ? n : next_chunk_first(ord, wi);
+  }
+  __device__ __forceinline__ bool begin(const RowSched& ord, uint32_t n, int wi, const int32_t* __restrict__ rowptr) {
+    q = blockIdx.x; iend = 0; n_rows = n;
+    i = next_chunk_first(ord, wi);
+    if (i == ROW_END) return false;
+    i2 = advance(i, ord, wi);
+    i2c = min(i2, n_rows - 1u);
+    b = __ldg(rowptr + i); e = __ldg(rowptr + i + 1);
+    b2 = __ldg(rowptr + i2c); e2 = __ldg(rowptr + i2c + 1);
+    return true;
+  }
+  __device__ __forceinline__ void look_ahead(const RowSched& ord, int wi, const int32_t* __restrict__ rowptr) {
+    i3 = advance(i2, ord, wi);
+    i3c = min(i3, n_rows - 1u);
+    b3 = __ldg(rowptr + i3c); e3 = __ldg(rowptr + i3c + 1);
+  }
+  __device__ __forceinline__ bool shift() {
+    if (i2 == ROW_END) return false;
+    i = i2; b = b2; e = e2;
+    i2 = i3; i2c = i3c; b2 = b3; e2 = e3;
+    return true;
+  }
+};
+
+// entry `lane` of the index window starting at position p0 of a row ending at e_: clamped into the row (lanes past the
+// end repeat the last entry: a valid address whose weight is 0), branch-free so that the load stays where it is written
+__device__ __forceinline__ int window_entry(const int32_t* __restrict__ idx, int p0, int e_, int lane) {
+  return ldg_i32_ordered(idx + max(min(p0 + lane, e_ - 1), 0));
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float lrelu(float s, float slope) { return s > 0.f ? s : s * slope; }
+// max over the warp through the integer reduction unit (REDUX): monotone float <-> int map, one instruction per head
+__device__ __forceinline__ float warp_max_redux(float v) {
+  int k = __float_as_int(v);
+  k ^= (k >> 31) & 0x7fffffff;
+  k = __reduce_max_sync(0xffffffffu, k);
+  k ^= (k >> 31) & 0x7fffffff;
+  return __int_as_float(k);
+}
+__device__ __forceinline__ float pick4(const float (&v)[4], int h) {   // v[h] for a per-lane h without local memory
+  return h == 0 ? v[0] : (h == 1 ? v[1] : (h == 2 ? v[2] : v[3]));
+}
+
+struct GatzArgs {
+  const void* x; uint32_t xrow_bytes;        // gathered rows [*, F] (fwd / bwd_dst: x; bwd_src: g = d out)
+  const float* a; uint32_t lda;              // fp32 [N, >= 2H]: columns 0..H-1 a_src, H..2H-1 a_dst (stride in floats)
+  void* z; uint32_t zrow_bytes;              // fwd: z [N, H*F];  bwd_src: y [N, H*C]
+  const void* dz; uint32_t dzrow_bytes;      // bwd_dst: dz [N, H*F]
+  const int32_t* rowptr; const int32_t* col; const int32_t* perm;
+  float* smax; float* ssum;                  // [N, H] softmax statistics (ssum includes PyG's + 1e-16)
+  float* alpha_e; float* de_e;               // [nnz, H] target-major
+  float* d_a; uint32_t ldda;                 // [N, >= 2H]
+  uint32_t n_rows;
+  float slope, p_drop;
+  uint64_t seed;
+  RowSched ord;
+};
+
+template <int VPL> struct GatzCfg { static constexpr int BU = (VPL == 1) ? 8 : 4; };   // gathered rows in flight per warp
+
+// acc[h] += w[h](entry off+u) * row(entry off+u) for u < BU (default: a full batch; entries past the row's end carry
+// weight 0 and re-read the row's last entry)
+template <typename T, int VPL, int BU = GatzCfg<VPL>::BU, typename Mid>
+__device__ __forceinline__ void gatz_gather_fma(float (&acc)[GH][VPL][Vec<T>::N], const char* xb, uint32_t xrow_bytes,
+                                                int cl, const float (&w)[GH], int off, Mid&& mid) {
+  constexpr int VN = Vec<T>::N;
+  uint4 buf[BU][VPL];
+#pragma unroll
+  for (int u = 0; u < BU; ++u) {
+    const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, off + u);
+    const char* p = xb + (uint64_t)c * xrow_bytes;
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_row16(p + 512 * v);
+  }
+  mid();                                     // the softmax of this row: needs a_src only, runs while the rows are in flight
+#pragma unroll
+  for (int u = 0; u < BU; ++u) {
+    float wu[GH];
+#pragma unroll
+    for (int h = 0; h < GH; ++h) wu[h] = __shfl_sync(0xffffffffu, w[h], off + u);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      float f[VN];
+      unpack_row16(buf[u][v], f, T());
+#pragma unroll
+      for (int h = 0; h < GH; ++h)
+#pragma unroll
+        for (int k = 0; k < VN; k += 2) ffma2_acc(acc[h][v][k], acc[h][v][k + 1], wu[h], f[k], f[k + 1]);
+    }
+  }
+}
+
+template <typename T, int VPL>
+__device__ __forceinline__ void gatz_store(char* zrow, const float (&acc)[GH][VPL][Vec<T>::N], int lane) {
+#pragma unroll
+  for (int h = 0; h < GH; ++h)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      Vec<T> o;
+      o.from_float(acc[h][v]);
+      __stcs(reinterpret_cast<uint4*>(zrow + (h * VPL + v) * 512 + lane * 16), *reinterpret_cast<uint4*>(&o.v));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ forward
+// Rows longer than 32 entries (cold on meshes): three sweeps over the scores (max, sum, weights + gather).
+template <typename T, int VPL>
+__device__ __noinline__ void gatz_fwd_long(const GatzArgs a, uint32_t i, int b, int e) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  const float4 ad4 = ldg_f4(a.a + (uint64_t)i * a.lda + GH);
+  const float ad[GH] = {ad4.x, ad4.y, ad4.z, ad4.w};
+  float m[GH], zs[GH];
+#pragma unroll
+  for (int h = 0; h < GH; ++h) { m[h] = -INFINITY; zs[h] = 0.f; }
+  for (int p0 = b; p0 < e; p0 += 32) {
+    const int c = window_entry(a.col, p0, e, lane);
+    const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)c * a.lda);
+    const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+#pragma unroll
+    for (int h = 0; h < GH; ++h) m[h] = fmaxf(m[h], warp_max_redux(p0 + lane < e ? lrelu(as[h] + ad[h], a.slope) : -INFINITY));
+  }
+  for (int p0 = b; p0 < e; p0 += 32) {
+    const int c = window_entry(a.col, p0, e, lane);
+    const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)c * a.lda);
+    const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+    float p[GH];
+#pragma unroll
+    for (int h = 0; h < GH; ++h) p[h] = p0 + lane < e ? __expf(lrelu(as[h] + ad[h], a.slope) - m[h]) : 0.f;
+    warp_sum4(p[0], p[1], p[2], p[3]);
+#pragma unroll
+    for (int h = 0; h < GH; ++h) zs[h] += p[h];
+  }
+  float inv[GH];
+#pragma unroll
+  for (int h = 0; h < GH; ++h) { zs[h] += 1e-16f; inv[h] = 1.0f / zs[h]; }
+  float acc[GH][VPL][VN];
+#pragma unroll
+  for (int h = 0; h < GH; ++h)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[h][v][k] = 0.f;
+  for (int p0 = b; p0 < e; p0 += 32) {
+    const int c = window_entry(a.col, p0, e, lane);
+    const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)c * a.lda);
+    const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+    float w[GH];
+#pragma unroll
+    for (int h = 0; h < GH; ++h) w[h] = p0 + lane < e ? __expf(lrelu(as[h] + ad[h], a.slope) - m[h]) * inv[h] : 0.f;
+    if (a.p_drop > 0.f) {
+      float sc[4];
+      dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, sc);
+#pragma unroll
+      for (int h = 0; h < GH; ++h) w[h] *= sc[h];
+    }
+    const int n = min(32, e - p0);
+    for (int j = 0; j < n; j += GatzCfg<VPL>::BU) gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, c, w, j, []() {});
+  }
+  if (a.smax && lane < GH) {
+    a.smax[(uint64_t)i * GH + lane] = pick4(m, lane);
+    a.ssum[(uint64_t)i * GH + lane] = pick4(zs, lane);
+  }
+  gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)i * a.zrow_bytes, acc, lane);
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256, 2) gatz_fwd_kernel(const GatzArgs a) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int BU = GatzCfg<VPL>::BU;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  WarpRows r;
+  if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
+  int cl = window_entry(a.col, r.b, r.e, lane);
+  while (true) {
+    const int cl2 = window_entry(a.col, r.b2, r.e2, lane);
+    r.look_ahead(a.ord, wi, a.rowptr);
+    const int len = r.e - r.b;
+    if (len > 32) {
+      gatz_fwd_long<T, VPL>(a, r.i, r.b, r.e);
+    } else {
+      const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);          // a_src of this lane's entry
+      const float4 ad4 = ldg_f4(a.a + (uint64_t)r.i * a.lda + GH);               // a_dst of the row (uniform)
+      float acc[GH][VPL][VN];
+#pragma unroll
+      for (int h = 0; h < GH; ++h)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[h][v][k] = 0.f;
+      float w[GH], m[GH], zs[GH];
+      auto softmax = [&]() {                  // exact two-pass softmax: all scores of the row sit one per lane
+        const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+        const float ad[GH] = {ad4.x, ad4.y, ad4.z, ad4.w};
+#pragma unroll
+        for (int h = 0; h < GH; ++h) {
+          const float s = lane < len ? lrelu(as[h] + ad[h], a.slope) : -INFINITY;
+          m[h] = warp_max_redux(s);
+          w[h] = lane < len ? __expf(s - m[h]) : 0.f;
+          zs[h] = w[h];
+        }
+        warp_sum4(zs[0], zs[1], zs[2], zs[3]);
+#pragma unroll
+        for (int h = 0; h < GH; ++h) {
+          zs[h] += 1e-16f;
+          w[h] *= 1.0f / zs[h];
+        }
+        if (a.p_drop > 0.f) {
+          float sc[4];
+          dropout_scale4(a.seed, (uint64_t)(r.b + lane), a.p_drop, sc);
+#pragma unroll
+          for (int h = 0; h < GH; ++h) w[h] *= sc[h];
+        }
+      };
+      if (len > BU) {
+        gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, 0, softmax);
+        for (int j = BU; j < len; j += BU) gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, j, []() {});
+      } else if (len > 0) {                   // every mesh row at VPL = 1: straight-line code for exactly `len` entries
+        switch (len) {
+#define B2G_CASE(KK) case KK: if (KK <= BU) gatz_gather_fma<T, VPL, (KK <= BU ? KK : 1)>(acc, xb, a.xrow_bytes, cl, w, 0, softmax); break;
+          B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4) B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
+#undef B2G_CASE
+          default: break;
+        }
+      } else {
+#pragma unroll
+        for (int h = 0; h < GH; ++h) { m[h] = 0.f; zs[h] = 1e-16f; }
+      }
+      if (a.smax && lane < GH) {
+        a.smax[(uint64_t)r.i * GH + lane] = len > 0 ? pick4(m, lane) : 0.f;
+        a.ssum[(uint64_t)r.i * GH + lane] = pick4(zs, lane);
+      }
+      gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, acc, lane);
+    }
+    if (!r.shift()) break;
+    cl = cl2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward, target side
+// d alpha for the entries [off, off + 8) of the window held one per lane: gather 8 rows (2 x 4 when BU = 4), dot each
+// with the row's dz (4 heads), reduce the 32 partials across the warp with ONE transposed reduction (31 shuffles),
+// hand entry (off + u)'s four values to lane off + u.
+template <typename T, int VPL>
+__device__ __forceinline__ void gatz_dalpha8(float (&dal)[GH], const float (&dzf)[GH][VPL][Vec<T>::N], const char* xb,
+                                             uint32_t xrow_bytes, int cl, int off, int lane) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int BU = GatzCfg<VPL>::BU;
+  float part[32];
+#pragma unroll
+  for (int s0 = 0; s0 < 8; s0 += BU) {
+    uint4 buf[BU][VPL];
+#pragma unroll
+    for (int u = 0; u < BU; ++u) {
+      const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, off + s0 + u);
+      const char* p = xb + (uint64_t)c * xrow_bytes;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_row16(p + 512 * v);
+    }
+#pragma unroll
+    for (int u = 0; u < BU; ++u) {
+      float p0[GH], p1[GH];
+#pragma unroll
+      for (int h = 0; h < GH; ++h) { p0[h] = 0.f; p1[h] = 0.f; }
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        float f[VN];
+        unpack_row16(buf[u][v], f, T());
+#pragma unroll
+        for (int h = 0; h < GH; ++h)
+#pragma unroll
+          for (int k = 0; k < VN; k += 2) ffma2_mul(p0[h], p1[h], dzf[h][v][k], dzf[h][v][k + 1], f[k], f[k + 1]);
+      }
+#pragma unroll
+      for (int h = 0; h < GH; ++h) part[(s0 + u) * GH + h] = p0[h] + p1[h];
+    }
+  }
+  const float red = warp_transpose_sum32(part);          // lane 4u + h: d alpha of entry off + u, head h
+  const int src = ((lane - off) & 7) * GH;
+#pragma unroll
+  for (int h = 0; h < GH; ++h) {
+    const float v = __shfl_sync(0xffffffffu, red, src + h);
+    if (lane >= off && lane < off + 8) dal[h] = v;
+  }
+}
+
+// One window of <= 32 entries [p0, p0 + n): alpha from the saved statistics, d alpha, and - given t = sum_k alpha_k
+// d alpha_k over the WHOLE row - d e; writes alpha_e / de_e, returns this window's contribution to d a_dst.
+template <typename T, int VPL>
+__device__ __forceinline__ void gatz_bwd_window(const GatzArgs& a, const float (&dzf)[GH][VPL][Vec<T>::N], const char* xb,
+                                                int cl, int p0, int n, int lane, const float (&ad)[GH],
+                                                const float (&sm)[GH], const float (&rinv)[GH], float (&alpha)[GH],
+                                                float (&dal)[GH], float (&sraw)[GH], float (&mask)[GH]) {
+  const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
+  const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+#pragma unroll
+  for (int h = 0; h < GH; ++h) {
+    sraw[h] = as[h] + ad[h];
+    alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
+    mask[h] = 1.0f;
+    dal[h] = 0.f;
+  }
+  if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, mask);
+  for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(dal, dzf, xb, a.xrow_bytes, cl, j, lane);
+#pragma unroll
+  for (int h = 0; h < GH; ++h) dal[h] *= mask[h];         // d(alpha) of the pre-dropout probability
+}
+
+template <typename T, int VPL>
+__device__ __forceinline__ void gatz_load_dz(const GatzArgs& a, uint32_t i, int lane, float (&dzf)[GH][VPL][Vec<T>::N]) {
+  const char* dzr = reinterpret_cast<const char*>(a.dz) + (uint64_t)i * a.dzrow_bytes + lane * 16;
+#pragma unroll
+  for (int h = 0; h < GH; ++h)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      uint4 u;
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(dzr + (h * VPL + v) * 512));
+      unpack_row16(u, dzf[h][v], T());
+    }
+}
+
+template <typename T, int VPL>
+__device__ __forceinline__ void gatz_bwd_finish(const GatzArgs& a, int p0, int n, int lane, const float (&alpha)[GH],
+                                                const float (&dal)[GH], const float (&sraw)[GH], const float (&mask)[GH],
+                                                const float (&t)[GH], float (&dad)[GH]) {
+  float de[GH];
+#pragma unroll
+  for (int h = 0; h < GH; ++h) {
+    const float ds = alpha[h] * (dal[h] - t[h]);
+    de[h] = ds * (sraw[h] > 0.f ? 1.0f : a.slope);
+    dad[h] += de[h];
+  }
+  if (lane < n) {
+    *reinterpret_cast<float4*>(a.alpha_e + (uint64_t)(p0 + lane) * GH) =
+        make_float4(alpha[0] * mask[0], alpha[1] * mask[1], alpha[2] * mask[2], alpha[3] * mask[3]);
+    *reinterpret_cast<float4*>(a.de_e + (uint64_t)(p0 + lane) * GH) = make_float4(de[0], de[1], de[2], de[3]);
+  }
+}
+
+template <typename T, int VPL>
+__device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int b, int e) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  float dzf[GH][VPL][VN];
+  gatz_load_dz<T, VPL>(a, i, lane, dzf);
+  const float4 ad4 = ldg_f4(a.a + (uint64_t)i * a.lda + GH);
+  const float4 sm4 = ldg_f4(a.smax + (uint64_t)i * GH), ss4 = ldg_f4(a.ssum + (uint64_t)i * GH);
+  const float ad[GH] = {ad4.x, ad4.y, ad4.z, ad4.w}, sm[GH] = {sm4.x, sm4.y, sm4.z, sm4.w};
+  const float rinv[GH] = {1.0f / ss4.x, 1.0f / ss4.y, 1.0f / ss4.z, 1.0f / ss4.w};
+  float t[GH] = {0.f, 0.f, 0.f, 0.f};
+  // sweep 1: d alpha of every entry (parked in de_e), t = sum alpha * d alpha
+  for (int p0 = b; p0 < e; p0 += 32) {
+    const int n = min(32, e - p0);
+    const int cl = window_entry(a.col, p0, e, lane);
+    float alpha[GH], dal[GH], sraw[GH], mask[GH];
+    gatz_bwd_window<T, VPL>(a, dzf, xb, cl, p0, n, lane, ad, sm, rinv, alpha, dal, sraw, mask);
+    if (lane < n) *reinterpret_cast<float4*>(a.de_e + (uint64_t)(p0 + lane) * GH) = make_float4(dal[0], dal[1], dal[2], dal[3]);
+    float pr[GH];
+#pragma unroll
+    for (int h = 0; h < GH; ++h) pr[h] = alpha[h] * dal[h];
+    warp_sum4(pr[0], pr[1], pr[2], pr[3]);
+#pragma unroll
+    for (int h = 0; h < GH; ++h) t[h] += pr[h];
+  }
+  // sweep 2: d e
+  float dad[GH] = {0.f, 0.f, 0.f, 0.f};
+  for (int p0 = b; p0 < e; p0 += 32) {
+    const int n = min(32, e - p0);
+    const int cl = window_entry(a.col, p0, e, lane);
+    const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
+    const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+    float alpha[GH], dal[GH] = {0.f, 0.f, 0.f, 0.f}, sraw[GH], mask[GH] = {1.f, 1.f, 1.f, 1.f};
+    if (lane < n) {
+      const float4 d4 = *reinterpret_cast<const float4*>(a.de_e + (uint64_t)(p0 + lane) * GH);
+      dal[0] = d4.x; dal[1] = d4.y; dal[2] = d4.z; dal[3] = d4.w;
+    }
+    if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, mask);
+#pragma unroll
+    for (int h = 0; h < GH; ++h) {
+      sraw[h] = as[h] + ad[h];
+      alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
+    }
+    gatz_bwd_finish<T, VPL>(a, p0, n, lane, alpha, dal, sraw, mask, t, dad);
+  }
+  warp_sum4(dad[0], dad[1], dad[2], dad[3]);
+  if (lane < GH) a.d_a[(uint64_t)i * a.ldda + GH + lane] = pick4(dad, lane);
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  WarpRows r;
+  if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
+  int cl = window_entry(a.col, r.b, r.e, lane);
+  while (true) {
+    const int cl2 = window_entry(a.col, r.b2, r.e2, lane);
+    r.look_ahead(a.ord, wi, a.rowptr);
+    const int len = r.e - r.b;
+    if (len > 32) {
+      gatz_bwd_dst_long<T, VPL>(a, r.i, r.b, r.e);
+    } else {
+      float dzf[GH][VPL][VN];
+      gatz_load_dz<T, VPL>(a, r.i, lane, dzf);
+      const float4 ad4 = ldg_f4(a.a + (uint64_t)r.i * a.lda + GH);
+      const float4 sm4 = ldg_f4(a.smax + (uint64_t)r.i * GH), ss4 = ldg_f4(a.ssum + (uint64_t)r.i * GH);
+      const float ad[GH] = {ad4.x, ad4.y, ad4.z, ad4.w}, sm[GH] = {sm4.x, sm4.y, sm4.z, sm4.w};
+      const float rinv[GH] = {1.0f / ss4.x, 1.0f / ss4.y, 1.0f / ss4.z, 1.0f / ss4.w};
+      float alpha[GH], dal[GH], sraw[GH], mask[GH];
+      gatz_bwd_window<T, VPL>(a, dzf, xb, cl, r.b, len, lane, ad, sm, rinv, alpha, dal, sraw, mask);
+      float t[GH];
+#pragma unroll
+      for (int h = 0; h < GH; ++h) t[h] = alpha[h] * dal[h];
+      warp_sum4(t[0], t[1], t[2], t[3]);
+      float dad[GH] = {0.f, 0.f, 0.f, 0.f};
+      gatz_bwd_finish<T, VPL>(a, r.b, len, lane, alpha, dal, sraw, mask, t, dad);
+      warp_sum4(dad[0], dad[1], dad[2], dad[3]);
+      if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + GH + lane] = pick4(dad, lane);
+    }
+    if (!r.shift()) break;
+    cl = cl2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ backward, source side
+// Row j of the TRANSPOSED CSR: entries (i = col[t], p = perm[t] = the edge's position in the target-major CSR).
+//   y_j[h] = sum_t alpha_e[p, h] * g_i,   d a_src[j, h] = sum_t de_e[p, h]
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256, 2) gatz_bwd_src_kernel(const GatzArgs a) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int BU = GatzCfg<VPL>::BU;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  WarpRows r;
+  if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
+  int cl = window_entry(a.col, r.b, r.e, lane), pl = window_entry(a.perm, r.b, r.e, lane);
+  while (true) {
+    const int cl2 = window_entry(a.col, r.b2, r.e2, lane), pl2 = window_entry(a.perm, r.b2, r.e2, lane);
+    r.look_ahead(a.ord, wi, a.rowptr);
+    float acc[GH][VPL][VN];
+#pragma unroll
+    for (int h = 0; h < GH; ++h)
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+#pragma unroll
+        for (int k = 0; k < VN; ++k) acc[h][v][k] = 0.f;
+    float das[GH] = {0.f, 0.f, 0.f, 0.f};
+    for (int p0 = r.b; p0 < r.e; p0 += 32) {                 // one window on meshes
+      if (p0 != r.b) {
+        cl = window_entry(a.col, p0, r.e, lane);
+        pl = window_entry(a.perm, p0, r.e, lane);
+      }
+      const int n = min(32, r.e - p0);
+      const float4 al4 = ldg_f4(a.alpha_e + (uint64_t)(uint32_t)pl * GH);
+      const float4 de4 = ldg_f4(a.de_e + (uint64_t)(uint32_t)pl * GH);
+      const bool on = lane < n;
+      const float w[GH] = {on ? al4.x : 0.f, on ? al4.y : 0.f, on ? al4.z : 0.f, on ? al4.w : 0.f};
+      if (on) { das[0] += de4.x; das[1] += de4.y; das[2] += de4.z; das[3] += de4.w; }
+      if (n > BU) {
+        for (int j = 0; j < n; j += BU) gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, j, []() {});
+      } else {
+        switch (n) {
+#define B2G_CASE(KK) case KK: if (KK <= BU) gatz_gather_fma<T, VPL, (KK <= BU ? KK : 1)>(acc, xb, a.xrow_bytes, cl, w, 0, []() {}); break;
+          B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4) B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
+#undef B2G_CASE
+          default: break;
+        }
+      }
+    }
+    warp_sum4(das[0], das[1], das[2], das[3]);
+    if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + lane] = pick4(das, lane);
+    gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, acc, lane);
+    if (!r.shift()) break;
+    cl = cl2; pl = pl2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ a = x V^T
+// Warp per row, 4 consecutive rows per step: 32 partial dot products reduced with one transposed reduction; lane
+// 8r + m ends up with a[row r, m] -> one coalesced 128-byte store per step when lda = 8.
+struct RowdotArgs {
+  const void* x; uint32_t xrow_bytes;
+  const float* V; int ldv;                   // fp32 [8, F]
+  float* out; uint32_t ldo;                  // fp32 [N, >= 8]
+  uint32_t n_rows;
+};
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256, 2) rowdot8_kernel(const RowdotArgs a) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  float vr[8][VPL][VN];                      // this lane's slice of the 8 vectors
+#pragma unroll
+  for (int m = 0; m < 8; ++m)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int k = 0; k < VN; ++k) vr[m][v][k] = __ldg(a.V + (int64_t)m * a.ldv + (v * 32 + lane) * VN + k);
+  const uint32_t warps = gridDim.x * 8u, w = blockIdx.x * 8u + (threadIdx.x >> 5);
+  const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  for (uint32_t i0 = w * 4u; i0 < a.n_rows; i0 += warps * 4u) {
+    uint4 buf[4][VPL];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const uint32_t i = min(i0 + r, a.n_rows - 1u);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(buf[r][v].x), "=r"(buf[r][v].y), "=r"(buf[r][v].z), "=r"(buf[r][v].w)
+                     : "l"(xb + (uint64_t)i * a.xrow_bytes + 512 * v));
+    }
+    float part[32];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float p0[8], p1[8];
+#pragma unroll
+      for (int m = 0; m < 8; ++m) { p0[m] = 0.f; p1[m] = 0.f; }
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        float f[VN];
+        unpack_row16(buf[r][v], f, T());
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+#pragma unroll
+          for (int k = 0; k < VN; k += 2) ffma2_mul(p0[m], p1[m], vr[m][v][k], vr[m][v][k + 1], f[k], f[k + 1]);
+      }
+#pragma unroll
+      for (int m = 0; m < 8; ++m) part[r * 8 + m] = p0[m] + p1[m];
+    }
+    const float red = warp_transpose_sum32(part);
+    const uint32_t i = i0 + (lane >> 3);
+    if (i < a.n_rows) a.out[(uint64_t)i * a.ldo + (lane & 7)] = red;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+template <typename K>
+static inline int64_t gatz_blocks(K kernel, const RowSched& ord) {
+  const int64_t cap = resident_ctas(kernel, 256);
+  return ord.n_chunks < cap ? (int64_t)ord.n_chunks : cap;
+}
+
+template <typename T, int VPL>
+static int gatz_launch(int which, const GatzArgs& a, cudaStream_t st) {
+  if (which == 0) gatz_fwd_kernel<T, VPL><<<(unsigned)gatz_blocks(gatz_fwd_kernel<T, VPL>, a.ord), 256, 0, st>>>(a);
+  else if (which == 1) gatz_bwd_dst_kernel<T, VPL><<<(unsigned)gatz_blocks(gatz_bwd_dst_kernel<T, VPL>, a.ord), 256, 0, st>>>(a);
+  else gatz_bwd_src_kernel<T, VPL><<<(unsigned)gatz_blocks(gatz_bwd_src_kernel<T, VPL>, a.ord), 256, 0, st>>>(a);
+  count_launch();
+  return cuda_status();
+}
+
+static int gatz_dispatch(int which, int dt, int row_bytes, const GatzArgs& a, cudaStream_t st) {
+  if (dt == B2G_F32) return row_bytes == 512 ? gatz_launch<float, 1>(which, a, st) : gatz_launch<float, 2>(which, a, st);
+  return row_bytes == 512 ? gatz_launch<__nv_bfloat16, 1>(which, a, st) : gatz_launch<__nv_bfloat16, 2>(which, a, st);
+}
+
+static inline int esz(int dt) { return dt == B2G_F32 ? 4 : 2; }
+static inline bool fits32(int64_t v) { return v >= 0 && v < (1ll << 32); }
+
+}  // namespace b2g
+
+using namespace b2g;
+
+extern "C" {
+
+int b2g_gatz_supported(int64_t n, int H, int F, int dt) {
+  if (dt != B2G_F32 && dt != B2G_BF16) return 0;
+  const int64_t rb = (int64_t)F * esz(dt);       // bf16 rows of 1 KB would need 64 accumulator registers per head set: not built
+  const bool shape = (dt == B2G_BF16) ? rb == 512 : (rb == 512 || rb == 1024);
+  return (H == GH && shape && n >= 1 && n < (1ll << 32) - (1ll << 25)) ? 1 : 0;
+}
+
+int b2g_rowdot8(const void* x, int64_t ldx, const float* V, int64_t ldv, float* out, int64_t ldo, int64_t n, int F,
+                int dt, void* stream) {
+  if (n < 0 || !b2g_gatz_supported(n > 0 ? n : 1, GH, F, dt)) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  if (!x || !V || !out || !aligned16(x) || (ldx * esz(dt)) % 16 || !fits32(ldx * esz(dt)) || ldo < 8 || !fits32(ldo)) return B2G_E_ARG;
+  RowdotArgs a{x, (uint32_t)(ldx * esz(dt)), V, (int)ldv, out, (uint32_t)ldo, (uint32_t)n};
+  const int rb = F * esz(dt);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t want = ceil_div(n, 32);
+#define B2G_RD(T, VPL)                                                                   \
+  {                                                                                      \
+    int64_t blocks = resident_ctas(rowdot8_kernel<T, VPL>, 256);                         \
+    if (want < blocks) blocks = want;                                                    \
+    rowdot8_kernel<T, VPL><<<(unsigned)blocks, 256, 0, st>>>(a);                         \
+  }
+  if (dt == B2G_F32) { if (rb == 512) B2G_RD(float, 1) else B2G_RD(float, 2) }
+  else { if (rb == 512) B2G_RD(__nv_bfloat16, 1) else B2G_RD(__nv_bfloat16, 2) }
+#undef B2G_RD
+  count_launch();
+  return cuda_status();
+}
+
+static int gatz_common(GatzArgs& a, int64_t n, int F, int dt, int64_t band) {
+  if (!b2g_gatz_supported(n, GH, F, dt)) return B2G_E_UNSUPPORTED;
+  if (!make_row_sched(n, band, a.ord)) return B2G_E_UNSUPPORTED;
+  a.n_rows = (uint32_t)n;
+  return B2G_OK;
+}
+
+int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, void* z, int64_t ldz, int64_t n, int H,
+                 int F, int dt, float slope, const int32_t* rowptr, const int32_t* col, float* smax, float* ssum,
+                 float p_drop, uint64_t seed, int64_t band, void* stream) {
+  if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  const int es = esz(dt);
+  if (!x || !a_srcdst || !z || !rowptr || !col || (smax == nullptr) != (ssum == nullptr)) return B2G_E_ARG;
+  if (!aligned16(x) || !aligned16(z) || !aligned16(a_srcdst) || (ldx * es) % 16 || (ldz * es) % 16 || lda % 4 || lda < 2 * GH)
+    return B2G_E_ALIGN;
+  if (!fits32(ldx * es) || !fits32(ldz * es) || !fits32(lda)) return B2G_E_SHAPE;
+  GatzArgs a{};
+  const int rc = gatz_common(a, n, F, dt, band);
+  if (rc) return rc;
+  a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.a = a_srcdst; a.lda = (uint32_t)lda; a.z = z; a.zrow_bytes = (uint32_t)(ldz * es);
+  a.rowptr = rowptr; a.col = col; a.smax = smax; a.ssum = ssum; a.slope = slope; a.p_drop = p_drop; a.seed = seed;
+  return gatz_dispatch(0, dt, F * es, a, (cudaStream_t)stream);
+}
+
+int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, const void* dz, int64_t lddz,
+                     int64_t n, int H, int F, int dt, float slope, const int32_t* rowptr, const int32_t* col,
+                     const float* smax, const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* de_e,
+                     float* d_a, int64_t ldda, int64_t band, void* stream) {
+  if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  const int es = esz(dt);
+  if (!x || !a_srcdst || !dz || !rowptr || !col || !smax || !ssum || !alpha_e || !de_e || !d_a) return B2G_E_ARG;
+  if (!aligned16(x) || !aligned16(dz) || !aligned16(a_srcdst) || !aligned16(smax) || !aligned16(ssum) || !aligned16(alpha_e) ||
+      !aligned16(de_e) || (ldx * es) % 16 || (lddz * es) % 16 || lda % 4 || lda < 2 * GH || ldda < 2 * GH)
+    return B2G_E_ALIGN;
+  if (!fits32(ldx * es) || !fits32(lddz * es) || !fits32(lda) || !fits32(ldda)) return B2G_E_SHAPE;
+  GatzArgs a{};
+  const int rc = gatz_common(a, n, F, dt, band);
+  if (rc) return rc;
+  a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.a = a_srcdst; a.lda = (uint32_t)lda; a.dz = dz; a.dzrow_bytes = (uint32_t)(lddz * es);
+  a.rowptr = rowptr; a.col = col; a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum);
+  a.slope = slope; a.p_drop = p_drop; a.seed = seed; a.alpha_e = alpha_e; a.de_e = de_e; a.d_a = d_a; a.ldda = (uint32_t)ldda;
+  return gatz_dispatch(1, dt, F * es, a, (cudaStream_t)stream);
+}
+
+int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const float* de_e, void* y, int64_t ldy,
+                     float* d_a, int64_t ldda, int64_t n, int H, int C, int dt, const int32_t* rowptr_t,
+                     const int32_t* col_t, const int32_t* perm, int64_t band, void* stream) {
+  if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  const int es = esz(dt);
+  if (!g || !alpha_e || !de_e || !y || !d_a || !rowptr_t || !col_t || !perm) return B2G_E_ARG;
+  if (!aligned16(g) || !aligned16(y) || !aligned16(alpha_e) || !aligned16(de_e) || (ldg * es) % 16 || (ldy * es) % 16 || ldda < 2 * GH)
+    return B2G_E_ALIGN;
+  if (!fits32(ldg * es) || !fits32(ldy * es) || !fits32(ldda)) return B2G_E_SHAPE;
+  GatzArgs a{};
+  const int rc = gatz_common(a, n, C, dt, band);
+  if (rc) return rc;
+  a.x = g; a.xrow_bytes = (uint32_t)(ldg * es); a.z = y; a.zrow_bytes = (uint32_t)(ldy * es);
+  a.rowptr = rowptr_t; a.col = col_t; a.perm = perm; a.alpha_e = const_cast<float*>(alpha_e); a.de_e = const_cast<float*>(de_e);
+  a.d_a = d_a; a.ldda = (uint32_t)ldda;
+  return gatz_dispatch(2, dt, C * es, a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

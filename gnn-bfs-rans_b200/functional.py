@@ -173,6 +173,60 @@ class GATFn(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None, None, None
 
 
+class GATZFn(torch.autograd.Function):
+    """GATConv(heads=4, concat=False) core, aggregate-first (csrc/gat_rows.cu): a = x V^T, z = per-head attention-
+    weighted sums of the F-wide rows of x, out = z Wc^T + b with Wc[c, hF+f] = W[hC+c, f] / H.  `wc` and `v` are
+    assembled (differentiably) by the module from lin.weight / att_src / att_dst, which get their gradients through
+    them.  4x fewer gathered bytes than projecting first (the [N, H*C] matrix is never gathered)."""
+
+    @staticmethod
+    def forward(ctx, x, wc, v, bias, graph: Graph, H: int, slope: float, p_drop: float):
+        csr = graph.csr("sl", False)
+        need_grad = x.requires_grad or wc.requires_grad or v.requires_grad
+        seed = _next_seed() if p_drop > 0 else 0
+        a = ops.rowdot8(x, v)
+        z, smax, ssum = ops.gatz_fwd(x, a, H, slope, csr.rowptr, csr.col, p_drop, seed, need_grad, band=graph.band())
+        out, _ = ops.linear_fwd(z, wc, bias.float() if bias is not None else None)
+        if need_grad:
+            ctx.save_for_backward(x, wc, v, z, a, smax, ssum)
+            ctx.cfg = (graph, H, slope, p_drop, seed, bias is not None)
+            ctx.ei_keepalive = graph.edge_index
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wc, v, z, a, smax, ssum = ctx.saved_tensors
+        graph, H, slope, p_drop, seed, has_bias = ctx.cfg
+        N, F = x.shape
+        C = wc.shape[0]
+        g = g.contiguous()
+        csr, csr_t, perm = graph.csr("sl", False), graph.csr("sl", True), graph.perm("sl")
+        gwc = gv = gx = None
+        if ctx.needs_input_grad[1]:
+            dw, _ = ops.linear_wgrad(g, z, want_bias=False)                 # dWc = g^T z  [C, H*F]
+            gwc = _cast_like(dw, wc)
+        del z
+        dz, _ = ops.linear_fwd(g, wc.t().contiguous(), None)                # dz = g Wc    [N, H*F]
+        # [y | d a] so that dx = y (W/H) + d a V is ONE GEMM against [Wc_src ; V]
+        ka = H * C + 2 * H
+        y_aug = torch.empty((N, ka), dtype=x.dtype, device=x.device)
+        d_a = ops.gatz_bwd(x, a, dz, g, H, slope, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
+                           y_aug[:, :H * C], band=graph.band())
+        del dz
+        y_aug[:, H * C:] = d_a
+        if ctx.needs_input_grad[0]:
+            # Wc[c, hF+f] = W[hC+c, f]/H  ->  (W/H)[hC+c, f] = Wc[c, hF+f]: rows of the [H*C, F] matrix
+            w_src = wc.view(C, H, F).permute(1, 0, 2).reshape(H * C, F)
+            w_aug = torch.cat([w_src, v.to(wc.dtype)], dim=0)               # [H*C + 2H, F]
+            gx = ops.linear_dgrad(y_aug, w_aug)
+        if ctx.needs_input_grad[2]:
+            da_t = d_a.to(x.dtype) if x.dtype != torch.float32 else d_a
+            dv, _ = ops.linear_wgrad(da_t, x, want_bias=False)              # dV = d a^T x [2H, F]
+            gv = _cast_like(dv, v)
+        gb = ops.colsum(g) if (has_bias and ctx.needs_input_grad[3]) else None
+        return gx, gwc, gv, gb, None, None, None, None
+
+
 class TConvFn(torch.autograd.Function):
     """TransformerConv core: [q | k | v | skip] = x @ W_cat.T + b_cat in one GEMM, then the fused
     q.k score / softmax / aggregate / head-mean / +skip kernel."""

@@ -180,8 +180,29 @@ class GATConv(MessagePassing):
         _check_x(x, edge_index)
         g = graph_of(edge_index, x.shape[0])
         p = self.dropout if self.training else 0.0
+        if self._aggregate_first(x):
+            wc, v = self._wc_v(x.dtype)
+            return Fn.GATZFn.apply(x, wc, v, self.bias, g, self.heads, self.negative_slope, p)
         return Fn.GATFn.apply(x, self._w_aug(x.dtype), self.bias, g, self.heads, self.out_channels, self.concat,
                               self.negative_slope, p)
+
+    def _aggregate_first(self, x) -> bool:
+        """heads averaged (concat=False, the reference's configuration) and 512 / 1024-byte feature rows: aggregate the
+        F-wide input rows per head first, project after (gat_rows.cu).  B2G_GAT_PATH=project forces the other order."""
+        import os
+        if self.concat or os.environ.get("B2G_GAT_PATH", "") == "project":
+            return False
+        from . import ops
+        return x.shape[0] >= 1 and ops.gatz_supported(x.shape[0], self.heads, self.in_channels, x.dtype) and \
+            (self.heads * self.in_channels * x.element_size()) % 16 == 0
+
+    def _wc_v(self, dtype):
+        H, C, F = self.heads, self.out_channels, self.in_channels
+        Wv = self.lin.weight.view(H, C, F)
+        wc = (Wv.permute(1, 0, 2).reshape(C, H * F) / H).to(dtype)               # out = z @ wc.T
+        vs = torch.einsum('hc,hcf->hf', self.att_src[0], Wv)                     # a_src = x @ vs^T
+        vd = torch.einsum('hc,hcf->hf', self.att_dst[0], Wv)
+        return wc, torch.cat([vs, vd], dim=0).float()                            # V stays fp32 (8 x F)
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})'

@@ -279,6 +279,56 @@ def gat_bwd(xw, a, gout, H, C, concat, slope, csr, csr_t, perm, smax, ssum, p_dr
     return d_a
 
 
+# ------------------------------------------------------------------------------------------ K4, aggregate-first
+def gatz_supported(n: int, H: int, F: int, dtype) -> bool:
+    dt = F32 if dtype == torch.float32 else (BF16 if dtype == torch.bfloat16 else -1)
+    return dt >= 0 and bool(_lib.load().b2g_gatz_supported(int(max(n, 1)), int(H), int(F), dt))
+
+
+def rowdot8(x, V) -> torch.Tensor:
+    """a[N,8] (fp32) = x[N,F] @ V[8,F]^T."""
+    _cuda(x, V)
+    x = _rows(x)
+    V = V.float().contiguous()
+    N, F = x.shape
+    out = torch.empty((N, 8), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().b2g_rowdot8(_p(x), _ld(x), _p(V), V.stride(0), _p(out), 8, N, F, _dt(x), _stream()), "rowdot8")
+    return out
+
+
+def gatz_fwd(x, a, H, slope, rowptr, col, p_drop, seed, save_stats, band=0, out=None):
+    """z[N, H*F] = per-head attention-weighted sums of the F-wide rows of x; a = [a_src | a_dst] fp32 [N, 2H]."""
+    x = _rows(x)
+    N, F = x.shape
+    z = out if out is not None else torch.empty((N, H * F), dtype=x.dtype, device=x.device)
+    smax = torch.empty((N, H), dtype=torch.float32, device=x.device) if save_stats else None
+    ssum = torch.empty((N, H), dtype=torch.float32, device=x.device) if save_stats else None
+    _lib.check(_lib.load().b2g_gatz_fwd(_p(x), _ld(x), _p(a), a.stride(0), _p(z), _ld(z), N, H, F, _dt(x), float(slope),
+                                        _p(rowptr), _p(col), _p(smax), _p(ssum), float(p_drop), int(seed), int(band),
+                                        _stream()), "gatz_fwd")
+    return z, smax, ssum
+
+
+def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, y_out, band=0):
+    """-> d_a fp32 [N, 2H]; writes y = [sum_i alpha_ij1 g_i | ...] into y_out (a [N, H*C] view, any row stride)."""
+    lib = _lib.load()
+    x, dz, g = _rows(x), _rows(dz), _rows(g)
+    N, F = x.shape
+    C = g.shape[1]
+    dev = x.device
+    nnz = csr[1].numel()
+    alpha_e = torch.empty((max(nnz, 1), H), dtype=torch.float32, device=dev)
+    de_e = torch.empty((max(nnz, 1), H), dtype=torch.float32, device=dev)
+    d_a = torch.empty((N, 2 * H), dtype=torch.float32, device=dev)
+    st = _stream()
+    _lib.check(lib.b2g_gatz_bwd_dst(_p(x), _ld(x), _p(a), a.stride(0), _p(dz), _ld(dz), N, H, F, _dt(x), float(slope),
+                                    _p(csr[0]), _p(csr[1]), _p(smax), _p(ssum), float(p_drop), int(seed), _p(alpha_e),
+                                    _p(de_e), _p(d_a), 2 * H, int(band), st), "gatz_bwd_dst")
+    _lib.check(lib.b2g_gatz_bwd_src(_p(g), _ld(g), _p(alpha_e), _p(de_e), _p(y_out), _ld(y_out), _p(d_a), 2 * H, N, H, C,
+                                    _dt(x), _p(csr_t[0]), _p(csr_t[1]), _p(perm), int(band), st), "gatz_bwd_src")
+    return d_a
+
+
 # ------------------------------------------------------------------------------------------ K5
 def tconv_fwd(q, k, v, skip, H, C, concat, rowptr, col, p_drop, seed, save_stats):
     lib = _lib.load()

@@ -176,6 +176,37 @@ int b2g_gat_bwd_src(const void* gout, int64_t ldg, const float* alpha_e, const f
                     int concat, const int32_t* rowptr_t, const int32_t* col_t, const int32_t* perm,
                     void* stream);
 
+/* ------------------------------------------------------------------------------------- K4, aggregate-first path
+ * GATConv(heads = 4, concat = False) (gnn_model.py:65-68,168) for feature rows of 512 or 1024 bytes.  By linearity
+ *   out_i = 1/H sum_h W_h (sum_j alpha_ijh x_j) + b = z_i Wc^T + b,  z_i = [sum_j alpha_ij1 x_j | ... | sum_j alpha_ijH x_j]
+ * so the kernels gather the F-wide INPUT rows once per edge for all heads instead of the H*C-wide projected rows
+ * (gat_rows.cu).  b2g_gatz_supported: 1 when these entry points cover (n, H, F, dt). */
+int b2g_gatz_supported(int64_t n, int H, int F, int dt);
+/* out[n, 0..7] = x[n, F] . V[8, F]^T (fp32 V, fp32 out with row stride ldo >= 8): the attention logits
+ * a_src | a_dst of all heads in one pass over x (V = [W_h^T att_src_h ; W_h^T att_dst_h]). */
+int b2g_rowdot8(const void* x, int64_t ldx, const float* V, int64_t ldv, float* out, int64_t ldo, int64_t n, int F,
+                int dt, void* stream);
+/* z [n, H*F] from x [*, F] and a = [a_src | a_dst] fp32 [*, >= 2H] (row stride lda floats): LeakyReLU(slope) scores,
+ * exact max-subtracted segment softmax over each target's CSR row (PyG softmax, + 1e-16 in the denominator), optional
+ * attention dropout (Philox keyed by the CSR position), weighted sum per head.  smax/ssum [n,H] (both or neither)
+ * receive the statistics the backward pass needs. */
+int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, void* z, int64_t ldz, int64_t n, int H,
+                 int F, int dt, float slope, const int32_t* rowptr, const int32_t* col, float* smax, float* ssum,
+                 float p_drop, uint64_t seed, int64_t band, void* stream);
+/* Target side of the backward pass: given dz [n, H*F] writes the per-edge attention weights alpha_e [nnz,H] (after
+ * dropout), the per-edge logit gradients de_e [nnz,H] (both in target-major CSR order) and d a_dst into columns
+ * H..2H-1 of d_a (row stride ldda floats). */
+int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, const void* dz, int64_t lddz,
+                     int64_t n, int H, int F, int dt, float slope, const int32_t* rowptr, const int32_t* col,
+                     const float* smax, const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* de_e,
+                     float* d_a, int64_t ldda, int64_t band, void* stream);
+/* Source side: over the transposed CSR (rowptr_t, col_t, perm = position of each entry in the target-major CSR)
+ * y[j] = [sum_i alpha_ij1 g_i | ... | sum_i alpha_ijH g_i] ([n, H*C], g = d out [*, C]) and d a_src into columns
+ * 0..H-1 of d_a. */
+int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const float* de_e, void* y, int64_t ldy,
+                     float* d_a, int64_t ldda, int64_t n, int H, int C, int dt, const int32_t* rowptr_t,
+                     const int32_t* col_t, const int32_t* perm, int64_t band, void* stream);
+
 /* ===================================================================================== K5
  * TransformerConv (gnn_model.py:77-80,170) fused q.k score + segment-softmax + aggregate +
  * head-mean + skip.  q,k,v: [N,H*C]; skip: [N, concat?H*C:C] or NULL.
