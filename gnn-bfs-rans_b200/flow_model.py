@@ -11,7 +11,9 @@ from typing import Optional
 import torch
 import torch.nn as tnn
 
+from . import functional as Fn
 from . import nn as gnn
+from . import ops
 
 LAYER_TYPES = ('GCN', 'GAT', 'GIN', 'Transformer')
 
@@ -31,12 +33,15 @@ def _make_layer(layer_type: str, width: int, dropout: float):
 class FlowGNN(tnn.Module):
     def __init__(self, input_dim: int = 3, hidden_dim: int = 128, output_dim: int = 8, num_layers: int = 4,
                  layer_type: str = 'GCN', use_edge_attr: bool = True, dropout: float = 0.1,
-                 use_batch_norm: bool = True, validate_edges: bool = True):
+                 use_batch_norm: bool = True, validate_edges: bool = True, fused_glue: bool = False):
         super().__init__()
         self.input_dim, self.hidden_dim, self.output_dim = input_dim, hidden_dim, output_dim
         self.num_layers, self.layer_type = num_layers, layer_type
         self.use_edge_attr, self.use_batch_norm = use_edge_attr, use_batch_norm
         self.validate_edges = validate_edges     # the reference's two .item() syncs per forward (:131-132)
+        # opt-in: residual add + BatchNorm + ReLU + dropout (:184-192) as the two passes of csrc/bn.cu
+        # instead of four torch ops.  Same arithmetic; the dropout mask comes from the library's Philox stream.
+        self.fused_glue = fused_glue
         self.input_proj = tnn.Linear(input_dim, hidden_dim)
         self.gnn_layers = tnn.ModuleList(_make_layer(layer_type, hidden_dim, dropout) for _ in range(num_layers))
         self.batch_norms = tnn.ModuleList(gnn.BatchNorm(hidden_dim) for _ in range(num_layers)) if use_batch_norm else None
@@ -76,6 +81,9 @@ class FlowGNN(tnn.Module):
             except RuntimeError as e:                                              # :173-181
                 raise RuntimeError(f"Message passing failed in layer {i} ({self.layer_type}): {e}\n"
                                    f"  num_nodes: {n}, num_edges: {edge_index.shape[1]}, x shape: {tuple(h.shape)}") from e
+            if self.fused_glue and self.use_batch_norm and ops.bn_supported(h):
+                h = Fn.batch_norm(h, h_new, self.batch_norms[i].module, relu=True, p_drop=self.dropout.p)
+                continue
             h = h + h_new
             if self.use_batch_norm:
                 h = self.batch_norms[i](h)

@@ -272,5 +272,59 @@ class TConvFn(torch.autograd.Function):
         return gx, gw, gb, None, None, None, None, None, None
 
 
+class BatchNormFn(torch.autograd.Function):
+    """y = dropout(relu(BatchNorm(x (+ r)))) over node features [N, C] (csrc/bn.cu).  With r = None, relu = False,
+    p_drop = 0 this is torch_geometric.nn.BatchNorm.forward (gnn_model.py:188); the other arguments fuse the caller's
+    residual add / ReLU / dropout (gnn_model.py:184-192)."""
+
+    @staticmethod
+    def forward(ctx, x, r, weight, bias, mean, rstd, relu: bool, p_drop: float, training: bool):
+        need_grad = any(t is not None and t.requires_grad for t in (x, r, weight, bias))
+        seed = _next_seed() if p_drop > 0 else 0
+        gamma = weight.float().contiguous() if weight is not None else None
+        beta = bias.float().contiguous() if bias is not None else None
+        y, s = ops.bn_apply(x, r, mean, rstd, gamma, beta, relu, p_drop, seed, keep_s=need_grad)
+        if need_grad:
+            ctx.save_for_backward(x if r is None else s, y if relu else None, mean, rstd, gamma)
+            ctx.cfg = (relu, 1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0, training, r is not None,
+                       weight is not None, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        s, y, mean, rstd, gamma = ctx.saved_tensors
+        relu, drop_scale, training, has_r, has_w, has_b = ctx.cfg
+        ds, sums = ops.bn_bwd(dy.contiguous(), y, s, mean, rstd, gamma, relu, drop_scale, training)
+        gw = sums[1] if (has_w and ctx.needs_input_grad[2]) else None
+        gb = sums[0] if (has_b and ctx.needs_input_grad[3]) else None
+        return ds, (ds if has_r else None), gw, gb, None, None, None, None, None
+
+
+def batch_norm(x, r, bn: "torch.nn.BatchNorm1d", relu: bool = False, p_drop: float = 0.0):
+    """BatchNorm1d semantics (batch statistics + running-stat update in training, running statistics in eval) on the
+    library's kernels; `bn` is the torch module that owns weight / bias / running_* (torch_geometric.nn.BatchNorm.module)."""
+    training = bn.training or (bn.running_mean is None and bn.running_var is None)
+    if training:
+        stats = ops.bn_stats(x.detach(), r.detach() if r is not None else None, bn.eps)
+        mean, rstd = stats[0], stats[1]
+        if bn.training and bn.track_running_stats and bn.running_mean is not None:
+            with torch.no_grad():
+                n = x.shape[0]
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked += 1
+                f = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+                bn.running_mean.mul_(1 - f).add_(mean.to(bn.running_mean.dtype), alpha=f)
+                unbiased = stats[2] * (n / max(n - 1, 1))
+                bn.running_var.mul_(1 - f).add_(unbiased.to(bn.running_var.dtype), alpha=f)
+    else:
+        mean = bn.running_mean.float().contiguous()
+        rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
+    p = p_drop if bn.training else 0.0
+    w = bn.weight if bn.affine else None
+    b = bn.bias if bn.affine else None
+    out = BatchNormFn.apply(x, r, w, b, mean, rstd, relu, p, training)
+    return out if w is None else _cast_like(out, x)
+
+
 def linear(x, weight, bias=None, act: int = 0):
     return LinearFn.apply(x, weight, bias, act)

@@ -330,7 +330,10 @@ class BatchNorm(tnn.Module):
         self.module.reset_parameters()
 
     def forward(self, x):
-        return self.module(x)
+        from . import ops
+        if ops.bn_supported(x):
+            return Fn.batch_norm(x, None, self.module)            # csrc/bn.cu
+        return self.module(x)                                      # host tensors / odd widths: torch's own BatchNorm1d
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.module.num_features})'

@@ -379,3 +379,56 @@ def rows_scatter_add(x, idx, src):
     _lib.check(lib.b2g_rows_scatter_add(_p(x), _ld(x), _p(idx), idx.numel(), _p(src), _ld(src), x.shape[1], _dt(x),
                                         _stream()), "rows_scatter_add")
     return x
+
+
+# ------------------------------------------------------------------------------------------ BatchNorm + fused glue
+def bn_supported(x) -> bool:
+    if not x.is_cuda or x.dim() != 2 or x.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    rb = x.shape[1] * x.element_size()
+    return x.shape[0] >= 1 and rb % 16 == 0 and rb <= 4096
+
+
+def bn_stats(x, r, eps: float) -> torch.Tensor:
+    """[3, C] fp32: mean, 1/sqrt(var + eps), biased var of s = x (+ r) over the rows."""
+    lib = _lib.load()
+    x = _rows(x)
+    r = _rows(r) if r is not None else None
+    N, C = x.shape
+    stats = torch.empty((3, C), dtype=torch.float32, device=x.device)
+    ws = _ws(lib.b2g_bn_workspace_bytes(C), x.device)
+    _lib.check(lib.b2g_bn_stats(_p(x), _ld(x), _p(r), _ld(r) if r is not None else 0, N, C, _dt(x), float(eps), _p(stats),
+                                _p(ws), _stream()), "bn_stats")
+    return stats
+
+
+def bn_apply(x, r, mean, rstd, gamma, beta, relu: bool, p_drop: float, seed: int, keep_s: bool):
+    """y = dropout(relu(gamma (s - mean) rstd + beta)), s = x (+ r).  Returns (y, s | None)."""
+    lib = _lib.load()
+    x = _rows(x)
+    r = _rows(r) if r is not None else None
+    N, C = x.shape
+    y = torch.empty((N, C), dtype=x.dtype, device=x.device)
+    s = torch.empty((N, C), dtype=x.dtype, device=x.device) if (keep_s and r is not None) else None
+    _lib.check(lib.b2g_bn_apply(_p(x), _ld(x), _p(r), _ld(r) if r is not None else 0, _p(y), _ld(y), _p(s),
+                                _ld(s) if s is not None else 0, N, C, _dt(x), _p(mean), _p(rstd), _p(gamma), _p(beta),
+                                int(relu), float(p_drop), int(seed), _stream()), "bn_apply")
+    return y, s
+
+
+def bn_bwd(dy, y, s, mean, rstd, gamma, relu: bool, drop_scale: float, training: bool):
+    """-> (ds [N,C], sums fp32 [2,C] = (sum dz, sum dz * xhat))."""
+    lib = _lib.load()
+    dy, s = _rows(dy), _rows(s)
+    y = _rows(y) if y is not None else None
+    N, C = s.shape
+    sums = torch.empty((2, C), dtype=torch.float32, device=s.device)
+    ws = _ws(lib.b2g_bn_workspace_bytes(C), s.device)
+    st = _stream()
+    _lib.check(lib.b2g_bn_bwd_stats(_p(dy), _ld(dy), _p(y), _ld(y) if y is not None else 0, _p(s), _ld(s), N, C, _dt(s),
+                                    _p(mean), _p(rstd), int(relu), float(drop_scale), _p(sums), _p(ws), st), "bn_bwd_stats")
+    ds = torch.empty((N, C), dtype=s.dtype, device=s.device)
+    _lib.check(lib.b2g_bn_bwd_apply(_p(dy), _ld(dy), _p(y), _ld(y) if y is not None else 0, _p(s), _ld(s), _p(ds), _ld(ds),
+                                    N, C, _dt(s), _p(mean), _p(rstd), _p(gamma), _p(sums), int(relu), float(drop_scale),
+                                    int(training), st), "bn_bwd_apply")
+    return ds, sums

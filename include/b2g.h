@@ -262,6 +262,29 @@ int b2g_rows_gather(const void* x, int64_t ldx, const int32_t* idx, int64_t n_id
 int b2g_rows_scatter_add(void* x, int64_t ldx, const int32_t* idx, int64_t n_idx, const void* in,
                          int64_t ldi, int F, int dt, void* stream);
 
+/* ===================================================================================== BatchNorm (+ fused glue)
+ * torch_geometric.nn.BatchNorm over node features [n, C] (gnn_model.py:9,87,188) and, optionally fused around it, the
+ * caller's residual add / ReLU / dropout (gnn_model.py:184-192):  s = x (+ r),
+ *   y = dropout(relu(gamma (s - mean) rstd + beta)).   C * sizeof(dt) must be a multiple of 16 and <= 4096 bytes.
+ * b2g_bn_stats: stats[0..C) = mean, [C..2C) = 1/sqrt(biased var + eps), [2C..3C) = biased variance of s (training).
+ * b2g_bn_apply: mean / rstd = batch statistics (training) or running statistics (eval); s_out (may be NULL) receives
+ *   s when r != NULL (kept for the backward pass); relu / p_drop fuse the activation and an inverted dropout
+ *   (Philox keyed by the element index).
+ * b2g_bn_bwd_stats: sums[0..C) = sum dz, [C..2C) = sum dz * xhat with dz = dy (* drop_scale where y > 0 when relu).
+ * b2g_bn_bwd_apply: ds = gamma rstd (dz - sums0/n - xhat sums1/n) (training) or gamma rstd dz (eval). */
+int64_t b2g_bn_workspace_bytes(int C);
+int b2g_bn_stats(const void* x, int64_t ldx, const void* r, int64_t ldr, int64_t n, int C, int dt, float eps,
+                 float* stats, void* ws, void* stream);
+int b2g_bn_apply(const void* x, int64_t ldx, const void* r, int64_t ldr, void* y, int64_t ldy, void* s_out, int64_t lds,
+                 int64_t n, int C, int dt, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                 int relu, float p_drop, uint64_t seed, void* stream);
+int b2g_bn_bwd_stats(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* s, int64_t lds, int64_t n,
+                     int C, int dt, const float* mean, const float* rstd, int relu, float drop_scale, float* sums,
+                     void* ws, void* stream);
+int b2g_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, const void* s, int64_t lds, void* ds,
+                     int64_t ldds, int64_t n, int C, int dt, const float* mean, const float* rstd, const float* gamma,
+                     const float* sums, int relu, float drop_scale, int training, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
