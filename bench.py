@@ -272,10 +272,13 @@ def main():
             kms, alg, kname = None, None, "attn_fwd_kernel (K4/K5)"
             if args.layer == "GAT":
                 csr = g.csr("sl", False)
-                xw = torch.randn(part.n_local, H * F, device=dev).to(dtype)
+                xin = torch.randn(part.n_local, F, device=dev).to(dtype)
                 a = torch.randn(part.n_local, 2 * H, device=dev)
-                kfn = lambda: ops.gat_fwd(xw, a, H, F, False, 0.2, csr.rowptr, csr.col, None, 0.0, 0, False)
-                alg = N * H * F * s + N * F * s + 2 * 4 * N * H + 4 * csr.nnz + 4 * (N + 1)
+                zbuf = torch.empty(N, H * F, device=dev, dtype=dtype)
+                kfn = lambda: ops.gatz_fwd(xin, a, H, 0.2, csr.rowptr, csr.col, 0.0, 0, False, band=g.band(), out=zbuf)
+                # aggregate-first kernel: read x once, a [N,2H] fp32, indices; write z [N, H*F]
+                alg = N * F * s + N * H * F * s + 2 * 4 * N * H + 4 * csr.nnz + 4 * (N + 1)
+                kname = "gatz_fwd_kernel (K4 aggregate-first, gat_rows.cu)"
             else:
                 csr = g.csr("raw", False)
                 y = torch.randn(part.n_local, 3 * H * F + F, device=dev).to(dtype)
@@ -415,19 +418,20 @@ def run_extras(b2g, ops, part, dev, timed):
                 out[key] = {"error": str(e)[:200]}
             torch.cuda.empty_cache()
 
-    # FlowGNN train step (hidden 256, 4 layers, bf16) on the largest of these meshes that fits
+    # FlowGNN train step (fwd + loss + bwd + clip + Adam; hidden 256, 4 layers, bf16, train.py:170-189) on a 2.5 M-cell
+    # block of the same mesh: the reference caller as is (drop-in layers + BatchNorm) and with the glue fused
+    # (FlowGNN(fused_glue=True): residual + BatchNorm + ReLU + dropout in the two passes of csrc/bn.cu)
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    n_sub = N // 4
+    o, nb = hex_mesh_faces(NX, NY, NZ // 4, device=dev)
+    sub_ei = ops.build_graph_edges(o, nb, 1, None, n_sub, n_sub)
     for lt in ("GCN", "GAT"):
-        for frac in (4,):     # 2.5 M cells: the caller's own torch ops keep ~17 [N,256] tensors per layer alive
-            n_sub = N // frac
+        for fused in (False, True):
+            key = f"train_step_FlowGNN_{lt}_L4_F256_bf16" + ("_fused_glue" if fused else "")
             try:
                 torch.manual_seed(0)
-                sub_ei = ei if frac == 1 else None
-                if frac != 1:
-                    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
-                    o, nb = hex_mesh_faces(NX, NY, NZ // frac, device=dev)
-                    sub_ei = ops.build_graph_edges(o, nb, 1, None, n_sub, n_sub)
                 torch.cuda.reset_peak_memory_stats()
-                model = FlowGNN(3, F, 7, 4, lt, dropout=0.1).to(dev).to(torch.bfloat16).train()
+                model = FlowGNN(3, F, 7, 4, lt, dropout=0.1, fused_glue=fused).to(dev).to(torch.bfloat16).train()
                 opt = torch.optim.Adam(model.parameters(), lr=3e-4, weight_decay=1e-5)
                 xin = torch.rand(n_sub, 3, device=dev, dtype=torch.bfloat16)
                 y = torch.rand(n_sub, 7, device=dev, dtype=torch.bfloat16)
@@ -438,15 +442,13 @@ def run_extras(b2g, ops, part, dev, timed):
                     loss.backward()
                     torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
                     opt.step()
-                ms = timed_grad(step, 3, 2)
-                out[f"train_step_FlowGNN_{lt}_L4_F256_bf16"] = {"ms": ms, "cells": n_sub, "edges": int(sub_ei.shape[1]),
-                                                             "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
+                ms = timed_grad(step, 5, 2)
+                out[key] = {"ms": ms, "cells": n_sub, "edges": int(sub_ei.shape[1]),
+                            "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
                 del model, opt, xin, y
-                torch.cuda.empty_cache()
-                break
             except Exception as e:
-                out[f"train_step_FlowGNN_{lt}_cells{n_sub}"] = {"error": str(e)[:160]}
-                torch.cuda.empty_cache()
+                out[key] = {"error": str(e)[:160]}
+            torch.cuda.empty_cache()
     return out
 
 
