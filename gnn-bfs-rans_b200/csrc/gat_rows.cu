@@ -93,6 +93,13 @@ __device__ __forceinline__ float pick4(const float (&v)[4], int h) {   // v[h] f
   return h == 0 ? v[0] : (h == 1 ? v[1] : (h == 2 ? v[2] : v[3]));
 }
 
+template <typename T>
+__device__ __forceinline__ void ld16_rows(const char* p, float (&f)[Vec<T>::N]) {
+  uint4 u;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(p));
+  unpack_row16(u, f, T());
+}
+
 struct GatzArgs {
   const void* x; uint32_t xrow_bytes;        // gathered rows [*, F] (fwd / bwd_dst: x; bwd_src: g = d out)
   const float* a; uint32_t lda;              // fp32 [N, >= 2H]: columns 0..H-1 a_src, H..2H-1 a_dst (stride in floats)
@@ -101,6 +108,7 @@ struct GatzArgs {
   const int32_t* rowptr; const int32_t* col; const int32_t* perm;
   float* smax; float* ssum;                  // [N, H] softmax statistics (ssum includes PyG's + 1e-16)
   float* alpha_e; float* de_e;               // [nnz, H] target-major
+  const float* alpha_in;                     // TransformerConv backward: the forward pass's (pre-dropout) alpha [nnz, H]
   float* d_a; uint32_t ldda;                 // [N, >= 2H]
   uint32_t n_rows;
   float slope, p_drop;
@@ -340,24 +348,52 @@ __device__ __forceinline__ void gatz_dalpha8(float (&dal)[GH], const float (&dzf
 
 // One window of <= 32 entries [p0, p0 + n): alpha from the saved statistics, d alpha, and - given t = sum_k alpha_k
 // d alpha_k over the WHOLE row - d e; writes alpha_e / de_e, returns this window's contribution to d a_dst.
-template <typename T, int VPL>
+// kT = false: GATConv (alpha recomputed from a_src / a_dst and the saved statistics; LeakyReLU in front of the softmax).
+// kT = true : TransformerConv (alpha read back from the forward pass; `ad` carries d s_alpha, the gradient of the
+//             per-head weight sums that multiply the value bias; the logits enter the softmax directly: sraw = 1).
+template <typename T, int VPL, bool kT>
 __device__ __forceinline__ void gatz_bwd_window(const GatzArgs& a, const float (&dzf)[GH][VPL][Vec<T>::N], const char* xb,
                                                 int cl, int p0, int n, int lane, const float (&ad)[GH],
                                                 const float (&sm)[GH], const float (&rinv)[GH], float (&alpha)[GH],
                                                 float (&dal)[GH], float (&sraw)[GH], float (&mask)[GH]) {
-  const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
-  const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+  if (kT) {
+    const float4 al4 = ldg_f4(a.alpha_in + (uint64_t)max(min(p0 + lane, p0 + n - 1), 0) * GH);
+    const float al[GH] = {al4.x, al4.y, al4.z, al4.w};
 #pragma unroll
-  for (int h = 0; h < GH; ++h) {
-    sraw[h] = as[h] + ad[h];
-    alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
-    mask[h] = 1.0f;
-    dal[h] = 0.f;
+    for (int h = 0; h < GH; ++h) { sraw[h] = 1.0f; alpha[h] = lane < n ? al[h] : 0.f; }
+  } else {
+    const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
+    const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+#pragma unroll
+    for (int h = 0; h < GH; ++h) {
+      sraw[h] = as[h] + ad[h];
+      alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
+    }
   }
+#pragma unroll
+  for (int h = 0; h < GH; ++h) { mask[h] = 1.0f; dal[h] = 0.f; }
   if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, mask);
   for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(dal, dzf, xb, a.xrow_bytes, cl, j, lane);
 #pragma unroll
-  for (int h = 0; h < GH; ++h) dal[h] *= mask[h];         // d(alpha) of the pre-dropout probability
+  for (int h = 0; h < GH; ++h) dal[h] = (dal[h] + (kT ? ad[h] : 0.f)) * mask[h];   // d(alpha) of the pre-dropout probability
+}
+
+// the row's per-head side inputs: GAT (a_dst, softmax max, 1 / softmax sum) or TransformerConv (d s_alpha from dz_aug)
+template <typename T, bool kT>
+__device__ __forceinline__ void gatz_bwd_row_inputs(const GatzArgs& a, uint32_t i, int hf_bytes, float (&ad)[GH],
+                                                    float (&sm)[GH], float (&rinv)[GH]) {
+  if (kT) {
+    float f[Vec<T>::N];
+    ld16_rows<T>(reinterpret_cast<const char*>(a.dz) + (uint64_t)i * a.dzrow_bytes + hf_bytes, f);
+#pragma unroll
+    for (int h = 0; h < GH; ++h) { ad[h] = f[h]; sm[h] = 0.f; rinv[h] = 1.f; }
+  } else {
+    const float4 ad4 = ldg_f4(a.a + (uint64_t)i * a.lda + GH);
+    const float4 sm4 = ldg_f4(a.smax + (uint64_t)i * GH), ss4 = ldg_f4(a.ssum + (uint64_t)i * GH);
+    ad[0] = ad4.x; ad[1] = ad4.y; ad[2] = ad4.z; ad[3] = ad4.w;
+    sm[0] = sm4.x; sm[1] = sm4.y; sm[2] = sm4.z; sm[3] = sm4.w;
+    rinv[0] = 1.0f / ss4.x; rinv[1] = 1.0f / ss4.y; rinv[2] = 1.0f / ss4.z; rinv[3] = 1.0f / ss4.w;
+  }
 }
 
 template <typename T, int VPL>
@@ -392,24 +428,22 @@ __device__ __forceinline__ void gatz_bwd_finish(const GatzArgs& a, int p0, int n
   }
 }
 
-template <typename T, int VPL>
+template <typename T, int VPL, bool kT>
 __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int b, int e) {
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
   float dzf[GH][VPL][VN];
   gatz_load_dz<T, VPL>(a, i, lane, dzf);
-  const float4 ad4 = ldg_f4(a.a + (uint64_t)i * a.lda + GH);
-  const float4 sm4 = ldg_f4(a.smax + (uint64_t)i * GH), ss4 = ldg_f4(a.ssum + (uint64_t)i * GH);
-  const float ad[GH] = {ad4.x, ad4.y, ad4.z, ad4.w}, sm[GH] = {sm4.x, sm4.y, sm4.z, sm4.w};
-  const float rinv[GH] = {1.0f / ss4.x, 1.0f / ss4.y, 1.0f / ss4.z, 1.0f / ss4.w};
+  float ad[GH], sm[GH], rinv[GH];
+  gatz_bwd_row_inputs<T, kT>(a, i, GH * VPL * 512, ad, sm, rinv);
   float t[GH] = {0.f, 0.f, 0.f, 0.f};
   // sweep 1: d alpha of every entry (parked in de_e), t = sum alpha * d alpha
   for (int p0 = b; p0 < e; p0 += 32) {
     const int n = min(32, e - p0);
     const int cl = window_entry(a.col, p0, e, lane);
     float alpha[GH], dal[GH], sraw[GH], mask[GH];
-    gatz_bwd_window<T, VPL>(a, dzf, xb, cl, p0, n, lane, ad, sm, rinv, alpha, dal, sraw, mask);
+    gatz_bwd_window<T, VPL, kT>(a, dzf, xb, cl, p0, n, lane, ad, sm, rinv, alpha, dal, sraw, mask);
     if (lane < n) *reinterpret_cast<float4*>(a.de_e + (uint64_t)(p0 + lane) * GH) = make_float4(dal[0], dal[1], dal[2], dal[3]);
     float pr[GH];
 #pragma unroll
@@ -423,26 +457,35 @@ __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int
   for (int p0 = b; p0 < e; p0 += 32) {
     const int n = min(32, e - p0);
     const int cl = window_entry(a.col, p0, e, lane);
-    const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
-    const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
     float alpha[GH], dal[GH] = {0.f, 0.f, 0.f, 0.f}, sraw[GH], mask[GH] = {1.f, 1.f, 1.f, 1.f};
     if (lane < n) {
       const float4 d4 = *reinterpret_cast<const float4*>(a.de_e + (uint64_t)(p0 + lane) * GH);
       dal[0] = d4.x; dal[1] = d4.y; dal[2] = d4.z; dal[3] = d4.w;
     }
     if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, mask);
+    if (kT) {
+      const float4 al4 = ldg_f4(a.alpha_in + (uint64_t)max(min(p0 + lane, p0 + n - 1), 0) * GH);
+      const float al[GH] = {al4.x, al4.y, al4.z, al4.w};
 #pragma unroll
-    for (int h = 0; h < GH; ++h) {
-      sraw[h] = as[h] + ad[h];
-      alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
+      for (int h = 0; h < GH; ++h) { sraw[h] = 1.0f; alpha[h] = lane < n ? al[h] : 0.f; }
+    } else {
+      const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
+      const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+#pragma unroll
+      for (int h = 0; h < GH; ++h) {
+        sraw[h] = as[h] + ad[h];
+        alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
+      }
     }
     gatz_bwd_finish<T, VPL>(a, p0, n, lane, alpha, dal, sraw, mask, t, dad);
   }
-  warp_sum4(dad[0], dad[1], dad[2], dad[3]);
-  if (lane < GH) a.d_a[(uint64_t)i * a.ldda + GH + lane] = pick4(dad, lane);
+  if (!kT) {
+    warp_sum4(dad[0], dad[1], dad[2], dad[3]);
+    if (lane < GH) a.d_a[(uint64_t)i * a.ldda + GH + lane] = pick4(dad, lane);
+  }
 }
 
-template <typename T, int VPL>
+template <typename T, int VPL, bool kT>
 __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) {
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
@@ -455,24 +498,181 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
     r.look_ahead(a.ord, wi, a.rowptr);
     const int len = r.e - r.b;
     if (len > 32) {
-      gatz_bwd_dst_long<T, VPL>(a, r.i, r.b, r.e);
+      gatz_bwd_dst_long<T, VPL, kT>(a, r.i, r.b, r.e);
     } else {
       float dzf[GH][VPL][VN];
       gatz_load_dz<T, VPL>(a, r.i, lane, dzf);
-      const float4 ad4 = ldg_f4(a.a + (uint64_t)r.i * a.lda + GH);
-      const float4 sm4 = ldg_f4(a.smax + (uint64_t)r.i * GH), ss4 = ldg_f4(a.ssum + (uint64_t)r.i * GH);
-      const float ad[GH] = {ad4.x, ad4.y, ad4.z, ad4.w}, sm[GH] = {sm4.x, sm4.y, sm4.z, sm4.w};
-      const float rinv[GH] = {1.0f / ss4.x, 1.0f / ss4.y, 1.0f / ss4.z, 1.0f / ss4.w};
+      float ad[GH], sm[GH], rinv[GH];
+      gatz_bwd_row_inputs<T, kT>(a, r.i, GH * VPL * 512, ad, sm, rinv);
       float alpha[GH], dal[GH], sraw[GH], mask[GH];
-      gatz_bwd_window<T, VPL>(a, dzf, xb, cl, r.b, len, lane, ad, sm, rinv, alpha, dal, sraw, mask);
+      gatz_bwd_window<T, VPL, kT>(a, dzf, xb, cl, r.b, len, lane, ad, sm, rinv, alpha, dal, sraw, mask);
       float t[GH];
 #pragma unroll
       for (int h = 0; h < GH; ++h) t[h] = alpha[h] * dal[h];
       warp_sum4(t[0], t[1], t[2], t[3]);
       float dad[GH] = {0.f, 0.f, 0.f, 0.f};
       gatz_bwd_finish<T, VPL>(a, r.b, len, lane, alpha, dal, sraw, mask, t, dad);
-      warp_sum4(dad[0], dad[1], dad[2], dad[3]);
-      if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + GH + lane] = pick4(dad, lane);
+      if (!kT) {
+        warp_sum4(dad[0], dad[1], dad[2], dad[3]);
+        if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + GH + lane] = pick4(dad, lane);
+      }
+    }
+    if (!r.shift()) break;
+    cl = cl2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ TransformerConv forward
+// TransformerConv(heads = 4, concat = False) (gnn_model.py:77-80,170) by the same linearity:
+//   q_ih . k_jh = x_j . (Wk_h^T q_ih) + q_ih . bk_h; the second term is constant along the softmax axis and drops out, so
+//   with u_i = x_i Mq + cq (ONE GEMM; Mq_h = Wq_h^T Wk_h / sqrt(C), cq_h = bq_h^T Wk_h / sqrt(C)) the logits are
+//   e_ijh = u_ih . x_j, and  out_i = 1/H sum_h (Wv_h z_ih + bv_h s_ih) + Ws x_i + bs  with z_ih = sum_j alpha_ijh x_j and
+//   s_ih = sum_j alpha_ijh (1 without dropout).  The kernel writes  z_aug_i = [z_i1 .. z_iH | s_i1 .. s_iH 0 0 0 0 | x_i]
+//   so that the value projection, its bias and the skip connection are ONE GEMM (k = H*F + 8 + F).
+// Only F-wide rows of x are gathered (twice: logits, then weighted sum; the second pass hits L1) instead of the H*C-wide
+// rows of k and v (4 KB per edge at H = 4, C = 256, bf16).
+struct TzScratch { float v[GH]; };
+
+template <typename T, int VPL>
+__device__ __forceinline__ void tz_store_tail(const GatzArgs& a, uint32_t i, int lane, const float (&ssum)[GH]) {
+  constexpr int VN = Vec<T>::N;
+  char* zrow = reinterpret_cast<char*>(a.z) + (uint64_t)i * a.zrow_bytes + GH * VPL * 512;
+  if (lane < 8 / VN) {                        // s_alpha (H values) + zero padding: 8 elements of T
+    float f[VN];
+#pragma unroll
+    for (int k = 0; k < VN; ++k) {
+      const int idx = lane * VN + k;
+      f[k] = idx < GH ? pick4(ssum, idx) : 0.f;
+    }
+    Vec<T> o;
+    o.from_float(f);
+    *reinterpret_cast<uint4*>(zrow + lane * 16) = *reinterpret_cast<uint4*>(&o.v);
+  }
+  const char* xi = reinterpret_cast<const char*>(a.x) + (uint64_t)i * a.xrow_bytes + lane * 16;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+    __stcs(reinterpret_cast<uint4*>(zrow + 8 * sizeof(T) + v * 512 + lane * 16), ldg_row16(xi + 512 * v));
+}
+
+template <typename T, int VPL>
+__device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, int e) {
+  constexpr int VN = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  float uf[GH][VPL][VN];
+  gatz_load_dz<T, VPL>(a, i, lane, uf);
+  float m[GH], zs[GH];
+#pragma unroll
+  for (int h = 0; h < GH; ++h) { m[h] = -INFINITY; zs[h] = 0.f; }
+  // sweep 1: logits (parked in alpha_e or, without a backward pass, recomputed), running max
+  for (int p0 = b; p0 < e; p0 += 32) {
+    const int n = min(32, e - p0);
+    const int cl = window_entry(a.col, p0, e, lane);
+    float s[GH] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane);
+#pragma unroll
+    for (int h = 0; h < GH; ++h) m[h] = fmaxf(m[h], warp_max_redux(lane < n ? s[h] : -INFINITY));
+  }
+  for (int p0 = b; p0 < e; p0 += 32) {
+    const int n = min(32, e - p0);
+    const int cl = window_entry(a.col, p0, e, lane);
+    float s[GH] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane);
+    float p[GH];
+#pragma unroll
+    for (int h = 0; h < GH; ++h) p[h] = lane < n ? __expf(s[h] - m[h]) : 0.f;
+    warp_sum4(p[0], p[1], p[2], p[3]);
+#pragma unroll
+    for (int h = 0; h < GH; ++h) zs[h] += p[h];
+  }
+  float inv[GH], ssum[GH] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int h = 0; h < GH; ++h) inv[h] = 1.0f / (zs[h] + 1e-16f);
+  float acc[GH][VPL][VN];
+#pragma unroll
+  for (int h = 0; h < GH; ++h)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[h][v][k] = 0.f;
+  for (int p0 = b; p0 < e; p0 += 32) {
+    const int n = min(32, e - p0);
+    const int cl = window_entry(a.col, p0, e, lane);
+    float s[GH] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane);
+    float w[GH];
+#pragma unroll
+    for (int h = 0; h < GH; ++h) w[h] = lane < n ? __expf(s[h] - m[h]) * inv[h] : 0.f;
+    if (a.alpha_e && lane < n) *reinterpret_cast<float4*>(a.alpha_e + (uint64_t)(p0 + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
+    if (a.p_drop > 0.f) {
+      float sc[4];
+      dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, sc);
+#pragma unroll
+      for (int h = 0; h < GH; ++h) w[h] *= sc[h];
+    }
+    float ws[GH] = {w[0], w[1], w[2], w[3]};
+    warp_sum4(ws[0], ws[1], ws[2], ws[3]);
+#pragma unroll
+    for (int h = 0; h < GH; ++h) ssum[h] += ws[h];
+    for (int j = 0; j < n; j += GatzCfg<VPL>::BU) gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, j, []() {});
+  }
+  gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)i * a.zrow_bytes, acc, lane);
+  tz_store_tail<T, VPL>(a, i, lane, ssum);
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int BU = GatzCfg<VPL>::BU;
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  WarpRows r;
+  if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
+  int cl = window_entry(a.col, r.b, r.e, lane);
+  while (true) {
+    const int cl2 = window_entry(a.col, r.b2, r.e2, lane);
+    r.look_ahead(a.ord, wi, a.rowptr);
+    const int len = r.e - r.b;
+    if (len > 32) {
+      tz_fwd_long<T, VPL>(a, r.i, r.b, r.e);
+    } else {
+      float w[GH] = {0.f, 0.f, 0.f, 0.f}, ssum[GH] = {0.f, 0.f, 0.f, 0.f};
+      {                                       // logits: u_i (registers) . x_j, one entry per lane
+        float uf[GH][VPL][VN];
+        gatz_load_dz<T, VPL>(a, r.i, lane, uf);
+        for (int j = 0; j < len; j += 8) gatz_dalpha8<T, VPL>(w, uf, xb, a.xrow_bytes, cl, j, lane);
+      }
+      float zs[GH];
+#pragma unroll
+      for (int h = 0; h < GH; ++h) {
+        const float s = lane < len ? w[h] : -INFINITY;
+        const float m = warp_max_redux(s);
+        w[h] = lane < len ? __expf(s - m) : 0.f;
+        zs[h] = w[h];
+      }
+      warp_sum4(zs[0], zs[1], zs[2], zs[3]);
+#pragma unroll
+      for (int h = 0; h < GH; ++h) w[h] *= 1.0f / (zs[h] + 1e-16f);
+      if (a.alpha_e && lane < len) *reinterpret_cast<float4*>(a.alpha_e + (uint64_t)(r.b + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
+      if (a.p_drop > 0.f) {
+        float sc[4];
+        dropout_scale4(a.seed, (uint64_t)(r.b + lane), a.p_drop, sc);
+#pragma unroll
+        for (int h = 0; h < GH; ++h) w[h] *= sc[h];
+      }
+#pragma unroll
+      for (int h = 0; h < GH; ++h) ssum[h] = w[h];
+      warp_sum4(ssum[0], ssum[1], ssum[2], ssum[3]);
+      float acc[GH][VPL][VN];
+#pragma unroll
+      for (int h = 0; h < GH; ++h)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[h][v][k] = 0.f;
+      for (int j = 0; j < len; j += BU) gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, j, []() {});
+      gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, acc, lane);
+      tz_store_tail<T, VPL>(a, r.i, lane, ssum);
     }
     if (!r.shift()) break;
     cl = cl2;
@@ -490,9 +690,13 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_src_kernel(const GatzArgs a) 
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
   WarpRows r;
   if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
-  int cl = window_entry(a.col, r.b, r.e, lane), pl = window_entry(a.perm, r.b, r.e, lane);
+  // perm == NULL: the weights are already in this CSR's order (position = entry index)
+  auto perm_entry = [&](int p0, int e_) -> int {
+    return a.perm ? window_entry(a.perm, p0, e_, lane) : max(min(p0 + lane, e_ - 1), 0);
+  };
+  int cl = window_entry(a.col, r.b, r.e, lane), pl = perm_entry(r.b, r.e);
   while (true) {
-    const int cl2 = window_entry(a.col, r.b2, r.e2, lane), pl2 = window_entry(a.perm, r.b2, r.e2, lane);
+    const int cl2 = window_entry(a.col, r.b2, r.e2, lane), pl2 = perm_entry(r.b2, r.e2);
     r.look_ahead(a.ord, wi, a.rowptr);
     float acc[GH][VPL][VN];
 #pragma unroll
@@ -505,7 +709,7 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_src_kernel(const GatzArgs a) 
     for (int p0 = r.b; p0 < r.e; p0 += 32) {                 // one window on meshes
       if (p0 != r.b) {
         cl = window_entry(a.col, p0, r.e, lane);
-        pl = window_entry(a.perm, p0, r.e, lane);
+        pl = perm_entry(p0, r.e);
       }
       const int n = min(32, r.e - p0);
       const float4 al4 = ldg_f4(a.alpha_e + (uint64_t)(uint32_t)pl * GH);
@@ -524,8 +728,10 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_src_kernel(const GatzArgs a) 
         }
       }
     }
-    warp_sum4(das[0], das[1], das[2], das[3]);
-    if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + lane] = pick4(das, lane);
+    if (a.d_a) {
+      warp_sum4(das[0], das[1], das[2], das[3]);
+      if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + lane] = pick4(das, lane);
+    }
     gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, acc, lane);
     if (!r.shift()) break;
     cl = cl2; pl = pl2;
@@ -599,8 +805,10 @@ static inline int64_t gatz_blocks(K kernel, const RowSched& ord) {
 template <typename T, int VPL>
 static int gatz_launch(int which, const GatzArgs& a, cudaStream_t st) {
   if (which == 0) gatz_fwd_kernel<T, VPL><<<(unsigned)gatz_blocks(gatz_fwd_kernel<T, VPL>, a.ord), 256, 0, st>>>(a);
-  else if (which == 1) gatz_bwd_dst_kernel<T, VPL><<<(unsigned)gatz_blocks(gatz_bwd_dst_kernel<T, VPL>, a.ord), 256, 0, st>>>(a);
-  else gatz_bwd_src_kernel<T, VPL><<<(unsigned)gatz_blocks(gatz_bwd_src_kernel<T, VPL>, a.ord), 256, 0, st>>>(a);
+  else if (which == 1) gatz_bwd_dst_kernel<T, VPL, false><<<(unsigned)gatz_blocks(gatz_bwd_dst_kernel<T, VPL, false>, a.ord), 256, 0, st>>>(a);
+  else if (which == 2) gatz_bwd_src_kernel<T, VPL><<<(unsigned)gatz_blocks(gatz_bwd_src_kernel<T, VPL>, a.ord), 256, 0, st>>>(a);
+  else if (which == 3) tz_fwd_kernel<T, VPL><<<(unsigned)gatz_blocks(tz_fwd_kernel<T, VPL>, a.ord), 256, 0, st>>>(a);
+  else gatz_bwd_dst_kernel<T, VPL, true><<<(unsigned)gatz_blocks(gatz_bwd_dst_kernel<T, VPL, true>, a.ord), 256, 0, st>>>(a);
   count_launch();
   return cuda_status();
 }
@@ -700,8 +908,9 @@ int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const flo
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
-  if (!g || !alpha_e || !de_e || !y || !d_a || !rowptr_t || !col_t || !perm) return B2G_E_ARG;
-  if (!aligned16(g) || !aligned16(y) || !aligned16(alpha_e) || !aligned16(de_e) || (ldg * es) % 16 || (ldy * es) % 16 || ldda < 2 * GH)
+  if (!g || !alpha_e || !de_e || !y || !rowptr_t || !col_t) return B2G_E_ARG;     // perm NULL = identity, d_a NULL = not wanted
+  if (!aligned16(g) || !aligned16(y) || !aligned16(alpha_e) || !aligned16(de_e) || (ldg * es) % 16 || (ldy * es) % 16 ||
+      (d_a && ldda < GH))
     return B2G_E_ALIGN;
   if (!fits32(ldg * es) || !fits32(ldy * es) || !fits32(ldda)) return B2G_E_SHAPE;
   GatzArgs a{};
@@ -711,6 +920,47 @@ int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const flo
   a.rowptr = rowptr_t; a.col = col_t; a.perm = perm; a.alpha_e = const_cast<float*>(alpha_e); a.de_e = const_cast<float*>(de_e);
   a.d_a = d_a; a.ldda = (uint32_t)ldda;
   return gatz_dispatch(2, dt, C * es, a, (cudaStream_t)stream);
+}
+
+/* TransformerConv, aggregate-first (see tz_fwd_kernel).  u [n, H*F] = x Mq + cq; z_aug [n, H*F + 8 + F]. */
+int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_aug, int64_t ldz, int64_t n, int H, int F,
+               int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, float p_drop, uint64_t seed,
+               int64_t band, void* stream) {
+  if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  const int es = esz(dt);
+  if (!x || !u || !z_aug || !rowptr || !col) return B2G_E_ARG;
+  if (!aligned16(x) || !aligned16(u) || !aligned16(z_aug) || (alpha_e && !aligned16(alpha_e)) || (ldx * es) % 16 ||
+      (ldu * es) % 16 || (ldz * es) % 16 || ldz < (int64_t)H * F + 8 + F)
+    return B2G_E_ALIGN;
+  if (!fits32(ldx * es) || !fits32(ldu * es) || !fits32(ldz * es)) return B2G_E_SHAPE;
+  GatzArgs a{};
+  const int rc = gatz_common(a, n, F, dt, band);
+  if (rc) return rc;
+  a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = u; a.dzrow_bytes = (uint32_t)(ldu * es); a.z = z_aug;
+  a.zrow_bytes = (uint32_t)(ldz * es); a.rowptr = rowptr; a.col = col; a.alpha_e = alpha_e; a.p_drop = p_drop; a.seed = seed;
+  return gatz_dispatch(3, dt, F * es, a, (cudaStream_t)stream);
+}
+
+/* Target side of the TransformerConv backward pass: dz_aug [n, >= H*F + 8] (columns H*F..H*F+3 = d s_alpha), alpha_in =
+ * the forward pass's alpha [nnz,H]; writes alpha_e (after dropout) and de_e [nnz,H] in target-major CSR order. */
+int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz, const float* alpha_in, int64_t n, int H,
+                   int F, int dt, const int32_t* rowptr, const int32_t* col, float p_drop, uint64_t seed, float* alpha_e,
+                   float* de_e, int64_t band, void* stream) {
+  if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  const int es = esz(dt);
+  if (!x || !dz_aug || !alpha_in || !rowptr || !col || !alpha_e || !de_e) return B2G_E_ARG;
+  if (!aligned16(x) || !aligned16(dz_aug) || !aligned16(alpha_in) || !aligned16(alpha_e) || !aligned16(de_e) ||
+      (ldx * es) % 16 || (lddz * es) % 16 || lddz < (int64_t)H * F + 8)
+    return B2G_E_ALIGN;
+  if (!fits32(ldx * es) || !fits32(lddz * es)) return B2G_E_SHAPE;
+  GatzArgs a{};
+  const int rc = gatz_common(a, n, F, dt, band);
+  if (rc) return rc;
+  a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = dz_aug; a.dzrow_bytes = (uint32_t)(lddz * es); a.alpha_in = alpha_in;
+  a.rowptr = rowptr; a.col = col; a.p_drop = p_drop; a.seed = seed; a.alpha_e = alpha_e; a.de_e = de_e;
+  return gatz_dispatch(4, dt, F * es, a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -326,5 +326,81 @@ def batch_norm(x, r, bn: "torch.nn.BatchNorm1d", relu: bool = False, p_drop: flo
     return out if w is None else _cast_like(out, x)
 
 
+class TConvZFn(torch.autograd.Function):
+    """TransformerConv(heads=4, concat=False) core, aggregate-first (csrc/gat_rows.cu):
+        u = x Mq^T + cq   (logits e_ijh = u_ih . x_j; Mq_h = Wk_h^T Wq_h / sqrt(C), cq_h = Wk_h^T bq_h / sqrt(C))
+        z_aug = [per-head attention-weighted sums of x | per-head weight sums, 0 0 0 0 | x]
+        out = z_aug W_out^T + b_out   (value projection / H, value bias / H, skip connection in one GEMM)
+    `mq` [H*F, F], `cq` [H*F], `w_out` [C, H*F + 8 + F], `b_out` [C] are assembled (differentiably) by the module."""
+
+    @staticmethod
+    def forward(ctx, x, mq, cq, w_out, b_out, graph: Graph, H: int, p_drop: float):
+        csr = graph.csr("raw", False)
+        need_grad = any(t is not None and t.requires_grad for t in (x, mq, cq, w_out, b_out))
+        seed = _next_seed() if p_drop > 0 else 0
+        u, _ = ops.linear_fwd(x, mq, cq)
+        z_aug, alpha = ops.tz_fwd(x, u, H, csr.rowptr, csr.col, p_drop, seed, need_grad, band=graph.band())
+        del u
+        out, _ = ops.linear_fwd(z_aug, w_out, b_out)
+        if need_grad:
+            ctx.save_for_backward(x, mq, cq, w_out, z_aug, alpha)
+            ctx.cfg = (graph, H, p_drop, seed, b_out is not None)
+            ctx.ei_keepalive = graph.edge_index
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, mq, cq, w_out, z_aug, alpha = ctx.saved_tensors
+        graph, H, p_drop, seed, has_bout = ctx.cfg
+        N, F = x.shape
+        C = w_out.shape[0]
+        HF = H * F
+        g = g.contiguous()
+        csr, csr_t, perm = graph.csr("raw", False), graph.csr("raw", True), graph.perm("raw")
+        band = graph.band()
+        gw_out = None
+        if ctx.needs_input_grad[3]:
+            dw, _ = ops.linear_wgrad(g, z_aug, want_bias=False)               # d W_out = g^T z_aug  [C, H*F + 8 + F]
+            gw_out = _cast_like(dw, w_out)
+        del z_aug
+        # gradients of z and of the weight sums s: dz_aug = g W_out[:, :H*F + 8]
+        dz_aug, _ = ops.linear_fwd(g, w_out[:, :HF + 8].t().contiguous(), None)
+        alpha_e, de_e = ops.tz_bwd_dst(x, dz_aug, alpha, H, csr.rowptr, csr.col, p_drop, seed, band=band)
+        del dz_aug
+        # dx = [y | w | t 0 | du | g] W_aug as ONE GEMM, every block a sum of F-wide rows:
+        #   y_j = [sum_i alpha'_ijh g_i]_h, w_j = [sum_i de_ijh x_i]_h, t_jh = sum_i de_ijh   (transposed CSR)
+        #   du_i = [sum_j de_ijh x_j]_h                                                       (target-major CSR)
+        # using  sum_i de_ijh u_ih = Mq_h w_jh + cq_h t_jh  and  sum_i alpha'_ijh dz_ih = Wv_h^T y_jh
+        o_y, o_w, o_t, o_du, o_g = 0, H * C, H * C + HF, H * C + HF + 8, H * C + 2 * HF + 8
+        big = torch.empty((N, o_g + C), dtype=x.dtype, device=x.device)
+        t_rows = torch.zeros((N, 8), dtype=torch.float32, device=x.device)
+        ops.seg_wsum4(g, alpha_e, csr_t.rowptr, csr_t.col, perm, big[:, o_y:o_y + H * C], band=band)
+        ops.seg_wsum4(x, de_e, csr_t.rowptr, csr_t.col, perm, big[:, o_w:o_w + HF], d_a=t_rows, band=band)
+        ops.seg_wsum4(x, de_e, csr.rowptr, csr.col, None, big[:, o_du:o_du + HF], band=band)
+        del alpha_e, de_e
+        big[:, o_t:o_t + 8] = t_rows
+        big[:, o_g:] = g
+        du = big[:, o_du:o_du + HF]
+        gmq = gcq = gx = None
+        if ctx.needs_input_grad[1]:
+            dm, _ = ops.linear_wgrad(du, x, want_bias=False)                  # d Mq = du^T x  [H*F, F]
+            gmq = _cast_like(dm, mq)
+        if cq is not None and ctx.needs_input_grad[2]:
+            gcq = _cast_like(ops.colsum(du), cq)
+        if ctx.needs_input_grad[0]:
+            wd = w_out.dtype
+            w_y = w_out[:, :HF].view(C, H, F).permute(1, 0, 2).reshape(H * C, F)       # y_jh[c]  -> W_out[c, hF + :]
+            w_w = mq.view(H, F, F).transpose(1, 2).reshape(HF, F)                       # w_jh[f'] -> Mq_h[:, f']
+            w_t = torch.zeros((8, F), dtype=wd, device=x.device)
+            if cq is not None:
+                w_t[:H] = cq.view(H, F).to(wd)                                         # t_jh     -> cq_h
+            w_aug = torch.cat([w_y, w_w.to(wd), w_t, mq.to(wd), w_out[:, HF + 8:]], dim=0)   # du_ih -> Mq_h^T, g -> Ws
+            gx = ops.linear_dgrad(big, w_aug)
+        gb = ops.colsum(g) if (has_bout and ctx.needs_input_grad[4]) else None
+        if gb is not None:
+            gb = _cast_like(gb, w_out) if False else gb
+        return gx, gmq, gcq, gw_out, gb, None, None, None
+
+
 def linear(x, weight, bias=None, act: int = 0):
     return LinearFn.apply(x, weight, bias, act)

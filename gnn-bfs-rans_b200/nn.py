@@ -194,7 +194,7 @@ class GATConv(MessagePassing):
             return False
         from . import ops
         return x.shape[0] >= 1 and ops.gatz_supported(x.shape[0], self.heads, self.in_channels, x.dtype) and \
-            (self.heads * self.in_channels * x.element_size()) % 16 == 0
+            ops.gatz_supported(x.shape[0], self.heads, self.out_channels, x.dtype)
 
     def _wc_v(self, dtype):
         H, C, F = self.heads, self.out_channels, self.in_channels
@@ -297,6 +297,10 @@ class TransformerConv(MessagePassing):
             self._warned_edge_attr = True
         _check_x(x, edge_index)
         g = graph_of(edge_index, x.shape[0])
+        p = self.dropout if self.training else 0.0
+        if self._aggregate_first(x):
+            mq, cq, w_out, b_out = self._folded(x.dtype)
+            return Fn.TConvZFn.apply(x, mq, cq, w_out, b_out, g, self.heads, p)
         ws = [self.lin_query.weight, self.lin_key.weight, self.lin_value.weight]
         bs = [self.lin_query.bias, self.lin_key.bias, self.lin_value.bias]
         if self.root_weight:
@@ -307,6 +311,36 @@ class TransformerConv(MessagePassing):
         b_cat = torch.cat(bs, 0).float()
         p = self.dropout if self.training else 0.0
         return Fn.TConvFn.apply(x, w_cat, b_cat, g, self.heads, self.out_channels, self.concat, p, self.root_weight)
+
+    def _aggregate_first(self, x) -> bool:
+        """heads averaged (concat=False, the reference's configuration) and 512 / 1024-byte feature rows: logits and
+        weighted sums over the F-wide input rows, projections after (gat_rows.cu).  B2G_TCONV_PATH=project forces
+        the q/k/v-first kernels."""
+        import os
+        if self.concat or os.environ.get("B2G_TCONV_PATH", "") == "project":
+            return False
+        from . import ops
+        return x.shape[0] >= 1 and ops.gatz_supported(x.shape[0], self.heads, self.in_channels, x.dtype) and \
+            ops.gatz_supported(x.shape[0], self.heads, self.out_channels, x.dtype)
+
+    def _folded(self, dtype):
+        """(mq [H*F, F], cq [H*F], w_out [C, H*F + 8 + F], b_out [C]) from the q/k/v/skip parameters (differentiable).
+        The key bias only shifts every logit of a softmax row by the same amount: it drops out (its exact gradient is 0)."""
+        H, C, F = self.heads, self.out_channels, self.in_channels
+        Wq, Wk, Wv = (l.weight.view(H, C, F) for l in (self.lin_query, self.lin_key, self.lin_value))
+        sc = 1.0 / math.sqrt(C)
+        mq = (torch.einsum('hcf,hcg->hfg', Wk, Wq) * sc).reshape(H * F, F)          # u_h = Mq_h x,  Mq_h = Wk_h^T Wq_h / sqrt(C)
+        cq = (torch.einsum('hcf,hc->hf', Wk, self.lin_query.bias.view(H, C)) * sc).reshape(H * F)
+        cq = cq + 0.0 * self.lin_key.bias.sum()                                      # keeps lin_key.bias in the graph (grad = 0)
+        wv = Wv.permute(1, 0, 2).reshape(C, H * F) / H
+        bv = self.lin_value.bias.view(H, C).t() / H                                  # [C, H]: multiplies the weight sums s_ih
+        pad = wv.new_zeros((C, 8 - H))
+        if self.root_weight:
+            wsk, b_out = self.lin_skip.weight, self.lin_skip.bias
+        else:
+            wsk, b_out = wv.new_zeros((C, F)), None
+        w_out = torch.cat([wv, bv, pad, wsk], dim=1)
+        return mq.to(dtype), cq.float(), w_out.to(dtype), (b_out.float() if b_out is not None else None)
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.in_channels}, {self.out_channels}, heads={self.heads})'

@@ -329,6 +329,42 @@ def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, 
     return d_a
 
 
+def seg_wsum4(x, w_e, rowptr, col, perm, out, d_a=None, band=0):
+    """out[i] = [sum_t w_e[p_t,0] x[col_t] | ... | sum_t w_e[p_t,3] x[col_t]] over row i of (rowptr, col), p_t = perm[t] or t
+    (gat_rows.cu gatz_bwd_src_kernel).  d_a (optional, fp32 [N, >= 4]) receives the row sums of w_e's companion."""
+    lib = _lib.load()
+    x = _rows(x)
+    N = out.shape[0]
+    C = x.shape[1]
+    _lib.check(lib.b2g_gatz_bwd_src(_p(x), _ld(x), _p(w_e), _p(w_e), _p(out), _ld(out), _p(d_a),
+                                    d_a.stride(0) if d_a is not None else 0, N, 4, C, _dt(x), _p(rowptr), _p(col), _p(perm),
+                                    int(band), _stream()), "seg_wsum4")
+    return out
+
+
+def tz_fwd(x, u, H, rowptr, col, p_drop, seed, save_alpha, band=0):
+    """z_aug [N, H*F + 8 + F] (see include/b2g.h b2g_tz_fwd) and the pre-dropout attention weights [nnz, H] | None."""
+    x, u = _rows(x), _rows(u)
+    N, F = x.shape
+    z = torch.empty((N, H * F + 8 + F), dtype=x.dtype, device=x.device)
+    alpha = torch.empty((max(col.numel(), 1), H), dtype=torch.float32, device=x.device) if save_alpha else None
+    _lib.check(_lib.load().b2g_tz_fwd(_p(x), _ld(x), _p(u), _ld(u), _p(z), _ld(z), N, H, F, _dt(x), _p(rowptr), _p(col),
+                                      _p(alpha), float(p_drop), int(seed), int(band), _stream()), "tz_fwd")
+    return z, alpha
+
+
+def tz_bwd_dst(x, dz_aug, alpha, H, rowptr, col, p_drop, seed, band=0):
+    """-> (alpha_e after dropout, de_e) fp32 [nnz, H], target-major."""
+    x, dz_aug = _rows(x), _rows(dz_aug)
+    N, F = x.shape
+    alpha_e = torch.empty_like(alpha)
+    de_e = torch.empty_like(alpha)
+    _lib.check(_lib.load().b2g_tz_bwd_dst(_p(x), _ld(x), _p(dz_aug), _ld(dz_aug), _p(alpha), N, H, F, _dt(x), _p(rowptr),
+                                          _p(col), float(p_drop), int(seed), _p(alpha_e), _p(de_e), int(band), _stream()),
+               "tz_bwd_dst")
+    return alpha_e, de_e
+
+
 # ------------------------------------------------------------------------------------------ K5
 def tconv_fwd(q, k, v, skip, H, C, concat, rowptr, col, p_drop, seed, save_stats):
     lib = _lib.load()

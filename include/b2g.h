@@ -207,6 +207,22 @@ int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const flo
                      float* d_a, int64_t ldda, int64_t n, int H, int C, int dt, const int32_t* rowptr_t,
                      const int32_t* col_t, const int32_t* perm, int64_t band, void* stream);
 
+/* TransformerConv(heads = 4, concat = False) (gnn_model.py:77-80,170), aggregate-first (gat_rows.cu): the logits are
+ * e_ijh = u_ih . x_j with u = x Mq + cq (a K6 GEMM; the key bias drops out of the softmax), and
+ *   z_aug[i] = [sum_j alpha_ij1 x_j | ... | sum_j alpha_ijH x_j | s_i1 .. s_iH 0 0 0 0 | x_i]   (s_ih = sum_j alpha_ijh)
+ * so that value projection, value bias and skip connection are one K6 GEMM with k = H*F + 8 + F.  alpha_e (may be
+ * NULL) receives the pre-dropout attention weights [nnz, H] for the backward pass. */
+int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_aug, int64_t ldz, int64_t n, int H, int F,
+               int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, float p_drop, uint64_t seed,
+               int64_t band, void* stream);
+/* Target side of its backward pass: dz_aug [n, >= H*F + 8] (columns H*F .. H*F+H-1 = d s), alpha_in = the forward
+ * pass's alpha_e; writes alpha_e (after dropout) and de_e [nnz, H] (gradients of the logits), target-major.  The
+ * remaining sums (d u, and y / w over the transposed CSR) are b2g_gatz_bwd_src calls: perm == NULL there means the
+ * weights are already in the order of the CSR passed in, d_a == NULL skips the logit-gradient row sums. */
+int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz, const float* alpha_in, int64_t n, int H,
+                   int F, int dt, const int32_t* rowptr, const int32_t* col, float p_drop, uint64_t seed, float* alpha_e,
+                   float* de_e, int64_t band, void* stream);
+
 /* ===================================================================================== K5
  * TransformerConv (gnn_model.py:77-80,170) fused q.k score + segment-softmax + aggregate +
  * head-mean + skip.  q,k,v: [N,H*C]; skip: [N, concat?H*C:C] or NULL.
