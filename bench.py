@@ -449,6 +449,68 @@ def run_extras(b2g, ops, part, dev, timed):
             except Exception as e:
                 out[key] = {"error": str(e)[:160]}
             torch.cuda.empty_cache()
+    # ---- BASELINE.json cfg2: the shipped BFS case (12 225 internal cells, mode A graph) through FlowGNN(GAT, L=4, H=4,
+    # hidden 128), fp32 and bf16: inference forward and train step.  Launch-bound at this size (~100 kernels of a few us).
+    try:
+        import numpy as np
+        z = np.load(os.path.join(ROOT, "tests", "golden", "shipped_mesh.npz"))
+        mesh = dict(owner=z['owner'], neighbour=z['neighbour'], cell_centers=z['cell_centers'], n_cells=int(z['n_cells']))
+        gdata = b2g.GraphConstructor(mesh).build_graph(node_features=mesh['cell_centers'], filter_internal=True,
+                                                       n_internal_cells=12225)
+        ei2 = gdata.edge_index.to(dev)
+        n2 = int(gdata.num_nodes)
+        for dt_name, dtype in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+            for lt in ("GCN", "GAT"):
+                torch.manual_seed(0)
+                model = FlowGNN(3, 128, 7, 4, lt, dropout=0.1).to(dev).to(dtype)
+                xin = torch.rand(n2, 3, device=dev, dtype=dtype)
+                y = torch.rand(n2, 7, device=dev, dtype=dtype)
+                model.eval()
+                ms_f = timed(lambda: model(xin, ei2), 20, 5)
+                model.train()
+                opt = torch.optim.Adam(model.parameters(), lr=3e-4, weight_decay=1e-5)
+
+                def step2():
+                    opt.zero_grad(set_to_none=True)
+                    loss = (model(xin, ei2) - y).float().square().mean()
+                    loss.backward()
+                    torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+                    opt.step()
+                ms_t = timed_grad(step2, 20, 5)
+                out[f"cfg2_shipped_BFS_FlowGNN_{lt}_L4_F128_{dt_name}"] = {"cells": n2, "edges": int(ei2.shape[1]),
+                                                                           "forward_ms": ms_f, "train_step_ms": ms_t}
+                del model, opt
+    except Exception as e:
+        out["cfg2_shipped_BFS"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json cfg3: 2-D unstructured mesh, ~1 M cells (Delaunay dual of 500 500 points, cell ids = triangle ids:
+    # spatially incoherent order on purpose), GIN and TransformerConv hidden 256, bf16: layer forward and forward+backward
+    try:
+        from gnn_bfs_rans_b200.synthetic import delaunay_dual_faces
+        own, nbr, _ = delaunay_dual_faces(500500, seed=1)
+        n3 = int(max(own.max(), nbr.max())) + 1
+        ei3 = ops.build_graph_edges(torch.from_numpy(own).to(dev), torch.from_numpy(nbr).to(dev), 1, None, n3, n3)
+        for lt in ("GIN", "Transformer"):
+            torch.manual_seed(0)
+            layer = mk(lt).to(dev).to(torch.bfloat16).eval()
+            x3 = torch.empty(n3, F, device=dev, dtype=torch.bfloat16).normal_()
+            ms_f = timed(lambda: layer(x3, ei3), 10, 3)
+            xg = x3.clone().requires_grad_(True)
+            g3 = torch.empty(n3, F, device=dev, dtype=torch.bfloat16).normal_()
+
+            def fb3():
+                xg.grad = None
+                layer.zero_grad(set_to_none=True)
+                layer(xg, ei3).backward(g3)
+            ms_b = timed_grad(fb3, 5, 2)
+            e3 = int(ei3.shape[1])
+            out[f"cfg3_delaunay_{lt}_F256_bf16"] = {"cells": n3, "edges": e3, "forward_ms": ms_f, "fwd_bwd_ms": ms_b,
+                                                    "fwd_edges_per_sec": e3 / (ms_f * 1e-3)}
+            del layer, x3, xg, g3
+    except Exception as e:
+        out["cfg3_delaunay"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
     return out
 
 

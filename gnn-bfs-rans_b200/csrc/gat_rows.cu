@@ -116,7 +116,13 @@ struct GatzArgs {
   RowSched ord;
 };
 
-template <int VPL> struct GatzCfg { static constexpr int BU = (VPL == 1) ? 8 : 4; };   // gathered rows in flight per warp
+#ifndef B2G_GATZ_BU
+#define B2G_GATZ_BU 8
+#endif
+#ifndef B2G_GATZ_MINB
+#define B2G_GATZ_MINB 2
+#endif
+template <int VPL> struct GatzCfg { static constexpr int BU = (VPL == 1) ? B2G_GATZ_BU : 4; };   // gathered rows in flight per warp
 
 // acc[h] += w[h](entry off+u) * row(entry off+u) for u < BU (default: a full batch; entries past the row's end carry
 // weight 0 and re-read the row's last entry)
@@ -226,7 +232,7 @@ __device__ __noinline__ void gatz_fwd_long(const GatzArgs a, uint32_t i, int b, 
 }
 
 template <typename T, int VPL>
-__global__ void __launch_bounds__(256, 2) gatz_fwd_kernel(const GatzArgs a) {
+__global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_fwd_kernel(const GatzArgs a) {
   constexpr int VN = Vec<T>::N;
   constexpr int BU = GatzCfg<VPL>::BU;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
@@ -683,7 +689,7 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
 // Row j of the TRANSPOSED CSR: entries (i = col[t], p = perm[t] = the edge's position in the target-major CSR).
 //   y_j[h] = sum_t alpha_e[p, h] * g_i,   d a_src[j, h] = sum_t de_e[p, h]
 template <typename T, int VPL>
-__global__ void __launch_bounds__(256, 2) gatz_bwd_src_kernel(const GatzArgs a) {
+__global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_bwd_src_kernel(const GatzArgs a) {
   constexpr int VN = Vec<T>::N;
   constexpr int BU = GatzCfg<VPL>::BU;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
