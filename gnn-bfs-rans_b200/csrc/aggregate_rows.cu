@@ -59,7 +59,7 @@ struct RowsCfg {
 #define B2G_ROWS_MINB 4
 #endif
 template <int VPL, bool kW>
-constexpr int rows_minb() { return (VPL == 1) ? (kW ? 3 : B2G_ROWS_MINB) : 2; }   // CTAs per SM the register budget is planned for
+constexpr int rows_minb() { return (VPL == 1) ? (kW ? 3 : B2G_ROWS_MINB) : 2; }   // kW at 4 CTAs/SM measured slower (3.69 vs 3.35 ms)   // CTAs per SM the register budget is planned for
 
 template <typename T, int VPL, bool kEpi>
 __device__ __forceinline__ void rows_store(const RowsArgs& a, float (&acc)[VPL][Vec<T>::N], uint32_t i, int lane) {
@@ -157,26 +157,30 @@ __device__ __noinline__ void rows_long(const RowsArgs a, uint32_t i, int b, int 
 }
 
 // K entries held one per lane in (cl, wl): K loads, then the K adds / FMAs.
-template <typename T, int VPL, bool kW, int K>
+// `wfn` turns the lane's loaded scale into its entry weight; it runs AFTER the K row loads have been issued: the issue
+// stream is in order, and arithmetic on a just-requested col_scale value ahead of the gathers would hold them back for a
+// full memory latency (measured on the weighted GCN-backward variant: 3.43 ms against 2.64 ms unweighted).
+template <typename T, int VPL, bool kW, int K, typename WFn>
 __device__ __forceinline__ void rows_batch(float (&acc)[VPL][Vec<T>::N], const char* xb, uint32_t xrow_bytes, int cl,
-                                           float wl) {
+                                           WFn&& wfn) {
   uint4 buf[K][VPL];
-  float w[K];
 #pragma unroll
   for (int u = 0; u < K; ++u) {
     const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, u);
-    if (kW) w[u] = __shfl_sync(0xffffffffu, wl, u);
     const char* p = xb + (uint64_t)c * xrow_bytes;             // one IMAD.WIDE.U32
 #pragma unroll
     for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_row16(p + 512 * v);
   }
+  const float wl = kW ? wfn() : 1.0f;
 #pragma unroll
-  for (int u = 0; u < K; ++u)
+  for (int u = 0; u < K; ++u) {
+    const float w = kW ? __shfl_sync(0xffffffffu, wl, u) : 1.0f;
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-      if (kW) fma_row16<T>(acc[v], w[u], buf[u][v]);
+      if (kW) fma_row16<T>(acc[v], w, buf[u][v]);
       else add_row16(acc[v], buf[u][v], T());
     }
+  }
 }
 
 template <typename T, int VPL, bool kW, bool kSelf, bool kRS, bool kEpi>
@@ -187,6 +191,9 @@ __global__ void __launch_bounds__(256, (rows_minb<VPL, kW>())) seg_rows_kernel(c
   constexpr int NS = kSelf ? 1 : 0;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  // opaque to the optimiser: otherwise nvcc re-derives base + lane * 16 per neighbour (IMAD.WIDE + IADD3 + IADD3.X instead
+  // of ONE IMAD.WIDE.U32 with the per-lane base as the 64-bit addend)
+  asm volatile("" : "+l"(xb));
   const int32_t* __restrict__ rowptr = a.rowptr;
   const int32_t* __restrict__ col = a.col;
 
@@ -239,20 +246,20 @@ __global__ void __launch_bounds__(256, (rows_minb<VPL, kW>())) seg_rows_kernel(c
     if (len > BU) {
       rows_long<T, VPL, kW, kSelf, kRS, kEpi>(a, i, b, e);
     } else {
-      float rs = 1.0f, wl = 1.0f;
+      float rs = 1.0f, csv = 1.0f;
       if ((kW || kRS) && a.row_scale) rs = __ldg(a.row_scale + i);
-      if (kW) {
+      if (kW && a.col_scale) csv = __ldg(a.col_scale + cl);        // cl is a valid (clamped) index on every lane
+      auto wfn = [&]() -> float {
         const int t = lane - NS;
-        wl = (t < 0) ? a.self_coef : 0.f;
-        if (t >= 0 && t < e - b) wl = (a.col_scale ? __ldg(a.col_scale + cl) : 1.0f) * rs;
-      }
+        return (t < 0) ? a.self_coef : ((t < e - b) ? csv * rs : 0.f);
+      };
       float acc[VPL][VN];
 #pragma unroll
       for (int v = 0; v < VPL; ++v)
 #pragma unroll
         for (int k = 0; k < VN; ++k) acc[v][k] = 0.f;
       switch (len) {
-#define B2G_CASE(KK) case KK: rows_batch<T, VPL, kW, KK>(acc, xb, a.xrow_bytes, cl, wl); break;
+#define B2G_CASE(KK) case KK: rows_batch<T, VPL, kW, KK>(acc, xb, a.xrow_bytes, cl, wfn); break;
         B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4)
         B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
 #undef B2G_CASE

@@ -175,6 +175,7 @@ __device__ __noinline__ void gatz_fwd_long(const GatzArgs a, uint32_t i, int b, 
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  asm volatile("" : "+l"(xb));     // keep the per-lane base in a register pair: one IMAD.WIDE.U32 per gathered row
   const float4 ad4 = ldg_f4(a.a + (uint64_t)i * a.lda + GH);
   const float ad[GH] = {ad4.x, ad4.y, ad4.z, ad4.w};
   float m[GH], zs[GH];
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_fwd_kernel(const Gatz
   constexpr int BU = GatzCfg<VPL>::BU;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  asm volatile("" : "+l"(xb));     // keep the per-lane base in a register pair: one IMAD.WIDE.U32 per gathered row
   WarpRows r;
   if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
   int cl = window_entry(a.col, r.b, r.e, lane);
@@ -309,9 +311,11 @@ __global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_fwd_kernel(const Gatz
 // d alpha for the entries [off, off + 8) of the window held one per lane: gather 8 rows (2 x 4 when BU = 4), dot each
 // with the row's dz (4 heads), reduce the 32 partials across the warp with ONE transposed reduction (31 shuffles),
 // hand entry (off + u)'s four values to lane off + u.
-template <typename T, int VPL>
+// `mid` runs once, after the first rows have been requested: whatever has to be done to the row's own just-loaded data
+// (unpacking dz / u) must not sit in the in-order issue stream ahead of the gathers.
+template <typename T, int VPL, typename Mid>
 __device__ __forceinline__ void gatz_dalpha8(float (&dal)[GH], const float (&dzf)[GH][VPL][Vec<T>::N], const char* xb,
-                                             uint32_t xrow_bytes, int cl, int off, int lane) {
+                                             uint32_t xrow_bytes, int cl, int off, int lane, Mid&& mid) {
   constexpr int VN = Vec<T>::N;
   constexpr int BU = GatzCfg<VPL>::BU;
   float part[32];
@@ -325,6 +329,7 @@ __device__ __forceinline__ void gatz_dalpha8(float (&dal)[GH], const float (&dzf
 #pragma unroll
       for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_row16(p + 512 * v);
     }
+    if (s0 == 0) mid();
 #pragma unroll
     for (int u = 0; u < BU; ++u) {
       float p0[GH], p1[GH];
@@ -357,29 +362,31 @@ __device__ __forceinline__ void gatz_dalpha8(float (&dal)[GH], const float (&dzf
 // kT = false: GATConv (alpha recomputed from a_src / a_dst and the saved statistics; LeakyReLU in front of the softmax).
 // kT = true : TransformerConv (alpha read back from the forward pass; `ad` carries d s_alpha, the gradient of the
 //             per-head weight sums that multiply the value bias; the logits enter the softmax directly: sraw = 1).
-template <typename T, int VPL, bool kT>
+template <typename T, int VPL, bool kT, typename First>
 __device__ __forceinline__ void gatz_bwd_window(const GatzArgs& a, const float (&dzf)[GH][VPL][Vec<T>::N], const char* xb,
                                                 int cl, int p0, int n, int lane, const float (&ad)[GH],
                                                 const float (&sm)[GH], const float (&rinv)[GH], float (&alpha)[GH],
-                                                float (&dal)[GH], float (&sraw)[GH], float (&mask)[GH]) {
-  if (kT) {
-    const float4 al4 = ldg_f4(a.alpha_in + (uint64_t)max(min(p0 + lane, p0 + n - 1), 0) * GH);
-    const float al[GH] = {al4.x, al4.y, al4.z, al4.w};
+                                                float (&dal)[GH], float (&sraw)[GH], float (&mask)[GH], First&& first) {
+  // requests first (nothing below may consume them before the gathers of gatz_dalpha8 are in flight)
+  const float4 in4 = kT ? ldg_f4(a.alpha_in + (uint64_t)max(min(p0 + lane, p0 + n - 1), 0) * GH)
+                        : ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
 #pragma unroll
-    for (int h = 0; h < GH; ++h) { sraw[h] = 1.0f; alpha[h] = lane < n ? al[h] : 0.f; }
-  } else {
-    const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
-    const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+  for (int h = 0; h < GH; ++h) dal[h] = 0.f;
+  gatz_dalpha8<T, VPL>(dal, dzf, xb, a.xrow_bytes, cl, 0, lane, first);
+  for (int j = 8; j < n; j += 8) gatz_dalpha8<T, VPL>(dal, dzf, xb, a.xrow_bytes, cl, j, lane, []() {});
+  const float in[GH] = {in4.x, in4.y, in4.z, in4.w};
 #pragma unroll
-    for (int h = 0; h < GH; ++h) {
-      sraw[h] = as[h] + ad[h];
+  for (int h = 0; h < GH; ++h) {
+    if (kT) {
+      sraw[h] = 1.0f;
+      alpha[h] = lane < n ? in[h] : 0.f;
+    } else {
+      sraw[h] = in[h] + ad[h];
       alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
     }
+    mask[h] = 1.0f;
   }
-#pragma unroll
-  for (int h = 0; h < GH; ++h) { mask[h] = 1.0f; dal[h] = 0.f; }
   if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, mask);
-  for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(dal, dzf, xb, a.xrow_bytes, cl, j, lane);
 #pragma unroll
   for (int h = 0; h < GH; ++h) dal[h] = (dal[h] + (kT ? ad[h] : 0.f)) * mask[h];   // d(alpha) of the pre-dropout probability
 }
@@ -402,18 +409,30 @@ __device__ __forceinline__ void gatz_bwd_row_inputs(const GatzArgs& a, uint32_t 
   }
 }
 
-template <typename T, int VPL>
-__device__ __forceinline__ void gatz_load_dz(const GatzArgs& a, uint32_t i, int lane, float (&dzf)[GH][VPL][Vec<T>::N]) {
+// the row's own H*F-wide vector (dz_i, or u_i in the TransformerConv forward): requested raw, unpacked later
+template <int VPL>
+__device__ __forceinline__ void gatz_load_dz_raw(const GatzArgs& a, uint32_t i, int lane, uint4 (&raw)[GH][VPL]) {
   const char* dzr = reinterpret_cast<const char*>(a.dz) + (uint64_t)i * a.dzrow_bytes + lane * 16;
 #pragma unroll
   for (int h = 0; h < GH; ++h)
 #pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-      uint4 u;
+    for (int v = 0; v < VPL; ++v)
       asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(dzr + (h * VPL + v) * 512));
-      unpack_row16(u, dzf[h][v], T());
-    }
+                   : "=r"(raw[h][v].x), "=r"(raw[h][v].y), "=r"(raw[h][v].z), "=r"(raw[h][v].w)
+                   : "l"(dzr + (h * VPL + v) * 512));
+}
+template <typename T, int VPL>
+__device__ __forceinline__ void gatz_unpack_dz(const uint4 (&raw)[GH][VPL], float (&dzf)[GH][VPL][Vec<T>::N]) {
+#pragma unroll
+  for (int h = 0; h < GH; ++h)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) unpack_row16(raw[h][v], dzf[h][v], T());
+}
+template <typename T, int VPL>
+__device__ __forceinline__ void gatz_load_dz(const GatzArgs& a, uint32_t i, int lane, float (&dzf)[GH][VPL][Vec<T>::N]) {
+  uint4 raw[GH][VPL];
+  gatz_load_dz_raw<VPL>(a, i, lane, raw);
+  gatz_unpack_dz<T, VPL>(raw, dzf);
 }
 
 template <typename T, int VPL>
@@ -439,6 +458,7 @@ __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  asm volatile("" : "+l"(xb));     // keep the per-lane base in a register pair: one IMAD.WIDE.U32 per gathered row
   float dzf[GH][VPL][VN];
   gatz_load_dz<T, VPL>(a, i, lane, dzf);
   float ad[GH], sm[GH], rinv[GH];
@@ -449,7 +469,7 @@ __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int
     const int n = min(32, e - p0);
     const int cl = window_entry(a.col, p0, e, lane);
     float alpha[GH], dal[GH], sraw[GH], mask[GH];
-    gatz_bwd_window<T, VPL, kT>(a, dzf, xb, cl, p0, n, lane, ad, sm, rinv, alpha, dal, sraw, mask);
+    gatz_bwd_window<T, VPL, kT>(a, dzf, xb, cl, p0, n, lane, ad, sm, rinv, alpha, dal, sraw, mask, []() {});
     if (lane < n) *reinterpret_cast<float4*>(a.de_e + (uint64_t)(p0 + lane) * GH) = make_float4(dal[0], dal[1], dal[2], dal[3]);
     float pr[GH];
 #pragma unroll
@@ -496,6 +516,7 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  asm volatile("" : "+l"(xb));     // keep the per-lane base in a register pair: one IMAD.WIDE.U32 per gathered row
   WarpRows r;
   if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
   int cl = window_entry(a.col, r.b, r.e, lane);
@@ -507,11 +528,19 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
       gatz_bwd_dst_long<T, VPL, kT>(a, r.i, r.b, r.e);
     } else {
       float dzf[GH][VPL][VN];
-      gatz_load_dz<T, VPL>(a, r.i, lane, dzf);
+      uint4 dzraw[GH][VPL];
+      gatz_load_dz_raw<VPL>(a, r.i, lane, dzraw);
       float ad[GH], sm[GH], rinv[GH];
-      gatz_bwd_row_inputs<T, kT>(a, r.i, GH * VPL * 512, ad, sm, rinv);
       float alpha[GH], dal[GH], sraw[GH], mask[GH];
-      gatz_bwd_window<T, VPL, kT>(a, dzf, xb, cl, r.b, len, lane, ad, sm, rinv, alpha, dal, sraw, mask);
+      if (len > 0) {
+        gatz_bwd_window<T, VPL, kT>(a, dzf, xb, cl, r.b, len, lane, ad, sm, rinv, alpha, dal, sraw, mask, [&]() {
+          gatz_unpack_dz<T, VPL>(dzraw, dzf);                     // after the first gathers are in flight
+          gatz_bwd_row_inputs<T, kT>(a, r.i, GH * VPL * 512, ad, sm, rinv);
+        });
+      } else {
+#pragma unroll
+        for (int h = 0; h < GH; ++h) { alpha[h] = 0.f; dal[h] = 0.f; sraw[h] = 1.f; mask[h] = 1.f; }
+      }
       float t[GH];
 #pragma unroll
       for (int h = 0; h < GH; ++h) t[h] = alpha[h] * dal[h];
@@ -565,6 +594,7 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  asm volatile("" : "+l"(xb));     // keep the per-lane base in a register pair: one IMAD.WIDE.U32 per gathered row
   float uf[GH][VPL][VN];
   gatz_load_dz<T, VPL>(a, i, lane, uf);
   float m[GH], zs[GH];
@@ -575,7 +605,7 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
     const int n = min(32, e - p0);
     const int cl = window_entry(a.col, p0, e, lane);
     float s[GH] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane);
+    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane, []() {});
 #pragma unroll
     for (int h = 0; h < GH; ++h) m[h] = fmaxf(m[h], warp_max_redux(lane < n ? s[h] : -INFINITY));
   }
@@ -583,7 +613,7 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
     const int n = min(32, e - p0);
     const int cl = window_entry(a.col, p0, e, lane);
     float s[GH] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane);
+    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane, []() {});
     float p[GH];
 #pragma unroll
     for (int h = 0; h < GH; ++h) p[h] = lane < n ? __expf(s[h] - m[h]) : 0.f;
@@ -605,7 +635,7 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
     const int n = min(32, e - p0);
     const int cl = window_entry(a.col, p0, e, lane);
     float s[GH] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane);
+    for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane, []() {});
     float w[GH];
 #pragma unroll
     for (int h = 0; h < GH; ++h) w[h] = lane < n ? __expf(s[h] - m[h]) * inv[h] : 0.f;
@@ -632,6 +662,7 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
   constexpr int BU = GatzCfg<VPL>::BU;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  asm volatile("" : "+l"(xb));     // keep the per-lane base in a register pair: one IMAD.WIDE.U32 per gathered row
   WarpRows r;
   if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
   int cl = window_entry(a.col, r.b, r.e, lane);
@@ -643,10 +674,12 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
       tz_fwd_long<T, VPL>(a, r.i, r.b, r.e);
     } else {
       float w[GH] = {0.f, 0.f, 0.f, 0.f}, ssum[GH] = {0.f, 0.f, 0.f, 0.f};
-      {                                       // logits: u_i (registers) . x_j, one entry per lane
+      if (len > 0) {                          // logits: u_i (registers) . x_j, one entry per lane
         float uf[GH][VPL][VN];
-        gatz_load_dz<T, VPL>(a, r.i, lane, uf);
-        for (int j = 0; j < len; j += 8) gatz_dalpha8<T, VPL>(w, uf, xb, a.xrow_bytes, cl, j, lane);
+        uint4 uraw[GH][VPL];
+        gatz_load_dz_raw<VPL>(a, r.i, lane, uraw);
+        gatz_dalpha8<T, VPL>(w, uf, xb, a.xrow_bytes, cl, 0, lane, [&]() { gatz_unpack_dz<T, VPL>(uraw, uf); });
+        for (int j = 8; j < len; j += 8) gatz_dalpha8<T, VPL>(w, uf, xb, a.xrow_bytes, cl, j, lane, []() {});
       }
       float zs[GH];
 #pragma unroll
@@ -694,6 +727,7 @@ __global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_bwd_src_kernel(const 
   constexpr int BU = GatzCfg<VPL>::BU;
   const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  asm volatile("" : "+l"(xb));     // keep the per-lane base in a register pair: one IMAD.WIDE.U32 per gathered row
   WarpRows r;
   if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
   // perm == NULL: the weights are already in this CSR's order (position = entry index)
@@ -721,13 +755,17 @@ __global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_bwd_src_kernel(const 
       const float4 al4 = ldg_f4(a.alpha_e + (uint64_t)(uint32_t)pl * GH);
       const float4 de4 = ldg_f4(a.de_e + (uint64_t)(uint32_t)pl * GH);
       const bool on = lane < n;
-      const float w[GH] = {on ? al4.x : 0.f, on ? al4.y : 0.f, on ? al4.z : 0.f, on ? al4.w : 0.f};
-      if (on) { das[0] += de4.x; das[1] += de4.y; das[2] += de4.z; das[3] += de4.w; }
+      float w[GH];
+      auto weights = [&]() {                  // after the row loads are issued (in-order issue: see aggregate_rows.cu rows_batch)
+        w[0] = on ? al4.x : 0.f; w[1] = on ? al4.y : 0.f; w[2] = on ? al4.z : 0.f; w[3] = on ? al4.w : 0.f;
+        if (on) { das[0] += de4.x; das[1] += de4.y; das[2] += de4.z; das[3] += de4.w; }
+      };
       if (n > BU) {
-        for (int j = 0; j < n; j += BU) gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, j, []() {});
+        gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, 0, weights);
+        for (int j = BU; j < n; j += BU) gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, j, []() {});
       } else {
         switch (n) {
-#define B2G_CASE(KK) case KK: if (KK <= BU) gatz_gather_fma<T, VPL, (KK <= BU ? KK : 1)>(acc, xb, a.xrow_bytes, cl, w, 0, []() {}); break;
+#define B2G_CASE(KK) case KK: if (KK <= BU) gatz_gather_fma<T, VPL, (KK <= BU ? KK : 1)>(acc, xb, a.xrow_bytes, cl, w, 0, weights); break;
           B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4) B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
 #undef B2G_CASE
           default: break;
@@ -766,6 +804,7 @@ __global__ void __launch_bounds__(256, 2) rowdot8_kernel(const RowdotArgs a) {
       for (int k = 0; k < VN; ++k) vr[m][v][k] = __ldg(a.V + (int64_t)m * a.ldv + (v * 32 + lane) * VN + k);
   const uint32_t warps = gridDim.x * 8u, w = blockIdx.x * 8u + (threadIdx.x >> 5);
   const char* xb = reinterpret_cast<const char*>(a.x) + lane * 16;
+  asm volatile("" : "+l"(xb));     // keep the per-lane base in a register pair: one IMAD.WIDE.U32 per gathered row
   for (uint32_t i0 = w * 4u; i0 < a.n_rows; i0 += warps * 4u) {
     uint4 buf[4][VPL];
 #pragma unroll

@@ -77,7 +77,7 @@ class Graph:
         # B2G_PANEL_ORDER=0 switches the hint off (linear sweep) for A/B runs.
         if os.environ.get("B2G_PANEL_ORDER", "1") == "0":
             return 0
-        return self.band_raw()
+        return self.band_owned()
 
     def band_raw(self) -> int:
         """max |source - target| (cached): rows [r0, r1) only read rows [r0 - band, r1 + band)."""
@@ -85,6 +85,20 @@ class Graph:
             ei = self.edge_index
             self._band = int((ei[0] - ei[1]).abs().max()) if ei.shape[1] else 0
         return self._band
+
+    def band_owned(self) -> int:
+        """The band over edges whose SOURCE is also a target-range node.  A partition's local graph numbers its ghost
+        nodes after the owned ones (`distributed.py`): their |source - target| is ~N and would hide the band structure
+        of the owned block from the row scheduler, although only a thin shell of rows reads ghosts."""
+        if not hasattr(self, "_band_owned"):
+            ei = self.edge_index
+            if ei.shape[1] == 0:
+                self._band_owned = 0
+            else:
+                n_tgt = ei[1].max() + 1
+                d = (ei[0] - ei[1]).abs()
+                self._band_owned = int(torch.where(ei[0] < n_tgt, d, torch.zeros_like(d)).max())
+        return self._band_owned
 
     def dinv(self) -> torch.Tensor:
         """GCN deg^-1/2 over the self-loop-replaced list (in-degree by target)."""
