@@ -108,3 +108,30 @@ def test_short_training_run_reduces_loss():
             opt.step()
             losses.append(float(loss))
         assert losses[-1] < 0.5 * losses[0], (lt, losses[0], losses[-1])
+
+
+@pytest.mark.parametrize("layer_type", ["GCN", "GAT", "GIN", "Transformer"])
+def test_cuda_graph_forward_equals_eager(layer_type):
+    """graphs.GraphedForward replays the eval forward of the static-mesh model from one CUDA graph: bit-identical to the
+    eager call, also for new inputs copied into the captured buffer."""
+    import gnn_bfs_rans_b200 as b2g
+    from gnn_bfs_rans_b200.flow_model import FlowGNN
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    from gnn_bfs_rans_b200 import ops
+    nx, ny, nz = 16, 12, 10
+    N = nx * ny * nz
+    o, n = hex_mesh_faces(nx, ny, nz, device='cuda')
+    ei = ops.build_graph_edges(o, n, 1, None, N, N)
+    torch.manual_seed(0)
+    model = FlowGNN(3, 128, 7, 3, layer_type, dropout=0.1).cuda().eval()
+    x0 = torch.rand(N, 3, device='cuda')
+    gf = b2g.graphs.GraphedForward(model, x0, ei)
+    for seed in (1, 2):
+        x = torch.rand(N, 3, device='cuda', generator=torch.Generator(device='cuda').manual_seed(seed))
+        with torch.no_grad():
+            ref = model(x, ei)
+        assert torch.equal(gf(x), ref)
+    with pytest.raises(ValueError):
+        gf(torch.rand(N + 1, 3, device='cuda'))
+    with pytest.raises(RuntimeError):
+        b2g.graphs.GraphedForward(model.train(), x0, ei)
