@@ -188,7 +188,10 @@ class GATZFn(torch.autograd.Function):
         z, smax, ssum = ops.gatz_fwd(x, a, H, slope, csr.rowptr, csr.col, p_drop, seed, need_grad, band=graph.band())
         out, _ = ops.linear_fwd(z, wc, bias.float() if bias is not None else None)
         if need_grad:
-            ctx.save_for_backward(x, wc, v, z, a, smax, ssum)
+            # B2G_RECOMPUTE=1: do not keep z [N, H*F] (25.6 GB per layer at 12.5 M cells, cfg5) for the weight gradient;
+            # the backward pass re-runs the aggregation (same seed -> same dropout mask -> same bits)
+            recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"
+            ctx.save_for_backward(x, wc, v, None if recompute else z, a, smax, ssum)
             ctx.cfg = (graph, H, slope, p_drop, seed, bias is not None)
             ctx.ei_keepalive = graph.edge_index
         return out
@@ -201,6 +204,8 @@ class GATZFn(torch.autograd.Function):
         C = wc.shape[0]
         g = g.contiguous()
         csr, csr_t, perm = graph.csr("sl", False), graph.csr("sl", True), graph.perm("sl")
+        if z is None and ctx.needs_input_grad[1]:
+            z, _, _ = ops.gatz_fwd(x, a, H, slope, csr.rowptr, csr.col, p_drop, seed, False, band=graph.band())
         gwc = gv = gx = None
         if ctx.needs_input_grad[1]:
             dw, _ = ops.linear_wgrad(g, z, want_bias=False)                 # dWc = g^T z  [C, H*F]
@@ -343,7 +348,8 @@ class TConvZFn(torch.autograd.Function):
         del u
         out, _ = ops.linear_fwd(z_aug, w_out, b_out)
         if need_grad:
-            ctx.save_for_backward(x, mq, cq, w_out, z_aug, alpha)
+            recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"     # see GATZFn: z_aug is re-derived in backward
+            ctx.save_for_backward(x, mq, cq, w_out, None if recompute else z_aug, alpha)
             ctx.cfg = (graph, H, p_drop, seed, b_out is not None)
             ctx.ei_keepalive = graph.edge_index
         return out
@@ -358,6 +364,10 @@ class TConvZFn(torch.autograd.Function):
         g = g.contiguous()
         csr, csr_t, perm = graph.csr("raw", False), graph.csr("raw", True), graph.perm("raw")
         band = graph.band()
+        if z_aug is None and ctx.needs_input_grad[3]:
+            u, _ = ops.linear_fwd(x, mq, cq)
+            z_aug, _ = ops.tz_fwd(x, u, H, csr.rowptr, csr.col, p_drop, seed, False, band=band)
+            del u
         gw_out = None
         if ctx.needs_input_grad[3]:
             dw, _ = ops.linear_wgrad(g, z_aug, want_bias=False)               # d W_out = g^T z_aug  [C, H*F + 8 + F]

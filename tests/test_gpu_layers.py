@@ -220,3 +220,22 @@ def test_state_dict_compat_and_errors():
     with pytest.warns(UserWarning):
         a = t(x, ei, edge_attr=torch.randn(40, 4, device='cuda'))  # reference call shape (gnn_model.py:170)
     assert torch.equal(a, t(x, ei))
+
+
+@pytest.mark.parametrize("kind", ["GAT", "Transformer"])
+def test_recompute_mode_gives_identical_gradients(kind, monkeypatch):
+    """B2G_RECOMPUTE=1 drops the [N, H*F] aggregate from the saved tensors and re-derives it in backward (same Philox
+    seed -> same dropout mask): every gradient is bit-identical to the keep-everything mode."""
+    ei = multigraph(1500, 9000, 11).cuda()
+    grads = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("B2G_RECOMPUTE", mode)
+        m = make_layer(kind, 128, 128, torch.float32).train()          # dropout 0.1 active
+        torch.manual_seed(5)
+        x = torch.randn(1500, 128, device='cuda', requires_grad=True)
+        torch.manual_seed(99)                                          # same attention-dropout seeds in both runs (torch CPU generator)
+        out = m(x, ei)
+        out.square().mean().backward()
+        grads[mode] = [x.grad.clone()] + [p.grad.clone() for p in m.parameters()]
+    for a, b in zip(grads["0"], grads["1"]):
+        assert torch.equal(a, b)
