@@ -285,9 +285,7 @@ int bulk_seg_sum(int, const void*, int64_t, const void*, int64_t, void*, int64_t
 int rows_seg_sum(const void*, int64_t, void*, int64_t, int64_t, int, int, const int32_t*, const int32_t*, const float*,
                  const float*, float, const float*, int, int64_t, int64_t, cudaStream_t);
 int rows_set_sched(int chunk_rows, int panel_rows);
-int64_t g_maxlen_hint = 0;
 int g_seg_impl = 0;   // 0 = auto, 1 = register gather (LDG), 2 = cp.async.bulk ring, 3 = cp.async (LDGSTS) ring
-int64_t g_band_hint = 0;
 }  // namespace b2g
 
 using namespace b2g;
@@ -299,16 +297,7 @@ static inline bool row_ok(const void* p, int64_t ld, int dt) {
 
 extern "C" {
 
-int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out, int64_t ldo, int64_t n_rows,
-                int F, int dt, const int32_t* rowptr, const int32_t* col, const float* row_scale,
-                const float* col_scale, float self_coef, const float* bias, int relu, void* stream);
-
 int b2g_set_seg_sched(int chunk_rows, int panel_rows) { return rows_set_sched(chunk_rows, panel_rows); }
-
-int b2g_seg_sum_hinted(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
-                       int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
-                       const int32_t* col, const float* row_scale, const float* col_scale,
-                       float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, void* stream);
 
 int b2g_set_seg_impl(int impl) {
   if (impl < 0 || impl > 3) return B2G_E_ARG;
@@ -316,31 +305,10 @@ int b2g_set_seg_impl(int impl) {
   return B2G_OK;
 }
 
-int b2g_seg_sum_banded(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
-                       int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
-                       const int32_t* col, const float* row_scale, const float* col_scale,
-                       float self_coef, const float* bias, int relu, int64_t band, void* stream) {
-  return b2g_seg_sum_hinted(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale, self_coef,
-                            bias, relu, band, 0, stream);
-}
-
-int b2g_seg_sum_hinted(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
-                       int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
-                       const int32_t* col, const float* row_scale, const float* col_scale,
-                       float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, void* stream) {
-  g_band_hint = band > 0 ? band : 0;
-  g_maxlen_hint = max_row_len > 0 ? max_row_len : 0;
-  const int rc = b2g_seg_sum(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale,
-                             self_coef, bias, relu, stream);
-  g_band_hint = 0;
-  g_maxlen_hint = 0;
-  return rc;
-}
-
-int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
-                int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
-                const int32_t* col, const float* row_scale, const float* col_scale,
-                float self_coef, const float* bias, int relu, void* stream) {
+static int seg_sum_impl(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out, int64_t ldo, int64_t n_rows,
+                        int F, int dt, const int32_t* rowptr, const int32_t* col, const float* row_scale,
+                        const float* col_scale, float self_coef, const float* bias, int relu, int64_t band,
+                        int64_t max_row_len, void* stream) {
   if (n_rows < 0 || F <= 0 || (dt != B2G_F32 && dt != B2G_BF16)) return B2G_E_ARG;
   if (n_rows == 0) return B2G_OK;
   if (!x || !out || !rowptr) return B2G_E_ARG;
@@ -356,12 +324,36 @@ int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, vo
   // rows of whole 512-byte multiples (F = 256 bf16, F = 128/256 fp32, ...): warp-per-row fast path (aggregate_rows.cu)
   if (g_seg_impl != 1 && !x_self) {
     const int rc = rows_seg_sum(x, ldx, out, ldo, n_rows, nvec, dt, rowptr, col, row_scale, col_scale, self_coef, bias, relu,
-                                g_band_hint, g_maxlen_hint, st);
+                                band > 0 ? band : 0, max_row_len > 0 ? max_row_len : 0, st);
     if (rc != B2G_E_UNSUPPORTED) return rc;
   }
   if (dt == B2G_F32)
     return dispatch_seg_sum<float>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);
   return dispatch_seg_sum<__nv_bfloat16>(nvec, x, ldx, x_self, ldxs, out, ldo, n_rows, rowptr, col, row_scale, col_scale, self_coef, bias, relu, st);
+}
+
+int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                const int32_t* col, const float* row_scale, const float* col_scale,
+                float self_coef, const float* bias, int relu, void* stream) {
+  return seg_sum_impl(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale, self_coef, bias, relu,
+                      0, 0, stream);
+}
+
+int b2g_seg_sum_banded(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                       int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                       const int32_t* col, const float* row_scale, const float* col_scale,
+                       float self_coef, const float* bias, int relu, int64_t band, void* stream) {
+  return seg_sum_impl(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale, self_coef, bias, relu,
+                      band, 0, stream);
+}
+
+int b2g_seg_sum_hinted(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                       int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                       const int32_t* col, const float* row_scale, const float* col_scale,
+                       float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, void* stream) {
+  return seg_sum_impl(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale, self_coef, bias, relu,
+                      band, max_row_len, stream);
 }
 
 int64_t b2g_colsum_workspace_bytes(int F) { return F > 0 ? (int64_t)COLSUM_BLOCKS * F * 4 : B2G_E_ARG; }
