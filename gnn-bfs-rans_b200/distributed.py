@@ -269,3 +269,27 @@ def allreduce_gradients(params, world: int):
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+def flow_forward_partitioned(model, x_owned: torch.Tensor, part: Partition, group=True) -> torch.Tensor:
+    """`FlowGNN.forward` (gnn_model.py:159-197) for ONE rank's share of a partitioned mesh: per layer a differentiable
+    halo exchange of the layer input (HaloFn), the layer on the local graph, and residual + BatchNorm + ReLU + dropout
+    on the owned rows with the BatchNorm statistics combined over all ranks (csrc/bn.cu + all_gather / all_reduce of
+    [C]-sized vectors).  Output rows = the owned cells.  With the loss normalised by GLOBAL counts and
+    `allreduce_gradients` afterwards, a step equals the single-process step on the whole mesh (tested on 2 GPUs)."""
+    from . import functional as Fn
+    from . import ops
+    part.prepare_graph()
+    h = model.input_proj(x_owned)
+    for i, layer in enumerate(model.gnn_layers):
+        hf = HaloFn.apply(h, part)
+        h_new = layer(hf, part.edge_index)[:part.n_owned]
+        if model.use_batch_norm and ops.bn_supported(h):
+            h = Fn.batch_norm(h, h_new, model.batch_norms[i].module, relu=True, p_drop=model.dropout.p,
+                              group=group if part.world > 1 else None)
+        else:
+            h = h + h_new
+            if model.use_batch_norm:
+                raise RuntimeError("b2g: partitioned BatchNorm needs a CUDA [N, C] input with 16-byte-multiple rows")
+            h = model.dropout(torch.relu(h))
+    return model.output_proj(h)

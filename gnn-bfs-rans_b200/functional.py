@@ -283,8 +283,9 @@ class BatchNormFn(torch.autograd.Function):
     residual add / ReLU / dropout (gnn_model.py:184-192)."""
 
     @staticmethod
-    def forward(ctx, x, r, weight, bias, mean, rstd, relu: bool, p_drop: float, training: bool):
+    def forward(ctx, x, r, weight, bias, mean, rstd, relu: bool, p_drop: float, training: bool, reduce_sums=None):
         need_grad = any(t is not None and t.requires_grad for t in (x, r, weight, bias))
+        ctx.reduce_sums = reduce_sums
         seed = _next_seed() if p_drop > 0 else 0
         gamma = weight.float().contiguous() if weight is not None else None
         beta = bias.float().contiguous() if bias is not None else None
@@ -299,22 +300,48 @@ class BatchNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         s, y, mean, rstd, gamma = ctx.saved_tensors
         relu, drop_scale, training, has_r, has_w, has_b = ctx.cfg
-        ds, sums = ops.bn_bwd(dy.contiguous(), y, s, mean, rstd, gamma, relu, drop_scale, training)
-        gw = sums[1] if (has_w and ctx.needs_input_grad[2]) else None
+        ds, sums = ops.bn_bwd(dy.contiguous(), y, s, mean, rstd, gamma, relu, drop_scale, training,
+                              reduce_sums=ctx.reduce_sums)
+        gw = sums[1] if (has_w and ctx.needs_input_grad[2]) else None      # this process's share (all-reduced with the rest)
         gb = sums[0] if (has_b and ctx.needs_input_grad[3]) else None
-        return ds, (ds if has_r else None), gw, gb, None, None, None, None, None
+        return ds, (ds if has_r else None), gw, gb, None, None, None, None, None, None
 
 
-def batch_norm(x, r, bn: "torch.nn.BatchNorm1d", relu: bool = False, p_drop: float = 0.0):
+def batch_norm(x, r, bn: "torch.nn.BatchNorm1d", relu: bool = False, p_drop: float = 0.0, group=None):
     """BatchNorm1d semantics (batch statistics + running-stat update in training, running statistics in eval) on the
-    library's kernels; `bn` is the torch module that owns weight / bias / running_* (torch_geometric.nn.BatchNorm.module)."""
+    library's kernels; `bn` is the torch module that owns weight / bias / running_* (torch_geometric.nn.BatchNorm.module).
+    `group` (a torch.distributed process group, or True for the default one): the rows of x are one rank's share of the
+    batch; statistics and the backward column sums are combined over the group so that the result equals the
+    single-process BatchNorm over all rows."""
+    import torch.distributed as dist
+    sync = group is not None and dist.is_initialized() and dist.get_world_size(None if group is True else group) > 1
+    pg = None if group is True else group
     training = bn.training or (bn.running_mean is None and bn.running_var is None)
+    reduce_sums = None
+    n = x.shape[0]
     if training:
         stats = ops.bn_stats(x.detach(), r.detach() if r is not None else None, bn.eps)
-        mean, rstd = stats[0], stats[1]
+        if sync:                                    # Chan et al. parallel mean / variance over the ranks' (n, mean, var)
+            C = x.shape[1]
+            loc = torch.cat([stats[0], stats[2], stats.new_full((1,), float(n))])
+            allv = [torch.empty_like(loc) for _ in range(dist.get_world_size(pg))]
+            dist.all_gather(allv, loc, group=pg)
+            allv = torch.stack(allv).double()
+            cnt = allv[:, 2 * C]
+            n_tot = cnt.sum()
+            mean_g = (allv[:, :C] * cnt[:, None]).sum(0) / n_tot
+            var_g = ((allv[:, C:2 * C] + (allv[:, :C] - mean_g) ** 2) * cnt[:, None]).sum(0) / n_tot
+            stats = torch.stack([mean_g.float(), torch.rsqrt(var_g + bn.eps).float(), var_g.float()])
+            n = int(n_tot.item())
+            n_glob = n
+
+            def reduce_sums(sums, n_local):
+                t = sums.clone()
+                dist.all_reduce(t, group=pg)
+                return t * (float(n_local) / float(n_glob))       # the kernel divides by its own row count
+        mean, rstd = stats[0].contiguous(), stats[1].contiguous()
         if bn.training and bn.track_running_stats and bn.running_mean is not None:
             with torch.no_grad():
-                n = x.shape[0]
                 if bn.num_batches_tracked is not None:
                     bn.num_batches_tracked += 1
                 f = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
@@ -327,7 +354,7 @@ def batch_norm(x, r, bn: "torch.nn.BatchNorm1d", relu: bool = False, p_drop: flo
     p = p_drop if bn.training else 0.0
     w = bn.weight if bn.affine else None
     b = bn.bias if bn.affine else None
-    out = BatchNormFn.apply(x, r, w, b, mean, rstd, relu, p, training)
+    out = BatchNormFn.apply(x, r, w, b, mean, rstd, relu, p, training, reduce_sums)
     return out if w is None else _cast_like(out, x)
 
 

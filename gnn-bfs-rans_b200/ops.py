@@ -452,8 +452,10 @@ def bn_apply(x, r, mean, rstd, gamma, beta, relu: bool, p_drop: float, seed: int
     return y, s
 
 
-def bn_bwd(dy, y, s, mean, rstd, gamma, relu: bool, drop_scale: float, training: bool):
-    """-> (ds [N,C], sums fp32 [2,C] = (sum dz, sum dz * xhat))."""
+def bn_bwd(dy, y, s, mean, rstd, gamma, relu: bool, drop_scale: float, training: bool, reduce_sums=None):
+    """-> (ds [N,C], sums fp32 [2,C] = (sum dz, sum dz * xhat) over THIS process's rows).
+    `reduce_sums(sums, n_local) -> sums'` (optional) maps the local column sums to what the elementwise pass should use
+    (multi-GPU BatchNorm: all-reduce, rescaled so that sums' / n_local == global sums / global N)."""
     lib = _lib.load()
     dy, s = _rows(dy), _rows(s)
     y = _rows(y) if y is not None else None
@@ -463,8 +465,9 @@ def bn_bwd(dy, y, s, mean, rstd, gamma, relu: bool, drop_scale: float, training:
     st = _stream()
     _lib.check(lib.b2g_bn_bwd_stats(_p(dy), _ld(dy), _p(y), _ld(y) if y is not None else 0, _p(s), _ld(s), N, C, _dt(s),
                                     _p(mean), _p(rstd), int(relu), float(drop_scale), _p(sums), _p(ws), st), "bn_bwd_stats")
+    used = reduce_sums(sums, N).contiguous() if reduce_sums is not None else sums
     ds = torch.empty((N, C), dtype=s.dtype, device=s.device)
     _lib.check(lib.b2g_bn_bwd_apply(_p(dy), _ld(dy), _p(y), _ld(y) if y is not None else 0, _p(s), _ld(s), _p(ds), _ld(ds),
-                                    N, C, _dt(s), _p(mean), _p(rstd), _p(gamma), _p(sums), int(relu), float(drop_scale),
-                                    int(training), st), "bn_bwd_apply")
+                                    N, C, _dt(s), _p(mean), _p(rstd), _p(gamma), _p(used), int(relu), float(drop_scale),
+                                    int(training), _stream()), "bn_bwd_apply")
     return ds, sums

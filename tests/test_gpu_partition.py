@@ -134,3 +134,67 @@ def test_two_gpu_nccl_halo_forward_backward():
         p.join(timeout=60)
     for rank, e_out, e_gx, e_gw in res:
         assert e_out < 1e-5 and e_gx < 1e-5 and e_gw < 1e-5, res
+
+
+def _flow_worker(rank, world, port, q, layer_type):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from gnn_bfs_rans_b200 import ops
+        from gnn_bfs_rans_b200.distributed import slab_partition_hex, flow_forward_partitioned, allreduce_gradients
+        from gnn_bfs_rans_b200.flow_model import FlowGNN
+        from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+        dev = f"cuda:{rank}"
+        nx, ny, nz = 12, 10, 8
+        nb = nx * ny * nz
+        N = nb * world
+        part = slab_partition_hex(nx, ny, nz, world, rank, dev)
+        torch.manual_seed(0)
+        model = FlowGNN(3, 128, 7, 3, layer_type, dropout=0.0).to(dev).train()
+        ref_model = FlowGNN(3, 128, 7, 3, layer_type, dropout=0.0).to(dev).train()
+        ref_model.load_state_dict(model.state_dict())
+        torch.manual_seed(3)
+        x_all = torch.rand(N, 3, device=dev)
+        y_all = torch.rand(N, 7, device=dev)
+        sl = slice(rank * nb, (rank + 1) * nb)
+        out = flow_forward_partitioned(model, x_all[sl], part)
+        loss = (out - y_all[sl]).square().sum() / (N * 7)              # normalised by GLOBAL counts
+        loss.backward()
+        allreduce_gradients(list(model.parameters()), world)
+        # monolithic reference (whole mesh on this rank)
+        o, n = hex_mesh_faces(nx, ny, nz * world, device=dev)
+        ei = ops.build_graph_edges(o, n, 1, None, N, N)
+        ref = ref_model(x_all, ei)
+        ((ref - y_all).square().sum() / (N * 7)).backward()
+        e_out = rel(out.detach(), ref.detach()[sl])
+        e_g = 0.0
+        gmax = max(float(p.grad.abs().max()) for p in ref_model.parameters())
+        for (name, p), pr in zip(model.named_parameters(), ref_model.parameters()):
+            e_g = max(e_g, float((p.grad - pr.grad).abs().max()) / max(float(pr.grad.abs().max()), 5e-2 * gmax))
+        e_rm = max(rel(b, br) for (nm, b), br in zip(model.named_buffers(), ref_model.buffers()) if b.dtype.is_floating_point)
+        q.put((rank, e_out, e_g, e_rm))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+@pytest.mark.parametrize("layer_type", ["GCN", "GAT"])
+def test_two_gpu_partitioned_flowgnn_step_equals_monolithic(layer_type):
+    """Whole model on 2 ranks (halo exchange per layer, BatchNorm statistics combined over the ranks, loss normalised by
+    global counts, flat gradient all-reduce) == the single-process model on the whole mesh: outputs, every parameter
+    gradient and the BatchNorm running statistics."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_flow_worker, args=(r, 2, port, q, layer_type)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, e_out, e_g, e_rm in res:
+        assert e_out < 2e-5 and e_g < 2e-4 and e_rm < 1e-5, res
