@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--small", action="store_true", help="64^3 mesh: for ncu captures and CPU-side debugging")
     ap.add_argument("--no-extras", action="store_true", help="skip the per-layer-type / train-step extras")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--train-step", action="store_true",
+                    help="also time the partitioned FlowGNN train step (GAT L=6 F=256 bf16, cfg5 shape, weak scaling)")
+    ap.add_argument("--train-cells", type=int, default=2500000, help="cells per GPU for --train-step")
+    ap.add_argument("--train-checkpoint", action="store_true", help="re-run each layer block in backward (memory)")
     return ap.parse_args()
 
 
@@ -344,6 +348,51 @@ def main():
     if rank == 0 and world == 1 and not args.no_extras:
         extras = run_extras(b2g, ops, part, dev, timed)
 
+    # ---- opt-in: cfg5-shaped train step, partitioned (halo exchange per layer, synchronised BatchNorm, gradient all-reduce)
+    train_line = None
+    if args.train_step:
+        from gnn_bfs_rans_b200.distributed import flow_forward_partitioned, allreduce_gradients
+        from gnn_bfs_rans_b200.flow_model import FlowGNN
+        del x
+        torch.cuda.empty_cache()
+        nzs = max(2, args.train_cells // (nx * ny))
+        tpart = slab_partition_hex(nx, ny, nzs, world, rank, dev)
+        n_glob = tpart.n_owned * world
+        torch.manual_seed(0)
+        tmodel = FlowGNN(3, F, 7, 6, "GAT", dropout=0.1).to(dev).to(torch.bfloat16).train()
+        topt = torch.optim.Adam(tmodel.parameters(), lr=3e-4, weight_decay=1e-5)
+        txin = torch.rand(tpart.n_owned, 3, device=dev, dtype=torch.bfloat16)
+        ty = torch.rand(tpart.n_owned, 7, device=dev, dtype=torch.bfloat16)
+
+        def tstep():
+            topt.zero_grad(set_to_none=True)
+            o = flow_forward_partitioned(tmodel, txin, tpart, checkpoint_layers=args.train_checkpoint)
+            loss = (o - ty).float().square().sum() / (n_glob * 7)
+            loss.backward()
+            allreduce_gradients(list(tmodel.parameters()), world)
+            torch.nn.utils.clip_grad_norm_(tmodel.parameters(), 1.0)
+            topt.step()
+        for _ in range(2):
+            tstep()
+        barrier()
+        torch.cuda.reset_peak_memory_stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            tstep()
+        e1.record()
+        barrier()
+        tms = e0.elapsed_time(e1) / 3
+        if world > 1:
+            t = torch.tensor([tms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = float(t)
+        train_line = {"model": "FlowGNN GAT L=6 F=256 bf16 (cfg5 shape), fwd + loss + bwd + gradient all-reduce + clip + Adam",
+                      "cells_per_gpu": tpart.n_owned, "cells_total": n_glob, "ms_per_step": tms,
+                      "cells_per_sec": n_glob / (tms * 1e-3), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                      "recompute": os.environ.get("B2G_RECOMPUTE", "0"), "checkpoint_layers": bool(args.train_checkpoint)}
+        del tmodel, topt
+
     # ---- CPU baseline (rank 0, N=1, bounded sample)
     cb = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -361,6 +410,8 @@ def main():
                            "cache_policy": "inputs (>5 GB) larger than the 126 MB L2; CSR cached across steps in `value`"},
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
                 "gpu_launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cb, "extras": extras}
+        if train_line is not None:
+            line["train_step_partitioned"] = train_line
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

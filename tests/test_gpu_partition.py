@@ -136,7 +136,7 @@ def test_two_gpu_nccl_halo_forward_backward():
         assert e_out < 1e-5 and e_gx < 1e-5 and e_gw < 1e-5, res
 
 
-def _flow_worker(rank, world, port, q, layer_type):
+def _flow_worker(rank, world, port, q, layer_type, ckpt=False):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -160,7 +160,7 @@ def _flow_worker(rank, world, port, q, layer_type):
         x_all = torch.rand(N, 3, device=dev)
         y_all = torch.rand(N, 7, device=dev)
         sl = slice(rank * nb, (rank + 1) * nb)
-        out = flow_forward_partitioned(model, x_all[sl], part)
+        out = flow_forward_partitioned(model, x_all[sl], part, checkpoint_layers=ckpt)
         loss = (out - y_all[sl]).square().sum() / (N * 7)              # normalised by GLOBAL counts
         loss.backward()
         allreduce_gradients(list(model.parameters()), world)
@@ -181,8 +181,8 @@ def _flow_worker(rank, world, port, q, layer_type):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-@pytest.mark.parametrize("layer_type", ["GCN", "GAT"])
-def test_two_gpu_partitioned_flowgnn_step_equals_monolithic(layer_type):
+@pytest.mark.parametrize("layer_type,ckpt", [("GCN", False), ("GAT", False), ("GAT", True)])
+def test_two_gpu_partitioned_flowgnn_step_equals_monolithic(layer_type, ckpt):
     """Whole model on 2 ranks (halo exchange per layer, BatchNorm statistics combined over the ranks, loss normalised by
     global counts, flat gradient all-reduce) == the single-process model on the whole mesh: outputs, every parameter
     gradient and the BatchNorm running statistics."""
@@ -190,7 +190,7 @@ def test_two_gpu_partitioned_flowgnn_step_equals_monolithic(layer_type):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_flow_worker, args=(r, 2, port, q, layer_type)) for r in range(2)]
+    procs = [ctx.Process(target=_flow_worker, args=(r, 2, port, q, layer_type, ckpt)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(2)]
