@@ -301,47 +301,82 @@ def main():
             except Exception:
                 pass
 
-    # ---- e2e: host buffers in, host buffer out, CSR rebuilt each step (fresh edge_index tensor)
+    # ---- e2e: host buffers in, host buffer out, CSR rebuilt each step (fresh edge_index tensor), at N GPUs.
+    # N = 1: the public host-buffer entry with the copies pipelined against the kernels (streaming.py).
+    # N > 1: every rank moves its own share (pinned host -> device), rebuilds its local CSR (+ the ghost deg^-1/2
+    #        exchange), runs the layer with the halo exchange and copies its rows back; wall clock, max over ranks.
     e2e = None
-    if world == 1:
-        with torch.no_grad():
-            hx = x[:N].cpu().pin_memory()
-            hei = ei.cpu().pin_memory()
-            hout = torch.empty((N, F), dtype=dtype).pin_memory()
 
-            if args.layer == "GCN":     # public host-buffer entry: copies pipelined with the kernels (streaming.py)
+    def host_mem_ok(need_bytes):
+        try:
+            for ln in open("/proc/meminfo"):
+                if ln.startswith("MemAvailable:"):
+                    return int(ln.split()[1]) * 1024 > 1.5 * need_bytes
+        except Exception:
+            pass
+        return True
+
+    need = (N * F * (2 if args.dtype == "bf16" else 4) * 2 + ei.numel() * 8) * world
+    if not host_mem_ok(need):
+        e2e = {"value": None, "unit": "edges/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "note": f"skipped: {need / 1e9:.0f} GB of pinned host buffers would not fit this box's free memory"}
+    else:
+        with torch.no_grad():
+            hx = torch.empty((N, F), dtype=dtype, pin_memory=True)
+            hx.copy_(x[:N])
+            hei = torch.empty(tuple(ei.shape), dtype=torch.int64, pin_memory=True)
+            hei.copy_(ei)
+            hout = torch.empty((N, F), dtype=dtype, pin_memory=True)
+
+            if args.layer == "GCN":
                 def e2e_step():
-                    b2g.streaming.gcn_forward_host(layer, hx, hei, hout)
-                e2e_api = "gnn_bfs_rans_b200.streaming.gcn_forward_host(layer, x_host, edge_index_host, out_host)"
-            else:
+                    b2g.streaming.gcn_forward_host(layer, hx, hei, hout, partition=part if world > 1 else None)
+                e2e_api = ("gnn_bfs_rans_b200.streaming.gcn_forward_host(layer, x_host, edge_index_host, out_host"
+                           + (", partition=...) on every rank (one halo exchange of the projected boundary rows)" if world > 1 else ")"))
+                ei_keep = part.edge_index
+            elif world == 1:
                 def e2e_step():
                     dx = hx.to(dev, non_blocking=True)
                     dei = hei.to(dev, non_blocking=True)
                     o = layer(dx, dei)
                     hout.copy_(o, non_blocking=True)
                 e2e_api = "layer(x.to(dev), edge_index.to(dev)) -> pinned host copy"
+            else:
+                ei_keep = part.edge_index
+
+                def e2e_step():
+                    dx = hx.to(dev, non_blocking=True)
+                    dei = hei.to(dev, non_blocking=True)
+                    part.edge_index, part._dinv_ready = dei, False      # a fresh edge_index: local CSR + ghost dinv rebuilt
+                    o = part.wrap_forward(layer)(dx, dei)
+                    hout.copy_(o, non_blocking=True)
+                e2e_api = ("per rank: x.to(dev), edge_index.to(dev), Partition.wrap_forward(layer) (CSR rebuild, halo "
+                           "exchange over NCCL), pinned host copy of the owned rows")
 
             steps_e = max(3, min(args.steps, 5))
             for _ in range(2):
                 e2e_step()
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(steps_e):
                 e2e_step()
             e1.record()
-            torch.cuda.synchronize()
+            barrier()
             wall = (time.perf_counter() - t0) / steps_e
             ems = max(e0.elapsed_time(e1) / steps_e, wall * 1e3)
+            if world > 1:
+                t = torch.tensor([ems], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ems = float(t)
+                part.edge_index, part._dinv_ready = ei_keep, False
+                part.prepare_graph()
             e2e = {"value": e_total / (ems * 1e-3), "unit": "edges/s", "ms_per_step": ems,
-                   "h2d_bytes_per_step": hx.numel() * hx.element_size() + hei.numel() * 8,
-                   "d2h_bytes_per_step": hout.numel() * hout.element_size(), "steps": steps_e,
+                   "h2d_bytes_per_step": (hx.numel() * hx.element_size() + hei.numel() * 8) * world,
+                   "d2h_bytes_per_step": hout.numel() * hout.element_size() * world, "steps": steps_e,
                    "includes": "H2D x + edge_index, CSR rebuild, layer forward, D2H output", "api": e2e_api}
             del hx, hei, hout
-    else:
-        e2e = {"value": None, "unit": "edges/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
-               "note": "measured at N=1 only"}
 
     # ---- extras: other layer types / fp32 / fwd+bwd / FlowGNN train step (not the headline)
     extras = {}

@@ -42,9 +42,15 @@ def _pinned(t: torch.Tensor, what: str) -> torch.Tensor:
 
 @torch.no_grad()
 def gcn_forward_host(layer: GCNConv, x_host: torch.Tensor, edge_index_host: torch.Tensor,
-                     out_host: Optional[torch.Tensor] = None, rows_per_chunk: int = 1 << 19) -> torch.Tensor:
+                     out_host: Optional[torch.Tensor] = None, rows_per_chunk: int = 1 << 19,
+                     partition=None) -> torch.Tensor:
     """GCNConv.forward(x, edge_index) (gnn_model.py:63,166) for host-resident `x` [N,F] and `edge_index` [2,E]
-    (int64); returns the host tensor [N, out_channels] (pinned).  Inference only (no autograd graph)."""
+    (int64); returns the host tensor [N, out_channels] (pinned).  Inference only (no autograd graph).
+
+    partition (distributed.Partition, optional): `x_host` / the result hold this rank's OWNED rows and `edge_index_host`
+    is the rank's local edge list (ghost sources numbered after the owned rows).  The projected ghost rows are fetched
+    from their owners with ONE halo exchange after the last owned chunk is projected; only the row chunks that read a
+    ghost wait for it."""
     if not isinstance(layer, GCNConv):
         raise NotImplementedError("b2g.streaming: pipelined host forward exists for GCNConv; use layer(x.cuda(), ei.cuda()) otherwise")
     w = layer.lin.weight
@@ -58,6 +64,12 @@ def gcn_forward_host(layer: GCNConv, x_host: torch.Tensor, edge_index_host: torc
     hx = _pinned(x_host.contiguous(), "x")
     hei = _pinned(edge_index_host.long().contiguous(), "edge_index")
     N, F_in = hx.shape
+    n_local = N
+    multi = partition is not None and partition.world > 1
+    if partition is not None:
+        if N != partition.n_owned:
+            raise ValueError(f"x_host must hold the partition's {partition.n_owned} owned rows, got {N}")
+        n_local = partition.n_local
     F_out = layer.out_channels
     if out_host is None:
         out_host = torch.empty((N, F_out), dtype=hx.dtype).pin_memory()
@@ -90,37 +102,55 @@ def gcn_forward_host(layer: GCNConv, x_host: torch.Tensor, edge_index_host: torc
         for t in (dei, dx):
             t.record_stream(s_cmp)
         s_cmp.wait_event(ev_ei)
-        g = Graph(dei, N)
+        g = Graph(dei, n_local)
         csr = g.csr("sl", False)
         dinv = g.dinv()
-        band = g.band_raw()                    # one device reduction + host sync; the x copies are already queued
+        ghost_chunks = set()
+        if multi:                              # ghost rows have no in-edges locally: their deg^-1/2 comes from the owners
+            buf = torch.zeros((n_local, 4), dtype=torch.float32, device=dev)
+            buf[:, 0] = dinv
+            partition.exchange(buf)
+            dinv[N:] = buf[N:, 0]
+            pos = torch.nonzero(csr.col >= N).squeeze(1)          # CSR positions that read a ghost row
+            if pos.numel():
+                rows = torch.searchsorted(csr.rowptr.long(), pos, right=True) - 1
+                ghost_chunks = set(torch.unique(rows // R).tolist())
+        # rows [r0, r1) read owned rows within +-band of themselves (ghost reads are tracked per chunk above):
+        # one device reduction + host sync; the x copies are already queued
+        dsrc, ddst = dei[0], dei[1]
+        band = int(torch.where(dsrc < N, (dsrc - ddst).abs(), torch.zeros_like(dsrc)).max()) if dei.shape[1] else 0
         wt = w if w.dtype == hx.dtype else w.to(hx.dtype)
         bias = layer.bias.float() if layer.bias is not None else None
-        xs = torch.empty((N, F_out), dtype=hx.dtype, device=dev)
+        xs = torch.empty((n_local, F_out), dtype=hx.dtype, device=dev)
         out = torch.empty((N, F_out), dtype=hx.dtype, device=dev)
         out.record_stream(s_out)
-        done_rows, nxt = 0, 0                  # rows projected so far / next chunk to aggregate
+        done_rows, pending = 0, list(range(len(bounds)))           # rows projected so far / chunks not yet aggregated
 
-        def aggregate_ready(final: bool):
-            nonlocal nxt
-            while nxt < len(bounds):
-                r0, r1 = bounds[nxt]
-                if not final and min(r1 + band, N) > done_rows:
-                    break
-                ops.seg_sum(xs, csr.rowptr[r0:r1 + 1], csr.col, r1 - r0, dinv[r0:r1], None, 0.0, None, bias,
-                            out=out[r0:r1], band=g.band())
-                e = torch.cuda.Event()
-                e.record(s_cmp)
-                with torch.cuda.stream(s_out):
-                    s_out.wait_event(e)
-                    out_host[r0:r1].copy_(out[r0:r1], non_blocking=True)
-                nxt += 1
+        def aggregate(c):
+            r0, r1 = bounds[c]
+            ops.seg_sum(xs, csr.rowptr[r0:r1 + 1], csr.col, r1 - r0, dinv[r0:r1], None, 0.0, None, bias,
+                        out=out[r0:r1], band=g.band())
+            e = torch.cuda.Event()
+            e.record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e)
+                out_host[r0:r1].copy_(out[r0:r1], non_blocking=True)
+
+        def aggregate_ready(ghosts_in: bool):
+            for c in list(pending):
+                r0, r1 = bounds[c]
+                if min(r1 + band, N) > done_rows or (c in ghost_chunks and not ghosts_in):
+                    continue
+                aggregate(c)
+                pending.remove(c)
 
         for c, (r0, r1) in enumerate(bounds):
             s_cmp.wait_event(ev_x[c])
             ops.linear_fwd(dx[r0:r1], wt, None, row_scale=dinv[r0:r1], out=xs[r0:r1])
             done_rows = r1
             aggregate_ready(False)
+        if multi:
+            partition.exchange(xs)             # projected (and dinv-scaled) boundary rows -> the neighbours' ghost rows
         aggregate_ready(True)
     cur.wait_stream(s_out)
     cur.wait_stream(s_cmp)

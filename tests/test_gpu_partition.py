@@ -198,3 +198,54 @@ def test_two_gpu_partitioned_flowgnn_step_equals_monolithic(layer_type, ckpt):
         p.join(timeout=60)
     for rank, e_out, e_g, e_rm in res:
         assert e_out < 2e-5 and e_g < 2e-4 and e_rm < 1e-5, res
+
+
+def _stream_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import gnn_bfs_rans_b200 as b2g
+        from gnn_bfs_rans_b200 import ops
+        from gnn_bfs_rans_b200.distributed import slab_partition_hex
+        from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+        dev = f"cuda:{rank}"
+        nx, ny, nz, F = 16, 12, 40, 256
+        nb = nx * ny * nz
+        N = nb * world
+        part = slab_partition_hex(nx, ny, nz, world, rank, dev)
+        torch.manual_seed(0)
+        layer = b2g.nn.GCNConv(F, F).to(dev).eval()
+        with torch.no_grad():
+            layer.bias.uniform_(-1, 1)
+        torch.manual_seed(3)
+        x_all = torch.randn(N, F)
+        sl = slice(rank * nb, (rank + 1) * nb)
+        out = b2g.streaming.gcn_forward_host(layer, x_all[sl], part.edge_index.cpu(), rows_per_chunk=2048, partition=part)
+        o, n = hex_mesh_faces(nx, ny, nz * world, device=dev)
+        ei = ops.build_graph_edges(o, n, 1, None, N, N)
+        with torch.no_grad():
+            ref = layer(x_all.to(dev), ei)[sl].cpu()
+        q.put((rank, rel(out, ref)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_host_pipelined_gcn_with_halo():
+    """streaming.gcn_forward_host(partition=...) on 2 ranks (chunked copies, one halo exchange of the projected boundary
+    rows, ghost-reading chunks deferred) == the owned rows of the monolithic layer output."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stream_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, e in res:
+        assert e < 1e-5, res
