@@ -214,7 +214,7 @@ class GATZFn(torch.autograd.Function):
         dz, _ = ops.linear_fwd(g, wc.t().contiguous(), None)                # dz = g Wc    [N, H*F]
         # [y | d a] so that dx = y (W/H) + d a V is ONE GEMM against [Wc_src ; V]
         ka = H * C + 2 * H
-        y_aug = torch.empty((N, ka), dtype=x.dtype, device=x.device)
+        y_aug = ops.empty_rows(N, ka, x.dtype, x.device)
         d_a = ops.gatz_bwd(x, a, dz, g, H, slope, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
                            y_aug[:, :H * C], band=graph.band())
         del dz
@@ -401,7 +401,8 @@ class TConvZFn(torch.autograd.Function):
             gw_out = _cast_like(dw, w_out)
         del z_aug
         # gradients of z and of the weight sums s: dz_aug = g W_out[:, :H*F + 8]
-        dz_aug, _ = ops.linear_fwd(g, w_out[:, :HF + 8].t().contiguous(), None)
+        dz_aug, _ = ops.linear_fwd(g, w_out[:, :HF + 8].t().contiguous(), None,
+                                   out=ops.empty_rows(N, HF + 8, x.dtype, x.device))
         alpha_e, de_e = ops.tz_bwd_dst(x, dz_aug, alpha, H, csr.rowptr, csr.col, p_drop, seed, band=band)
         del dz_aug
         # dx = [y | w | t 0 | du | g] W_aug as ONE GEMM, every block a sum of F-wide rows:
@@ -409,7 +410,7 @@ class TConvZFn(torch.autograd.Function):
         #   du_i = [sum_j de_ijh x_j]_h                                                       (target-major CSR)
         # using  sum_i de_ijh u_ih = Mq_h w_jh + cq_h t_jh  and  sum_i alpha'_ijh dz_ih = Wv_h^T y_jh
         o_y, o_w, o_t, o_du, o_g = 0, H * C, H * C + HF, H * C + HF + 8, H * C + 2 * HF + 8
-        big = torch.empty((N, o_g + C), dtype=x.dtype, device=x.device)
+        big = ops.empty_rows(N, o_g + C, x.dtype, x.device)
         t_rows = torch.zeros((N, 8), dtype=torch.float32, device=x.device)
         ops.seg_wsum4(g, alpha_e, csr_t.rowptr, csr_t.col, perm, big[:, o_y:o_y + H * C], band=band)
         ops.seg_wsum4(x, de_e, csr_t.rowptr, csr_t.col, perm, big[:, o_w:o_w + HF], d_a=t_rows, band=band)

@@ -3,6 +3,8 @@ device memory and the stream; every computation is a libb2g.so kernel.  No CPU f
 non-CUDA tensor raises RuntimeError."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -46,6 +48,15 @@ def _rows(t: torch.Tensor) -> torch.Tensor:
 
 def _ld(t):
     return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def empty_rows(n: int, width: int, dtype, device) -> torch.Tensor:
+    """[n, width] view of a buffer whose row stride is a whole number of 128-byte lines: rows of a GEMM operand that start
+    mid-line make every TMA box straddle two lines (measured: the k = 1032 dgrad GEMM ran at 3.3 TB/s instead of 4.8)."""
+    es = torch.empty((), dtype=dtype).element_size()
+    per = 128 // es if os.environ.get("B2G_PAD_ROWS", "1") != "0" else 1
+    ld = (width + per - 1) // per * per
+    return torch.empty((n, ld), dtype=dtype, device=device)[:, :width]
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -346,7 +357,7 @@ def tz_fwd(x, u, H, rowptr, col, p_drop, seed, save_alpha, band=0):
     """z_aug [N, H*F + 8 + F] (see include/b2g.h b2g_tz_fwd) and the pre-dropout attention weights [nnz, H] | None."""
     x, u = _rows(x), _rows(u)
     N, F = x.shape
-    z = torch.empty((N, H * F + 8 + F), dtype=x.dtype, device=x.device)
+    z = empty_rows(N, H * F + 8 + F, x.dtype, x.device)
     alpha = torch.empty((max(col.numel(), 1), H), dtype=torch.float32, device=x.device) if save_alpha else None
     _lib.check(_lib.load().b2g_tz_fwd(_p(x), _ld(x), _p(u), _ld(u), _p(z), _ld(z), N, H, F, _dt(x), _p(rowptr), _p(col),
                                       _p(alpha), float(p_drop), int(seed), int(band), _stream()), "tz_fwd")
