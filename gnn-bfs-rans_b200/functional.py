@@ -28,23 +28,18 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act: int):
         need_grad = x.requires_grad or weight.requires_grad or (bias is not None and bias.requires_grad)
-        fuse_act = act if not need_grad else 0       # relu backward needs the pre-activation sign
-        y, _ = ops.linear_fwd(x, weight, bias, act=fuse_act)
-        if act and not fuse_act:
-            ctx.save_for_backward(x, weight, y)
-            ctx.act = act
-            ctx.has_bias = bias is not None
-            return torch.relu(y)
-        ctx.save_for_backward(x, weight, None)
-        ctx.act = 0
+        y, _ = ops.linear_fwd(x, weight, bias, act=act)       # ReLU always in the GEMM epilogue
+        # relu'(pre) == (relu(pre) > 0): the backward pass needs the OUTPUT, which autograd keeps alive anyway
+        ctx.save_for_backward(x, weight, y if (act and need_grad) else None)
+        ctx.act = act
         ctx.has_bias = bias is not None
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, weight, pre = ctx.saved_tensors
-        if pre is not None:
-            gy = gy * (pre > 0).to(gy.dtype)
+        x, weight, out = ctx.saved_tensors
+        if out is not None:
+            gy = torch.ops.aten.threshold_backward(gy.contiguous(), out, 0.0)      # one pass: gy where out > 0
         gy = gy.contiguous()
         gx = ops.linear_dgrad(gy, weight) if ctx.needs_input_grad[0] else None
         gw = gb = None
