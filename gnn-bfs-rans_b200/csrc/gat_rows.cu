@@ -672,6 +672,91 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
     const int len = r.e - r.b;
     if (len > 32) {
       tz_fwd_long<T, VPL>(a, r.i, r.b, r.e);
+    } else if (VPL == 1 && len > 0 && len <= 8) {
+      // every mesh row: ONE gather of the (<= 8) neighbour rows serves both the logits and the weighted sums (the rows
+      // stay in registers across the softmax; u_i is dead by then).  ncu on the two-gather version: 32 GB of reads for
+      // 26 GB compulsory, and the second gather's latency sat in the middle of every row's dependency chain.
+      uint4 buf[8][VPL];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, u);
+        const char* p = xb + (uint64_t)c * a.xrow_bytes;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_row16(p + 512 * v);
+      }
+      float w[GH];
+      {
+        uint4 uraw[GH][VPL];
+        gatz_load_dz_raw<VPL>(a, r.i, lane, uraw);
+        float uf[GH][VPL][VN];
+        gatz_unpack_dz<T, VPL>(uraw, uf);
+        float part[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float p0[GH], p1[GH];
+#pragma unroll
+          for (int h = 0; h < GH; ++h) { p0[h] = 0.f; p1[h] = 0.f; }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            float f[VN];
+            unpack_row16(buf[u][v], f, T());
+#pragma unroll
+            for (int h = 0; h < GH; ++h)
+#pragma unroll
+              for (int k = 0; k < VN; k += 2) ffma2_mul(p0[h], p1[h], uf[h][v][k], uf[h][v][k + 1], f[k], f[k + 1]);
+          }
+#pragma unroll
+          for (int h = 0; h < GH; ++h) part[u * GH + h] = p0[h] + p1[h];
+        }
+        const float red = warp_transpose_sum32(part);        // lane 4u + h: logit of entry u, head h
+#pragma unroll
+        for (int h = 0; h < GH; ++h) w[h] = __shfl_sync(0xffffffffu, red, ((lane & 7) << 2) + h);
+      }
+      float zs[GH], ssum[GH];
+#pragma unroll
+      for (int h = 0; h < GH; ++h) {
+        const float s = lane < len ? w[h] : -INFINITY;
+        const float m = warp_max_redux(s);
+        w[h] = lane < len ? __expf(s - m) : 0.f;
+        zs[h] = w[h];
+      }
+      warp_sum4(zs[0], zs[1], zs[2], zs[3]);
+#pragma unroll
+      for (int h = 0; h < GH; ++h) w[h] *= 1.0f / (zs[h] + 1e-16f);
+      if (a.alpha_e && lane < len) *reinterpret_cast<float4*>(a.alpha_e + (uint64_t)(r.b + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
+      if (a.p_drop > 0.f) {
+        float sc[4];
+        dropout_scale4(a.seed, (uint64_t)(r.b + lane), a.p_drop, sc);
+#pragma unroll
+        for (int h = 0; h < GH; ++h) w[h] *= sc[h];
+      }
+#pragma unroll
+      for (int h = 0; h < GH; ++h) ssum[h] = w[h];
+      warp_sum4(ssum[0], ssum[1], ssum[2], ssum[3]);
+      float acc[GH][VPL][VN];
+#pragma unroll
+      for (int h = 0; h < GH; ++h)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[h][v][k] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {                          // entries past the row's end carry weight 0
+        float wu[GH];
+#pragma unroll
+        for (int h = 0; h < GH; ++h) wu[h] = __shfl_sync(0xffffffffu, w[h], u);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          float f[VN];
+          unpack_row16(buf[u][v], f, T());
+#pragma unroll
+          for (int h = 0; h < GH; ++h)
+#pragma unroll
+            for (int k = 0; k < VN; k += 2) ffma2_acc(acc[h][v][k], acc[h][v][k + 1], wu[h], f[k], f[k + 1]);
+        }
+      }
+      gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, acc, lane);
+      tz_store_tail<T, VPL>(a, r.i, lane, ssum);
     } else {
       float w[GH] = {0.f, 0.f, 0.f, 0.f}, ssum[GH] = {0.f, 0.f, 0.f, 0.f};
       if (len > 0) {                          // logits: u_i (registers) . x_j, one entry per lane
