@@ -438,8 +438,7 @@ __device__ __forceinline__ void gatz_load_dz(const GatzArgs& a, uint32_t i, int 
 template <typename T, int VPL>
 __device__ __forceinline__ void gatz_bwd_finish(const GatzArgs& a, int p0, int n, int lane, const float (&alpha)[GH],
                                                 const float (&dal)[GH], const float (&sraw)[GH], const float (&mask)[GH],
-                                                const float (&t)[GH], float (&dad)[GH]) {
-  float de[GH];
+                                                const float (&t)[GH], float (&dad)[GH], float (&de)[GH]) {
 #pragma unroll
   for (int h = 0; h < GH; ++h) {
     const float ds = alpha[h] * (dal[h] - t[h]);
@@ -480,6 +479,13 @@ __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int
   }
   // sweep 2: d e
   float dad[GH] = {0.f, 0.f, 0.f, 0.f};
+  float du[GH][VPL][VN];
+#pragma unroll
+  for (int h = 0; h < GH; ++h)
+#pragma unroll
+    for (int v = 0; v < VPL; ++v)
+#pragma unroll
+      for (int k = 0; k < VN; ++k) du[h][v][k] = 0.f;
   for (int p0 = b; p0 < e; p0 += 32) {
     const int n = min(32, e - p0);
     const int cl = window_entry(a.col, p0, e, lane);
@@ -503,11 +509,16 @@ __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int
         alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
       }
     }
-    gatz_bwd_finish<T, VPL>(a, p0, n, lane, alpha, dal, sraw, mask, t, dad);
+    float de[GH];
+    gatz_bwd_finish<T, VPL>(a, p0, n, lane, alpha, dal, sraw, mask, t, dad, de);
+    if (kT && a.z)                              // du_i += sum_j de_ij x_j (TransformerConv: gradient of u_i)
+      for (int j = 0; j < n; j += GatzCfg<VPL>::BU) gatz_gather_fma<T, VPL>(du, xb, a.xrow_bytes, cl, de, j, []() {});
   }
   if (!kT) {
     warp_sum4(dad[0], dad[1], dad[2], dad[3]);
     if (lane < GH) a.d_a[(uint64_t)i * a.ldda + GH + lane] = pick4(dad, lane);
+  } else if (a.z) {
+    gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)i * a.zrow_bytes, du, lane);
   }
 }
 
@@ -526,6 +537,86 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
     const int len = r.e - r.b;
     if (len > 32) {
       gatz_bwd_dst_long<T, VPL, kT>(a, r.i, r.b, r.e);
+    } else if (kT && VPL == 1 && len > 0 && len <= 8 && a.z) {
+      // TransformerConv, every mesh row: ONE gather serves d alpha (dots with dz_i) and du_i = sum_j de_ij x_j (the
+      // rows stay in registers; dz_i is dead after the dots), instead of a separate weighted-row-sum launch.
+      uint4 buf[8][VPL];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, u);
+        const char* p = xb + (uint64_t)c * a.xrow_bytes;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_row16(p + 512 * v);
+      }
+      const float4 al4 = ldg_f4(a.alpha_in + (uint64_t)max(min(r.b + lane, r.e - 1), 0) * GH);
+      float dal[GH];
+      {
+        uint4 dzraw[GH][VPL];
+        gatz_load_dz_raw<VPL>(a, r.i, lane, dzraw);
+        float dzf[GH][VPL][VN];
+        gatz_unpack_dz<T, VPL>(dzraw, dzf);
+        float part[32];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float p0[GH], p1[GH];
+#pragma unroll
+          for (int h = 0; h < GH; ++h) { p0[h] = 0.f; p1[h] = 0.f; }
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            float f[VN];
+            unpack_row16(buf[u][v], f, T());
+#pragma unroll
+            for (int h = 0; h < GH; ++h)
+#pragma unroll
+              for (int k = 0; k < VN; k += 2) ffma2_mul(p0[h], p1[h], dzf[h][v][k], dzf[h][v][k + 1], f[k], f[k + 1]);
+          }
+#pragma unroll
+          for (int h = 0; h < GH; ++h) part[u * GH + h] = p0[h] + p1[h];
+        }
+        const float red = warp_transpose_sum32(part);
+#pragma unroll
+        for (int h = 0; h < GH; ++h) dal[h] = __shfl_sync(0xffffffffu, red, ((lane & 7) << 2) + h);
+      }
+      float ad[GH], sm[GH], rinv[GH];
+      gatz_bwd_row_inputs<T, kT>(a, r.i, GH * VPL * 512, ad, sm, rinv);     // ad = d s_alpha of the row
+      const float al[GH] = {al4.x, al4.y, al4.z, al4.w};
+      float alpha[GH], sraw[GH], mask[GH] = {1.f, 1.f, 1.f, 1.f};
+      if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(r.b + lane), a.p_drop, mask);
+#pragma unroll
+      for (int h = 0; h < GH; ++h) {
+        sraw[h] = 1.0f;
+        alpha[h] = lane < len ? al[h] : 0.f;
+        dal[h] = (dal[h] + ad[h]) * mask[h];
+      }
+      float t[GH];
+#pragma unroll
+      for (int h = 0; h < GH; ++h) t[h] = alpha[h] * dal[h];
+      warp_sum4(t[0], t[1], t[2], t[3]);
+      float dad[GH] = {0.f, 0.f, 0.f, 0.f}, de[GH];
+      gatz_bwd_finish<T, VPL>(a, r.b, len, lane, alpha, dal, sraw, mask, t, dad, de);
+      float du[GH][VPL][VN];
+#pragma unroll
+      for (int h = 0; h < GH; ++h)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int k = 0; k < VN; ++k) du[h][v][k] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {                          // de is 0 on lanes past the row's end
+        float wu[GH];
+#pragma unroll
+        for (int h = 0; h < GH; ++h) wu[h] = __shfl_sync(0xffffffffu, de[h], u);
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          float f[VN];
+          unpack_row16(buf[u][v], f, T());
+#pragma unroll
+          for (int h = 0; h < GH; ++h)
+#pragma unroll
+            for (int k = 0; k < VN; k += 2) ffma2_acc(du[h][v][k], du[h][v][k + 1], wu[h], f[k], f[k + 1]);
+        }
+      }
+      gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, du, lane);
     } else {
       float dzf[GH][VPL][VN];
       uint4 dzraw[GH][VPL];
@@ -545,11 +636,21 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
 #pragma unroll
       for (int h = 0; h < GH; ++h) t[h] = alpha[h] * dal[h];
       warp_sum4(t[0], t[1], t[2], t[3]);
-      float dad[GH] = {0.f, 0.f, 0.f, 0.f};
-      gatz_bwd_finish<T, VPL>(a, r.b, len, lane, alpha, dal, sraw, mask, t, dad);
+      float dad[GH] = {0.f, 0.f, 0.f, 0.f}, de[GH];
+      gatz_bwd_finish<T, VPL>(a, r.b, len, lane, alpha, dal, sraw, mask, t, dad, de);
       if (!kT) {
         warp_sum4(dad[0], dad[1], dad[2], dad[3]);
         if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + GH + lane] = pick4(dad, lane);
+      } else if (a.z) {                          // du_i = sum_j de_ij x_j (rows of 9..32 entries, or VPL = 2: second gather)
+        float du[GH][VPL][VN];
+#pragma unroll
+        for (int h = 0; h < GH; ++h)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v)
+#pragma unroll
+            for (int k = 0; k < VN; ++k) du[h][v][k] = 0.f;
+        for (int j = 0; j < len; j += GatzCfg<VPL>::BU) gatz_gather_fma<T, VPL>(du, xb, a.xrow_bytes, cl, de, j, []() {});
+        gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, du, lane);
       }
     }
     if (!r.shift()) break;
@@ -1076,7 +1177,7 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_a
  * the forward pass's alpha [nnz,H]; writes alpha_e (after dropout) and de_e [nnz,H] in target-major CSR order. */
 int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz, const float* alpha_in, int64_t n, int H,
                    int F, int dt, const int32_t* rowptr, const int32_t* col, float p_drop, uint64_t seed, float* alpha_e,
-                   float* de_e, int64_t band, void* stream) {
+                   float* de_e, void* du, int64_t lddu, int64_t band, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
@@ -1090,6 +1191,11 @@ int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz,
   if (rc) return rc;
   a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = dz_aug; a.dzrow_bytes = (uint32_t)(lddz * es); a.alpha_in = alpha_in;
   a.rowptr = rowptr; a.col = col; a.p_drop = p_drop; a.seed = seed; a.alpha_e = alpha_e; a.de_e = de_e;
+  if (du) {
+    if (!aligned16(du) || (lddu * es) % 16 || lddu < (int64_t)H * F) return B2G_E_ALIGN;
+    if (!fits32(lddu * es)) return B2G_E_SHAPE;
+    a.z = du; a.zrow_bytes = (uint32_t)(lddu * es);
+  }
   return gatz_dispatch(4, dt, F * es, a, (cudaStream_t)stream);
 }
 

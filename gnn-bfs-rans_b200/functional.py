@@ -398,8 +398,7 @@ class TConvZFn(torch.autograd.Function):
         # gradients of z and of the weight sums s: dz_aug = g W_out[:, :H*F + 8]
         dz_aug, _ = ops.linear_fwd(g, w_out[:, :HF + 8].t().contiguous(), None,
                                    out=ops.empty_rows(N, HF + 8, x.dtype, x.device))
-        alpha_e, de_e = ops.tz_bwd_dst(x, dz_aug, alpha, H, csr.rowptr, csr.col, p_drop, seed, band=band)
-        del dz_aug
+        # (tz_bwd_dst runs below, once the buffer that receives du exists)
         # dx = [y | w | t 0 | du | g] W_aug as ONE GEMM, every block a sum of F-wide rows:
         #   y_j = [sum_i alpha'_ijh g_i]_h, w_j = [sum_i de_ijh x_i]_h, t_jh = sum_i de_ijh   (transposed CSR)
         #   du_i = [sum_j de_ijh x_j]_h                                                       (target-major CSR)
@@ -407,9 +406,15 @@ class TConvZFn(torch.autograd.Function):
         o_y, o_w, o_t, o_du, o_g = 0, H * C, H * C + HF, H * C + HF + 8, H * C + 2 * HF + 8
         big = ops.empty_rows(N, o_g + C, x.dtype, x.device)
         t_rows = torch.zeros((N, 8), dtype=torch.float32, device=x.device)
+        fuse_du = os.environ.get("B2G_TZ_FUSE_DU", "1") != "0"
+        alpha_e, de_e = ops.tz_bwd_dst(x, dz_aug, alpha, H, csr.rowptr, csr.col, p_drop, seed,
+                                       big[:, o_du:o_du + HF] if fuse_du else None,
+                                       band=band)          # du comes out of the same gather as d alpha
+        del dz_aug
+        if not fuse_du:
+            ops.seg_wsum4(x, de_e, csr.rowptr, csr.col, None, big[:, o_du:o_du + HF], band=band)
         ops.seg_wsum4(g, alpha_e, csr_t.rowptr, csr_t.col, perm, big[:, o_y:o_y + H * C], band=band)
         ops.seg_wsum4(x, de_e, csr_t.rowptr, csr_t.col, perm, big[:, o_w:o_w + HF], d_a=t_rows, band=band)
-        ops.seg_wsum4(x, de_e, csr.rowptr, csr.col, None, big[:, o_du:o_du + HF], band=band)
         del alpha_e, de_e
         big[:, o_t:o_t + 8] = t_rows
         big[:, o_g:] = g

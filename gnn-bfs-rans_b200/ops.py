@@ -364,14 +364,16 @@ def tz_fwd(x, u, H, rowptr, col, p_drop, seed, save_alpha, band=0):
     return z, alpha
 
 
-def tz_bwd_dst(x, dz_aug, alpha, H, rowptr, col, p_drop, seed, band=0):
-    """-> (alpha_e after dropout, de_e) fp32 [nnz, H], target-major."""
+def tz_bwd_dst(x, dz_aug, alpha, H, rowptr, col, p_drop, seed, du_out, band=0):
+    """-> (alpha_e after dropout, de_e) fp32 [nnz, H], target-major; writes du = [sum_j de_ijh x_j]_h into du_out
+    (a [N, H*F] view, any row stride) from the same gather."""
     x, dz_aug = _rows(x), _rows(dz_aug)
     N, F = x.shape
     alpha_e = torch.empty_like(alpha)
     de_e = torch.empty_like(alpha)
     _lib.check(_lib.load().b2g_tz_bwd_dst(_p(x), _ld(x), _p(dz_aug), _ld(dz_aug), _p(alpha), N, H, F, _dt(x), _p(rowptr),
-                                          _p(col), float(p_drop), int(seed), _p(alpha_e), _p(de_e), int(band), _stream()),
+                                          _p(col), float(p_drop), int(seed), _p(alpha_e), _p(de_e), _p(du_out),
+                                          _ld(du_out) if du_out is not None else 0, int(band), _stream()),
                "tz_bwd_dst")
     return alpha_e, de_e
 

@@ -217,11 +217,12 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_a
                int64_t band, void* stream);
 /* Target side of its backward pass: dz_aug [n, >= H*F + 8] (columns H*F .. H*F+H-1 = d s), alpha_in = the forward
  * pass's alpha_e; writes alpha_e (after dropout) and de_e [nnz, H] (gradients of the logits), target-major.  The
- * remaining sums (d u, and y / w over the transposed CSR) are b2g_gatz_bwd_src calls: perm == NULL there means the
- * weights are already in the order of the CSR passed in, d_a == NULL skips the logit-gradient row sums. */
+ * `du` (may be NULL) [n, H*F] receives d u_i = [sum_j de_ij1 x_j | ...] from the same gather.  The sums over the
+ * transposed CSR (y, w) are b2g_gatz_bwd_src calls: perm == NULL there means the weights are already in the order of
+ * the CSR passed in, d_a == NULL skips the logit-gradient row sums. */
 int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz, const float* alpha_in, int64_t n, int H,
                    int F, int dt, const int32_t* rowptr, const int32_t* col, float p_drop, uint64_t seed, float* alpha_e,
-                   float* de_e, int64_t band, void* stream);
+                   float* de_e, void* du, int64_t lddu, int64_t band, void* stream);
 
 /* ===================================================================================== K5
  * TransformerConv (gnn_model.py:77-80,170) fused q.k score + segment-softmax + aggregate +
