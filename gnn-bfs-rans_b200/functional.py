@@ -302,6 +302,24 @@ class BatchNormFn(torch.autograd.Function):
         return ds, (ds if has_r else None), gw, gb, None, None, None, None, None, None
 
 
+def combine_batch_stats(mean, var, n: int, eps: float, group=None):
+    """Per-rank (mean [C], biased var [C], row count n) -> the statistics of the union of all ranks' rows: Chan et al.'s
+    parallel formula over an all_gather of 2C + 1 numbers per rank (in fp64).  Returns ([3, C] = mean, 1/sqrt(var + eps),
+    var in fp32, global row count).  Pure torch: works on any backend (gloo test on CPU, NCCL in the product)."""
+    import torch.distributed as dist
+    C = mean.numel()
+    loc = torch.cat([mean.float(), var.float(), mean.new_full((1,), float(n), dtype=torch.float32)])
+    allv = [torch.empty_like(loc) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(allv, loc, group=group)
+    allv = torch.stack(allv).double()
+    cnt = allv[:, 2 * C]
+    n_tot = cnt.sum()
+    mean_g = (allv[:, :C] * cnt[:, None]).sum(0) / n_tot
+    var_g = ((allv[:, C:2 * C] + (allv[:, :C] - mean_g) ** 2) * cnt[:, None]).sum(0) / n_tot
+    stats = torch.stack([mean_g.float(), torch.rsqrt(var_g + eps).float(), var_g.float()])
+    return stats, int(n_tot.item())
+
+
 def batch_norm(x, r, bn: "torch.nn.BatchNorm1d", relu: bool = False, p_drop: float = 0.0, group=None):
     """BatchNorm1d semantics (batch statistics + running-stat update in training, running statistics in eval) on the
     library's kernels; `bn` is the torch module that owns weight / bias / running_* (torch_geometric.nn.BatchNorm.module).
@@ -316,18 +334,8 @@ def batch_norm(x, r, bn: "torch.nn.BatchNorm1d", relu: bool = False, p_drop: flo
     n = x.shape[0]
     if training:
         stats = ops.bn_stats(x.detach(), r.detach() if r is not None else None, bn.eps)
-        if sync:                                    # Chan et al. parallel mean / variance over the ranks' (n, mean, var)
-            C = x.shape[1]
-            loc = torch.cat([stats[0], stats[2], stats.new_full((1,), float(n))])
-            allv = [torch.empty_like(loc) for _ in range(dist.get_world_size(pg))]
-            dist.all_gather(allv, loc, group=pg)
-            allv = torch.stack(allv).double()
-            cnt = allv[:, 2 * C]
-            n_tot = cnt.sum()
-            mean_g = (allv[:, :C] * cnt[:, None]).sum(0) / n_tot
-            var_g = ((allv[:, C:2 * C] + (allv[:, :C] - mean_g) ** 2) * cnt[:, None]).sum(0) / n_tot
-            stats = torch.stack([mean_g.float(), torch.rsqrt(var_g + bn.eps).float(), var_g.float()])
-            n = int(n_tot.item())
+        if sync:
+            stats, n = combine_batch_stats(stats[0], stats[2], n, bn.eps, pg)
             n_glob = n
 
             def reduce_sums(sums, n_local):

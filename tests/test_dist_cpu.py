@@ -135,3 +135,39 @@ def test_halo_exchange_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] and r[2] and r[3] for r in res), res
+
+
+def _stats_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gnn_bfs_rans_b200.functional import combine_batch_stats
+        torch.manual_seed(0)
+        full = torch.randn(1000, 16, dtype=torch.float64) * 3 + 5
+        cuts = [0, 130, 1000] if world == 2 else [0, 100, 400, 401, 1000]     # very uneven shares, one of a single row
+        mine = full[cuts[rank]:cuts[rank + 1]]
+        stats, n = combine_batch_stats(mine.mean(0), mine.var(0, unbiased=False), mine.shape[0], 1e-5)
+        ref_mean, ref_var = full.mean(0), full.var(0, unbiased=False)
+        err = max(float((stats[0].double() - ref_mean).abs().max() / ref_mean.abs().max()),
+                  float((stats[2].double() - ref_var).abs().max() / ref_var.abs().max()),
+                  float((stats[1].double() - (ref_var + 1e-5).rsqrt()).abs().max() / (ref_var + 1e-5).rsqrt().abs().max()))
+        q.put((rank, n, err))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gloo_batchnorm_statistics_combine_to_the_global_ones(world):
+    """The synchronised BatchNorm of flow_forward_partitioned: per-rank (n, mean, var) of uneven shares combine to the
+    statistics of the whole batch on every rank (gloo, CPU)."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_stats_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, n, err in res:
+        assert n == 1000 and err < 1e-6, res
