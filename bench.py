@@ -570,9 +570,19 @@ def run_extras(b2g, ops, part, dev, timed):
                     torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
                     opt.step()
                 ms_t = timed_grad(step2, 20, 5)
+                ms_tg = None
+                try:                    # the whole step (zero_grad, fwd, loss, bwd, clip, Adam) replayed from one CUDA graph
+                    opt_c = torch.optim.Adam(model.parameters(), lr=3e-4, weight_decay=1e-5, capturable=True)
+                    gts = b2g.graphs.GraphedTrainStep(model, opt_c, lambda o, t: (o - t).float().square().mean(), xin, y, ei2,
+                                                      max_grad_norm=1.0)
+                    ms_tg = timed_grad(lambda: gts.step(xin, y), 50, 5)
+                    del gts, opt_c
+                except Exception as e:
+                    ms_tg = "error: " + str(e)[:120]
                 out[f"cfg2_shipped_BFS_FlowGNN_{lt}_L4_F128_{dt_name}"] = {"cells": n2, "edges": int(ei2.shape[1]),
                                                                            "forward_ms": ms_f, "forward_cuda_graph_ms": ms_g,
-                                                                           "train_step_ms": ms_t}
+                                                                           "train_step_ms": ms_t,
+                                                                           "train_step_cuda_graph_ms": ms_tg}
                 del model, opt
     except Exception as e:
         out["cfg2_shipped_BFS"] = {"error": str(e)[:200]}

@@ -19,6 +19,8 @@ SIGNATURES = {
     "b2g_error_string": (cp, [i32]),
     "b2g_launch_count": (i64, []),
     "b2g_launch_count_reset": (None, []),
+    "b2g_dropout_epoch_advance": (i32, [vp]),
+    "b2g_dropout_epoch_set": (i32, [u64, vp]),
     "b2g_build_edge_index": (i32, [vp, vp, i64, i64, vp, vp]),
     "b2g_mask_to_map_workspace_bytes": (i64, [i64]),
     "b2g_mask_to_map": (i32, [vp, i64, vp, vp, vp, vp]),

@@ -3,6 +3,21 @@
 
 namespace b2g {
 int64_t g_launches = 0;
+
+static uint64_t* g_epoch[64] = {nullptr};
+const uint64_t* dropout_epoch_ptr() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_epoch[dev]) {
+    uint64_t* p = nullptr;
+    if (cudaMalloc(&p, sizeof(uint64_t)) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    cudaMemset(p, 0, sizeof(uint64_t));
+    g_epoch[dev] = p;
+  }
+  return g_epoch[dev];
+}
+__global__ void epoch_advance_kernel(uint64_t* e) { *e += 1; }
+__global__ void epoch_set_kernel(uint64_t* e, uint64_t v) { *e = v; }
 }
 
 extern "C" {
@@ -11,6 +26,22 @@ int b2g_version(void) { return B2G_VERSION; }
 
 int64_t b2g_launch_count(void) { return b2g::g_launches; }
 void b2g_launch_count_reset(void) { b2g::g_launches = 0; }
+
+int b2g_dropout_epoch_advance(void* stream) {
+  uint64_t* e = const_cast<uint64_t*>(b2g::dropout_epoch_ptr());
+  if (!e) return B2G_E_UNSUPPORTED;
+  b2g::epoch_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(e);
+  b2g::count_launch();
+  return b2g::cuda_status();
+}
+
+int b2g_dropout_epoch_set(uint64_t value, void* stream) {
+  uint64_t* e = const_cast<uint64_t*>(b2g::dropout_epoch_ptr());
+  if (!e) return B2G_E_UNSUPPORTED;
+  b2g::epoch_set_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(e, value);
+  b2g::count_launch();
+  return b2g::cuda_status();
+}
 
 const char* b2g_error_string(int code) {
   switch (code) {

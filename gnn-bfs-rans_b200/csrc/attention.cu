@@ -95,7 +95,7 @@ struct AttnArgs {
   int64_t n_rows; int C; int concat; float slope; float qk_scale;
   const int32_t* rowptr; const int32_t* col;
   const float* bias; float* smax; float* ssum;
-  float p_drop; uint64_t seed;
+  float p_drop; uint64_t seed; const uint64_t* epoch;
   float* alpha_e; float* ds_e; float* d_a_dst; int64_t ldda;
 };
 
@@ -196,14 +196,14 @@ __global__ void __launch_bounds__(256, (H * CV <= 4 && MODE == MODE_GAT) ? 2 : 1
       if (a.p_drop > 0.f && lane < n) {
         if (H == 4) {
           float sc[4];
-          dropout_scale4(a.seed, (uint64_t)(base + lane), a.p_drop, sc);
+          dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(base + lane), a.p_drop, sc);
 #pragma unroll
           for (int h = 0; h < H; ++h) p_l[h] *= sc[h & 3];
         } else {
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             float sc[4];
-            dropout_scale4(a.seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, sc);
+            dropout_scale4(mix_epoch(a.seed, a.epoch) ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, sc);
             p_l[h] *= sc[0];
           }
         }
@@ -363,14 +363,14 @@ __global__ void __launch_bounds__(256, 2) gat_fwd_small_kernel(const AttnArgs a)
     if (a.p_drop > 0.f && lane < n) {
       if (H == 4) {
         float s4[4];
-        dropout_scale4(a.seed, (uint64_t)(b + lane), a.p_drop, s4);
+        dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(b + lane), a.p_drop, s4);
 #pragma unroll
         for (int h = 0; h < H; ++h) al[h] *= s4[h & 3];
       } else {
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           float s4[4];
-          dropout_scale4(a.seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(b + lane), a.p_drop, s4);
+          dropout_scale4(mix_epoch(a.seed, a.epoch) ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(b + lane), a.p_drop, s4);
           al[h] *= s4[0];
         }
       }
@@ -548,14 +548,14 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dst_kernel(const AttnArgs a) 
       if (a.p_drop > 0.f && lane < n) {
         if (H == 4) {
           float s4[4];
-          dropout_scale4(a.seed, (uint64_t)(base + lane), a.p_drop, s4);
+          dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(base + lane), a.p_drop, s4);
 #pragma unroll
           for (int h = 0; h < H; ++h) sc[h] = s4[h & 3];
         } else {
 #pragma unroll
           for (int h = 0; h < H; ++h) {
             float s4[4];
-            dropout_scale4(a.seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, s4);
+            dropout_scale4(mix_epoch(a.seed, a.epoch) ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, s4);
             sc[h] = s4[0];
           }
         }
@@ -615,8 +615,8 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dst_kernel(const AttnArgs a) 
             }
             if (a.p_drop > 0.f) {
               float s4[4];
-              if (H == 4) { dropout_scale4(a.seed, (uint64_t)(base + lane), a.p_drop, s4); scm = s4[h & 3]; }
-              else { dropout_scale4(a.seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, s4); scm = s4[0]; }
+              if (H == 4) { dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(base + lane), a.p_drop, s4); scm = s4[h & 3]; }
+              else { dropout_scale4(mix_epoch(a.seed, a.epoch) ^ (0x9E3779B97F4A7C15ull * (uint64_t)(h + 1)), (uint64_t)(base + lane), a.p_drop, s4); scm = s4[0]; }
             }
             a.alpha_e[(int64_t)(base + lane) * H + h] = al * scm;
           }
@@ -890,7 +890,7 @@ int b2g_gat_fwd(const void* xw, int64_t ldxw, const float* a_src, const float* a
   AttnArgs a{};
   a.val = xw; a.ldv = ldxw; a.a_src = a_src; a.a_dst = a_dst; a.lda = lda; a.out = out; a.ldo = ldo;
   a.n_rows = n_rows; a.C = C; a.concat = concat; a.slope = slope; a.rowptr = rowptr; a.col = col;
-  a.bias = bias; a.smax = smax; a.ssum = ssum; a.p_drop = p_drop; a.seed = seed;
+  a.bias = bias; a.smax = smax; a.ssum = ssum; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   // every row fits one lane-per-edge chunk and heads are averaged: single-accumulator fast path
   const int which = (max_degree > 0 && max_degree <= 32 && !concat) ? 3 : 0;
   return dispatch_dt(MODE_GAT, which, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
@@ -908,7 +908,7 @@ int b2g_gat_bwd_dst(const void* xw, int64_t ldxw, const float* a_src, const floa
   AttnArgs a{};
   a.val = xw; a.ldv = ldxw; a.a_src = a_src; a.a_dst = a_dst; a.lda = lda; a.gout = gout; a.ldg = ldg;
   a.n_rows = n_rows; a.C = C; a.concat = concat; a.slope = slope; a.rowptr = rowptr; a.col = col;
-  a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum); a.p_drop = p_drop; a.seed = seed;
+  a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum); a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   a.alpha_e = alpha_e; a.ds_e = ds_e; a.d_a_dst = d_a_dst; a.ldda = ldda;
   return dispatch_dt(MODE_GAT, 1, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
 }
@@ -941,7 +941,7 @@ int b2g_tconv_fwd(const void* q, const void* k, const void* v, int64_t ldqkv, co
   a.val = v; a.ldv = ldqkv; a.q = q; a.k = k; a.ldqk = ldqkv; a.skip = skip; a.lds = lds;
   a.out = out; a.ldo = ldo; a.n_rows = n_rows; a.C = C; a.concat = concat;
   a.qk_scale = 1.0f / sqrtf((float)C); a.rowptr = rowptr; a.col = col; a.smax = smax; a.ssum = ssum;
-  a.p_drop = p_drop; a.seed = seed;
+  a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   return dispatch_dt(MODE_TCONV, 0, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
 }
 
@@ -958,7 +958,7 @@ int b2g_tconv_bwd_dst(const void* q, const void* k, const void* v, int64_t ldqkv
   a.val = v; a.ldv = ldqkv; a.q = q; a.k = k; a.ldqk = ldqkv; a.gout = gout; a.ldg = ldg;
   a.dq = dq; a.lddq = lddq; a.n_rows = n_rows; a.C = C; a.concat = concat;
   a.qk_scale = 1.0f / sqrtf((float)C); a.rowptr = rowptr; a.col = col;
-  a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum); a.p_drop = p_drop; a.seed = seed;
+  a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum); a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   a.alpha_e = alpha_e; a.ds_e = ds_e;
   return dispatch_dt(MODE_TCONV, 1, dt, H, C, a, AttnSrcArgs{}, (cudaStream_t)stream);
 }

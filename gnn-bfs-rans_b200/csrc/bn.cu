@@ -34,7 +34,7 @@ struct BnArgs {
   const float* gamma; const float* beta; // [C] (may be null: 1 / 0)
   const float* sums;                     // backward apply: [2, C] = sum dz, sum dz * xhat
   float* partial;                        // [BN_BLOCKS, 2, C]
-  int relu; float p_drop; uint64_t seed; float drop_scale; int training;
+  int relu; float p_drop; uint64_t seed; float drop_scale; int training; const uint64_t* epoch;
 };
 
 // ---- column partial sums of (a, b) over this CTA's rows; kind 0: a = s - K, b = (s - K)^2;  kind 1: a = dz, b = dz * xhat
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(BN_THREADS) bn_apply_kernel(const BnArgs a) {
         const uint64_t t = (uint64_t)row * a.nvec + v;
 #pragma unroll
         for (int k4 = 0; k4 < VN; k4 += 4) {
-          const uint4 rnd = philox4x32(a.seed, t * (VN / 4) + (k4 >> 2));
+          const uint4 rnd = philox4x32(mix_epoch(a.seed, a.epoch), t * (VN / 4) + (k4 >> 2));
           const uint32_t w[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) o[k4 + k] = ((w[k] >> 8) * (1.0f / 16777216.0f) >= a.p_drop) ? o[k4 + k] * keep_scale : 0.f;
@@ -334,7 +334,7 @@ int b2g_bn_apply(const void* x, int64_t ldx, const void* r, int64_t ldr, void* y
   if (!rows_ok(x, ldx, dt) || !rows_ok(y, ldy, dt) || (r && !rows_ok(r, ldr, dt)) || (s_out && !rows_ok(s_out, lds, dt))) return B2G_E_ALIGN;
   BnArgs a{};
   a.x = x; a.ldx = ldx; a.r = r; a.ldr = ldr; a.y = y; a.ldy = ldy; a.s_out = s_out; a.lds = lds; a.n = n; a.C = C; a.nvec = nvec;
-  a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.beta = beta; a.relu = relu; a.p_drop = p_drop; a.seed = seed;
+  a.mean = mean; a.rstd = rstd; a.gamma = gamma; a.beta = beta; a.relu = relu; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   cudaStream_t st = (cudaStream_t)stream;
   if (dt == B2G_F32) bn_apply_kernel<float><<<bn_grid(n, nvec), BN_THREADS, 0, st>>>(a);
   else bn_apply_kernel<__nv_bfloat16><<<bn_grid(n, nvec), BN_THREADS, 0, st>>>(a);

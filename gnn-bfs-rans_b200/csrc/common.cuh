@@ -307,6 +307,17 @@ __device__ __forceinline__ void warp_sum4(float& a, float& b, float& c, float& d
   a = r0; b = r1; c = r2; d = r3;
 }
 
+// ---------------------------------------------------------------- dropout epoch (CUDA-graph replay)
+// Dropout seeds are kernel ARGUMENTS: a captured CUDA graph would replay the same masks forever.  The library therefore
+// keeps one 64-bit epoch per device in device memory; every dropout kernel mixes it into its seed, and
+// b2g_dropout_epoch_advance (one tiny launch, captured at the top of a training-step graph) increments it.  The epoch is 0
+// until advanced, so eager runs draw exactly the masks their seeds define; forward and backward of one step see the
+// same epoch.
+const uint64_t* dropout_epoch_ptr();          // host: this device's epoch word (allocated on first use), api.cu
+__device__ __forceinline__ uint64_t mix_epoch(uint64_t seed, const uint64_t* epoch) {
+  return epoch ? seed ^ (__ldg(epoch) * 0xD1B54A32D192ED03ull) : seed;
+}
+
 // ---------------------------------------------------------------- counter-based RNG for dropout
 // Philox-4x32-10 keyed by (seed), counter (element index).  One call -> 4 uniform floats in [0,1).
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {

@@ -113,6 +113,7 @@ struct GatzArgs {
   uint32_t n_rows;
   float slope, p_drop;
   uint64_t seed;
+  const uint64_t* epoch;                     // dropout epoch word (common.cuh), mixed into seed
   RowSched ord;
 };
 
@@ -218,7 +219,7 @@ __device__ __noinline__ void gatz_fwd_long(const GatzArgs a, uint32_t i, int b, 
     for (int h = 0; h < GH; ++h) w[h] = p0 + lane < e ? __expf(lrelu(as[h] + ad[h], a.slope) - m[h]) * inv[h] : 0.f;
     if (a.p_drop > 0.f) {
       float sc[4];
-      dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, sc);
+      dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(p0 + lane), a.p_drop, sc);
 #pragma unroll
       for (int h = 0; h < GH; ++h) w[h] *= sc[h];
     }
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_fwd_kernel(const Gatz
         }
         if (a.p_drop > 0.f) {
           float sc[4];
-          dropout_scale4(a.seed, (uint64_t)(r.b + lane), a.p_drop, sc);
+          dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + lane), a.p_drop, sc);
 #pragma unroll
           for (int h = 0; h < GH; ++h) w[h] *= sc[h];
         }
@@ -386,7 +387,7 @@ __device__ __forceinline__ void gatz_bwd_window(const GatzArgs& a, const float (
     }
     mask[h] = 1.0f;
   }
-  if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, mask);
+  if (a.p_drop > 0.f) dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(p0 + lane), a.p_drop, mask);
 #pragma unroll
   for (int h = 0; h < GH; ++h) dal[h] = (dal[h] + (kT ? ad[h] : 0.f)) * mask[h];   // d(alpha) of the pre-dropout probability
 }
@@ -494,7 +495,7 @@ __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int
       const float4 d4 = *reinterpret_cast<const float4*>(a.de_e + (uint64_t)(p0 + lane) * GH);
       dal[0] = d4.x; dal[1] = d4.y; dal[2] = d4.z; dal[3] = d4.w;
     }
-    if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, mask);
+    if (a.p_drop > 0.f) dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(p0 + lane), a.p_drop, mask);
     if (kT) {
       const float4 al4 = ldg_f4(a.alpha_in + (uint64_t)max(min(p0 + lane, p0 + n - 1), 0) * GH);
       const float al[GH] = {al4.x, al4.y, al4.z, al4.w};
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
       gatz_bwd_row_inputs<T, kT>(a, r.i, GH * VPL * 512, ad, sm, rinv);     // ad = d s_alpha of the row
       const float al[GH] = {al4.x, al4.y, al4.z, al4.w};
       float alpha[GH], sraw[GH], mask[GH] = {1.f, 1.f, 1.f, 1.f};
-      if (a.p_drop > 0.f) dropout_scale4(a.seed, (uint64_t)(r.b + lane), a.p_drop, mask);
+      if (a.p_drop > 0.f) dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + lane), a.p_drop, mask);
 #pragma unroll
       for (int h = 0; h < GH; ++h) {
         sraw[h] = 1.0f;
@@ -743,7 +744,7 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
     if (a.alpha_e && lane < n) *reinterpret_cast<float4*>(a.alpha_e + (uint64_t)(p0 + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
     if (a.p_drop > 0.f) {
       float sc[4];
-      dropout_scale4(a.seed, (uint64_t)(p0 + lane), a.p_drop, sc);
+      dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(p0 + lane), a.p_drop, sc);
 #pragma unroll
       for (int h = 0; h < GH; ++h) w[h] *= sc[h];
     }
@@ -827,7 +828,7 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
       if (a.alpha_e && lane < len) *reinterpret_cast<float4*>(a.alpha_e + (uint64_t)(r.b + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
       if (a.p_drop > 0.f) {
         float sc[4];
-        dropout_scale4(a.seed, (uint64_t)(r.b + lane), a.p_drop, sc);
+        dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + lane), a.p_drop, sc);
 #pragma unroll
         for (int h = 0; h < GH; ++h) w[h] *= sc[h];
       }
@@ -881,7 +882,7 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
       if (a.alpha_e && lane < len) *reinterpret_cast<float4*>(a.alpha_e + (uint64_t)(r.b + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
       if (a.p_drop > 0.f) {
         float sc[4];
-        dropout_scale4(a.seed, (uint64_t)(r.b + lane), a.p_drop, sc);
+        dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + lane), a.p_drop, sc);
 #pragma unroll
         for (int h = 0; h < GH; ++h) w[h] *= sc[h];
       }
@@ -1108,7 +1109,7 @@ int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda,
   const int rc = gatz_common(a, n, F, dt, band);
   if (rc) return rc;
   a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.a = a_srcdst; a.lda = (uint32_t)lda; a.z = z; a.zrow_bytes = (uint32_t)(ldz * es);
-  a.rowptr = rowptr; a.col = col; a.smax = smax; a.ssum = ssum; a.slope = slope; a.p_drop = p_drop; a.seed = seed;
+  a.rowptr = rowptr; a.col = col; a.smax = smax; a.ssum = ssum; a.slope = slope; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   return gatz_dispatch(0, dt, F * es, a, (cudaStream_t)stream);
 }
 
@@ -1129,7 +1130,7 @@ int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t 
   if (rc) return rc;
   a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.a = a_srcdst; a.lda = (uint32_t)lda; a.dz = dz; a.dzrow_bytes = (uint32_t)(lddz * es);
   a.rowptr = rowptr; a.col = col; a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum);
-  a.slope = slope; a.p_drop = p_drop; a.seed = seed; a.alpha_e = alpha_e; a.de_e = de_e; a.d_a = d_a; a.ldda = (uint32_t)ldda;
+  a.slope = slope; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.alpha_e = alpha_e; a.de_e = de_e; a.d_a = d_a; a.ldda = (uint32_t)ldda;
   return gatz_dispatch(1, dt, F * es, a, (cudaStream_t)stream);
 }
 
@@ -1169,7 +1170,7 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_a
   const int rc = gatz_common(a, n, F, dt, band);
   if (rc) return rc;
   a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = u; a.dzrow_bytes = (uint32_t)(ldu * es); a.z = z_aug;
-  a.zrow_bytes = (uint32_t)(ldz * es); a.rowptr = rowptr; a.col = col; a.alpha_e = alpha_e; a.p_drop = p_drop; a.seed = seed;
+  a.zrow_bytes = (uint32_t)(ldz * es); a.rowptr = rowptr; a.col = col; a.alpha_e = alpha_e; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   return gatz_dispatch(3, dt, F * es, a, (cudaStream_t)stream);
 }
 
@@ -1190,7 +1191,7 @@ int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz,
   const int rc = gatz_common(a, n, F, dt, band);
   if (rc) return rc;
   a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = dz_aug; a.dzrow_bytes = (uint32_t)(lddz * es); a.alpha_in = alpha_in;
-  a.rowptr = rowptr; a.col = col; a.p_drop = p_drop; a.seed = seed; a.alpha_e = alpha_e; a.de_e = de_e;
+  a.rowptr = rowptr; a.col = col; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.alpha_e = alpha_e; a.de_e = de_e;
   if (du) {
     if (!aligned16(du) || (lddu * es) % 16 || lddu < (int64_t)H * F) return B2G_E_ALIGN;
     if (!fits32(lddu * es)) return B2G_E_SHAPE;

@@ -49,3 +49,67 @@ class GraphedForward:
         self.x.copy_(x)
         self.graph.replay()
         return self.out
+
+
+class GraphedTrainStep:
+    """One optimisation step — zero_grad, forward, loss, backward, (clip), optimizer.step — on a static mesh, captured
+    once and replayed from a CUDA graph (train.py:170-189 on the shipped 12 k-node case is ~400 launches of a few
+    microseconds: launch-bound).  `step(x, y)` copies the sample into the static buffers, replays, and returns the loss
+    tensor of that step (device; read it with .item() only when needed).
+
+    Dropout (attention dropout inside GATConv / TransformerConv, the fused glue of FlowGNN(fused_glue=True)) draws new
+    masks on every replay through the library's device-side epoch (include/b2g.h b2g_dropout_epoch_advance), captured as
+    the first node of the graph.  torch's own nn.Dropout uses torch's graph-safe Philox offsets.
+
+    Requirements: `optimizer` must be capturable (e.g. torch.optim.Adam(..., capturable=True)); `loss_fn(out, y)` must not
+    synchronise; BatchNorm running statistics, parameters and optimizer state are updated in place as usual."""
+
+    def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, loss_fn, x: torch.Tensor,
+                 y: torch.Tensor, edge_index: torch.Tensor, max_grad_norm: float = None, warmup: int = 3):
+        from . import _lib
+        if not x.is_cuda or not edge_index.is_cuda:
+            raise RuntimeError("b2g.graphs: CUDA tensors required (no CPU fallback)")
+        for grp in optimizer.param_groups:
+            if "capturable" in grp and not grp["capturable"]:
+                raise RuntimeError("b2g.graphs: construct the optimizer with capturable=True")
+        n = x.shape[0]
+        if edge_index.numel() and (int(edge_index.min()) < 0 or int(edge_index.max()) >= n):
+            raise ValueError("edge_index has entries outside [0, num_nodes): filter it before capturing")
+        self.model, self.optimizer, self.edge_index = model, optimizer, edge_index
+        self._restore = getattr(model, "validate_edges", None)
+        if self._restore is not None:
+            model.validate_edges = False
+        self.x, self.y = x.clone(), y.clone()
+        lib = _lib.load()
+        params = [p for grp in optimizer.param_groups for p in grp["params"]]
+
+        def one_step():
+            _lib.check(lib.b2g_dropout_epoch_advance(torch.cuda.current_stream().cuda_stream), "dropout_epoch_advance")
+            optimizer.zero_grad(set_to_none=True)
+            loss = loss_fn(model(self.x, edge_index), self.y)
+            loss.backward()
+            if max_grad_norm is not None:
+                torch.nn.utils.clip_grad_norm_(params, max_grad_norm)
+            optimizer.step()
+            return loss
+
+        side = torch.cuda.Stream(x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(warmup, 1)):           # real steps: CSR caches, kernel attributes, optimizer state
+                one_step()
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        torch.cuda.synchronize(x.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = one_step()
+        if self._restore is not None:
+            model.validate_edges = self._restore
+
+    def step(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        if x.shape != self.x.shape or y.shape != self.y.shape:
+            raise ValueError("GraphedTrainStep: x / y shapes differ from the captured ones")
+        self.x.copy_(x)
+        self.y.copy_(y)
+        self.graph.replay()
+        return self.loss

@@ -279,6 +279,15 @@ int b2g_rows_gather(const void* x, int64_t ldx, const int32_t* idx, int64_t n_id
 int b2g_rows_scatter_add(void* x, int64_t ldx, const int32_t* idx, int64_t n_idx, const void* in,
                          int64_t ldi, int F, int dt, void* stream);
 
+/* ------------------------------------------------------------------------------------- dropout epoch
+ * Dropout seeds are call arguments, so a captured CUDA graph would replay identical masks.  Every dropout kernel of the
+ * library (attention dropout of GATConv / TransformerConv, the fused BatchNorm-ReLU-dropout) mixes a per-device 64-bit
+ * epoch, kept in device memory, into its seed.  b2g_dropout_epoch_advance increments it with one tiny launch on `stream`
+ * (capture it at the top of a training-step graph: graphs.GraphedTrainStep); b2g_dropout_epoch_set writes it.  The epoch
+ * is 0 until advanced: eager runs draw exactly the masks their seeds define. */
+int b2g_dropout_epoch_advance(void* stream);
+int b2g_dropout_epoch_set(uint64_t value, void* stream);
+
 /* ===================================================================================== BatchNorm (+ fused glue)
  * torch_geometric.nn.BatchNorm over node features [n, C] (gnn_model.py:9,87,188) and, optionally fused around it, the
  * caller's residual add / ReLU / dropout (gnn_model.py:184-192):  s = x (+ r),
