@@ -30,8 +30,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_DUMMY = {}
+
+
 def _p(t):
-    return None if t is None else t.data_ptr()
+    """Device pointer of a tensor argument.  An EMPTY tensor (e.g. the column array of a graph without edges) has no
+    storage; the gather kernels prefetch index 0 of their index arrays unconditionally (clamped, branch-free loads), so
+    empty arguments point at a small zero-filled dummy buffer on the same device instead of NULL."""
+    if t is None:
+        return None
+    if t.numel() == 0 and t.is_cuda:
+        d = _DUMMY.get(t.device)
+        if d is None:
+            d = _DUMMY[t.device] = torch.zeros(64, dtype=torch.int64, device=t.device)
+        return d.data_ptr()
+    return t.data_ptr()
 
 
 def _rows(t: torch.Tensor) -> torch.Tensor:

@@ -117,7 +117,9 @@ int b2g_csr_perm(const int32_t* eid_a, const int32_t* eid_b, int64_t nnz, int32_
  * row_scale / col_scale / bias may be NULL (=1 / =1 / =0); accumulation in fp32 in CSR order.
  * x: [*, F] dtype `dt`, row stride ldx; out: [n_rows, F] dtype `dt`, row stride ldo.
  * `x_self` (may be NULL -> x) is the matrix the self term reads (rows indexed by i).
- * relu != 0 applies max(.,0) last. */
+ * relu != 0 applies max(.,0) last.
+ * The fast paths prefetch col[clamp(position)] with unconditional loads: `col` (and `perm` where one is taken) must
+ * point at >= 1 readable int32 even when the CSR has no entries at all (the Python host passes a dummy word). */
 /* Kernel choice for b2g_seg_sum: 0 = auto, 1 = register gather (LDG.128 per lane), 2 = bulk-async gather
  * (one cp.async.bulk per neighbour row into shared memory).  Results are bit-identical. */
 int b2g_set_seg_impl(int impl);

@@ -112,7 +112,8 @@ KINDS = ["GCN", "GAT", "GIN", "Transformer", "GATcat", "Transformercat"]
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("kind", KINDS)
-@pytest.mark.parametrize("N,E,F,C", [(300, 2500, 64, 64), (1000, 6000, 128, 128), (64, 300, 256, 256), (9, 0, 32, 32)])
+@pytest.mark.parametrize("N,E,F,C", [(300, 2500, 64, 64), (1000, 6000, 128, 128), (64, 300, 256, 256), (9, 0, 32, 32),
+                                     (50, 0, 128, 128), (1500, 0, 128, 128), (200, 150, 256, 256)])
 def test_forward_and_grads(kind, dtype, N, E, F, C):
     ei = multigraph(N, E, N + E) if E else torch.zeros((2, 0), dtype=torch.long)
     m = make_layer(kind, F, C, dtype)
