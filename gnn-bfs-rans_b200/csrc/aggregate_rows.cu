@@ -58,6 +58,10 @@ struct RowsCfg {
 #ifndef B2G_ROWS_MINB
 #define B2G_ROWS_MINB 4
 #endif
+#ifndef B2G_ROWS_WARPS
+#define B2G_ROWS_WARPS 8                     // warps per CTA (measured: 4 warps x 8-9 CTAs/SM is slower, 2.60-2.86 vs 2.56 ms)
+#endif
+constexpr int ROWS_THREADS = 32 * B2G_ROWS_WARPS;
 template <int VPL, bool kW>
 constexpr int rows_minb() { return (VPL == 1) ? (kW ? 3 : B2G_ROWS_MINB) : 2; }   // kW at 4 CTAs/SM measured slower (3.69 vs 3.35 ms)   // CTAs per SM the register budget is planned for
 
@@ -184,7 +188,7 @@ __device__ __forceinline__ void rows_batch(float (&acc)[VPL][Vec<T>::N], const c
 }
 
 template <typename T, int VPL, bool kW, bool kSelf, bool kRS, bool kEpi>
-__global__ void __launch_bounds__(256, (rows_minb<VPL, kW>())) seg_rows_kernel(const RowsArgs a) {
+__global__ void __launch_bounds__(ROWS_THREADS, (rows_minb<VPL, kW>())) seg_rows_kernel(const RowsArgs a) {
   constexpr int VN = Vec<T>::N;
   constexpr int BU = RowsCfg<VPL>::BU;
   constexpr uint32_t END = 0xffffffffu;
@@ -228,7 +232,7 @@ __global__ void __launch_bounds__(256, (rows_minb<VPL, kW>())) seg_rows_kernel(c
   if (i == END) return;
   auto advance = [&](uint32_t i_) -> uint32_t {
     if (i_ == END) return END;
-    const uint32_t n = i_ + 8u;
+    const uint32_t n = i_ + (uint32_t)B2G_ROWS_WARPS;
     return n < iend ? n : first_row_of_next_chunk();
   };
   uint32_t i2 = advance(i);
@@ -282,9 +286,9 @@ __global__ void __launch_bounds__(256, (rows_minb<VPL, kW>())) seg_rows_kernel(c
 template <typename T, int VPL, bool kW, bool kSelf, bool kRS, bool kEpi>
 static int launch_rows_variant(const RowsArgs& a, cudaStream_t st) {
   int64_t blocks = a.ord.n_chunks;
-  const int64_t cap = resident_ctas(seg_rows_kernel<T, VPL, kW, kSelf, kRS, kEpi>, 256);
+  const int64_t cap = resident_ctas(seg_rows_kernel<T, VPL, kW, kSelf, kRS, kEpi>, ROWS_THREADS);
   if (blocks > cap) blocks = cap;
-  seg_rows_kernel<T, VPL, kW, kSelf, kRS, kEpi><<<(unsigned)blocks, 256, 0, st>>>(a);
+  seg_rows_kernel<T, VPL, kW, kSelf, kRS, kEpi><<<(unsigned)blocks, ROWS_THREADS, 0, st>>>(a);
   count_launch();
   return cuda_status();
 }
