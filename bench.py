@@ -316,6 +316,7 @@ def main():
             pass
         return True
 
+    numa_bound = b2g.streaming.bind_host_to_gpu_numa(dev) if world > 1 else False   # pinned buffers on the GPU's NUMA node
     need = (N * F * (2 if args.dtype == "bf16" else 4) * 2 + ei.numel() * 8) * world
     if not host_mem_ok(need):
         e2e = {"value": None, "unit": "edges/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
@@ -375,7 +376,8 @@ def main():
             e2e = {"value": e_total / (ems * 1e-3), "unit": "edges/s", "ms_per_step": ems,
                    "h2d_bytes_per_step": (hx.numel() * hx.element_size() + hei.numel() * 8) * world,
                    "d2h_bytes_per_step": hout.numel() * hout.element_size() * world, "steps": steps_e,
-                   "includes": "H2D x + edge_index, CSR rebuild, layer forward, D2H output", "api": e2e_api}
+                   "includes": "H2D x + edge_index, CSR rebuild, layer forward, D2H output", "api": e2e_api,
+                   "host_numa_bound": bool(numa_bound)}
             del hx, hei, hout
 
     # ---- extras: other layer types / fp32 / fwd+bwd / FlowGNN train step (not the headline)
