@@ -376,6 +376,7 @@ constexpr int T3_A = TC_BM * T3_BK * 4;                 // 16 KB
 constexpr int T3_B = TC_BN * T3_BK * 4;                 // 32 KB
 constexpr int T3_STAGE = 2 * T3_A + 2 * T3_B;           // A_hi, A_lo, B_hi, B_lo = 96 KB
 constexpr int T3_STAGES = 2;
+constexpr int T3_KCHUNK = 256;                           // longest reduction accumulated in TMEM in one go (fp32 path)
 constexpr int T3_SMEM = T3_STAGES * T3_STAGE + 128;
 static_assert(T3_SMEM + 1024 <= 232448, "3xTF32 shared-memory plan exceeds 227 KB");
 
@@ -415,6 +416,7 @@ struct T3Params {
   float* aux;
   int64_t ldaux;
   int act;
+  int accum;                 // Y += result (k-chunked reductions: fp32 adds between chunks, see tc_linear_fwd_tf32x3)
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -565,10 +567,14 @@ tc_linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             for (int j = 0; j < 32; j += 4) {
               float4 o;
               float* of = reinterpret_cast<float*>(&o);
+              float4 old4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.accum) old4 = *reinterpret_cast<const float4*>(dst + j);
+              const float* oldf = reinterpret_cast<const float*>(&old4);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float x = __uint_as_float(r[j + e]);
                 if (p.row_scale) x *= rs;
+                x += oldf[e];
                 if (p.bias) x += __ldg(p.bias + cg0 + j + e);
                 if (p.act == 1) x = fmaxf(x, 0.f);
                 of[e] = x;
@@ -582,6 +588,7 @@ tc_linear_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
               if (cg < p.m) {
                 float x = __uint_as_float(r[j]);
                 if (p.row_scale) x *= rs;
+                if (p.accum && cg < p.m_main) x += p.Y[row * p.ldy + cg];
                 if (p.bias) x += __ldg(p.bias + cg);
                 if (p.act == 1) x = fmaxf(x, 0.f);
                 if (cg < p.m_main) p.Y[row * p.ldy + cg] = x;
@@ -831,8 +838,9 @@ void tc_set_tf32x3(int on) { g_tf32x3 = on ? 1 : 0; }
 
 bool tc_linear_supported(int64_t n, int m, int k, int dt, int which) {
   // fp32: the TMEM accumulation truncates, so the error grows ~linearly with the reduction length (measured: 3e-6 at
-  // k = 256, 2.6e-5 at k = 3328 against the 1e-5 gate) -> longer reductions stay on the exact-fp32 SIMT kernel.
-  if (dt == B2G_F32) return g_tf32x3 && which == 0 && n >= 1 && k >= 4 && k <= 512 && (k % 4) == 0 && m >= 1 && get_encode() != nullptr;
+  // k = 256, 2.6e-5 at k = 3328 against the 1e-5 gate) -> reductions longer than T3_KCHUNK are accumulated chunk by
+  // chunk with IEEE fp32 adds in the epilogue (tc_linear_fwd_tf32x3).
+  if (dt == B2G_F32) return g_tf32x3 && which == 0 && n >= 1 && k >= 4 && k <= 16384 && (k % 4) == 0 && m >= 1 && get_encode() != nullptr;
   if (dt != B2G_BF16) return false;
   if (which == 2) return n >= 1 && m % 8 == 0 && k % 8 == 0 && m >= 8 && k >= 8 && get_encode() != nullptr;
   if (which != 0) return false;
@@ -854,21 +862,32 @@ static int tc_linear_fwd_tf32x3(const void* X, int64_t ldx, const void* W, int64
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  float* wsplit = static_cast<float*>(ws);                     // [2m, k]: rows 0..m-1 = hi, m..2m-1 = lo
-  const int64_t total = (int64_t)m * k;
-  int64_t blocks = ceil_div(total, 256);
-  if (blocks > B2G_NUM_SMS * 4) blocks = B2G_NUM_SMS * 4;
-  split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(static_cast<const float*>(W), ldw, m, k, wsplit);
-  CUtensorMap map_a, map_b;
-  if (!make_map(&map_a, X, n, k, ldx, TC_BM, true) || !make_map(&map_b, wsplit, 2 * (int64_t)m, k, k, TC_BN, true))
-    return B2G_E_UNSUPPORTED;
-  T3Params p;
-  p.n = n; p.m = m; p.m_main = m_main; p.k = k; p.bias = bias; p.row_scale = row_scale;
-  p.Y = static_cast<float*>(Y); p.ldy = ldy; p.aux = aux; p.ldaux = ldaux; p.act = act;
-  const int64_t tiles = ceil_div(n, TC_BM) * ceil_div(m, TC_BN);
-  const unsigned grid = (unsigned)(tiles < B2G_NUM_SMS ? tiles : B2G_NUM_SMS);
-  tc_linear_tf32x3_kernel<<<grid, TC_THREADS, T3_SMEM, st>>>(map_a, map_b, p);
-  count_launch(2);
+  // The TMEM accumulation truncates: its error grows ~linearly with the reduction length (3e-6 at k = 256, 2.6e-5 at
+  // k = 3328 against the 1e-5 gate).  Longer reductions are therefore cut into chunks of T3_KCHUNK columns: one launch per
+  // chunk, each adding its fp32 partial product into Y with IEEE adds (bias / activation ride on the last chunk).
+  float* wsplit = static_cast<float*>(ws);                     // [2m, kc]: rows 0..m-1 = hi, m..2m-1 = lo
+  const int nchunks = (int)ceil_div(k, T3_KCHUNK);
+  if (nchunks > 1 && m_main != m) return B2G_E_UNSUPPORTED;    // the fp32 aux split only exists for single-chunk GEMMs
+  for (int c = 0; c < nchunks; ++c) {
+    const int c0 = c * T3_KCHUNK, kc = (k - c0 < T3_KCHUNK) ? k - c0 : T3_KCHUNK;
+    const bool last = c == nchunks - 1;
+    const float* Xc = static_cast<const float*>(X) + c0;
+    const float* Wc = static_cast<const float*>(W) + c0;
+    const int64_t total = (int64_t)m * kc;
+    int64_t blocks = ceil_div(total, 256);
+    if (blocks > B2G_NUM_SMS * 4) blocks = B2G_NUM_SMS * 4;
+    split_tf32_kernel<<<(unsigned)blocks, 256, 0, st>>>(Wc, ldw, m, kc, wsplit);
+    CUtensorMap map_a, map_b;
+    if (!make_map(&map_a, Xc, n, kc, ldx, TC_BM, true) || !make_map(&map_b, wsplit, 2 * (int64_t)m, kc, kc, TC_BN, true))
+      return B2G_E_UNSUPPORTED;
+    T3Params p;
+    p.n = n; p.m = m; p.m_main = m_main; p.k = kc; p.bias = last ? bias : nullptr; p.row_scale = row_scale;
+    p.Y = static_cast<float*>(Y); p.ldy = ldy; p.aux = aux; p.ldaux = ldaux; p.act = last ? act : 0; p.accum = c > 0 ? 1 : 0;
+    const int64_t tiles = ceil_div(n, TC_BM) * ceil_div(m, TC_BN);
+    const unsigned grid = (unsigned)(tiles < B2G_NUM_SMS ? tiles : B2G_NUM_SMS);
+    tc_linear_tf32x3_kernel<<<grid, TC_THREADS, T3_SMEM, st>>>(map_a, map_b, p);
+    count_launch(2);
+  }
   return cuda_status();
 }
 

@@ -18,7 +18,7 @@ IMPLS = [1, 0]   # SIMT forced, then auto (tcgen05 where covered)
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("n,k,m", [(1000, 128, 128), (4099, 256, 256), (777, 256, 1024), (130, 64, 40), (5, 8, 8),
-                                   (3000, 256, 3328)])
+                                   (3000, 256, 3328), (2000, 1032, 256), (1500, 3336, 256), (900, 520, 128)])
 def test_linear_fwd_bwd(impl, dtype, n, k, m):
     from gnn_bfs_rans_b200 import ops
     ops.GEMM_IMPL = impl
