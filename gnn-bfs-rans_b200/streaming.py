@@ -69,7 +69,7 @@ def _pinned(t: torch.Tensor, what: str) -> torch.Tensor:
 
 @torch.no_grad()
 def gcn_forward_host(layer: GCNConv, x_host: torch.Tensor, edge_index_host: torch.Tensor,
-                     out_host: Optional[torch.Tensor] = None, rows_per_chunk: int = 1 << 19,
+                     out_host: Optional[torch.Tensor] = None, rows_per_chunk: int = 1 << 18,
                      partition=None) -> torch.Tensor:
     """GCNConv.forward(x, edge_index) (gnn_model.py:63,166) for host-resident `x` [N,F] and `edge_index` [2,E]
     (int64); returns the host tensor [N, out_channels] (pinned).  Inference only (no autograd graph).
