@@ -157,6 +157,46 @@ __device__ __forceinline__ void gatz_gather_fma(float (&acc)[GH][VPL][Vec<T>::N]
   }
 }
 
+// ---- rows of <= 8 entries: ONE (entry, head) pair per lane (lane = 4 * entry + head).  The H segment softmaxes of the
+// row are then 3 + 3 xor-shuffles and one exp per lane instead of 4 x (reduce, exp, reduce) on entry-per-lane data
+// (~35 instead of ~110 instructions per row), per-edge [nnz, H] arrays are read / written fully coalesced, and the
+// transposed reduction of the logit / d-alpha dots (warp_transpose_sum32) already delivers this layout.
+__device__ __forceinline__ float head_max8(float v) {          // max over the 8 lanes that share lane & 3
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+}
+__device__ __forceinline__ float head_sum8(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  return v + __shfl_xor_sync(0xffffffffu, v, 16);
+}
+__device__ __forceinline__ float packed_keep_scale(uint64_t seed, uint64_t pos, float p_drop, int h) {
+  float sc[4];
+  dropout_scale4(seed, pos, p_drop, sc);                      // the same Philox draw as the entry-per-lane kernels
+  return pick4(sc, h);
+}
+// acc[h] += wp(entry u, head h) * buf[u] for the K gathered rows of a <= 8-entry row; wp is the packed weight
+template <typename T, int VPL, int K>
+__device__ __forceinline__ void packed_fma(float (&acc)[GH][VPL][Vec<T>::N], const uint4 (&buf)[8][VPL], float wp) {
+  constexpr int VN = Vec<T>::N;
+#pragma unroll
+  for (int u = 0; u < K; ++u) {
+    float wu[GH];
+#pragma unroll
+    for (int h = 0; h < GH; ++h) wu[h] = __shfl_sync(0xffffffffu, wp, 4 * u + h);
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      float f[VN];
+      unpack_row16(buf[u][v], f, T());
+#pragma unroll
+      for (int h = 0; h < GH; ++h)
+#pragma unroll
+        for (int k = 0; k < VN; k += 2) ffma2_acc(acc[h][v][k], acc[h][v][k + 1], wu[h], f[k], f[k + 1]);
+    }
+  }
+}
+
 template <typename T, int VPL>
 __device__ __forceinline__ void gatz_store(char* zrow, const float (&acc)[GH][VPL][Vec<T>::N], int lane) {
 #pragma unroll
@@ -249,6 +289,45 @@ __global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_fwd_kernel(const Gatz
     const int len = r.e - r.b;
     if (len > 32) {
       gatz_fwd_long<T, VPL>(a, r.i, r.b, r.e);
+    } else if (VPL == 1 && len > 0 && len <= 8) {
+      // every mesh row: packed (entry, head) softmax, one gather, exact-length FMA
+      const int u = lane >> 2, h = lane & 3;
+      const uint32_t cu = (uint32_t)__shfl_sync(0xffffffffu, cl, u);
+      float as, ad;
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(as) : "l"(a.a + (uint64_t)cu * a.lda + h));
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(ad) : "l"(a.a + (uint64_t)r.i * a.lda + GH + h));
+      uint4 buf[8][VPL];
+#pragma unroll
+      for (int e8 = 0; e8 < 8; ++e8) {                         // entries past the row's end re-read its last row (L1 hit)
+        const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, e8);
+        const char* p = xb + (uint64_t)c * a.xrow_bytes;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) buf[e8][v] = ldg_row16(p + 512 * v);
+      }
+      const float sc = u < len ? lrelu(as + ad, a.slope) : -INFINITY;
+      const float m = head_max8(sc);
+      float wp = u < len ? __expf(sc - m) : 0.f;
+      const float zs = head_sum8(wp) + 1e-16f;
+      wp *= 1.0f / zs;
+      if (a.p_drop > 0.f) wp *= packed_keep_scale(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + u), a.p_drop, h);
+      if (a.smax && lane < GH) {                               // lanes 0..3 = entry 0, head = lane
+        a.smax[(uint64_t)r.i * GH + lane] = m;
+        a.ssum[(uint64_t)r.i * GH + lane] = zs;
+      }
+      float acc[GH][VPL][VN];
+#pragma unroll
+      for (int hh = 0; hh < GH; ++hh)
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[hh][v][k] = 0.f;
+      switch (len) {
+#define B2G_CASE(KK) case KK: packed_fma<T, VPL, KK>(acc, buf, wp); break;
+        B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4) B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
+#undef B2G_CASE
+        default: break;
+      }
+      gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, acc, lane);
     } else {
       const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);          // a_src of this lane's entry
       const float4 ad4 = ldg_f4(a.a + (uint64_t)r.i * a.lda + GH);               // a_dst of the row (uniform)
@@ -786,7 +865,7 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
 #pragma unroll
         for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_row16(p + 512 * v);
       }
-      float w[GH];
+      float wp;
       {
         uint4 uraw[GH][VPL];
         gatz_load_dz_raw<VPL>(a, r.i, lane, uraw);
@@ -810,31 +889,21 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
 #pragma unroll
           for (int h = 0; h < GH; ++h) part[u * GH + h] = p0[h] + p1[h];
         }
-        const float red = warp_transpose_sum32(part);        // lane 4u + h: logit of entry u, head h
-#pragma unroll
-        for (int h = 0; h < GH; ++h) w[h] = __shfl_sync(0xffffffffu, red, ((lane & 7) << 2) + h);
+        wp = warp_transpose_sum32(part);                     // lane 4u + h: logit of entry u, head h
       }
-      float zs[GH], ssum[GH];
-#pragma unroll
-      for (int h = 0; h < GH; ++h) {
-        const float s = lane < len ? w[h] : -INFINITY;
-        const float m = warp_max_redux(s);
-        w[h] = lane < len ? __expf(s - m) : 0.f;
-        zs[h] = w[h];
+      const int pu = lane >> 2, ph = lane & 3;                // packed (entry, head) softmax, see head_max8
+      {
+        const float sc = pu < len ? wp : -INFINITY;
+        const float m = head_max8(sc);
+        wp = pu < len ? __expf(sc - m) : 0.f;
+        wp *= 1.0f / (head_sum8(wp) + 1e-16f);
       }
-      warp_sum4(zs[0], zs[1], zs[2], zs[3]);
+      if (a.alpha_e && pu < len) a.alpha_e[(uint64_t)(r.b + pu) * GH + ph] = wp;      // coalesced 4-byte stores
+      if (a.p_drop > 0.f) wp *= packed_keep_scale(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + pu), a.p_drop, ph);
+      const float ss = head_sum8(wp);                          // per-head weight sums (every lane of the head has it)
+      float ssum[GH];
 #pragma unroll
-      for (int h = 0; h < GH; ++h) w[h] *= 1.0f / (zs[h] + 1e-16f);
-      if (a.alpha_e && lane < len) *reinterpret_cast<float4*>(a.alpha_e + (uint64_t)(r.b + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
-      if (a.p_drop > 0.f) {
-        float sc[4];
-        dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + lane), a.p_drop, sc);
-#pragma unroll
-        for (int h = 0; h < GH; ++h) w[h] *= sc[h];
-      }
-#pragma unroll
-      for (int h = 0; h < GH; ++h) ssum[h] = w[h];
-      warp_sum4(ssum[0], ssum[1], ssum[2], ssum[3]);
+      for (int h = 0; h < GH; ++h) ssum[h] = __shfl_sync(0xffffffffu, ss, h);
       float acc[GH][VPL][VN];
 #pragma unroll
       for (int h = 0; h < GH; ++h)
@@ -842,20 +911,11 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
         for (int v = 0; v < VPL; ++v)
 #pragma unroll
           for (int k = 0; k < VN; ++k) acc[h][v][k] = 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {                          // entries past the row's end carry weight 0
-        float wu[GH];
-#pragma unroll
-        for (int h = 0; h < GH; ++h) wu[h] = __shfl_sync(0xffffffffu, w[h], u);
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          float f[VN];
-          unpack_row16(buf[u][v], f, T());
-#pragma unroll
-          for (int h = 0; h < GH; ++h)
-#pragma unroll
-            for (int k = 0; k < VN; k += 2) ffma2_acc(acc[h][v][k], acc[h][v][k + 1], wu[h], f[k], f[k + 1]);
-        }
+      switch (len) {                                            // exact-length FMA phase
+#define B2G_CASE(KK) case KK: packed_fma<T, VPL, KK>(acc, buf, wp); break;
+        B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4) B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
+#undef B2G_CASE
+        default: break;
       }
       gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, acc, lane);
       tz_store_tail<T, VPL>(a, r.i, lane, ssum);
