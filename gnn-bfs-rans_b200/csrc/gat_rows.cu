@@ -617,19 +617,31 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
     const int len = r.e - r.b;
     if (len > 32) {
       gatz_bwd_dst_long<T, VPL, kT>(a, r.i, r.b, r.e);
-    } else if (kT && VPL == 1 && len > 0 && len <= 8 && a.z) {
-      // TransformerConv, every mesh row: ONE gather serves d alpha (dots with dz_i) and du_i = sum_j de_ij x_j (the
-      // rows stay in registers; dz_i is dead after the dots), instead of a separate weighted-row-sum launch.
+    } else if (VPL == 1 && len > 0 && len <= 8 && (!kT || a.z)) {
+      // every mesh row, packed (entry, head)-per-lane layout (see head_max8): ONE gather serves the d alpha dots and -
+      // TransformerConv - du_i = sum_j de_ij x_j (the rows stay in registers; dz_i is dead after the dots).
+      const int u = lane >> 2, h = lane & 3;
       uint4 buf[8][VPL];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, u);
+      for (int e8 = 0; e8 < 8; ++e8) {
+        const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, e8);
         const char* p = xb + (uint64_t)c * a.xrow_bytes;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) buf[u][v] = ldg_row16(p + 512 * v);
+        for (int v = 0; v < VPL; ++v) buf[e8][v] = ldg_row16(p + 512 * v);
       }
-      const float4 al4 = ldg_f4(a.alpha_in + (uint64_t)max(min(r.b + lane, r.e - 1), 0) * GH);
-      float dal[GH];
+      // per-(entry, head) side inputs, requested before anything consumes the gathers
+      float in0 = 0.f, in1 = 0.f, in2 = 0.f, in3 = 0.f;
+      const int pos = max(min(r.b + u, r.e - 1), 0);
+      if (kT) {
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in0) : "l"(a.alpha_in + (uint64_t)pos * GH + h));      // alpha (forward)
+      } else {
+        const uint32_t cu = (uint32_t)__shfl_sync(0xffffffffu, cl, u);
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in0) : "l"(a.a + (uint64_t)cu * a.lda + h));           // a_src
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in1) : "l"(a.a + (uint64_t)r.i * a.lda + GH + h));     // a_dst
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in2) : "l"(a.smax + (uint64_t)r.i * GH + h));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in3) : "l"(a.ssum + (uint64_t)r.i * GH + h));
+      }
+      float dal;
       {
         uint4 dzraw[GH][VPL];
         gatz_load_dz_raw<VPL>(a, r.i, lane, dzraw);
@@ -637,66 +649,64 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
         gatz_unpack_dz<T, VPL>(dzraw, dzf);
         float part[32];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int e8 = 0; e8 < 8; ++e8) {
           float p0[GH], p1[GH];
 #pragma unroll
-          for (int h = 0; h < GH; ++h) { p0[h] = 0.f; p1[h] = 0.f; }
+          for (int hh = 0; hh < GH; ++hh) { p0[hh] = 0.f; p1[hh] = 0.f; }
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             float f[VN];
-            unpack_row16(buf[u][v], f, T());
+            unpack_row16(buf[e8][v], f, T());
 #pragma unroll
-            for (int h = 0; h < GH; ++h)
+            for (int hh = 0; hh < GH; ++hh)
 #pragma unroll
-              for (int k = 0; k < VN; k += 2) ffma2_mul(p0[h], p1[h], dzf[h][v][k], dzf[h][v][k + 1], f[k], f[k + 1]);
+              for (int k = 0; k < VN; k += 2) ffma2_mul(p0[hh], p1[hh], dzf[hh][v][k], dzf[hh][v][k + 1], f[k], f[k + 1]);
           }
 #pragma unroll
-          for (int h = 0; h < GH; ++h) part[u * GH + h] = p0[h] + p1[h];
+          for (int hh = 0; hh < GH; ++hh) part[e8 * GH + hh] = p0[hh] + p1[hh];
         }
-        const float red = warp_transpose_sum32(part);
-#pragma unroll
-        for (int h = 0; h < GH; ++h) dal[h] = __shfl_sync(0xffffffffu, red, ((lane & 7) << 2) + h);
+        dal = warp_transpose_sum32(part);                        // lane 4u + h: dz_ih . x_u
       }
-      float ad[GH], sm[GH], rinv[GH];
-      gatz_bwd_row_inputs<T, kT>(a, r.i, GH * VPL * 512, ad, sm, rinv);     // ad = d s_alpha of the row
-      const float al[GH] = {al4.x, al4.y, al4.z, al4.w};
-      float alpha[GH], sraw[GH], mask[GH] = {1.f, 1.f, 1.f, 1.f};
-      if (a.p_drop > 0.f) dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + lane), a.p_drop, mask);
+      float alpha, sraw = 1.0f;
+      if (kT) {
+        float f[Vec<T>::N];                                       // d s_alpha of the row: columns H*F .. H*F+3 of dz_aug
+        ld16_rows<T>(reinterpret_cast<const char*>(a.dz) + (uint64_t)r.i * a.dzrow_bytes + GH * VPL * 512, f);
+        float dsa[GH];
 #pragma unroll
-      for (int h = 0; h < GH; ++h) {
-        sraw[h] = 1.0f;
-        alpha[h] = lane < len ? al[h] : 0.f;
-        dal[h] = (dal[h] + ad[h]) * mask[h];
+        for (int hh = 0; hh < GH; ++hh) dsa[hh] = f[hh];
+        dal += pick4(dsa, h);
+        alpha = u < len ? in0 : 0.f;
+      } else {
+        sraw = in0 + in1;
+        alpha = u < len ? __expf(lrelu(sraw, a.slope) - in2) * (1.0f / in3) : 0.f;
       }
-      float t[GH];
+      const float mask = a.p_drop > 0.f ? packed_keep_scale(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + u), a.p_drop, h) : 1.0f;
+      dal *= mask;                                                // d(alpha) of the pre-dropout probability
+      const float t = head_sum8(alpha * dal);
+      const float de = alpha * (dal - t) * (sraw > 0.f ? 1.0f : a.slope);
+      if (u < len) {                                              // coalesced 4-byte stores, target-major
+        a.alpha_e[(uint64_t)(r.b + u) * GH + h] = alpha * mask;
+        a.de_e[(uint64_t)(r.b + u) * GH + h] = de;
+      }
+      if (!kT) {
+        const float dad = head_sum8(de);
+        if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + GH + lane] = dad;
+      } else {
+        float du[GH][VPL][VN];
 #pragma unroll
-      for (int h = 0; h < GH; ++h) t[h] = alpha[h] * dal[h];
-      warp_sum4(t[0], t[1], t[2], t[3]);
-      float dad[GH] = {0.f, 0.f, 0.f, 0.f}, de[GH];
-      gatz_bwd_finish<T, VPL>(a, r.b, len, lane, alpha, dal, sraw, mask, t, dad, de);
-      float du[GH][VPL][VN];
+        for (int hh = 0; hh < GH; ++hh)
 #pragma unroll
-      for (int h = 0; h < GH; ++h)
+          for (int v = 0; v < VPL; ++v)
 #pragma unroll
-        for (int v = 0; v < VPL; ++v)
-#pragma unroll
-          for (int k = 0; k < VN; ++k) du[h][v][k] = 0.f;
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {                          // de is 0 on lanes past the row's end
-        float wu[GH];
-#pragma unroll
-        for (int h = 0; h < GH; ++h) wu[h] = __shfl_sync(0xffffffffu, de[h], u);
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) {
-          float f[VN];
-          unpack_row16(buf[u][v], f, T());
-#pragma unroll
-          for (int h = 0; h < GH; ++h)
-#pragma unroll
-            for (int k = 0; k < VN; k += 2) ffma2_acc(du[h][v][k], du[h][v][k + 1], wu[h], f[k], f[k + 1]);
+            for (int k = 0; k < VN; ++k) du[hh][v][k] = 0.f;
+        switch (len) {
+#define B2G_CASE(KK) case KK: packed_fma<T, VPL, KK>(du, buf, de); break;
+          B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4) B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
+#undef B2G_CASE
+          default: break;
         }
+        gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, du, lane);
       }
-      gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, du, lane);
     } else {
       float dzf[GH][VPL][VN];
       uint4 dzraw[GH][VPL];
