@@ -443,8 +443,6 @@ class TConvZFn(torch.autograd.Function):
             w_aug = torch.cat([w_y, w_w.to(wd), w_t, mq.to(wd), w_out[:, HF + 8:]], dim=0)   # du_ih -> Mq_h^T, g -> Ws
             gx = ops.linear_dgrad(big, w_aug)
         gb = ops.colsum(g) if (has_bout and ctx.needs_input_grad[4]) else None
-        if gb is not None:
-            gb = _cast_like(gb, w_out) if False else gb
         return gx, gmq, gcq, gw_out, gb, None, None, None
 
 
