@@ -65,21 +65,28 @@ constexpr int ROWS_THREADS = 32 * B2G_ROWS_WARPS;
 template <int VPL, bool kW>
 constexpr int rows_minb() { return (VPL == 1) ? (kW ? 3 : B2G_ROWS_MINB) : 2; }   // kW at 4 CTAs/SM measured slower (3.69 vs 3.35 ms)   // CTAs per SM the register budget is planned for
 
+// The bias slice of a lane is the same for every row: it is loaded ONCE per warp (bias_regs) instead of two 16-byte
+// loads per row in the epilogue.
+template <typename T, int VPL>
+__device__ __forceinline__ void rows_load_bias(const RowsArgs& a, int lane, float (&bia)[VPL][Vec<T>::N]) {
+  constexpr int VN = Vec<T>::N;
+#pragma unroll
+  for (int v = 0; v < VPL; ++v)
+#pragma unroll
+    for (int k = 0; k < VN; ++k) bia[v][k] = a.bias ? __ldg(a.bias + (lane + 32 * v) * VN + k) : 0.f;
+}
+
 template <typename T, int VPL, bool kEpi>
-__device__ __forceinline__ void rows_store(const RowsArgs& a, float (&acc)[VPL][Vec<T>::N], uint32_t i, int lane) {
+__device__ __forceinline__ void rows_store(const RowsArgs& a, float (&acc)[VPL][Vec<T>::N], uint32_t i, int lane,
+                                           const float (&bia)[VPL][Vec<T>::N]) {
   constexpr int VN = Vec<T>::N;
   char* ob = reinterpret_cast<char*>(a.out) + (uint64_t)i * a.orow_bytes + lane * 16;
 #pragma unroll
   for (int v = 0; v < VPL; ++v) {
     if (kEpi) {
-      if (a.bias) {
-        const int vi = lane + 32 * v;
 #pragma unroll
-        for (int k = 0; k < VN; k += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(a.bias + vi * VN + k));
-          acc[v][k] += bb.x; acc[v][k + 1] += bb.y; acc[v][k + 2] += bb.z; acc[v][k + 3] += bb.w;
-        }
-      }
+      for (int k = 0; k < VN; ++k) acc[v][k] = __fadd_rn(acc[v][k], bia[v][k]);   // never contracted with the row-scale multiply:
+                                                                                   // same bits as the generic kernel
       if (a.relu) {
 #pragma unroll
         for (int k = 0; k < VN; ++k) acc[v][k] = fmaxf(acc[v][k], 0.f);
@@ -155,9 +162,11 @@ __device__ __noinline__ void rows_long(const RowsArgs a, uint32_t i, int b, int 
 #pragma unroll
     for (int v = 0; v < VPL; ++v)
 #pragma unroll
-      for (int k = 0; k < VN; ++k) acc[v][k] *= rs;
+      for (int k = 0; k < VN; ++k) acc[v][k] = __fmul_rn(acc[v][k], rs);
   }
-  rows_store<T, VPL, kEpi>(a, acc, i, lane);
+  float bia[VPL][VN];
+  if (kEpi) rows_load_bias<T, VPL>(a, lane, bia);
+  rows_store<T, VPL, kEpi>(a, acc, i, lane, bia);
 }
 
 // K entries held one per lane in (cl, wl): K loads, then the K adds / FMAs.
@@ -200,6 +209,9 @@ __global__ void __launch_bounds__(ROWS_THREADS, (rows_minb<VPL, kW>())) seg_rows
   asm volatile("" : "+l"(xb));
   const int32_t* __restrict__ rowptr = a.rowptr;
   const int32_t* __restrict__ col = a.col;
+
+  float bia[VPL][VN];
+  if (kEpi) rows_load_bias<T, VPL>(a, lane, bia);
 
   // this warp's rows: wi, wi + 8, ... of chunk q, then of chunk q + grid, ...
   uint32_t q = blockIdx.x, iend = 0;
@@ -273,9 +285,9 @@ __global__ void __launch_bounds__(ROWS_THREADS, (rows_minb<VPL, kW>())) seg_rows
 #pragma unroll
         for (int v = 0; v < VPL; ++v)
 #pragma unroll
-          for (int k = 0; k < VN; ++k) acc[v][k] *= rs;
+          for (int k = 0; k < VN; ++k) acc[v][k] = __fmul_rn(acc[v][k], rs);
       }
-      rows_store<T, VPL, kEpi>(a, acc, i, lane);
+      rows_store<T, VPL, kEpi>(a, acc, i, lane, bia);
     }
     if (i2 == END) break;
     i = i2; b = b2; e = e2; cl = cl2;
