@@ -115,7 +115,17 @@ def _nccl_worker(rank, world, port, q):
         e_out = rel(out.detach(), ref.detach()[rank * nb:(rank + 1) * nb])
         e_gx = rel(xo.grad, xr.grad[rank * nb:(rank + 1) * nb])
         e_gw = rel(layer.lin.weight.grad, ref_layer.lin.weight.grad)
-        q.put((rank, e_out, e_gx, e_gw))
+        # inference path of Partition.wrap_forward: exchange on a side stream behind the owned-row GEMM, same bits
+        with torch.no_grad():
+            fwd = part.wrap_forward(layer)
+            for _ in range(3):
+                o2 = fwd(xo.detach(), part.edge_index)
+            xf = torch.zeros(part.n_local, F, device=f"cuda:{rank}")
+            xf[:part.n_owned] = xo.detach()
+            part.exchange(xf)
+            o1 = layer(xf, part.edge_index)[:part.n_owned]
+        same = o2.shape == o1.shape and bool(torch.equal(o1, o2))
+        q.put((rank, e_out, e_gx, e_gw, same))
     finally:
         dist.destroy_process_group()
 
@@ -132,8 +142,9 @@ def test_two_gpu_nccl_halo_forward_backward():
     res = [q.get(timeout=300) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
-    for rank, e_out, e_gx, e_gw in res:
+    for rank, e_out, e_gx, e_gw, same in res:
         assert e_out < 1e-5 and e_gx < 1e-5 and e_gw < 1e-5, res
+        assert same, "overlapped halo forward (Partition.wrap_forward) differs from the blocking exchange + layer"
 
 
 def _flow_worker(rank, world, port, q, layer_type, ckpt=False):
