@@ -154,10 +154,12 @@ class Partition:
             return lambda x, ei: layer(x, ei)
         holder = {}
         from .nn import GCNConv
-        if isinstance(layer, GCNConv) and not torch.is_grad_enabled():
-            return self._gcn_forward_overlapped(layer, holder)
+        overlapped = self._gcn_forward_overlapped(layer, holder) if isinstance(layer, GCNConv) else None
 
         def fwd(x, ei):
+            if overlapped is not None and x.is_cuda and not (torch.is_grad_enabled() and (
+                    x.requires_grad or any(p.requires_grad for p in layer.parameters()))):
+                return overlapped(x, ei)
             if x.shape[0] == self.n_local:
                 xf = x
             else:
