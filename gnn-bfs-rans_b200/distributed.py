@@ -12,6 +12,7 @@ The plan (who sends which rows to whom) is computed WITHOUT communication: every
 sides from the same global partition vector, so send and receive orders agree by construction."""
 from __future__ import annotations
 
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -154,7 +155,10 @@ class Partition:
             return lambda x, ei: layer(x, ei)
         holder = {}
         from .nn import GCNConv
-        overlapped = self._gcn_forward_overlapped(layer, holder) if isinstance(layer, GCNConv) else None
+        # opt-in: measured at N = 2 on cfg4 it changes nothing (4.54 ms against 4.50 ms with the blocking exchange: the
+        # 9.6 MB exchange is not what the N = 2 step loses against N = 1), so the blocking path stays the default
+        overlapped = (self._gcn_forward_overlapped(layer, holder)
+                      if isinstance(layer, GCNConv) and os.environ.get("B2G_HALO_OVERLAP", "0") == "1" else None)
 
         def fwd(x, ei):
             if overlapped is not None and x.is_cuda and not (torch.is_grad_enabled() and (

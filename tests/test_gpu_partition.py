@@ -116,6 +116,7 @@ def _nccl_worker(rank, world, port, q):
         e_gx = rel(xo.grad, xr.grad[rank * nb:(rank + 1) * nb])
         e_gw = rel(layer.lin.weight.grad, ref_layer.lin.weight.grad)
         # inference path of Partition.wrap_forward: exchange on a side stream behind the owned-row GEMM, same bits
+        os.environ["B2G_HALO_OVERLAP"] = "1"
         with torch.no_grad():
             fwd = part.wrap_forward(layer)
             for _ in range(3):
