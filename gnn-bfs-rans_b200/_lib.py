@@ -57,6 +57,10 @@ SIGNATURES = {
     "b2g_linear_wgrad": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp, vp]),
     "b2g_colsum_workspace_bytes": (i64, [i32]),
     "b2g_colsum": (i32, [vp, i64, i64, i32, i32, vp, vp, vp]),
+    "b2g_mesh_num_cells": (i32, [vp, i64, vp, i64, vp, vp, vp]),
+    "b2g_mesh_workspace_bytes": (i64, [i64, i64]),
+    "b2g_mesh_cell_centers": (i32, [vp, i64, vp, i64, vp, i64, vp, vp, i64, i64, i64, vp, vp, vp, i64, vp]),
+    "b2g_mesh_internal_cells": (i32, [vp, i64, vp, i64, i64, vp, vp, vp, vp]),
     "b2g_bn_workspace_bytes": (i64, [i32]),
     "b2g_bn_stats": (i32, [vp, i64, vp, i64, i64, i32, i32, f32, vp, vp, vp]),
     "b2g_bn_apply": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp, i32, f32, u64, vp]),

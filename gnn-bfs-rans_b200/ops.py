@@ -139,6 +139,52 @@ def edge_attr(cell_centers_f64: torch.Tensor, edge_index: torch.Tensor) -> torch
     return out
 
 
+# ------------------------------------------------------------------------------------------ mesh ingest (§8f-3)
+def mesh_num_cells(owner: torch.Tensor, neighbour: torch.Tensor) -> int:
+    """openfoam_loader.py:197 on device: max(max(owner), max(neighbour)) + 1 (one host read of the result)."""
+    _cuda(owner, neighbour)
+    lib = _lib.load()
+    if owner.numel() + neighbour.numel() == 0:
+        raise ValueError("zero-size array to reduction operation maximum which has no identity")   # np.max, :197
+    out = torch.empty(1, dtype=torch.int64, device=owner.device)
+    _lib.check(lib.b2g_mesh_num_cells(_p(owner), owner.numel(), _p(neighbour), neighbour.numel(), _p(out),
+                                      _p(_ws(256, owner.device)), _stream()), "mesh_num_cells")
+    return int(out)
+
+
+def mesh_cell_centers(points: torch.Tensor, owner: torch.Tensor, neighbour: torch.Tensor, face_pts: torch.Tensor,
+                      face_off: torch.Tensor, n_cells: int, n_slots: int) -> torch.Tensor:
+    """openfoam_loader.py:191-227 on device.  points fp64 [P,3]; owner / neighbour / face_pts int32; face_off int64
+    [F+1]; n_slots = face_off[len(owner)] + face_off[len(neighbour)].  -> fp64 [n_cells, 3]."""
+    _cuda(points, owner, neighbour, face_pts, face_off)
+    lib = _lib.load()
+    dev = points.device
+    out = torch.empty((n_cells, 3), dtype=torch.float64, device=dev)
+    bad = torch.empty(1, dtype=torch.int64, device=dev)
+    nbytes = lib.b2g_mesh_workspace_bytes(n_cells, n_slots)
+    ws = _ws(nbytes, dev)
+    _lib.check(lib.b2g_mesh_cell_centers(_p(points), points.shape[0], _p(owner), owner.numel(), _p(neighbour),
+                                         neighbour.numel(), _p(face_off), _p(face_pts), face_off.numel() - 1, n_slots,
+                                         n_cells, _p(out), _p(bad), _p(ws), ws.numel(), _stream()), "mesh_cell_centers")
+    if int(bad):
+        raise IndexError(f"b2g.mesh: {int(bad)} cell / vertex ids out of range")        # :205-219 IndexError upstream
+    return out
+
+
+def mesh_internal_cells(owner: torch.Tensor, neighbour: torch.Tensor, n_cells: int) -> torch.Tensor:
+    """openfoam_loader.py:229-248 on device -> bool [n_cells]."""
+    _cuda(owner, neighbour)
+    lib = _lib.load()
+    dev = owner.device
+    mask = torch.empty(n_cells, dtype=torch.uint8, device=dev)
+    bad = torch.empty(1, dtype=torch.int64, device=dev)
+    _lib.check(lib.b2g_mesh_internal_cells(_p(owner), owner.numel(), _p(neighbour), neighbour.numel(), n_cells,
+                                           _p(mask), _p(bad), _p(_ws(256, dev)), _stream()), "mesh_internal_cells")
+    if int(bad):
+        raise IndexError(f"b2g.mesh: {int(bad)} cell ids out of range")
+    return mask.bool()
+
+
 # ------------------------------------------------------------------------------------------ K1
 def csr_build(edge_index: torch.Tensor, N: int, self_loops: bool, by_source: bool, want_dinv: bool):
     """-> (rowptr int32[N+1], col int32[nnz], eid int32[nnz], dinv fp32[N] | None)."""

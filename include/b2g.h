@@ -313,6 +313,29 @@ int b2g_bn_bwd_apply(const void* dy, int64_t lddy, const void* y, int64_t ldy, c
                      int64_t ldds, int64_t n, int C, int dt, const float* mean, const float* rstd, const float* gamma,
                      const float* sums, int relu, float drop_scale, int training, void* stream);
 
+/* ===================================================================================== mesh ingest
+ * The arrays /root/reference/openfoam_loader.py derives from the polyMesh connectivity with Python loops over every
+ * face, computed on the device from the flattened mesh (faces[i] = face_pts[face_off[i] .. face_off[i+1])):
+ *   b2g_mesh_num_cells      n_cells = max(max(owner), max(neighbour)) + 1            (openfoam_loader.py:197, :236);
+ *                           n_cells_out: device int64[1]; ws: >= 256 device bytes.
+ *   b2g_mesh_cell_centers   get_cell_centers (:191-227): centers [n_cells,3] fp64 = mean of the unique vertices of the
+ *                           faces a cell owns (face i of owner[i], i < n_owner) or neighbours (face i of neighbour[i],
+ *                           i < n_nb); cells without a face stay 0.  Vertices are added in ascending id (the reference
+ *                           adds in CPython set order: parity is 1e-13 absolute).  n_slots = face_off[n_owner] +
+ *                           face_off[n_nb]; ws of b2g_mesh_workspace_bytes(n_cells, n_slots).
+ *   b2g_mesh_internal_cells get_internal_cells (:229-248): mask [n_cells] uint8; ws: >= 256 device bytes.
+ * n_bad_out (device int64[1]) counts out-of-range cell / vertex ids (the reference raises IndexError or wraps negative
+ * ids; the host wrapper raises).  n_owner or n_nb > n_faces and n_nb > n_owner are B2G_E_ARG (IndexError upstream). */
+int b2g_mesh_num_cells(const int32_t* owner, int64_t n_owner, const int32_t* neighbour, int64_t n_nb, int64_t* n_cells_out,
+                       void* ws, void* stream);
+int64_t b2g_mesh_workspace_bytes(int64_t n_cells, int64_t n_slots);
+int b2g_mesh_cell_centers(const double* points, int64_t n_points, const int32_t* owner, int64_t n_owner,
+                          const int32_t* neighbour, int64_t n_nb, const int64_t* face_off, const int32_t* face_pts,
+                          int64_t n_faces, int64_t n_slots, int64_t n_cells, double* centers, int64_t* n_bad_out,
+                          void* ws, int64_t ws_bytes, void* stream);
+int b2g_mesh_internal_cells(const int32_t* owner, int64_t n_owner, const int32_t* neighbour, int64_t n_nb, int64_t n_cells,
+                            uint8_t* mask, int64_t* n_bad_out, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

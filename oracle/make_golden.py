@@ -63,6 +63,12 @@ def main():
         os.path.join(out, "shipped_mesh.npz"),
         owner=owner, neighbour=neighbour, cell_centers=mesh['cell_centers'],
         internal_mask=mesh['internal_mask'], n_cells=np.int64(mesh['n_cells']))
+    # the inputs of the loader's get_cell_centers (openfoam_loader.py:191-227) for the same case: points + ragged faces
+    sys.path.insert(0, ROOT)
+    from oracle import mesh_oracle
+    face_pts, face_off = mesh_oracle.flatten_faces(mesh['faces'])
+    np.savez_compressed(os.path.join(out, "shipped_polymesh.npz"), points=mesh['points'], face_pts=face_pts,
+                        face_off=face_off)
     gc = GraphConstructor(mesh)
     gold = dict(
         loader=dict(owner_sha256=sha(owner), neighbour_sha256=sha(neighbour),
