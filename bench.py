@@ -384,6 +384,7 @@ def main():
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
         extras = run_extras(b2g, ops, part, dev, timed)
+        extras.update(run_mesh_ingest(b2g, dev, timed, (nx, ny, nz)))
 
     # ---- opt-in: cfg5-shaped train step, partitioned (halo exchange per layer, synchronised BatchNorm, gradient all-reduce)
     train_line = None
@@ -452,6 +453,48 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_mesh_ingest(b2g, dev, timed, dims):
+    """Not the headline: the device mesh ingest (csrc/mesh.cu) on the bench mesh as a polyMesh — cell
+    centres + internal-cell mask + n_cells from points / faces / owner / neighbour already in HBM — and the numpy oracle
+    of the same computation on a bounded sample (the reference itself loops over every face in Python)."""
+    import time
+    import torch
+    from gnn_bfs_rans_b200.synthetic import hex_cell_centers, hex_polymesh
+    out = {}
+    try:
+        nx, ny, nz = dims
+        pts, own, nbr, fp, fo = hex_polymesh(nx, ny, nz, dev)
+        res = {}
+
+        def run():
+            res["d"] = b2g.mesh.derive_mesh(pts, own, nbr, (fp, fo), dev, as_numpy=False)
+        ms = timed(run, 5, 3)
+        d = res["d"]
+        n_cells, slots = d["n_cells"], int(fo[own.numel()]) + int(fo[nbr.numel()])
+        # K0m algorithmic bytes (DESIGN §4): ids + offsets read twice, vertex lists written + read, unique vertices, output
+        alg = 2 * (4 * (own.numel() + nbr.numel()) + 16 * (own.numel() + nbr.numel()) + 4 * slots) + 8 * slots \
+            + 24 * 8 * n_cells + 24 * n_cells + 2 * 4 * nbr.numel() + n_cells
+        ok = bool(torch.equal(d["cell_centers"][:nx * ny].cpu(), torch.from_numpy(hex_cell_centers(nx, ny, 1))))
+        out["mesh_ingest"] = {"cells": n_cells, "faces": int(own.numel()), "vertex_slots": slots, "ms": ms,
+                              "cells_per_sec": n_cells / (ms * 1e-3), "algorithmic_gb_s": alg / (ms * 1e-3) / 1e9,
+                              "first_plane_exact": ok, "all_internal": bool(d["internal_mask"].all())}
+        del pts, own, nbr, fp, fo, d, res
+        torch.cuda.empty_cache()
+        from oracle import mesh_oracle as mo                      # the checker, timed as the CPU baseline of this extra
+        sx, sy, sz = min(nx, 100), min(ny, 100), min(nz, 50)
+        p2, o2, n2, fp2, fo2 = [t.numpy() for t in hex_polymesh(sx, sy, sz)]
+        t0 = time.perf_counter()
+        mo.get_cell_centers(p2, o2, n2, fp2, fo2)
+        mo.get_internal_cells(o2, n2)
+        dt = time.perf_counter() - t0
+        out["mesh_ingest"]["cpu_oracle"] = {"sample": f"{sx}x{sy}x{sz} hex block, numpy restatement, 1 thread",
+                                            "cells_per_sec": sx * sy * sz / dt}
+    except Exception as e:
+        out["mesh_ingest"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_extras(b2g, ops, part, dev, timed):

@@ -29,6 +29,41 @@ def hex_mesh_faces(nx: int, ny: int, nz: int, device="cpu", boundary: bool = Fal
     return owner.contiguous(), nei.contiguous()
 
 
+def hex_polymesh(nx: int, ny: int, nz: int, device="cpu"):
+    """The same block as a polyMesh: (points fp64 [P,3], owner int32 [F], neighbour int32 [F_int], face_pts int32 [4F],
+    face_off int64 [F+1]).  Internal faces first, in hex_mesh_faces order (+x, +y, +z per owner), then the boundary faces
+    in owner order (-x, +x, -y, +y, -z, +z).  Vertex id = px + (nx+1) (py + (ny+1) pz), coordinates = (px, py, pz), so a
+    cell's centre is exactly (ix + .5, iy + .5, iz + .5) in fp64."""
+    dev = torch.device(device)
+    N = nx * ny * nz
+    ids = torch.arange(N, dtype=torch.int64, device=dev)
+    ix, iy, iz = ids % nx, (ids // nx) % ny, ids // (nx * ny)
+    sx, sy = 1, nx + 1
+    sz = (nx + 1) * (ny + 1)
+    v0 = ix * sx + iy * sy + iz * sz                                   # the cell's (0,0,0) corner
+
+    def quad(axis_off, a, b):                                           # 4 corners of the face at offset axis_off
+        return torch.stack([v0 + axis_off, v0 + axis_off + a, v0 + axis_off + a + b, v0 + axis_off + b], dim=1)
+
+    qx0, qx1 = quad(0, sy, sz), quad(sx, sy, sz)
+    qy0, qy1 = quad(0, sx, sz), quad(sy, sx, sz)
+    qz0, qz1 = quad(0, sx, sy), quad(sz, sx, sy)
+    has = torch.stack([ix < nx - 1, iy < ny - 1, iz < nz - 1], dim=1)
+    nb = torch.stack([ids + 1, ids + nx, ids + nx * ny], dim=1)
+    own = ids.unsqueeze(1).expand(-1, 3)
+    q_int = torch.stack([qx1, qy1, qz1], dim=1)[has]                   # [F_int, 4]
+    bnd = torch.stack([ix == 0, ix == nx - 1, iy == 0, iy == ny - 1, iz == 0, iz == nz - 1], dim=1)
+    q_bnd = torch.stack([qx0, qx1, qy0, qy1, qz0, qz1], dim=1)[bnd]
+    owner = torch.cat([own[has], ids.unsqueeze(1).expand(-1, 6)[bnd]]).to(torch.int32).contiguous()
+    neighbour = nb[has].to(torch.int32).contiguous()
+    face_pts = torch.cat([q_int, q_bnd]).to(torch.int32).reshape(-1).contiguous()
+    face_off = torch.arange(owner.numel() + 1, dtype=torch.int64, device=dev) * 4
+    P = (nx + 1) * (ny + 1) * (nz + 1)
+    pid = torch.arange(P, dtype=torch.int64, device=dev)
+    points = torch.stack([pid % (nx + 1), (pid // (nx + 1)) % (ny + 1), pid // sz], dim=1).to(torch.float64).contiguous()
+    return points, owner, neighbour, face_pts, face_off
+
+
 def hex_cell_centers(nx: int, ny: int, nz: int) -> np.ndarray:
     z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
     return np.stack([x.ravel() + 0.5, y.ravel() + 0.5, z.ravel() + 0.5], axis=1).astype(np.float64)

@@ -87,3 +87,14 @@ def test_errors_follow_the_reference():
         b2g.mesh.get_cell_centers(pts, np.array([0, 0], dtype=np.int32), np.zeros(0, dtype=np.int32), faces)
     with pytest.raises(RuntimeError):   # no CPU fallback
         b2g.ops.mesh_num_cells(torch.zeros(3, dtype=torch.int32), torch.zeros(1, dtype=torch.int32))
+
+
+def test_hex_block_known_answer():
+    """Structured block: the centre of cell (ix, iy, iz) is exactly (ix + .5, iy + .5, iz + .5) in fp64."""
+    b2g = _b2g()
+    from gnn_bfs_rans_b200.synthetic import hex_cell_centers, hex_polymesh
+    nx, ny, nz = 64, 48, 40
+    pts, own, nbr, fp, fo = hex_polymesh(nx, ny, nz, "cuda")
+    d = b2g.mesh.derive_mesh(pts, own, nbr, (fp, fo), as_numpy=False)
+    assert d["n_cells"] == nx * ny * nz and d["n_internal_cells"] == nx * ny * nz
+    assert np.array_equal(d["cell_centers"].cpu().numpy(), hex_cell_centers(nx, ny, nz))
