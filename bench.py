@@ -636,27 +636,29 @@ def run_extras(b2g, ops, part, dev, timed):
     # ---- BASELINE.json cfg3: 2-D unstructured mesh, ~1 M cells (Delaunay dual of 500 500 points, cell ids = triangle ids:
     # spatially incoherent order on purpose), GIN and TransformerConv hidden 256, bf16: layer forward and forward+backward
     try:
-        from gnn_bfs_rans_b200.synthetic import delaunay_dual_faces
-        own, nbr, _ = delaunay_dual_faces(500500, seed=1)
-        n3 = int(max(own.max(), nbr.max())) + 1
-        ei3 = ops.build_graph_edges(torch.from_numpy(own).to(dev), torch.from_numpy(nbr).to(dev), 1, None, n3, n3)
-        for lt in ("GIN", "Transformer"):
-            torch.manual_seed(0)
-            layer = mk(lt).to(dev).to(torch.bfloat16).eval()
-            x3 = torch.empty(n3, F, device=dev, dtype=torch.bfloat16).normal_()
-            ms_f = timed(lambda: layer(x3, ei3), 10, 3)
-            xg = x3.clone().requires_grad_(True)
-            g3 = torch.empty(n3, F, device=dev, dtype=torch.bfloat16).normal_()
+        from gnn_bfs_rans_b200.synthetic import delaunay_dual_faces, hilbert_renumber_2d
+        own0, nbr0, cen0 = delaunay_dual_faces(500500, seed=1)
+        n3 = int(max(own0.max(), nbr0.max())) + 1
+        own1, nbr1, _, _ = hilbert_renumber_2d(own0, nbr0, cen0)      # the "Hilbert-sorted variant" of SURVEY §8d cfg3
+        for tag, own, nbr in (("", own0, nbr0), ("_hilbert", own1, nbr1)):
+            ei3 = ops.build_graph_edges(torch.from_numpy(own).to(dev), torch.from_numpy(nbr).to(dev), 1, None, n3, n3)
+            for lt in ("GIN", "Transformer"):
+                torch.manual_seed(0)
+                layer = mk(lt).to(dev).to(torch.bfloat16).eval()
+                x3 = torch.empty(n3, F, device=dev, dtype=torch.bfloat16).normal_()
+                ms_f = timed(lambda: layer(x3, ei3), 10, 3)
+                xg = x3.clone().requires_grad_(True)
+                g3 = torch.empty(n3, F, device=dev, dtype=torch.bfloat16).normal_()
 
-            def fb3():
-                xg.grad = None
-                layer.zero_grad(set_to_none=True)
-                layer(xg, ei3).backward(g3)
-            ms_b = timed_grad(fb3, 5, 2)
-            e3 = int(ei3.shape[1])
-            out[f"cfg3_delaunay_{lt}_F256_bf16"] = {"cells": n3, "edges": e3, "forward_ms": ms_f, "fwd_bwd_ms": ms_b,
-                                                    "fwd_edges_per_sec": e3 / (ms_f * 1e-3)}
-            del layer, x3, xg, g3
+                def fb3():
+                    xg.grad = None
+                    layer.zero_grad(set_to_none=True)
+                    layer(xg, ei3).backward(g3)
+                ms_b = timed_grad(fb3, 5, 2)
+                e3 = int(ei3.shape[1])
+                out[f"cfg3_delaunay{tag}_{lt}_F256_bf16"] = {"cells": n3, "edges": e3, "forward_ms": ms_f, "fwd_bwd_ms": ms_b,
+                                                             "fwd_edges_per_sec": e3 / (ms_f * 1e-3)}
+                del layer, x3, xg, g3
     except Exception as e:
         out["cfg3_delaunay"] = {"error": str(e)[:200]}
     torch.cuda.empty_cache()

@@ -85,3 +85,39 @@ def delaunay_dual_faces(n_points: int, seed: int = 1):
     c = pts[tri.simplices].mean(axis=1)
     centres = np.concatenate([c, np.zeros((N, 1))], axis=1)
     return own[order].astype(np.int32), nb[order].astype(np.int32), centres
+
+
+def hilbert_index_2d(x: np.ndarray, y: np.ndarray, bits: int = 16) -> np.ndarray:
+    """Distance along the 2-D Hilbert curve of order `bits` for integer coordinates in [0, 2^bits) (the classic
+    xy -> d walk, vectorised over the points)."""
+    n = np.uint64(1) << np.uint64(bits)
+    x = x.astype(np.uint64).copy()
+    y = y.astype(np.uint64).copy()
+    d = np.zeros(x.shape, dtype=np.uint64)
+    s = n >> np.uint64(1)
+    while s > 0:
+        rx = (x & s) > 0
+        ry = (y & s) > 0
+        d += s * s * ((np.uint64(3) * rx.astype(np.uint64)) ^ ry.astype(np.uint64))
+        flip = (~ry) & rx                                 # rotate the quadrant so the sub-curve has the standard orientation
+        x = np.where(flip, n - np.uint64(1) - x, x)
+        y = np.where(flip, n - np.uint64(1) - y, y)
+        x, y = np.where(~ry, y, x), np.where(~ry, x, y)
+        s >>= np.uint64(1)
+    return d
+
+
+def hilbert_renumber_2d(owner: np.ndarray, neighbour: np.ndarray, centres: np.ndarray, bits: int = 16):
+    """Renumber the cells of a 2-D mesh along the Hilbert curve through their centres (cfg3's "Hilbert-sorted variant",
+    SURVEY §8d).  Returns (owner, neighbour, centres) of the renumbered mesh, again with owner < neighbour and the faces
+    sorted by (owner, neighbour), plus `order` (new id -> old id)."""
+    c = centres[:, :2]
+    lo, hi = c.min(axis=0), c.max(axis=0)
+    q = np.minimum(((c - lo) / np.maximum(hi - lo, 1e-300) * (2 ** bits)).astype(np.int64), 2 ** bits - 1)
+    order = np.argsort(hilbert_index_2d(q[:, 0], q[:, 1], bits), kind="stable")
+    rank = np.empty(len(order), dtype=np.int64)
+    rank[order] = np.arange(len(order))
+    a, b = rank[owner], rank[neighbour]
+    o2, n2 = np.minimum(a, b), np.maximum(a, b)
+    f = np.lexsort((n2, o2))
+    return o2[f].astype(np.int32), n2[f].astype(np.int32), centres[order], order
