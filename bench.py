@@ -271,6 +271,7 @@ def main():
             kms = timed(kfn, args.steps, 3)
             alg = 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1) + (4 * N if dinv is not None else 0)
             kname = "seg_rows_kernel (K2/K3, aggregate_rows.cu)"
+            gather_row_bytes = F * s
         else:
             H = 4
             kms, alg, kname = None, None, "attn_fwd_kernel (K4/K5)"
@@ -283,17 +284,22 @@ def main():
                 # aggregate-first kernel: read x once, a [N,2H] fp32, indices; write z [N, H*F]
                 alg = N * F * s + N * H * F * s + 2 * 4 * N * H + 4 * csr.nnz + 4 * (N + 1)
                 kname = "gatz_fwd_kernel (K4 aggregate-first, gat_rows.cu)"
+                gather_row_bytes = F * s
             else:
                 csr = g.csr("raw", False)
                 y = torch.randn(part.n_local, 3 * H * F + F, device=dev).to(dtype)
                 q, k, v, sk = y[:, :H * F], y[:, H * F:2 * H * F], y[:, 2 * H * F:3 * H * F], y[:, 3 * H * F:]
                 kfn = lambda: ops.tconv_fwd(q, k, v, sk, H, F, False, csr.rowptr, csr.col, 0.0, 0, False)
                 alg = 3 * N * H * F * s + 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1)
+                gather_row_bytes = 2 * H * F * s                       # k and v rows per edge
             kms = timed(kfn, args.steps, 3)
         ach = alg / (kms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes": alg, "kernel_ms": kms,
-                "kernel_edges_per_sec": e_agg_local / (kms * 1e-3), "peak_source": peak_src}
+                "kernel_edges_per_sec": e_agg_local / (kms * 1e-3), "peak_source": peak_src,
+                # secondary figure: bytes the gathers request, E * row bytes; L2 serves the re-reads, so it may
+                # exceed the HBM peak and is never the roofline fraction
+                "gather_model_gb_s": int(csr.nnz) * gather_row_bytes / (kms * 1e-3) / 1e9}
         tfile = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tfile):
             try:
