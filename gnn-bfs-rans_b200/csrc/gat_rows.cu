@@ -109,6 +109,8 @@ struct GatzArgs {
   float* smax; float* ssum;                  // [N, H] softmax statistics (ssum includes PyG's + 1e-16)
   float* alpha_e; float* de_e;               // [nnz, H] target-major
   const float* alpha_in;                     // TransformerConv backward: the forward pass's (pre-dropout) alpha [nnz, H]
+  const float* ebias;                        // TransformerConv with edge features (edge_dim): per-(entry, head) term added to
+                                             // the logits (forward) / to d alpha (backward), fp32 [nnz, H] target-major; or NULL
   float* d_a; uint32_t ldda;                 // [N, >= 2H]
   uint32_t n_rows;
   float slope, p_drop;
@@ -469,6 +471,10 @@ __device__ __forceinline__ void gatz_bwd_window(const GatzArgs& a, const float (
   if (a.p_drop > 0.f) dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(p0 + lane), a.p_drop, mask);
 #pragma unroll
   for (int h = 0; h < GH; ++h) dal[h] = (dal[h] + (kT ? ad[h] : 0.f)) * mask[h];   // d(alpha) of the pre-dropout probability
+  if (kT && a.ebias && lane < n) {            // edge-feature term of d alpha' (dm_ih . a_ij), same dropout mask
+    const float4 b4 = ldg_f4(a.ebias + (uint64_t)(p0 + lane) * GH);
+    dal[0] += b4.x * mask[0]; dal[1] += b4.y * mask[1]; dal[2] += b4.z * mask[2]; dal[3] += b4.w * mask[3];
+  }
 }
 
 // the row's per-head side inputs: GAT (a_dst, softmax max, 1 / softmax sum) or TransformerConv (d s_alpha from dz_aug)
@@ -675,6 +681,7 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
 #pragma unroll
         for (int hh = 0; hh < GH; ++hh) dsa[hh] = f[hh];
         dal += pick4(dsa, h);
+        if (a.ebias && u < len) dal += __ldg(a.ebias + (uint64_t)(r.b + u) * GH + h);
         alpha = u < len ? in0 : 0.f;
       } else {
         sraw = in0 + in1;
@@ -759,6 +766,14 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
 // rows of k and v (4 KB per edge at H = 4, C = 256, bf16).
 struct TzScratch { float v[GH]; };
 
+// edge-feature term of window [p0, p0 + n): s[h] += ebias[p0 + lane, h] (one entry per lane)
+__device__ __forceinline__ void tz_add_ebias(const GatzArgs& a, int p0, int n, int lane, float (&s)[GH]) {
+  if (a.ebias && lane < n) {
+    const float4 b4 = ldg_f4(a.ebias + (uint64_t)(p0 + lane) * GH);
+    s[0] += b4.x; s[1] += b4.y; s[2] += b4.z; s[3] += b4.w;
+  }
+}
+
 template <typename T, int VPL>
 __device__ __forceinline__ void tz_store_tail(const GatzArgs& a, uint32_t i, int lane, const float (&ssum)[GH]) {
   constexpr int VN = Vec<T>::N;
@@ -797,6 +812,7 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
     const int cl = window_entry(a.col, p0, e, lane);
     float s[GH] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane, []() {});
+    tz_add_ebias(a, p0, n, lane, s);
 #pragma unroll
     for (int h = 0; h < GH; ++h) m[h] = fmaxf(m[h], warp_max_redux(lane < n ? s[h] : -INFINITY));
   }
@@ -805,6 +821,7 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
     const int cl = window_entry(a.col, p0, e, lane);
     float s[GH] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane, []() {});
+    tz_add_ebias(a, p0, n, lane, s);
     float p[GH];
 #pragma unroll
     for (int h = 0; h < GH; ++h) p[h] = lane < n ? __expf(s[h] - m[h]) : 0.f;
@@ -827,6 +844,7 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
     const int cl = window_entry(a.col, p0, e, lane);
     float s[GH] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < n; j += 8) gatz_dalpha8<T, VPL>(s, uf, xb, a.xrow_bytes, cl, j, lane, []() {});
+    tz_add_ebias(a, p0, n, lane, s);
     float w[GH];
 #pragma unroll
     for (int h = 0; h < GH; ++h) w[h] = lane < n ? __expf(s[h] - m[h]) * inv[h] : 0.f;
@@ -902,6 +920,7 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
         wp = warp_transpose_sum32(part);                     // lane 4u + h: logit of entry u, head h
       }
       const int pu = lane >> 2, ph = lane & 3;                // packed (entry, head) softmax, see head_max8
+      if (a.ebias && pu < len) wp += __ldg(a.ebias + (uint64_t)(r.b + pu) * GH + ph);
       {
         const float sc = pu < len ? wp : -INFINITY;
         const float m = head_max8(sc);
@@ -937,6 +956,7 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
         gatz_load_dz_raw<VPL>(a, r.i, lane, uraw);
         gatz_dalpha8<T, VPL>(w, uf, xb, a.xrow_bytes, cl, 0, lane, [&]() { gatz_unpack_dz<T, VPL>(uraw, uf); });
         for (int j = 8; j < len; j += 8) gatz_dalpha8<T, VPL>(w, uf, xb, a.xrow_bytes, cl, j, lane, []() {});
+        tz_add_ebias(a, r.b, len, lane, w);
       }
       float zs[GH];
 #pragma unroll
@@ -1123,6 +1143,70 @@ static int gatz_dispatch(int which, int dt, int row_bytes, const GatzArgs& a, cu
 static inline int esz(int dt) { return dt == B2G_F32 ? 4 : 2; }
 static inline bool fits32(int64_t v) { return v >= 0 && v < (1ll << 32); }
 
+// ------------------------------------------------------------------------------------------ edge features (edge_dim)
+// TransformerConv(edge_dim = 4) in the aggregate-first form: with e_ijh = We_h a_ij (lin_edge, no bias) PyG
+// adds e to the keys and to the values.  By linearity  q_ih . e_ijh / sqrt(C) = r_ih . a_ij  with r_ih = We_h^T q_ih / sqrt(C)
+// (4 numbers per node and head: 16 more columns of the u GEMM) and  sum_j alpha'_ijh e_ijh = We_h m_ih  with
+// m_ih = sum_j alpha'_ijh a_ij (16 more columns of z_aug), so the [E, H*C] edge embedding never exists.  Two thin kernels,
+// one thread per target row over its CSR entries (16 bytes of edge attributes per entry, target-major order):
+//   edge_dot4 : out[p, h] = v[i(p), 4h .. 4h+3] . ea[p]      (logit term from r; d alpha' term from dm)
+//   edge_wsum4: out[i, 4h + c] = sum_p w[p, h] keep(p, h) ea[p, c]   (m from alpha and the dropout mask; dr from de)
+__global__ void __launch_bounds__(256) edge_dot4_kernel(const float* __restrict__ v, int64_t ldv,
+                                                        const float* __restrict__ ea, const int32_t* __restrict__ rowptr,
+                                                        int64_t n, float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = rowptr[i], e = rowptr[i + 1];
+    if (b == e) continue;
+    float4 r[GH];
+#pragma unroll
+    for (int h = 0; h < GH; ++h) r[h] = ldg_f4(v + i * ldv + 4 * h);
+    for (int p = b; p < e; ++p) {
+      const float4 a4 = ldg_f4(ea + (uint64_t)p * 4);
+      float o[GH];
+#pragma unroll
+      for (int h = 0; h < GH; ++h) o[h] = r[h].x * a4.x + r[h].y * a4.y + r[h].z * a4.z + r[h].w * a4.w;
+      *reinterpret_cast<float4*>(out + (uint64_t)p * GH) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) edge_wsum4_kernel(const float* __restrict__ w, const float* __restrict__ ea,
+                                                         const int32_t* __restrict__ rowptr, int64_t n, float p_drop,
+                                                         uint64_t seed, const uint64_t* epoch, char* __restrict__ out,
+                                                         int64_t orow_bytes) {
+  constexpr int VN = Vec<T>::N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float m[GH * 4];
+#pragma unroll
+    for (int k = 0; k < GH * 4; ++k) m[k] = 0.f;
+    const int b = rowptr[i], e = rowptr[i + 1];
+    for (int p = b; p < e; ++p) {
+      const float4 w4 = ldg_f4(w + (uint64_t)p * GH);
+      const float4 a4 = ldg_f4(ea + (uint64_t)p * 4);
+      float ws[GH] = {w4.x, w4.y, w4.z, w4.w};
+      if (p_drop > 0.f) {
+        float sc[4];
+        dropout_scale4(mix_epoch(seed, epoch), (uint64_t)p, p_drop, sc);
+#pragma unroll
+        for (int h = 0; h < GH; ++h) ws[h] *= sc[h];
+      }
+#pragma unroll
+      for (int h = 0; h < GH; ++h) {
+        m[4 * h + 0] += ws[h] * a4.x; m[4 * h + 1] += ws[h] * a4.y;
+        m[4 * h + 2] += ws[h] * a4.z; m[4 * h + 3] += ws[h] * a4.w;
+      }
+    }
+    char* o = out + i * orow_bytes;
+#pragma unroll
+    for (int k = 0; k < GH * 4; k += VN) {
+      Vec<T> ov;
+      ov.from_float(m + k);
+      *reinterpret_cast<uint4*>(o + k * sizeof(T)) = *reinterpret_cast<uint4*>(&ov.v);
+    }
+  }
+}
+
 }  // namespace b2g
 
 using namespace b2g;
@@ -1224,15 +1308,51 @@ int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const flo
   return gatz_dispatch(2, dt, C * es, a, (cudaStream_t)stream);
 }
 
+/* Edge-feature terms of TransformerConv(edge_dim = 4), aggregate-first (see edge_dot4_kernel).  ea_csr: fp32 [nnz, 4], the
+ * edge attributes in target-major CSR order; v: fp32 [n, ldv >= 4H]; out of edge_dot4: fp32 [nnz, H]; out of edge_wsum4:
+ * [n, 4H] of dtype dt with row stride ldo elements (w: fp32 [nnz, H]; p_drop > 0 applies the attention-dropout mask of
+ * (seed, device epoch), the one b2g_tz_fwd draws). */
+int b2g_edge_dot4(const float* v, int64_t ldv, const float* ea_csr, const int32_t* rowptr, int64_t n, int H, float* out,
+                  void* stream) {
+  if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  if (!v || !ea_csr || !rowptr || !out) return B2G_E_ARG;
+  if (!aligned16(v) || !aligned16(ea_csr) || !aligned16(out) || ldv % 4 || ldv < 4 * GH) return B2G_E_ALIGN;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)B2G_NUM_SMS * 16);
+  edge_dot4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(v, ldv, ea_csr, rowptr, n, out);
+  count_launch();
+  return cuda_status();
+}
+
+int b2g_edge_wsum4(const float* w, const float* ea_csr, const int32_t* rowptr, int64_t n, int H, float p_drop, uint64_t seed,
+                   void* out, int64_t ldo, int dt, void* stream) {
+  if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  const int es = esz(dt);
+  if (!w || !ea_csr || !rowptr || !out) return B2G_E_ARG;
+  if (!aligned16(w) || !aligned16(ea_csr) || !aligned16(out) || (ldo * es) % 16 || ldo < 4 * GH) return B2G_E_ALIGN;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)B2G_NUM_SMS * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dt == B2G_F32)
+    edge_wsum4_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(w, ea_csr, rowptr, n, p_drop, seed, dropout_epoch_ptr(),
+                                                                static_cast<char*>(out), ldo * es);
+  else
+    edge_wsum4_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(w, ea_csr, rowptr, n, p_drop, seed, dropout_epoch_ptr(),
+                                                                        static_cast<char*>(out), ldo * es);
+  count_launch();
+  return cuda_status();
+}
+
 /* TransformerConv, aggregate-first (see tz_fwd_kernel).  u [n, H*F] = x Mq + cq; z_aug [n, H*F + 8 + F]. */
 int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_aug, int64_t ldz, int64_t n, int H, int F,
-               int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, float p_drop, uint64_t seed,
-               int64_t band, void* stream) {
+               int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, const float* edge_bias, float p_drop,
+               uint64_t seed, int64_t band, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
   if (!x || !u || !z_aug || !rowptr || !col) return B2G_E_ARG;
-  if (!aligned16(x) || !aligned16(u) || !aligned16(z_aug) || (alpha_e && !aligned16(alpha_e)) || (ldx * es) % 16 ||
+  if (!aligned16(x) || !aligned16(u) || !aligned16(z_aug) || (alpha_e && !aligned16(alpha_e)) ||
+      (edge_bias && !aligned16(edge_bias)) || (ldx * es) % 16 ||
       (ldu * es) % 16 || (ldz * es) % 16 || ldz < (int64_t)H * F + 8 + F)
     return B2G_E_ALIGN;
   if (!fits32(ldx * es) || !fits32(ldu * es) || !fits32(ldz * es)) return B2G_E_SHAPE;
@@ -1241,6 +1361,7 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_a
   if (rc) return rc;
   a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = u; a.dzrow_bytes = (uint32_t)(ldu * es); a.z = z_aug;
   a.zrow_bytes = (uint32_t)(ldz * es); a.rowptr = rowptr; a.col = col; a.alpha_e = alpha_e; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
+  a.ebias = edge_bias;
   return gatz_dispatch(3, dt, F * es, a, (cudaStream_t)stream);
 }
 
@@ -1248,13 +1369,13 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_a
  * the forward pass's alpha [nnz,H]; writes alpha_e (after dropout) and de_e [nnz,H] in target-major CSR order. */
 int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz, const float* alpha_in, int64_t n, int H,
                    int F, int dt, const int32_t* rowptr, const int32_t* col, float p_drop, uint64_t seed, float* alpha_e,
-                   float* de_e, void* du, int64_t lddu, int64_t band, void* stream) {
+                   float* de_e, void* du, int64_t lddu, const float* edge_bias, int64_t band, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
   if (!x || !dz_aug || !alpha_in || !rowptr || !col || !alpha_e || !de_e) return B2G_E_ARG;
   if (!aligned16(x) || !aligned16(dz_aug) || !aligned16(alpha_in) || !aligned16(alpha_e) || !aligned16(de_e) ||
-      (ldx * es) % 16 || (lddz * es) % 16 || lddz < (int64_t)H * F + 8)
+      (edge_bias && !aligned16(edge_bias)) || (ldx * es) % 16 || (lddz * es) % 16 || lddz < (int64_t)H * F + 8)
     return B2G_E_ALIGN;
   if (!fits32(ldx * es) || !fits32(lddz * es)) return B2G_E_SHAPE;
   GatzArgs a{};
@@ -1262,6 +1383,7 @@ int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz,
   if (rc) return rc;
   a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = dz_aug; a.dzrow_bytes = (uint32_t)(lddz * es); a.alpha_in = alpha_in;
   a.rowptr = rowptr; a.col = col; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.alpha_e = alpha_e; a.de_e = de_e;
+  a.ebias = edge_bias;
   if (du) {
     if (!aligned16(du) || (lddu * es) % 16 || lddu < (int64_t)H * F) return B2G_E_ALIGN;
     if (!fits32(lddu * es)) return B2G_E_SHAPE;

@@ -366,84 +366,109 @@ class TConvZFn(torch.autograd.Function):
         u = x Mq^T + cq   (logits e_ijh = u_ih . x_j; Mq_h = Wk_h^T Wq_h / sqrt(C), cq_h = Wk_h^T bq_h / sqrt(C))
         z_aug = [per-head attention-weighted sums of x | per-head weight sums, 0 0 0 0 | x]
         out = z_aug W_out^T + b_out   (value projection / H, value bias / H, skip connection in one GEMM)
-    `mq` [H*F, F], `cq` [H*F], `w_out` [C, H*F + 8 + F], `b_out` [C] are assembled (differentiably) by the module."""
+    `mq` [H*F, F], `cq` [H*F], `w_out` [C, H*F + 8 + F], `b_out` [C] are assembled (differentiably) by the module.
+
+    Edge features (`ea` = edge attributes fp32 [nnz, 4] in target-major CSR order; TransformerConv(edge_dim=4)): `mq` / `cq`
+    carry 4H more rows (r_ih = We_h^T q_ih / sqrt(C); logits += r_ih . a_ij) and `w_out` 4H more columns at the end
+    (m_ih = sum_j alpha'_ijh a_ij; out += We_h m_ih / H) — see edge_dot4_kernel in gat_rows.cu."""
 
     @staticmethod
-    def forward(ctx, x, mq, cq, w_out, b_out, graph: Graph, H: int, p_drop: float):
+    def _forward_z(x, mq, cq, graph, H, p_drop, seed, save_alpha, ea):
         csr = graph.csr("raw", False)
+        HF = H * x.shape[1]
+        if ea is None:
+            u, _ = ops.linear_fwd(x, mq, cq)
+            return ops.tz_fwd(x, u, H, csr.rowptr, csr.col, p_drop, seed, save_alpha, band=graph.band())
+        u, r = ops.linear_fwd(x, mq, cq, m_main=HF)                          # r fp32 [N, 4H]
+        eb = ops.edge_dot4(r, ea, csr.rowptr, H)
+        z_aug, alpha = ops.tz_fwd(x, u, H, csr.rowptr, csr.col, p_drop, seed, True, band=graph.band(), edge_bias=eb,
+                                  extra_cols=4 * H)
+        ops.edge_wsum4(alpha, ea, csr.rowptr, H, z_aug[:, HF + 8 + x.shape[1]:], p_drop, seed)
+        return z_aug, alpha
+
+    @staticmethod
+    def forward(ctx, x, mq, cq, w_out, b_out, graph: Graph, H: int, p_drop: float, ea=None):
         need_grad = any(t is not None and t.requires_grad for t in (x, mq, cq, w_out, b_out))
         seed = _next_seed() if p_drop > 0 else 0
-        u, _ = ops.linear_fwd(x, mq, cq)
-        z_aug, alpha = ops.tz_fwd(x, u, H, csr.rowptr, csr.col, p_drop, seed, need_grad, band=graph.band())
-        del u
+        z_aug, alpha = TConvZFn._forward_z(x, mq, cq, graph, H, p_drop, seed, need_grad, ea)
         out, _ = ops.linear_fwd(z_aug, w_out, b_out)
         if need_grad:
             recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"     # see GATZFn: z_aug is re-derived in backward
-            ctx.save_for_backward(x, mq, cq, w_out, None if recompute else z_aug, alpha)
+            ctx.save_for_backward(x, mq, cq, w_out, None if recompute else z_aug, alpha, ea)
             ctx.cfg = (graph, H, p_drop, seed, b_out is not None)
             ctx.ei_keepalive = graph.edge_index
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, mq, cq, w_out, z_aug, alpha = ctx.saved_tensors
+        x, mq, cq, w_out, z_aug, alpha, ea = ctx.saved_tensors
         graph, H, p_drop, seed, has_bout = ctx.cfg
         N, F = x.shape
         C = w_out.shape[0]
         HF = H * F
+        E4 = 4 * H if ea is not None else 0                                 # width of the edge-feature blocks (r / m)
         g = g.contiguous()
         csr, csr_t, perm = graph.csr("raw", False), graph.csr("raw", True), graph.perm("raw")
         band = graph.band()
         if z_aug is None and ctx.needs_input_grad[3]:
-            u, _ = ops.linear_fwd(x, mq, cq)
-            z_aug, _ = ops.tz_fwd(x, u, H, csr.rowptr, csr.col, p_drop, seed, False, band=band)
-            del u
+            z_aug, _ = TConvZFn._forward_z(x, mq, cq, graph, H, p_drop, seed, False, ea)
         gw_out = None
         if ctx.needs_input_grad[3]:
-            dw, _ = ops.linear_wgrad(g, z_aug, want_bias=False)               # d W_out = g^T z_aug  [C, H*F + 8 + F]
+            dw, _ = ops.linear_wgrad(g, z_aug, want_bias=False)               # d W_out = g^T z_aug  [C, H*F + 8 + F (+ 4H)]
             gw_out = _cast_like(dw, w_out)
         del z_aug
-        # gradients of z and of the weight sums s: dz_aug = g W_out[:, :H*F + 8]
-        dz_aug, _ = ops.linear_fwd(g, w_out[:, :HF + 8].t().contiguous(), None,
-                                   out=ops.empty_rows(N, HF + 8, x.dtype, x.device))
+        # gradients of z, of the weight sums s (and of m): dz_aug = g W_out[:, :H*F + 8] (, dm = g W_out[:, -4H:] in fp32)
+        dab = None
+        if ea is None:
+            dz_aug, _ = ops.linear_fwd(g, w_out[:, :HF + 8].t().contiguous(), None,
+                                       out=ops.empty_rows(N, HF + 8, x.dtype, x.device))
+        else:
+            wcat = torch.cat([w_out[:, :HF + 8], w_out[:, HF + 8 + F:]], dim=1).t().contiguous()
+            dz_aug, dm = ops.linear_fwd(g, wcat, None, m_main=HF + 8, out=ops.empty_rows(N, HF + 8, x.dtype, x.device))
+            dab = ops.edge_dot4(dm, ea, csr.rowptr, H)                        # d alpha'_ijh += dm_ih . a_ij
+            del dm
         # (tz_bwd_dst runs below, once the buffer that receives du exists)
-        # dx = [y | w | t 0 | du | g] W_aug as ONE GEMM, every block a sum of F-wide rows:
+        # dx = [y | w | t 0 | du (dr) | g] W_aug as ONE GEMM, every block a sum of F-wide rows:
         #   y_j = [sum_i alpha'_ijh g_i]_h, w_j = [sum_i de_ijh x_i]_h, t_jh = sum_i de_ijh   (transposed CSR)
-        #   du_i = [sum_j de_ijh x_j]_h                                                       (target-major CSR)
+        #   du_i = [sum_j de_ijh x_j]_h  (dr_ih = sum_j de_ijh a_ij with edge features)          (target-major CSR)
         # using  sum_i de_ijh u_ih = Mq_h w_jh + cq_h t_jh  and  sum_i alpha'_ijh dz_ih = Wv_h^T y_jh
-        o_y, o_w, o_t, o_du, o_g = 0, H * C, H * C + HF, H * C + HF + 8, H * C + 2 * HF + 8
+        o_y, o_w, o_t, o_du = 0, H * C, H * C + HF, H * C + HF + 8
+        o_dr = o_du + HF
+        o_g = o_dr + E4
         big = ops.empty_rows(N, o_g + C, x.dtype, x.device)
         t_rows = torch.zeros((N, 8), dtype=torch.float32, device=x.device)
         fuse_du = os.environ.get("B2G_TZ_FUSE_DU", "1") != "0"
         alpha_e, de_e = ops.tz_bwd_dst(x, dz_aug, alpha, H, csr.rowptr, csr.col, p_drop, seed,
                                        big[:, o_du:o_du + HF] if fuse_du else None,
-                                       band=band)          # du comes out of the same gather as d alpha
-        del dz_aug
+                                       band=band, edge_bias=dab)          # du comes out of the same gather as d alpha
+        del dz_aug, dab
         if not fuse_du:
             ops.seg_wsum4(x, de_e, csr.rowptr, csr.col, None, big[:, o_du:o_du + HF], band=band)
+        if ea is not None:
+            ops.edge_wsum4(de_e, ea, csr.rowptr, H, big[:, o_dr:o_dr + E4])
         ops.seg_wsum4(g, alpha_e, csr_t.rowptr, csr_t.col, perm, big[:, o_y:o_y + H * C], band=band)
         ops.seg_wsum4(x, de_e, csr_t.rowptr, csr_t.col, perm, big[:, o_w:o_w + HF], d_a=t_rows, band=band)
         del alpha_e, de_e
         big[:, o_t:o_t + 8] = t_rows
         big[:, o_g:] = g
-        du = big[:, o_du:o_du + HF]
+        du = big[:, o_du:o_du + HF + E4]
         gmq = gcq = gx = None
         if ctx.needs_input_grad[1]:
-            dm, _ = ops.linear_wgrad(du, x, want_bias=False)                  # d Mq = du^T x  [H*F, F]
-            gmq = _cast_like(dm, mq)
+            dm_, _ = ops.linear_wgrad(du, x, want_bias=False)                 # d Mq = du^T x  [H*F (+ 4H), F]
+            gmq = _cast_like(dm_, mq)
         if cq is not None and ctx.needs_input_grad[2]:
             gcq = _cast_like(ops.colsum(du), cq)
         if ctx.needs_input_grad[0]:
             wd = w_out.dtype
             w_y = w_out[:, :HF].view(C, H, F).permute(1, 0, 2).reshape(H * C, F)       # y_jh[c]  -> W_out[c, hF + :]
-            w_w = mq.view(H, F, F).transpose(1, 2).reshape(HF, F)                       # w_jh[f'] -> Mq_h[:, f']
+            w_w = mq[:HF].view(H, F, F).transpose(1, 2).reshape(HF, F)                  # w_jh[f'] -> Mq_h[:, f']
             w_t = torch.zeros((8, F), dtype=wd, device=x.device)
             if cq is not None:
-                w_t[:H] = cq.view(H, F).to(wd)                                         # t_jh     -> cq_h
-            w_aug = torch.cat([w_y, w_w.to(wd), w_t, mq.to(wd), w_out[:, HF + 8:]], dim=0)   # du_ih -> Mq_h^T, g -> Ws
+                w_t[:H] = cq[:HF].view(H, F).to(wd)                                    # t_jh     -> cq_h
+            w_aug = torch.cat([w_y, w_w.to(wd), w_t, mq.to(wd), w_out[:, HF + 8:HF + 8 + F]], dim=0)   # du -> Mq^T, g -> Ws
             gx = ops.linear_dgrad(big, w_aug)
         gb = ops.colsum(g) if (has_bout and ctx.needs_input_grad[4]) else None
-        return gx, gmq, gcq, gw_out, gb, None, None, None
+        return gx, gmq, gcq, gw_out, gb, None, None, None, None
 
 
 def linear(x, weight, bias=None, act: int = 0):

@@ -104,6 +104,22 @@ class Graph:
         """GCN deg^-1/2 over the self-loop-replaced list (in-degree by target)."""
         return self.csr("sl", False).dinv
 
+    def edge_rows(self, variant: str, edge_attr: torch.Tensor) -> torch.Tensor:
+        """Per-edge rows (e.g. edge_attr [E, 4]) as fp32 in the order of the target-major CSR of `variant`; cached for the
+        tensor last passed (the reference hands the same edge_attr to every layer, gnn_model.py:170).  "raw" only: the
+        self-loop-replaced list has entries without an input edge."""
+        if variant != "raw":
+            raise NotImplementedError("edge_rows: only the raw edge list has one input edge per CSR entry")
+        key = (edge_attr.data_ptr(), edge_attr._version, tuple(edge_attr.shape), edge_attr.dtype)
+        hit = getattr(self, "_edge_rows", None)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        if not edge_attr.is_cuda:
+            raise RuntimeError("b2g: CUDA tensor required (this is the B200 path; there is no CPU fallback)")
+        rows = edge_attr.detach().float().index_select(0, self.csr("raw", False).eid.long()).contiguous()
+        self._edge_rows = (key, rows)
+        return rows
+
     def perm(self, variant: str) -> torch.Tensor:
         """Position in the target-major CSR of each entry of the source-major CSR."""
         p = self._perm.get(variant)

@@ -256,14 +256,20 @@ class GINConv(MessagePassing):
 
 class TransformerConv(MessagePassing):
     """TransformerConv(in, out, heads=4, concat=False, dropout=p) — gnn_model.py:77-80; forward at :170
-    (called with edge_attr=..., which PyG cannot consume without edge_dim: see forward)."""
+    (called with edge_attr=..., which PyG cannot consume without edge_dim: see forward).
+    edge_dim=4 (the "Transformer with edge features" the reference describes): PyG's `lin_edge`
+    (Linear(edge_dim, H*C, bias=False)); key_j + lin_edge(edge_attr) in the logits, value_j + lin_edge(edge_attr) in the
+    messages — computed without the [E, H*C] edge embedding (functional.TConvZFn)."""
 
     def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
                  beta: bool = False, dropout: float = 0.0, edge_dim: Optional[int] = None, bias: bool = True,
                  root_weight: bool = True, **kwargs):
         super().__init__(aggr='add')
-        if beta or edge_dim is not None:
-            raise NotImplementedError("b2g TransformerConv: only beta=False, edge_dim=None")
+        if beta:
+            raise NotImplementedError("b2g TransformerConv: only beta=False")
+        if edge_dim is not None and (edge_dim != 4 or concat or heads != 4):
+            raise NotImplementedError("b2g TransformerConv: edge_dim is built for edge_dim=4 (graph_constructor.py:58-90), "
+                                      "heads=4, concat=False")
         if not isinstance(in_channels, int):
             raise NotImplementedError("b2g TransformerConv: bipartite in_channels are not supported")
         self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
@@ -271,7 +277,7 @@ class TransformerConv(MessagePassing):
         self.lin_key = Linear(in_channels, heads * out_channels)
         self.lin_query = Linear(in_channels, heads * out_channels)
         self.lin_value = Linear(in_channels, heads * out_channels)
-        self.lin_edge = None
+        self.lin_edge = Linear(edge_dim, heads * out_channels, bias=False) if edge_dim is not None else None
         if root_weight:
             self.lin_skip = Linear(in_channels, heads * out_channels if concat else out_channels, bias=bias)
         else:
@@ -284,13 +290,15 @@ class TransformerConv(MessagePassing):
         self.lin_key.reset_parameters()
         self.lin_query.reset_parameters()
         self.lin_value.reset_parameters()
+        if self.lin_edge is not None:
+            self.lin_edge.reset_parameters()
         if self.root_weight:
             self.lin_skip.reset_parameters()
 
     def forward(self, x, edge_index, edge_attr=None, return_attention_weights=None):
         if return_attention_weights:
             raise NotImplementedError("b2g TransformerConv: return_attention_weights is not supported")
-        if edge_attr is not None and not self._warned_edge_attr:
+        if edge_attr is not None and self.lin_edge is None and not self._warned_edge_attr:
             # edge_dim=None => PyG has no lin_edge; its message() would add [E,4] to [E,H,C] and raise
             # (SURVEY §8a row 7).  Parity target = forward(x, edge_index); the attribute is ignored.
             warnings.warn("b2g TransformerConv: edge_attr ignored because edge_dim=None")
@@ -298,6 +306,15 @@ class TransformerConv(MessagePassing):
         _check_x(x, edge_index)
         g = graph_of(edge_index, x.shape[0])
         p = self.dropout if self.training else 0.0
+        use_edge = self.lin_edge is not None and edge_attr is not None          # PyG applies lin_edge only to a given edge_attr
+        if use_edge:
+            if edge_attr.dim() != 2 or edge_attr.shape != (edge_index.shape[1], self.edge_dim):
+                raise ValueError(f"edge_attr must be [{edge_index.shape[1]}, {self.edge_dim}], got {tuple(edge_attr.shape)}")
+            if not self._aggregate_first(x):
+                raise NotImplementedError("b2g TransformerConv(edge_dim): needs 512 / 1024-byte feature rows (the "
+                                          "aggregate-first kernels)")
+            mq, cq, w_out, b_out = self._folded(x.dtype, with_edge=True)
+            return Fn.TConvZFn.apply(x, mq, cq, w_out, b_out, g, self.heads, p, g.edge_rows("raw", edge_attr))
         if self._aggregate_first(x):
             mq, cq, w_out, b_out = self._folded(x.dtype)
             return Fn.TConvZFn.apply(x, mq, cq, w_out, b_out, g, self.heads, p)
@@ -323,9 +340,10 @@ class TransformerConv(MessagePassing):
         return x.shape[0] >= 1 and ops.gatz_supported(x.shape[0], self.heads, self.in_channels, x.dtype) and \
             ops.gatz_supported(x.shape[0], self.heads, self.out_channels, x.dtype)
 
-    def _folded(self, dtype):
+    def _folded(self, dtype, with_edge: bool = False):
         """(mq [H*F, F], cq [H*F], w_out [C, H*F + 8 + F], b_out [C]) from the q/k/v/skip parameters (differentiable).
-        The key bias only shifts every logit of a softmax row by the same amount: it drops out (its exact gradient is 0)."""
+        The key bias only shifts every logit of a softmax row by the same amount: it drops out (its exact gradient is 0).
+        with_edge: 4H more rows of mq / cq (r_ih = We_h^T q_ih / sqrt(C)) and 4H more columns of w_out (We_h / H)."""
         H, C, F = self.heads, self.out_channels, self.in_channels
         Wq, Wk, Wv = (l.weight.view(H, C, F) for l in (self.lin_query, self.lin_key, self.lin_value))
         sc = 1.0 / math.sqrt(C)
@@ -340,6 +358,13 @@ class TransformerConv(MessagePassing):
         else:
             wsk, b_out = wv.new_zeros((C, F)), None
         w_out = torch.cat([wv, bv, pad, wsk], dim=1)
+        if with_edge:
+            D = self.edge_dim
+            We = self.lin_edge.weight.view(H, C, D)
+            mr = (torch.einsum('hcd,hcf->hdf', We, Wq) * sc).reshape(H * D, F)       # r_h = Mr_h x + cr_h
+            cr = (torch.einsum('hcd,hc->hd', We, self.lin_query.bias.view(H, C)) * sc).reshape(H * D)
+            mq, cq = torch.cat([mq, mr], dim=0), torch.cat([cq, cr], dim=0)
+            w_out = torch.cat([w_out, We.permute(1, 0, 2).reshape(C, H * D) / H], dim=1)
         return mq.to(dtype), cq.float(), w_out.to(dtype), (b_out.float() if b_out is not None else None)
 
     def __repr__(self):

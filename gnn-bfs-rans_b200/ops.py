@@ -412,29 +412,49 @@ def seg_wsum4(x, w_e, rowptr, col, perm, out, d_a=None, band=0):
     return out
 
 
-def tz_fwd(x, u, H, rowptr, col, p_drop, seed, save_alpha, band=0):
-    """z_aug [N, H*F + 8 + F] (see include/b2g.h b2g_tz_fwd) and the pre-dropout attention weights [nnz, H] | None."""
+def tz_fwd(x, u, H, rowptr, col, p_drop, seed, save_alpha, band=0, edge_bias=None, extra_cols=0):
+    """z_aug [N, H*F + 8 + F (+ extra_cols, left for the caller to fill)] (see include/b2g.h b2g_tz_fwd) and the
+    pre-dropout attention weights [nnz, H] | None.  edge_bias: fp32 [nnz, H] added to the logits (edge features)."""
     x, u = _rows(x), _rows(u)
     N, F = x.shape
-    z = empty_rows(N, H * F + 8 + F, x.dtype, x.device)
+    z = empty_rows(N, H * F + 8 + F + extra_cols, x.dtype, x.device)
     alpha = torch.empty((max(col.numel(), 1), H), dtype=torch.float32, device=x.device) if save_alpha else None
     _lib.check(_lib.load().b2g_tz_fwd(_p(x), _ld(x), _p(u), _ld(u), _p(z), _ld(z), N, H, F, _dt(x), _p(rowptr), _p(col),
-                                      _p(alpha), float(p_drop), int(seed), int(band), _stream()), "tz_fwd")
+                                      _p(alpha), _p(edge_bias), float(p_drop), int(seed), int(band), _stream()), "tz_fwd")
     return z, alpha
 
 
-def tz_bwd_dst(x, dz_aug, alpha, H, rowptr, col, p_drop, seed, du_out, band=0):
+def tz_bwd_dst(x, dz_aug, alpha, H, rowptr, col, p_drop, seed, du_out, band=0, edge_bias=None):
     """-> (alpha_e after dropout, de_e) fp32 [nnz, H], target-major; writes du = [sum_j de_ijh x_j]_h into du_out
-    (a [N, H*F] view, any row stride) from the same gather."""
+    (a [N, H*F] view, any row stride) from the same gather.  edge_bias: fp32 [nnz, H] added to d alpha' (edge features)."""
     x, dz_aug = _rows(x), _rows(dz_aug)
     N, F = x.shape
     alpha_e = torch.empty_like(alpha)
     de_e = torch.empty_like(alpha)
     _lib.check(_lib.load().b2g_tz_bwd_dst(_p(x), _ld(x), _p(dz_aug), _ld(dz_aug), _p(alpha), N, H, F, _dt(x), _p(rowptr),
                                           _p(col), float(p_drop), int(seed), _p(alpha_e), _p(de_e), _p(du_out),
-                                          _ld(du_out) if du_out is not None else 0, int(band), _stream()),
+                                          _ld(du_out) if du_out is not None else 0, _p(edge_bias), int(band), _stream()),
                "tz_bwd_dst")
     return alpha_e, de_e
+
+
+def edge_dot4(v, ea_csr, rowptr, H):
+    """out[p, h] = v[i(p), 4h..4h+3] . ea_csr[p]: v fp32 [N, >= 4H] (any row stride), ea_csr fp32 [nnz, 4] -> fp32 [nnz, H]."""
+    _cuda(v, ea_csr, rowptr)
+    assert v.dtype == torch.float32 and ea_csr.dtype == torch.float32 and v.stride(1) == 1 and ea_csr.is_contiguous()
+    N = v.shape[0]
+    out = torch.empty((max(ea_csr.shape[0], 1), H), dtype=torch.float32, device=v.device)
+    _lib.check(_lib.load().b2g_edge_dot4(_p(v), v.stride(0), _p(ea_csr), _p(rowptr), N, H, _p(out), _stream()), "edge_dot4")
+    return out
+
+
+def edge_wsum4(w, ea_csr, rowptr, H, out, p_drop=0.0, seed=0):
+    """out[i, 4h + c] = sum_p w[p, h] keep(p, h) ea_csr[p, c] into `out` ([N, 4H] view of x's dtype, any row stride)."""
+    _cuda(w, ea_csr, rowptr, out)
+    assert w.dtype == torch.float32 and out.stride(1) == 1 and out.shape[1] == 4 * H
+    _lib.check(_lib.load().b2g_edge_wsum4(_p(w), _p(ea_csr), _p(rowptr), out.shape[0], H, float(p_drop), int(seed), _p(out),
+                                          out.stride(0), _dt(out), _stream()), "edge_wsum4")
+    return out
 
 
 # ------------------------------------------------------------------------------------------ K5

@@ -213,10 +213,12 @@ int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const flo
  * e_ijh = u_ih . x_j with u = x Mq + cq (a K6 GEMM; the key bias drops out of the softmax), and
  *   z_aug[i] = [sum_j alpha_ij1 x_j | ... | sum_j alpha_ijH x_j | s_i1 .. s_iH 0 0 0 0 | x_i]   (s_ih = sum_j alpha_ijh)
  * so that value projection, value bias and skip connection are one K6 GEMM with k = H*F + 8 + F.  alpha_e (may be
- * NULL) receives the pre-dropout attention weights [nnz, H] for the backward pass. */
+ * NULL) receives the pre-dropout attention weights [nnz, H] for the backward pass.  edge_bias (may be NULL): fp32
+ * [nnz, H] in target-major CSR order, added to the logits — the edge-feature term of TransformerConv(edge_dim)
+ * (b2g_edge_dot4 below). */
 int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_aug, int64_t ldz, int64_t n, int H, int F,
-               int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, float p_drop, uint64_t seed,
-               int64_t band, void* stream);
+               int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, const float* edge_bias, float p_drop,
+               uint64_t seed, int64_t band, void* stream);
 /* Target side of its backward pass: dz_aug [n, >= H*F + 8] (columns H*F .. H*F+H-1 = d s), alpha_in = the forward
  * pass's alpha_e; writes alpha_e (after dropout) and de_e [nnz, H] (gradients of the logits), target-major.  The
  * `du` (may be NULL) [n, H*F] receives d u_i = [sum_j de_ij1 x_j | ...] from the same gather.  The sums over the
@@ -224,7 +226,19 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_a
  * the CSR passed in, d_a == NULL skips the logit-gradient row sums. */
 int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz, const float* alpha_in, int64_t n, int H,
                    int F, int dt, const int32_t* rowptr, const int32_t* col, float p_drop, uint64_t seed, float* alpha_e,
-                   float* de_e, void* du, int64_t lddu, int64_t band, void* stream);
+                   float* de_e, void* du, int64_t lddu, const float* edge_bias, int64_t band, void* stream);
+/* Edge features of TransformerConv(edge_dim = 4) (PyG: key_j + lin_edge(edge_attr), value_j + the same),
+ * aggregate-first: with r_ih = We_h^T q_ih / sqrt(C) (16 more columns of the u GEMM) the logit term is r_ih . a_ij, and
+ * sum_j alpha'_ijh We_h a_ij = We_h m_ih with m_ih = sum_j alpha'_ijh a_ij (16 more columns of the output GEMM): the
+ * [E, H*C] edge embedding never exists.  ea_csr: fp32 [nnz, 4] edge attributes in target-major CSR order.
+ *   b2g_edge_dot4 : out[p, h] = v[i(p), 4h..4h+3] . ea_csr[p]       v fp32 [n, ldv >= 4H], out fp32 [nnz, H]
+ *                   (edge_bias of b2g_tz_fwd from v = r; edge_bias of b2g_tz_bwd_dst, the d alpha term, from v = d m)
+ *   b2g_edge_wsum4: out[i, 4h + c] = sum_p w[p, h] keep(p, h) ea_csr[p, c]   out [n, 4H] of dtype dt, row stride ldo
+ *                   (m from w = alpha with the attention-dropout mask of (p_drop, seed); d r from w = de_e, p_drop = 0) */
+int b2g_edge_dot4(const float* v, int64_t ldv, const float* ea_csr, const int32_t* rowptr, int64_t n, int H, float* out,
+                  void* stream);
+int b2g_edge_wsum4(const float* w, const float* ea_csr, const int32_t* rowptr, int64_t n, int H, float p_drop, uint64_t seed,
+                   void* out, int64_t ldo, int dt, void* stream);
 
 /* ===================================================================================== K5
  * TransformerConv (gnn_model.py:77-80,170) fused q.k score + segment-softmax + aggregate +

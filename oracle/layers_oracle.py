@@ -108,9 +108,11 @@ def gin_mlp(w1, b1, w2, b2):
 
 
 def transformer_conv(x, edge_index, wq, bq, wk, bk, wv, bv, ws, bs, heads=4, concat=False,
-                     dropout=0.0, training=False, return_alpha=False):
-    """TransformerConv(in,out,heads,concat,dropout).forward(x, edge_index) (edge_dim=None,
-    beta=False, root_weight=True) on the RAW edge list."""
+                     dropout=0.0, training=False, return_alpha=False, edge_attr=None, we=None):
+    """TransformerConv(in,out,heads,concat,dropout).forward(x, edge_index[, edge_attr]) (beta=False,
+    root_weight=True) on the RAW edge list.  edge_dim (PyG TransformerConv.message): with `we` = lin_edge.weight
+    [H*C, edge_dim] (no bias) and an edge_attr, e = lin_edge(edge_attr).view(-1, H, C) is added to key_j before the
+    logits and to value_j before the weighted sum."""
     N = x.shape[0]
     H = heads
     C = wq.shape[0] // H
@@ -118,10 +120,15 @@ def transformer_conv(x, edge_index, wq, bq, wk, bk, wv, bv, ws, bs, heads=4, con
     k = F.linear(x, wk, bk).view(N, H, C)
     v = F.linear(x, wv, bv).view(N, H, C)
     row, col = edge_index[0], edge_index[1]
-    alpha = (q.index_select(0, col) * k.index_select(0, row)).sum(-1) / math.sqrt(C)
+    k_j, v_j = k.index_select(0, row), v.index_select(0, row)
+    if we is not None and edge_attr is not None:
+        e = F.linear(edge_attr.to(x.dtype), we).view(-1, H, C)
+        k_j = k_j + e
+        v_j = v_j + e
+    alpha = (q.index_select(0, col) * k_j).sum(-1) / math.sqrt(C)
     alpha = segment_softmax(alpha, col, N)
     alpha = F.dropout(alpha, p=dropout, training=training)
-    out = scatter_sum(v.index_select(0, row) * alpha.view(-1, H, 1), col, N)
+    out = scatter_sum(v_j * alpha.view(-1, H, 1), col, N)
     out = out.reshape(N, H * C) if concat else out.mean(dim=1)
     out = out + F.linear(x, ws, bs)
     return (out, alpha) if return_alpha else out

@@ -240,3 +240,88 @@ def test_recompute_mode_gives_identical_gradients(kind, monkeypatch):
         grads[mode] = [x.grad.clone()] + [p.grad.clone() for p in m.parameters()]
     for a, b in zip(grads["0"], grads["1"]):
         assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------------------------------------- edge features (§8f-2)
+@pytest.mark.parametrize("dtype,F", [(torch.float32, 128), (torch.float32, 256), (torch.bfloat16, 256)])
+@pytest.mark.parametrize("N,E", [(300, 2500), (1000, 3000), (2000, 30000), (40, 0)])
+def test_transformer_edge_features_forward_and_grads(dtype, F, N, E):
+    """TransformerConv(edge_dim=4): lin_edge(edge_attr) joins keys and values (PyG message()); aggregate-first kernels with
+    the per-entry edge terms (edge_dot4 / edge_wsum4 + the edge_bias input of tz_fwd / tz_bwd_dst).  Rows of every length
+    class: <= 8 (packed path), 9..32, > 32 (hub target of `multigraph`)."""
+    import gnn_bfs_rans_b200 as b2g
+    from oracle import layers_oracle as lo
+    ei = multigraph(N, E, N + E) if E else torch.zeros((2, 0), dtype=torch.long)
+    torch.manual_seed(4321)
+    m = b2g.nn.TransformerConv(F, F, heads=4, concat=False, dropout=0.1, edge_dim=4)
+    with torch.no_grad():
+        for p_ in m.parameters():
+            if p_.dim() == 1:
+                p_.uniform_(-0.5, 0.5)
+    m = m.cuda().to(dtype).eval()
+    torch.manual_seed(11)
+    x = torch.randn(N, F).to(dtype)
+    ea = torch.randn(ei.shape[1], 4).to(dtype)
+    xg = x.cuda().requires_grad_(True)
+    out = m(xg, ei.cuda(), edge_attr=ea.cuda())
+    assert out.dtype == dtype and out.shape == (N, F)
+    gout = torch.randn(out.shape).to(dtype)
+    out.backward(gout.cuda())
+
+    def oracle(dt, xin):
+        p = {k: v.detach().cpu().to(dt).requires_grad_(True) for k, v in m.state_dict().items()}
+        o = lo.transformer_conv(xin, ei, p["lin_query.weight"], p["lin_query.bias"], p["lin_key.weight"], p["lin_key.bias"],
+                                p["lin_value.weight"], p["lin_value.bias"], p["lin_skip.weight"], p["lin_skip.bias"],
+                                heads=4, concat=False, edge_attr=ea.to(dt), we=p["lin_edge.weight"])
+        return o, p
+
+    x64 = x.double().requires_grad_(True)
+    ref, p = oracle(torch.float64, x64)
+    ref.backward(gout.double())
+    assert rel(out.detach(), ref.detach()) < TOL[dtype], "forward"
+    pairs = {"x": (xg.grad, x64.grad)}
+    for name, par in m.named_parameters():
+        if par.grad is None:
+            assert p[name].grad is None or float(p[name].grad.abs().max()) == 0.0, name
+            continue
+        pairs[name] = (par.grad, p[name].grad)
+    if E:
+        assert "lin_edge.weight" in pairs and float(pairs["lin_edge.weight"][0].abs().max()) > 0
+    pb = None
+    if dtype == torch.bfloat16:
+        xb = x.clone().requires_grad_(True)
+        refb, pbp = oracle(torch.bfloat16, xb)
+        refb.backward(gout)
+        pb = {"x": xb.grad}
+        pb.update({n: pbp[n].grad for n in pbp if pbp[n].grad is not None})
+    check_grads(pairs, dtype, pb)
+    # the edge terms matter (guards against a silently ignored edge_attr) and edge_attr=None is the plain layer
+    if E:
+        with torch.no_grad():
+            plain = m(x.cuda(), ei.cuda())
+        assert rel(out.detach(), plain.double().cpu()) > 1e-2
+    # recompute-in-backward path re-derives z_aug including the m block
+    os.environ["B2G_RECOMPUTE"] = "1"
+    try:
+        m.zero_grad(set_to_none=True)
+        xg2 = x.cuda().requires_grad_(True)
+        m(xg2, ei.cuda(), edge_attr=ea.cuda()).backward(gout.cuda())
+        assert torch.equal(xg2.grad, xg.grad)
+    finally:
+        os.environ.pop("B2G_RECOMPUTE", None)
+
+
+def test_transformer_edge_features_argument_errors():
+    import gnn_bfs_rans_b200 as b2g
+    with pytest.raises(NotImplementedError):
+        b2g.nn.TransformerConv(128, 128, heads=4, concat=False, edge_dim=3)
+    with pytest.raises(NotImplementedError):
+        b2g.nn.TransformerConv(128, 128, heads=2, concat=True, edge_dim=4)
+    m = b2g.nn.TransformerConv(128, 128, heads=4, concat=False, edge_dim=4).cuda()
+    ei = multigraph(50, 200, 1).cuda()
+    x = torch.randn(50, 128, device="cuda")
+    with pytest.raises(ValueError):
+        m(x, ei, edge_attr=torch.randn(199, 4, device="cuda"))
+    m32 = b2g.nn.TransformerConv(32, 32, heads=4, concat=False, edge_dim=4).cuda()      # 128-byte rows: no aggregate-first kernel
+    with pytest.raises(NotImplementedError):
+        m32(torch.randn(50, 32, device="cuda"), ei, edge_attr=torch.randn(200, 4, device="cuda"))

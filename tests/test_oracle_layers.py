@@ -92,6 +92,70 @@ def test_transformer_equals_per_edge_loops():
     torch.testing.assert_close(out, ref.mean(1) + x @ ws.T + bs, rtol=1e-9, atol=1e-12)
 
 
+def test_transformer_with_edge_features_equals_per_edge_loops():
+    """edge_dim (PyG TransformerConv.message): lin_edge(edge_attr) joins the keys and the values of every edge."""
+    N, F, H, C, D = 12, 6, 4, 3, 4
+    ei = graph(N)
+    E = ei.shape[1]
+    x = torch.randn(N, F, dtype=torch.float64)
+    ea = torch.randn(E, D, dtype=torch.float64)
+    mk = lambda o: (torch.randn(o, F, dtype=torch.float64), torch.randn(o, dtype=torch.float64))
+    (wq, bq), (wk, bk), (wv, bv), (ws, bs) = mk(H * C), mk(H * C), mk(H * C), mk(C)
+    we = torch.randn(H * C, D, dtype=torch.float64)
+    q, k, v = [(x @ w.T + b).view(N, H, C) for w, b in ((wq, bq), (wk, bk), (wv, bv))]
+    emb = (ea @ we.T).view(E, H, C)
+    edges = ei.t().tolist()
+    ref = torch.zeros(N, H, C, dtype=torch.float64)
+    for i in range(N):
+        inc = [(e, s) for e, (s, d) in enumerate(edges) if d == i]
+        if not inc:
+            continue
+        for h in range(H):
+            al = torch.softmax(torch.stack([(q[i, h] * (k[j, h] + emb[e, h])).sum() / math.sqrt(C) for e, j in inc]), 0)
+            for a, (e, j) in zip(al, inc):
+                ref[i, h] += a * (v[j, h] + emb[e, h])
+    out = lo.transformer_conv(x, ei, wq, bq, wk, bk, wv, bv, ws, bs, heads=H, edge_attr=ea, we=we)
+    torch.testing.assert_close(out, ref.mean(1) + x @ ws.T + bs, rtol=1e-9, atol=1e-12)
+    # without an edge_attr the lin_edge weights are unused (PyG applies lin_edge only to a given edge_attr)
+    torch.testing.assert_close(lo.transformer_conv(x, ei, wq, bq, wk, bk, wv, bv, ws, bs, heads=H, we=we),
+                               lo.transformer_conv(x, ei, wq, bq, wk, bk, wv, bv, ws, bs, heads=H))
+
+
+def test_transformer_edge_folding_algebra():
+    """The aggregate-first form the CUDA path uses (nn.TransformerConv._folded(with_edge=True)), evaluated densely on the
+    CPU in fp64: logits u_i . x_j + r_ih . a_ij, output [z | s | x | m] W_out^T + b — equals the oracle."""
+    from gnn_bfs_rans_b200.nn import TransformerConv
+    torch.manual_seed(5)
+    N, F, H, D = 14, 8, 4, 4
+    ei = graph(N)
+    E = ei.shape[1]
+    layer = TransformerConv(F, F, heads=H, concat=False, edge_dim=D).double()
+    assert list(layer.state_dict()) == ['lin_key.weight', 'lin_key.bias', 'lin_query.weight', 'lin_query.bias',
+                                        'lin_value.weight', 'lin_value.bias', 'lin_edge.weight', 'lin_skip.weight',
+                                        'lin_skip.bias']
+    assert layer.lin_edge.weight.shape == (H * F, D)
+    x = torch.randn(N, F, dtype=torch.float64)
+    ea = torch.randn(E, D, dtype=torch.float64)
+    mq, cq, w_out, b_out = layer._folded(torch.float64, with_edge=True)
+    HF = H * F
+    assert mq.shape == (HF + H * D, F) and cq.shape == (HF + H * D,) and w_out.shape == (F, HF + 8 + F + H * D)
+    ur = x @ mq.T + cq.double()
+    u, r = ur[:, :HF].view(N, H, F), ur[:, HF:].view(N, H, D)
+    src, dst = ei[0], ei[1]
+    logit = (u[dst] * x[src].unsqueeze(1)).sum(-1) + (r[dst] * ea.unsqueeze(1)).sum(-1)        # [E, H]
+    alpha = lo.segment_softmax(logit, dst, N)
+    z = torch.zeros(N, H, F, dtype=torch.float64).index_add_(0, dst, alpha.unsqueeze(-1) * x[src].unsqueeze(1))
+    sw = torch.zeros(N, H, dtype=torch.float64).index_add_(0, dst, alpha)
+    m = torch.zeros(N, H, D, dtype=torch.float64).index_add_(0, dst, alpha.unsqueeze(-1) * ea.unsqueeze(1))
+    z_aug = torch.cat([z.reshape(N, HF), sw, torch.zeros(N, 8 - H, dtype=torch.float64), x, m.reshape(N, H * D)], 1)
+    out = z_aug @ w_out.T + b_out.double()
+    p = {k: v.detach() for k, v in layer.state_dict().items()}
+    ref = lo.transformer_conv(x, ei, p['lin_query.weight'], p['lin_query.bias'], p['lin_key.weight'], p['lin_key.bias'],
+                              p['lin_value.weight'], p['lin_value.bias'], p['lin_skip.weight'], p['lin_skip.bias'],
+                              heads=H, edge_attr=ea, we=p['lin_edge.weight'])
+    torch.testing.assert_close(out, ref, rtol=1e-6, atol=1e-7)      # _folded hands the bias vectors over in fp32
+
+
 def test_segment_softmax_and_loops():
     src = torch.tensor([[1.0], [3.0], [2.0], [-1.0]], dtype=torch.float64)
     idx = torch.tensor([0, 0, 2, 2])
