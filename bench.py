@@ -555,6 +555,29 @@ def run_extras(b2g, ops, part, dev, timed):
                 out[key] = {"error": str(e)[:200]}
             torch.cuda.empty_cache()
 
+    # TransformerConv(edge_dim=4): the same layer consuming [dir, dist] edge attributes of the mesh
+    try:
+        torch.manual_seed(0)
+        layer = b2g.nn.TransformerConv(F, F, heads=4, concat=False, edge_dim=4).to(dev).to(torch.bfloat16).eval()
+        x = torch.empty(N, F, device=dev, dtype=torch.bfloat16).normal_()
+        ea = torch.empty(ei.shape[1], 4, device=dev, dtype=torch.float32).normal_()
+        ms = timed(lambda: layer(x, ei, edge_attr=ea), 5, 2)
+        e_agg = part.aggregated_edges("Transformer")
+        out["Transformer_edge_dim4_bf16_fwd"] = {"ms": ms, "edges_per_sec": e_agg / (ms * 1e-3)}
+        xg = x.requires_grad_(True)
+        gout = torch.empty(N, F, device=dev, dtype=torch.bfloat16).normal_()
+
+        def fbe():
+            xg.grad = None
+            layer.zero_grad(set_to_none=True)
+            layer(xg, ei, edge_attr=ea).backward(gout)
+        ms = timed_grad(fbe, 3, 2)
+        out["Transformer_edge_dim4_bf16_fwd_bwd"] = {"ms": ms, "edges_per_sec": e_agg / (ms * 1e-3)}
+        del layer, x, xg, gout, ea
+    except Exception as e:
+        out["Transformer_edge_dim4_bf16"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
+
     # FlowGNN train step (fwd + loss + bwd + clip + Adam; hidden 256, 4 layers, bf16, train.py:170-189) on a 2.5 M-cell
     # block of the same mesh: the reference caller as is (drop-in layers + BatchNorm) and with the glue fused
     # (FlowGNN(fused_glue=True): residual + BatchNorm + ReLU + dropout in the two passes of csrc/bn.cu)

@@ -18,7 +18,7 @@ from . import ops
 LAYER_TYPES = ('GCN', 'GAT', 'GIN', 'Transformer')
 
 
-def _make_layer(layer_type: str, width: int, dropout: float):
+def _make_layer(layer_type: str, width: int, dropout: float, edge_dim=None):
     if layer_type == 'GCN':
         return gnn.GCNConv(width, width)                                           # gnn_model.py:63
     if layer_type == 'GAT':
@@ -26,14 +26,15 @@ def _make_layer(layer_type: str, width: int, dropout: float):
     if layer_type == 'GIN':
         return gnn.GINConv(tnn.Sequential(tnn.Linear(width, width), tnn.ReLU(), tnn.Linear(width, width)))  # :70-75
     if layer_type == 'Transformer':
-        return gnn.TransformerConv(width, width, heads=4, concat=False, dropout=dropout)  # :77-80
+        return gnn.TransformerConv(width, width, heads=4, concat=False, dropout=dropout, edge_dim=edge_dim)  # :77-80
     raise ValueError(f"Unknown layer type: {layer_type}")                         # :82
 
 
 class FlowGNN(tnn.Module):
     def __init__(self, input_dim: int = 3, hidden_dim: int = 128, output_dim: int = 8, num_layers: int = 4,
                  layer_type: str = 'GCN', use_edge_attr: bool = True, dropout: float = 0.1,
-                 use_batch_norm: bool = True, validate_edges: bool = True, fused_glue: bool = False):
+                 use_batch_norm: bool = True, validate_edges: bool = True, fused_glue: bool = False,
+                 edge_dim: Optional[int] = None):
         super().__init__()
         self.input_dim, self.hidden_dim, self.output_dim = input_dim, hidden_dim, output_dim
         self.num_layers, self.layer_type = num_layers, layer_type
@@ -42,8 +43,14 @@ class FlowGNN(tnn.Module):
         # opt-in: residual add + BatchNorm + ReLU + dropout (:184-192) as the two passes of csrc/bn.cu
         # instead of four torch ops.  Same arithmetic; the dropout mask comes from the library's Philox stream.
         self.fused_glue = fused_glue
+        # opt-in: edge_dim=4 builds the Transformer layers with PyG's lin_edge so that the edge_attr the
+        # reference already passes (:170) is consumed — "Transformer with edge features" (THEORY_AND_METHODS.md:165-166).
+        # None = the reference's constructor call (:77-80), where the attribute cannot be used.
+        if edge_dim is not None and layer_type != 'Transformer':
+            raise ValueError("edge_dim is an option of layer_type='Transformer'")
+        self.edge_dim = edge_dim
         self.input_proj = tnn.Linear(input_dim, hidden_dim)
-        self.gnn_layers = tnn.ModuleList(_make_layer(layer_type, hidden_dim, dropout) for _ in range(num_layers))
+        self.gnn_layers = tnn.ModuleList(_make_layer(layer_type, hidden_dim, dropout, edge_dim) for _ in range(num_layers))
         self.batch_norms = tnn.ModuleList(gnn.BatchNorm(hidden_dim) for _ in range(num_layers)) if use_batch_norm else None
         h = hidden_dim
         self.output_proj = tnn.Sequential(

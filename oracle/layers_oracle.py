@@ -146,7 +146,7 @@ def glorot_(t):
         return t.uniform_(-a, a)
 
 
-def flow_gnn_forward(x, edge_index, params, layer_type, training=False):
+def flow_gnn_forward(x, edge_index, params, layer_type, training=False, edge_attr=None):
     """FlowGNN.forward (gnn_model.py:159-197) with dropout p=0 and BatchNorm in the given mode,
     expressed over the functional oracle layers.  `params` mirrors FlowGNN.state_dict()."""
     p = params
@@ -168,7 +168,8 @@ def flow_gnn_forward(x, edge_index, params, layer_type, training=False):
                                   p[g + 'lin_query.weight'], p[g + 'lin_query.bias'],
                                   p[g + 'lin_key.weight'], p[g + 'lin_key.bias'],
                                   p[g + 'lin_value.weight'], p[g + 'lin_value.bias'],
-                                  p[g + 'lin_skip.weight'], p[g + 'lin_skip.bias'])
+                                  p[g + 'lin_skip.weight'], p[g + 'lin_skip.bias'],
+                                  edge_attr=edge_attr, we=p.get(g + 'lin_edge.weight'))   # gnn_model.py:170 passes edge_attr
         else:
             raise ValueError(layer_type)
         h = h + hn

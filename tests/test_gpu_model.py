@@ -20,9 +20,13 @@ def grid_graph(nx, ny):
     return o[order].astype(np.int32), n[order].astype(np.int32)
 
 
-@pytest.mark.parametrize("layer_type", ["GCN", "GAT", "GIN", "Transformer"])
+@pytest.mark.parametrize("layer_type", ["GCN", "GAT", "GIN", "Transformer", "Transformer+edge"])
 @pytest.mark.parametrize("training", [False, True])
 def test_flowgnn_matches_oracle(layer_type, training):
+    # "Transformer+edge": FlowGNN(edge_dim=4), the Transformer layers consume the edge_attr the reference passes (§8f-2)
+    edge_dim = 4 if layer_type.endswith("+edge") else None
+    layer_type = layer_type.split("+")[0]
+    hidden = 128 if edge_dim else 64
     from gnn_bfs_rans_b200.flow_model import FlowGNN
     from gnn_bfs_rans_b200 import GraphConstructor
     from oracle import layers_oracle as lo
@@ -32,7 +36,7 @@ def test_flowgnn_matches_oracle(layer_type, training):
     g = GraphConstructor(dict(owner=o, neighbour=n, cell_centers=cc, n_cells=nx * ny)).build_graph(
         filter_internal=True, n_internal_cells=nx * ny)
     torch.manual_seed(0)
-    model = FlowGNN(3, 64, 7, 3, layer_type, dropout=0.0).cuda()
+    model = FlowGNN(3, hidden, 7, 3, layer_type, dropout=0.0, edge_dim=edge_dim).cuda()
     model.train(training)
     x = g.x.cuda().requires_grad_(True)
     out = model(x, g.edge_index.cuda(), g.edge_attr.cuda())
@@ -40,8 +44,11 @@ def test_flowgnn_matches_oracle(layer_type, training):
     pnames = {k for k, _ in model.named_parameters()}
     p = {k: v.detach().double().cpu().requires_grad_(k in pnames) for k, v in model.state_dict().items()}
     x64 = g.x.double().requires_grad_(True)
-    ref = lo.flow_gnn_forward(x64, g.edge_index, p, layer_type, training=training)
+    ref = lo.flow_gnn_forward(x64, g.edge_index, p, layer_type, training=training,
+                              edge_attr=g.edge_attr.double() if edge_dim else None)
     ref.square().mean().backward()
+    if edge_dim:
+        assert model.gnn_layers[0].lin_edge.weight.grad is not None and 'gnn_layers.0.lin_edge.weight' in p
     # whole-model gate: L layers + BatchNorm + head in fp32 (torch ops of the caller included), so the
     # per-layer 1e-5 compounds; gradients are gauged against the largest gradient of the model because
     # several (biases in front of a BatchNorm) are zero in exact arithmetic.
