@@ -15,6 +15,18 @@ import torch
 from . import ops
 
 
+def identity_cached(store: dict, name: str, tensor: torch.Tensor, make):
+    """make() cached in store[name] for as long as the SAME tensor object is passed with an unchanged version counter.
+    Keyed on a weak reference to the object, not on its data pointer: the allocator hands a freed block to the next tensor
+    of the same size, which would then be mistaken for the old one."""
+    hit = store.get(name)
+    if hit is not None and hit[0]() is tensor and hit[1] == tensor._version:
+        return hit[2]
+    value = make()
+    store[name] = (weakref.ref(tensor), tensor._version, value)
+    return value
+
+
 class CSR:
     """One orientation of one variant: rowptr/col/eid (+dinv)."""
     __slots__ = ("rowptr", "col", "eid", "dinv", "nnz")
@@ -110,15 +122,10 @@ class Graph:
         self-loop-replaced list has entries without an input edge."""
         if variant != "raw":
             raise NotImplementedError("edge_rows: only the raw edge list has one input edge per CSR entry")
-        key = (edge_attr.data_ptr(), edge_attr._version, tuple(edge_attr.shape), edge_attr.dtype)
-        hit = getattr(self, "_edge_rows", None)
-        if hit is not None and hit[0] == key:
-            return hit[1]
         if not edge_attr.is_cuda:
             raise RuntimeError("b2g: CUDA tensor required (this is the B200 path; there is no CPU fallback)")
-        rows = edge_attr.detach().float().index_select(0, self.csr("raw", False).eid.long()).contiguous()
-        self._edge_rows = (key, rows)
-        return rows
+        return identity_cached(self.__dict__, "_edge_rows", edge_attr,
+                               lambda: edge_attr.detach().float().index_select(0, self.csr("raw", False).eid.long()).contiguous())
 
     def perm(self, variant: str) -> torch.Tensor:
         """Position in the target-major CSR of each entry of the source-major CSR."""

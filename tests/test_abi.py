@@ -4,6 +4,7 @@ import os
 import re
 
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -93,3 +94,28 @@ def test_data_and_batch_semantics():
     assert b.batch.tolist() == [0, 0, 0] and b.edge_index.tolist() == [[0, 1], [1, 0]] and b.num_graphs == 1
     b3 = Batch.from_data_list([d, d.clone(), d.clone()])
     assert b3.edge_index[:, -2:].tolist() == [[6, 7], [7, 6]] and b3.x.shape == (12, 3) and b3.num_nodes == 9
+
+
+def test_identity_cache_follows_the_tensor_object_and_its_version():
+    """graph.identity_cached (used for edge_attr in CSR order): a hit needs the same tensor object, unmodified."""
+    from gnn_bfs_rans_b200.graph import identity_cached
+    store, calls = {}, []
+    a = torch.arange(6.0)
+
+    def make(t):
+        calls.append(1)
+        return t * 2
+
+    r1 = identity_cached(store, "k", a, lambda: make(a))
+    r2 = identity_cached(store, "k", a, lambda: make(a))
+    assert r1 is r2 and len(calls) == 1
+    a.add_(1)                                           # in-place change bumps the version counter
+    r3 = identity_cached(store, "k", a, lambda: make(a))
+    assert len(calls) == 2 and torch.equal(r3, a * 2)
+    b = a.clone()                                       # equal content, different object
+    identity_cached(store, "k", b, lambda: make(b))
+    assert len(calls) == 3
+    del b                                               # a dead referent never matches a new tensor
+    c = torch.arange(6.0)
+    identity_cached(store, "k", c, lambda: make(c))
+    assert len(calls) == 4
