@@ -75,8 +75,14 @@ def gcn_conv(x, edge_index, weight, bias=None):
 
 
 def gat_conv(x, edge_index, weight, att_src, att_dst, bias=None, heads=4, concat=False,
-             negative_slope=0.2, dropout=0.0, training=False, return_alpha=False):
-    """GATConv(in,out,heads,concat,dropout).forward(x, edge_index) with add_self_loops=True."""
+             negative_slope=0.2, dropout=0.0, training=False, return_alpha=False,
+             edge_attr=None, we=None, att_edge=None):
+    """GATConv(in,out,heads,concat,dropout).forward(x, edge_index[, edge_attr]) with add_self_loops=True.
+    edge_dim (PyG GATConv.forward / edge_updater): with `we` = lin_edge.weight [H*C, edge_dim] and `att_edge` [1,H,C],
+    the self loops are dropped WITH their attributes, every node's new loop gets the mean attribute of its incoming edges
+    (fill_value='mean'; 0 for a node without one), and alpha_edge = (lin_edge(edge_attr).view(-1,H,C) * att_edge).sum(-1)
+    joins a_src[j] + a_dst[i] in front of the LeakyReLU.  The messages stay x_j W (no edge term).
+    (Oracle for the next step of SURVEY §8f-2: the product's GATConv raises NotImplementedError for edge_dim.)"""
     N = x.shape[0]
     H = heads
     C = weight.shape[0] // H
@@ -85,7 +91,16 @@ def gat_conv(x, edge_index, weight, att_src, att_dst, bias=None, heads=4, concat
     a_d = (xs * att_dst.view(1, H, C)).sum(-1)
     ei = replace_self_loops(edge_index, N)
     row, col = ei[0], ei[1]
-    alpha = F.leaky_relu(a_s.index_select(0, row) + a_d.index_select(0, col), negative_slope)
+    logit = a_s.index_select(0, row) + a_d.index_select(0, col)
+    if edge_attr is not None and we is not None:
+        keep = edge_index[0] != edge_index[1]                               # remove_self_loops(edge_index, edge_attr)
+        ea = edge_attr[keep].to(x.dtype)
+        tgt = edge_index[1][keep]
+        cnt = scatter_sum(torch.ones_like(tgt, dtype=x.dtype), tgt, N).clamp_min(1)
+        loop_attr = scatter_sum(ea, tgt, N) / cnt.unsqueeze(-1)            # add_self_loops(..., fill_value='mean')
+        e = F.linear(torch.cat([ea, loop_attr], dim=0), we).view(-1, H, C)
+        logit = logit + (e * att_edge.view(1, H, C)).sum(-1)
+    alpha = F.leaky_relu(logit, negative_slope)
     alpha = segment_softmax(alpha, col, N)
     alpha = F.dropout(alpha, p=dropout, training=training)
     out = scatter_sum(alpha.unsqueeze(-1) * xs.index_select(0, row), col, N)

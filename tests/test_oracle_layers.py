@@ -71,6 +71,37 @@ def test_gat_equals_per_edge_loops():
     torch.testing.assert_close(lo.gat_conv(x, ei, W, a_s, a_d, None, heads=H, concat=True), ref.reshape(N, H * C), rtol=1e-9, atol=1e-12)
 
 
+def test_gat_with_edge_features_equals_per_edge_loops():
+    """GATConv(edge_dim): loops dropped with their attributes, new loops carry the mean incoming attribute, the edge term
+    enters the logits only."""
+    N, F, H, C, D = 12, 6, 4, 3, 4
+    ei = graph(N)
+    E = ei.shape[1]
+    x = torch.randn(N, F, dtype=torch.float64)
+    ea = torch.randn(E, D, dtype=torch.float64)
+    W = torch.randn(H * C, F, dtype=torch.float64)
+    a_s, a_d, a_e = (torch.randn(1, H, C, dtype=torch.float64) for _ in range(3))
+    we = torch.randn(H * C, D, dtype=torch.float64)
+    b = torch.randn(C, dtype=torch.float64)
+    xs = (x @ W.T).view(N, H, C)
+    edges = [(s, d, ea[e]) for e, (s, d) in enumerate(ei.t().tolist()) if s != d]
+    ref = torch.zeros(N, H, C, dtype=torch.float64)
+    for i in range(N):
+        inc = [(s, at) for s, d, at in edges if d == i]
+        mean_attr = torch.stack([at for _, at in inc]).mean(0) if inc else torch.zeros(D, dtype=torch.float64)
+        inc = inc + [(i, mean_attr)]
+        for h in range(H):
+            lg = []
+            for j, at in inc:
+                emb = (we @ at).view(H, C)
+                lg.append((xs[j, h] * a_s[0, h]).sum() + (xs[i, h] * a_d[0, h]).sum() + (emb[h] * a_e[0, h]).sum())
+            al = torch.softmax(torch.nn.functional.leaky_relu(torch.stack(lg), 0.2), 0)
+            for w, (j, _) in zip(al, inc):
+                ref[i, h] += w * xs[j, h]
+    out = lo.gat_conv(x, ei, W, a_s, a_d, b, heads=H, edge_attr=ea, we=we, att_edge=a_e)
+    torch.testing.assert_close(out, ref.mean(1) + b, rtol=1e-9, atol=1e-12)
+
+
 def test_transformer_equals_per_edge_loops():
     N, F, H, C = 12, 6, 4, 3
     ei = graph(N)
