@@ -165,6 +165,56 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+
+# ------------------------------------------------------------------------------------ parity of the timed outputs
+def sampled_parity(kind, layer, x, ei, n_nodes, out, plane, tol, count=4096, edge_attr=None):
+    """Checker, outside every timed region: `count` target rows of the output the timed run produced (first / last rows,
+    rows next to multiples of `plane` = block faces, random interior rows) against oracle/layers_oracle.py in fp64 on the
+    rows' one-hop closure (oracle/sampled.py), from the same weights and inputs.  max |mine - ref| / max |ref|."""
+    import torch
+    from oracle import sampled
+    rows = sampled.pick_rows(out.shape[0], count, plane=plane, seed=0)
+    nodes, ei_sub, pos = sampled.closure_subgraph(ei, rows.to(ei.device), n_nodes)
+    ref = sampled.layer_rows(kind, layer.state_dict(), x[nodes], ei_sub, pos)
+    mine = out[rows.to(out.device)].double().cpu()
+    err = float((mine - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    return {"rows": int(rows.numel()), "closure_nodes": int(nodes.numel()), "closure_edges": int(ei_sub.shape[1]),
+            "max_rel": err, "tol": tol, "ok": bool(err < tol),
+            "oracle": "oracle/layers_oracle.py fp64 on the one-hop closure of the sampled rows (oracle/sampled.py)"}
+
+
+def halo_check(b2g, layer, layer_name, world, rank, dev, dtype, tol):
+    """N > 1 checker: a small mesh (64 x 64 x 16 N) through the SAME slab_partition_hex / wrap_forward path (halo exchange
+    over NCCL included) against a monolithic run of the whole small mesh on this rank's GPU; every rank compares its owned
+    rows, and separately the two planes next to its slab cuts (the rows that read ghost rows)."""
+    import torch
+    import torch.distributed as dist
+    from gnn_bfs_rans_b200.distributed import slab_partition_hex
+    sx, sy, sz = 64, 64, 16
+    n0 = sx * sy * sz
+    with torch.no_grad():
+        ps = slab_partition_hex(sx, sy, sz, world, rank, dev)
+        g = torch.Generator().manual_seed(4242)
+        xg = torch.randn(n0 * world, F, generator=g).to(dtype).to(dev)          # the same global features on every rank
+        xl = torch.zeros(ps.n_local, F, device=dev, dtype=dtype)
+        xl[:n0] = xg[rank * n0:(rank + 1) * n0]
+        out_p = ps.wrap_forward(layer)(xl, ps.edge_index)[:n0].float()
+        mono = slab_partition_hex(sx, sy, sz * world, 1, 0, dev)
+        out_m = mono.wrap_forward(layer)(xg, mono.edge_index)[rank * n0:(rank + 1) * n0].float()
+        scale = out_m.abs().max().clamp_min(1e-30)
+        d = (out_p - out_m).abs()
+        plane = sx * sy
+        cut = torch.cat([d[:plane], d[-plane:]])
+        res = torch.tensor([float(d.max() / scale), float(cut.max() / scale), float((d.max(1).values > 0).sum()), float(n0)],
+                           device=dev, dtype=torch.float64)
+        allr = [torch.empty_like(res) for _ in range(world)]
+        dist.all_gather(allr, res)
+        allr = torch.stack(allr).cpu()
+    mx, mxc = float(allr[:, 0].max()), float(allr[:, 1].max())
+    return {"mesh": f"{sx}x{sy}x{sz * world} hex, {world} slabs", "layer": layer_name, "rows_per_rank": n0,
+            "max_rel_all_rows": mx, "max_rel_cut_planes": mxc, "rows_not_bit_equal": int(allr[:, 2].sum()), "tol": tol,
+            "ok": bool(mx < tol), "compares": "partitioned (wrap_forward + NCCL halo exchange) vs monolithic, same kernels"}
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -256,6 +306,21 @@ def main():
         e_total = int(t)
     value = e_total / (ms * 1e-3)
 
+    # ---- parity of what was just timed (checker, outside the timed region): sampled rows vs the fp64 oracle at N = 1,
+    # partitioned vs monolithic on a small mesh through the same exchange path at N > 1
+    tol = 2e-2 if args.dtype == "bf16" else 1e-5
+    parity = halo = None
+    try:
+        with torch.no_grad():
+            if world == 1:
+                parity = sampled_parity(args.layer, layer, x, ei, part.n_local, fwd(x, ei), nx * ny, tol)
+            else:
+                halo = halo_check(b2g, layer, args.layer, world, rank, dev, dtype, tol)
+    except Exception as e:  # the checker must not take the measurement down; a failure is reported as such
+        parity = {"error": str(e)[:200], "ok": False} if world == 1 else None
+        halo = {"error": str(e)[:200], "ok": False} if world > 1 else None
+    torch.cuda.empty_cache()
+
     # ---- roofline of the dominant kernel (K2 seg_sum for GCN/GIN; fused attention for GAT/Transformer)
     g = b2g.graph.graph_of(ei, part.n_local)
     roof = None
@@ -266,8 +331,9 @@ def main():
             dinv = g.dinv() if args.layer == "GCN" else None
             xin = torch.randn(part.n_local, F, device=dev).to(dtype)
             out = torch.empty(N, F, device=dev, dtype=dtype)
+            kbias = layer.bias.float() if args.layer == "GCN" and layer.bias is not None else None
             kfn = lambda: ops.seg_sum(xin, csr.rowptr, csr.col, N, dinv, None, 0.0 if args.layer == "GCN" else 1.0, None,
-                                      None, out=out, band=g.band())   # exactly the launch the layer forward makes
+                                      kbias, out=out, band=g.band())   # the launch the layer forward makes (same template instance)
             kms = timed(kfn, args.steps, 3)
             alg = 2 * N * F * s + 4 * csr.nnz + 4 * (N + 1) + (4 * N if dinv is not None else 0)
             kname = "seg_rows_kernel (K2/K3, aggregate_rows.cu)"
@@ -452,7 +518,7 @@ def main():
                            "cells_per_gpu": N, "edges_per_step": e_total, "hidden": F, "layer": args.layer,
                            "partition": "none" if world == 1 else f"RCB slabs x{world}, 1-ring halo exchange per layer (NCCL)",
                            "cache_policy": "inputs (>5 GB) larger than the 126 MB L2; CSR cached across steps in `value`"},
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
+                "parity_check": parity, "halo_check": halo, "clocks": clk, "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
                 "gpu_launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cb, "extras": extras}
         if train_line is not None:
             line["train_step_partitioned"] = train_line
@@ -539,6 +605,12 @@ def run_extras(b2g, ops, part, dev, timed):
                 ms = timed(lambda: layer(x, ei), 5, 2)
                 e_agg = part.aggregated_edges(lt)
                 out[key + "_fwd"] = {"ms": ms, "edges_per_sec": e_agg / (ms * 1e-3)}
+                try:
+                    with torch.no_grad():
+                        out[key + "_fwd"]["parity_check"] = sampled_parity(
+                            lt, layer, x, ei, N, layer(x, ei), NX * NY, 2e-2 if dt_name == "bf16" else 1e-5, count=2048)
+                except Exception as e:
+                    out[key + "_fwd"]["parity_check"] = {"error": str(e)[:200], "ok": False}
                 if dt_name == "bf16":
                     xg = x.requires_grad_(True)
 
@@ -676,6 +748,11 @@ def run_extras(b2g, ops, part, dev, timed):
                 layer = mk(lt).to(dev).to(torch.bfloat16).eval()
                 x3 = torch.empty(n3, F, device=dev, dtype=torch.bfloat16).normal_()
                 ms_f = timed(lambda: layer(x3, ei3), 10, 3)
+                try:
+                    with torch.no_grad():
+                        par3 = sampled_parity(lt, layer, x3, ei3, n3, layer(x3, ei3), 0, 2e-2, count=2048)
+                except Exception as e:
+                    par3 = {"error": str(e)[:200], "ok": False}
                 xg = x3.clone().requires_grad_(True)
                 g3 = torch.empty(n3, F, device=dev, dtype=torch.bfloat16).normal_()
 
@@ -686,7 +763,7 @@ def run_extras(b2g, ops, part, dev, timed):
                 ms_b = timed_grad(fb3, 5, 2)
                 e3 = int(ei3.shape[1])
                 out[f"cfg3_delaunay{tag}_{lt}_F256_bf16"] = {"cells": n3, "edges": e3, "forward_ms": ms_f, "fwd_bwd_ms": ms_b,
-                                                             "fwd_edges_per_sec": e3 / (ms_f * 1e-3)}
+                                                             "fwd_edges_per_sec": e3 / (ms_f * 1e-3), "parity_check": par3}
                 del layer, x3, xg, g3
     except Exception as e:
         out["cfg3_delaunay"] = {"error": str(e)[:200]}

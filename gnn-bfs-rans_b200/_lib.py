@@ -32,11 +32,10 @@ SIGNATURES = {
     "b2g_csr_count": (i32, [vp, i64, i64, i32, i32, vp, vp, vp, vp]),
     "b2g_csr_fill": (i32, [vp, i64, i64, i32, i32, vp, i64, vp, vp, vp, vp, vp]),
     "b2g_csr_perm": (i32, [vp, vp, i64, vp, vp, vp]),
-    "b2g_set_seg_impl": (i32, [i32]),
-    "b2g_set_seg_sched": (i32, [i32, i32]),
     "b2g_seg_sum": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, vp]),
     "b2g_seg_sum_banded": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, i64, vp]),
     "b2g_seg_sum_hinted": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, i64, i64, vp]),
+    "b2g_seg_sum_tuned": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp, vp, vp, vp, f32, vp, i32, i64, i64, i32, i32, i32, vp]),
     "b2g_gat_fwd": (i32, [vp, i64, vp, vp, i64, vp, i64, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, f32, u64, i32, vp]),
     "b2g_gat_bwd_dst": (i32, [vp, i64, vp, vp, i64, vp, i64, i64, i32, i32, i32, i32, f32, vp, vp, vp, vp, f32, u64, vp, vp, vp, i64, vp]),
     "b2g_gat_bwd_src": (i32, [vp, i64, vp, vp, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp]),

@@ -279,13 +279,8 @@ static inline unsigned grid_for(int64_t n, int threads, int per_sm = 8) {
 }  // namespace b2g
 
 namespace b2g {
-bool bulk_seg_sum_supported(int nvec, int64_t n_rows);
-int bulk_seg_sum(int, const void*, int64_t, const void*, int64_t, void*, int64_t, int64_t, int, int, const int32_t*,
-                 const int32_t*, const float*, const float*, float, const float*, int, cudaStream_t);
 int rows_seg_sum(const void*, int64_t, void*, int64_t, int64_t, int, int, const int32_t*, const int32_t*, const float*,
-                 const float*, float, const float*, int, int64_t, int64_t, cudaStream_t);
-int rows_set_sched(int chunk_rows, int panel_rows);
-int g_seg_impl = 0;   // 0 = auto, 1 = register gather (LDG), 2 = cp.async.bulk ring, 3 = cp.async (LDGSTS) ring
+                 const float*, float, const float*, int, int64_t, int64_t, int, int, cudaStream_t);
 }  // namespace b2g
 
 using namespace b2g;
@@ -297,18 +292,11 @@ static inline bool row_ok(const void* p, int64_t ld, int dt) {
 
 extern "C" {
 
-int b2g_set_seg_sched(int chunk_rows, int panel_rows) { return rows_set_sched(chunk_rows, panel_rows); }
-
-int b2g_set_seg_impl(int impl) {
-  if (impl < 0 || impl > 3) return B2G_E_ARG;
-  g_seg_impl = impl;
-  return B2G_OK;
-}
-
 static int seg_sum_impl(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out, int64_t ldo, int64_t n_rows,
                         int F, int dt, const int32_t* rowptr, const int32_t* col, const float* row_scale,
                         const float* col_scale, float self_coef, const float* bias, int relu, int64_t band,
-                        int64_t max_row_len, void* stream) {
+                        int64_t max_row_len, void* stream, int impl = 0, int chunk_rows = 0, int panel_rows = 0) {
+  if (impl < 0 || impl > 1) return B2G_E_ARG;
   if (n_rows < 0 || F <= 0 || (dt != B2G_F32 && dt != B2G_BF16)) return B2G_E_ARG;
   if (n_rows == 0) return B2G_OK;
   if (!x || !out || !rowptr) return B2G_E_ARG;
@@ -316,15 +304,10 @@ static int seg_sum_impl(const void* x, int64_t ldx, const void* x_self, int64_t 
   if (!row_ok(x, ldx, dt) || !row_ok(out, ldo, dt) || (x_self && !row_ok(x_self, ldxs, dt))) return B2G_E_ALIGN;
   const int nvec = F * elem_size(dt) / 16;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool bulk_ok = bulk_seg_sum_supported(nvec, n_rows);
-  if (g_seg_impl >= 2 && !bulk_ok) return B2G_E_UNSUPPORTED;
-  if (bulk_ok && g_seg_impl >= 2)
-    return bulk_seg_sum(g_seg_impl, x, ldx, x_self, ldxs, out, ldo, n_rows, nvec, dt, rowptr, col, row_scale, col_scale, self_coef,
-                        bias, relu, st);
   // rows of whole 512-byte multiples (F = 256 bf16, F = 128/256 fp32, ...): warp-per-row fast path (aggregate_rows.cu)
-  if (g_seg_impl != 1 && !x_self) {
+  if (impl != 1 && !x_self) {
     const int rc = rows_seg_sum(x, ldx, out, ldo, n_rows, nvec, dt, rowptr, col, row_scale, col_scale, self_coef, bias, relu,
-                                band > 0 ? band : 0, max_row_len > 0 ? max_row_len : 0, st);
+                                band > 0 ? band : 0, max_row_len > 0 ? max_row_len : 0, chunk_rows, panel_rows, st);
     if (rc != B2G_E_UNSUPPORTED) return rc;
   }
   if (dt == B2G_F32)
@@ -354,6 +337,15 @@ int b2g_seg_sum_hinted(const void* x, int64_t ldx, const void* x_self, int64_t l
                        float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, void* stream) {
   return seg_sum_impl(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale, self_coef, bias, relu,
                       band, max_row_len, stream);
+}
+
+int b2g_seg_sum_tuned(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                      int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                      const int32_t* col, const float* row_scale, const float* col_scale,
+                      float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, int impl,
+                      int chunk_rows, int panel_rows, void* stream) {
+  return seg_sum_impl(x, ldx, x_self, ldxs, out, ldo, n_rows, F, dt, rowptr, col, row_scale, col_scale, self_coef, bias, relu,
+                      band, max_row_len, stream, impl, chunk_rows, panel_rows);
 }
 
 int64_t b2g_colsum_workspace_bytes(int F) { return F > 0 ? (int64_t)COLSUM_BLOCKS * F * 4 : B2G_E_ARG; }

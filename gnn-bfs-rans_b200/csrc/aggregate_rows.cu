@@ -21,17 +21,6 @@
 
 namespace b2g {
 
-int g_seg_chunk = 32;
-int g_seg_panel = 8192;
-
-int rows_set_sched(int chunk_rows, int panel_rows) {
-  if (chunk_rows < 8 || (chunk_rows & (chunk_rows - 1)) || chunk_rows > 4096) return B2G_E_ARG;
-  if (panel_rows < chunk_rows || (panel_rows & (panel_rows - 1)) || panel_rows > (1 << 24)) return B2G_E_ARG;
-  g_seg_chunk = chunk_rows;
-  g_seg_panel = panel_rows;
-  return B2G_OK;
-}
-
 struct RowsArgs {
   const void* x;
   void* out;
@@ -328,13 +317,14 @@ static int launch_rows(const RowsArgs& a, cudaStream_t st) {
 // B2G_E_UNSUPPORTED = not a case of this fast path (the caller falls back to the generic kernel).
 int rows_seg_sum(const void* x, int64_t ldx, void* out, int64_t ldo, int64_t n_rows, int nvec, int dt,
                  const int32_t* rowptr, const int32_t* col, const float* row_scale, const float* col_scale,
-                 float self_coef, const float* bias, int relu, int64_t band, int64_t /*max_row_len*/, cudaStream_t st) {
+                 float self_coef, const float* bias, int relu, int64_t band, int64_t /*max_row_len*/, int chunk_rows,
+                 int panel_rows, cudaStream_t st) {
   const int es = dt == B2G_F32 ? 4 : 2;
   if (nvec != 32 && nvec != 64) return B2G_E_UNSUPPORTED;
   if (n_rows < 1024 || n_rows >= (1ll << 32) - (1ll << 25) || ldx * es >= (1ll << 32) || ldo * es >= (1ll << 32))
     return B2G_E_UNSUPPORTED;
   RowsArgs a{};
-  if (!make_row_sched(n_rows, band, a.ord)) return B2G_E_UNSUPPORTED;
+  if (!make_row_sched(n_rows, band, a.ord, chunk_rows, panel_rows)) return B2G_E_ARG;
   a.x = x; a.out = out; a.rowptr = rowptr; a.col = col; a.row_scale = row_scale; a.col_scale = col_scale; a.bias = bias;
   a.xrow_bytes = (uint32_t)(ldx * es);
   a.orow_bytes = (uint32_t)(ldo * es);

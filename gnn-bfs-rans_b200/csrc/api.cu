@@ -2,7 +2,7 @@
 #include "common.cuh"
 
 namespace b2g {
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 
 static uint64_t* g_epoch[64] = {nullptr};
 const uint64_t* dropout_epoch_ptr() {
@@ -24,8 +24,8 @@ extern "C" {
 
 int b2g_version(void) { return B2G_VERSION; }
 
-int64_t b2g_launch_count(void) { return b2g::g_launches; }
-void b2g_launch_count_reset(void) { b2g::g_launches = 0; }
+int64_t b2g_launch_count(void) { return b2g::g_launches.load(std::memory_order_relaxed); }
+void b2g_launch_count_reset(void) { b2g::g_launches.store(0, std::memory_order_relaxed); }
 
 int b2g_dropout_epoch_advance(void* stream) {
   uint64_t* e = const_cast<uint64_t*>(b2g::dropout_epoch_ptr());

@@ -4,18 +4,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/b2g.h"
 
 #define B2G_NUM_SMS 148  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 
 namespace b2g {
 
-extern int64_t g_launches;  // defined in api.cu
-inline void count_launch(int n = 1) { g_launches += n; }
+extern std::atomic<int64_t> g_launches;  // defined in api.cu: a diagnostic counter (b2g_launch_count), no effect on results
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 inline int cuda_status() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+// slot of the calling thread's current device in per-device lazily-initialised tables (kernel attribute opt-ins)
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); dev = 0; }
+  return dev;
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

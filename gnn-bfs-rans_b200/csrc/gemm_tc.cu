@@ -813,11 +813,12 @@ int64_t tc_wgrad_ws_bytes(int64_t n, int m, int k) {
 int tc_linear_wgrad(const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw, int64_t n,
                     int m, int k, void* ws, cudaStream_t st) {
   if (!aligned16(dY) || !aligned16(X) || (lddy * 2) % 16 || (ldx * 2) % 16) return B2G_E_ALIGN;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};                       // the opt-in is per device
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   WgParams p;
   wg_plan(n, m, k, p);
@@ -856,11 +857,12 @@ static int tc_linear_fwd_tf32x3(const void* X, int64_t ldx, const void* W, int64
   if (!ws) return B2G_E_ARG;
   if (!aligned16(X) || (ldx * 4) % 16) return B2G_E_ALIGN;
   if (m_main > 0 && (!aligned16(Y) || (ldy * 4) % 16)) return B2G_E_ALIGN;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tc_linear_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   // The TMEM accumulation truncates: its error grows ~linearly with the reduction length (3e-6 at k = 256, 2.6e-5 at
   // k = 3328 against the 1e-5 gate).  Longer reductions are therefore cut into chunks of T3_KCHUNK columns: one launch per
@@ -899,12 +901,13 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   if (dt != B2G_BF16) return B2G_E_UNSUPPORTED;
   if (!aligned16(X) || !aligned16(W) || (ldx * 2) % 16 || (ldw * 2) % 16) return B2G_E_ALIGN;
   if (m_main > 0 && (!aligned16(Y) || (ldy * 2) % 16)) return B2G_E_ALIGN;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_STR);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   CUtensorMap map_a, map_b;
   if (!make_map(&map_a, X, n, k, ldx, TC_BM) || !make_map(&map_b, W, m, k, ldw, TC_BN)) return B2G_E_UNSUPPORTED;

@@ -48,7 +48,12 @@ int b2g_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const
   cudaStream_t st = (cudaStream_t)stream;
   const bool tc = tc_linear_supported(n, m, k, dt, 0);
   if (impl == 2 && !tc) return B2G_E_UNSUPPORTED;
-  if (tc && impl != 1) return tc_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, ws, st);
+  if (tc && impl != 1) {
+    const int rc = tc_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, ws, st);
+    // shapes the tensor-core kernels decline at launch time (fp32 aux split with k > 256, tensors TMA cannot map):
+    // auto mode falls through to the exact-fp32 SIMT kernel instead of failing the request
+    if (rc != B2G_E_UNSUPPORTED || impl == 2) return rc;
+  }
   return simt_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, st);
 }
 

@@ -30,13 +30,18 @@ struct RowSched {
     return c0;
   }
 };
-extern int g_seg_chunk;                     // rows per CTA step (b2g_set_seg_sched)
-extern int g_seg_panel;                     // rows per panel of the band order (power-of-two multiple of the chunk)
+constexpr int ROWS_CHUNK_DEFAULT = 32;      // rows per CTA step
+constexpr int ROWS_PANEL_DEFAULT = 8192;    // rows per panel of the band order (power-of-two multiple of the chunk)
 
-static inline bool make_row_sched(int64_t n_rows, int64_t band, RowSched& o) {
+// chunk_rows / panel_rows <= 0 select the defaults; per call (b2g_seg_sum_tuned), no library-wide state
+static inline bool make_row_sched(int64_t n_rows, int64_t band, RowSched& o, int chunk_rows = 0, int panel_rows = 0) {
   o = RowSched{};
-  o.chunk_rows = (uint32_t)g_seg_chunk;
-  const int64_t panel = g_seg_panel;
+  if (chunk_rows <= 0) chunk_rows = ROWS_CHUNK_DEFAULT;
+  if (panel_rows <= 0) panel_rows = ROWS_PANEL_DEFAULT;
+  if (chunk_rows < 8 || (chunk_rows & (chunk_rows - 1)) || chunk_rows > 4096) return false;
+  if (panel_rows < chunk_rows || (panel_rows & (panel_rows - 1)) || panel_rows > (1 << 24)) return false;
+  o.chunk_rows = (uint32_t)chunk_rows;
+  const int64_t panel = panel_rows;
   if (band < 4 * panel || band * 2 > n_rows) {               // narrow band (already L2 friendly) or no band structure
     const int64_t nc = ceil_div(n_rows, o.chunk_rows);
     if (nc >= (1ll << 31)) return false;

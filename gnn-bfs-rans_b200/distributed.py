@@ -137,14 +137,18 @@ class Partition:
         ghost rows of a [n_local, 4] fp32 buffer in place (default: self.exchange over NCCL)."""
         from .graph import graph_of
         g = graph_of(self.edge_index, self.n_local)
-        if not self._dinv_ready and self.world > 1:
+        # the "ghost deg^-1/2 patched" flag lives on the Graph object: if the cache ever hands out a fresh Graph for this
+        # edge_index (eviction), it is patched again instead of being trusted
+        if self.world > 1 and not (self._dinv_ready and getattr(g, "_ghost_dinv_patched", False)):
             dinv = g.dinv()
             buf = torch.zeros((self.n_local, 4), dtype=torch.float32, device=dinv.device)
             buf[:, 0] = dinv
             (exchange or self.exchange)(buf)
             dinv[self.n_owned:] = buf[self.n_owned:, 0]
+            g._ghost_dinv_patched = True
+            g._pinned = True                 # graph.graph_of never evicts it while edge_index lives
         self._dinv_ready = True
-        self._graph = g          # keep the patched Graph alive (the cache only holds it while edge_index lives)
+        self._graph = g          # strong reference: the patched Graph lives as long as the partition
         return g
 
     def wrap_forward(self, layer):

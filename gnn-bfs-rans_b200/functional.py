@@ -355,6 +355,10 @@ def batch_norm(x, r, bn: "torch.nn.BatchNorm1d", relu: bool = False, p_drop: flo
         mean = bn.running_mean.float().contiguous()
         rstd = torch.rsqrt(bn.running_var.float() + bn.eps)
     p = p_drop if bn.training else 0.0
+    if p > 0 and not relu:
+        # the backward kernels regenerate the dropout mask from the saved OUTPUT (y > 0 after ReLU): without the ReLU
+        # there is nothing to read it from, and gradients would silently ignore the mask
+        raise NotImplementedError("b2g batch_norm: dropout (p_drop > 0) is fused only together with relu=True")
     w = bn.weight if bn.affine else None
     b = bn.bias if bn.affine else None
     out = BatchNormFn.apply(x, r, w, b, mean, rstd, relu, p, training, reduce_sums)

@@ -156,8 +156,13 @@ def graph_of(edge_index: torch.Tensor, num_nodes: int) -> Graph:
         del _CACHE[key]
     g = Graph(edge_index, num_nodes)
     _CACHE[key] = (weakref.ref(edge_index), g)
-    while len(_CACHE) > _CACHE_MAX:
-        _CACHE.popitem(last=False)
+    if len(_CACHE) > _CACHE_MAX:
+        # least recently used first; a pinned Graph (captured by a CUDA graph, or carrying a partition's patched ghost
+        # deg^-1/2) stays for as long as its edge_index lives: a fresh copy would not be equivalent
+        for k in [k for k, (_, gg) in _CACHE.items() if not getattr(gg, "_pinned", False)]:
+            if len(_CACHE) <= _CACHE_MAX or k == key:
+                break
+            del _CACHE[k]
     return g
 
 

@@ -25,6 +25,11 @@ class GraphedForward:
         n = x.shape[0]
         if edge_index.numel() and (int(edge_index.min()) < 0 or int(edge_index.max()) >= n):   # gnn_model.py:130-149, once
             raise ValueError("edge_index has entries outside [0, num_nodes): filter it before capturing")
+        # the captured kernels hold raw pointers into this Graph's CSR buffers: own it for the lifetime of the capture
+        # (graph_of's LRU would otherwise free it once enough other meshes have been seen)
+        from .graph import graph_of
+        self._graph = graph_of(edge_index, n)
+        self._graph._pinned = True
         self._restore = getattr(model, "validate_edges", None)
         if self._restore is not None:
             model.validate_edges = False
@@ -76,6 +81,9 @@ class GraphedTrainStep:
         if edge_index.numel() and (int(edge_index.min()) < 0 or int(edge_index.max()) >= n):
             raise ValueError("edge_index has entries outside [0, num_nodes): filter it before capturing")
         self.model, self.optimizer, self.edge_index = model, optimizer, edge_index
+        from .graph import graph_of
+        self._graph = graph_of(edge_index, n)         # owns the CSR buffers the captured kernels point into
+        self._graph._pinned = True
         self._restore = getattr(model, "validate_edges", None)
         if self._restore is not None:
             model.validate_edges = False

@@ -220,7 +220,9 @@ def csr_perm(eid_a, eid_b, id_space: int):
 
 # ------------------------------------------------------------------------------------------ K2/K3
 def seg_sum(x, rowptr, col, n_rows, row_scale=None, col_scale=None, self_coef=0.0, x_self=None, bias=None,
-            relu=False, out=None, band=0):
+            relu=False, out=None, band=0, tune=None):
+    """tune = (impl, chunk_rows, panel_rows): per-call kernel / row-schedule choice (tests, probes); results do not
+    depend on it."""
     _cuda(x)
     lib = _lib.load()
     x = _rows(x)
@@ -228,6 +230,13 @@ def seg_sum(x, rowptr, col, n_rows, row_scale=None, col_scale=None, self_coef=0.
     F = x.shape[1]
     if out is None:
         out = torch.empty((n_rows, F), dtype=x.dtype, device=x.device)
+    if tune is not None:
+        impl, chunk, panel = tune
+        _lib.check(lib.b2g_seg_sum_tuned(_p(x), _ld(x), _p(xs), _ld(xs) if xs is not None else 0, _p(out), _ld(out),
+                                         n_rows, F, _dt(x), _p(rowptr), _p(col), _p(row_scale), _p(col_scale),
+                                         float(self_coef), _p(bias), int(relu), int(band), 0, int(impl), int(chunk),
+                                         int(panel), _stream()), "seg_sum_tuned")
+        return out
     _lib.check(lib.b2g_seg_sum_banded(_p(x), _ld(x), _p(xs), _ld(xs) if xs is not None else 0, _p(out), _ld(out),
                                       n_rows, F, _dt(x), _p(rowptr), _p(col), _p(row_scale), _p(col_scale),
                                       float(self_coef), _p(bias), int(relu), int(band), _stream()), "seg_sum")

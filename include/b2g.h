@@ -120,14 +120,6 @@ int b2g_csr_perm(const int32_t* eid_a, const int32_t* eid_b, int64_t nnz, int32_
  * relu != 0 applies max(.,0) last.
  * The fast paths prefetch col[clamp(position)] with unconditional loads: `col` (and `perm` where one is taken) must
  * point at >= 1 readable int32 even when the CSR has no entries at all (the Python host passes a dummy word). */
-/* Kernel choice for b2g_seg_sum: 0 = auto, 1 = register gather (LDG.128 per lane), 2 = bulk-async gather
- * (one cp.async.bulk per neighbour row into shared memory).  Results are bit-identical. */
-int b2g_set_seg_impl(int impl);
-/* Row scheduling of the 512-byte-row fast path: the co-resident CTAs sweep the rows in chunks of `chunk_rows`
- * consecutive rows (power of two >= 8, default 32); with a band hint (b2g_seg_sum_banded) the sweep goes panel by
- * panel, `panel_rows` rows (power of two, default 8192) of every band-sized block at a time.  A tuning knob only:
- * results are bit-identical for every setting. */
-int b2g_set_seg_sched(int chunk_rows, int panel_rows);
 int b2g_seg_sum(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
                 int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
                 const int32_t* col, const float* row_scale, const float* col_scale,
@@ -149,6 +141,17 @@ int b2g_seg_sum_hinted(const void* x, int64_t ldx, const void* x_self, int64_t l
                        const int32_t* col, const float* row_scale, const float* col_scale,
                        float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len,
                        void* stream);
+
+/* Same with explicit tuning parameters, PER CALL (the library holds no mutable tuning state):
+ *   impl        0 = auto, 1 = the generic register-gather kernel (any 16-byte-multiple width)
+ *   chunk_rows  rows the co-resident CTAs take per step (power of two >= 8; <= 0 = default 32)
+ *   panel_rows  rows per panel of the band order (power of two >= chunk_rows; <= 0 = default 8192)
+ * Results are bit-identical for every setting (every row is computed exactly once, in CSR order). */
+int b2g_seg_sum_tuned(const void* x, int64_t ldx, const void* x_self, int64_t ldxs, void* out,
+                      int64_t ldo, int64_t n_rows, int F, int dt, const int32_t* rowptr,
+                      const int32_t* col, const float* row_scale, const float* col_scale,
+                      float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, int impl,
+                      int chunk_rows, int panel_rows, void* stream);
 
 /* ===================================================================================== K4
  * GATConv (gnn_model.py:65-68,168) fused edge-score + segment-softmax + aggregate + head-mean +

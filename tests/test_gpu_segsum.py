@@ -105,14 +105,9 @@ def test_band_order_is_a_permutation_of_the_rows(dtype, F, chunk, panel):
     for N, band in ((20000, 1000), (20011, 1037), (70000, 33000), (5000, 2600)):
         rowptr, col, rows = _csr(N, _mesh_deg, seed=N, band=band)
         x = torch.randn(N, F, device='cuda').to(dtype)
-        _lib.check(lib.b2g_set_seg_sched(32, 8192))
         lin = ops.seg_sum(x, rowptr, col, N, None, None, 0.0, None, None, band=0)
-        try:
-            _lib.check(lib.b2g_set_seg_sched(chunk, panel))
-            out = torch.full_like(x, float('nan'))
-            ops.seg_sum(x, rowptr, col, N, None, None, 0.0, None, None, out=out, band=band)
-        finally:
-            _lib.check(lib.b2g_set_seg_sched(32, 8192))
+        out = torch.full_like(x, float('nan'))
+        ops.seg_sum(x, rowptr, col, N, None, None, 0.0, None, None, out=out, band=band, tune=(0, chunk, panel))
         assert torch.equal(out, lin), f"N={N} band={band}"
         ref = _ref(x, rows, col, N, None, None, 0.0, None, False)
         tol = 1e-5 if dtype == torch.float32 else 2e-2
@@ -131,11 +126,7 @@ def test_fast_path_equals_generic_kernel_bitwise():
         fast = ops.seg_sum(x, rowptr, col, N, rs, None, 0.0, None, None)
         again = ops.seg_sum(x, rowptr, col, N, rs, None, 0.0, None, None)
         assert torch.equal(fast, again)                       # run-to-run deterministic
-        try:
-            lib.b2g_set_seg_impl(1)
-            gen = ops.seg_sum(x, rowptr, col, N, rs, None, 0.0, None, None)
-        finally:
-            lib.b2g_set_seg_impl(0)
+        gen = ops.seg_sum(x, rowptr, col, N, rs, None, 0.0, None, None, tune=(1, 0, 0))     # the generic kernel
         assert torch.equal(fast, gen)
 
 

@@ -204,3 +204,40 @@ def test_flow_gnn_forward_runs_for_all_layer_types():
         p = {k: v.double() for k, v in FlowGNN(3, 16, 7, 2, lt).state_dict().items()}
         out = lo.flow_gnn_forward(x, ei, p, lt, training=False)
         assert out.shape == (12, 7) and torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("kind", ["GCN", "GAT", "GIN", "Transformer"])
+def test_sampled_closure_rows_equal_full_graph_rows(kind):
+    """oracle/sampled.py: the one-hop closure sub-problem reproduces the full-graph oracle rows exactly (it is what
+    bench.py's parity_check evaluates at cfg3 / cfg4 sizes, where the full fp64 oracle cannot run)."""
+    from oracle import sampled
+    N, E, F, H = 400, 2400, 16, 4
+    rng = np.random.default_rng(5)
+    ei = torch.from_numpy(rng.integers(0, N - 3, size=(2, E)))
+    ei[1, :40] = ei[0, :40]
+    ei[1, 100:180] = 7                                   # hub target
+    torch.manual_seed(0)
+    x = torch.randn(N, F, dtype=torch.float64)
+    g = lambda *s: torch.randn(*s, dtype=torch.float64) * 0.3
+    if kind == "GCN":
+        p = {"lin.weight": g(F, F), "bias": g(F)}
+        full = lo.gcn_conv(x, ei, p["lin.weight"], p["bias"])
+    elif kind == "GAT":
+        p = {"lin.weight": g(H * F, F), "att_src": g(1, H, F), "att_dst": g(1, H, F), "bias": g(F)}
+        full = lo.gat_conv(x, ei, p["lin.weight"], p["att_src"], p["att_dst"], p["bias"], heads=H)
+    elif kind == "GIN":
+        p = {"nn.0.weight": g(F, F), "nn.0.bias": g(F), "nn.2.weight": g(F, F), "nn.2.bias": g(F), "eps": torch.zeros(1)}
+        full = lo.gin_conv(x, ei, lo.gin_mlp(p["nn.0.weight"], p["nn.0.bias"], p["nn.2.weight"], p["nn.2.bias"]))
+    else:
+        p = {f"lin_{n}.weight": g(H * F, F) for n in ("query", "key", "value")}
+        p.update({f"lin_{n}.bias": g(H * F) for n in ("query", "key", "value")})
+        p.update({"lin_skip.weight": g(F, F), "lin_skip.bias": g(F)})
+        full = lo.transformer_conv(x, ei, p["lin_query.weight"], p["lin_query.bias"], p["lin_key.weight"], p["lin_key.bias"],
+                                   p["lin_value.weight"], p["lin_value.bias"], p["lin_skip.weight"], p["lin_skip.bias"], heads=H)
+    rows = sampled.pick_rows(N, 60, plane=50, seed=1)
+    assert rows.numel() == 60 and int(rows.min()) == 0 and int(rows.max()) == N - 1
+    rows = torch.unique(torch.cat([rows, torch.tensor([7, N - 2])]))        # the hub and an isolated node
+    nodes, ei_sub, pos = sampled.closure_subgraph(ei, rows, N)
+    assert nodes.numel() < N and ei_sub.shape[1] < E
+    sub = sampled.layer_rows(kind, p, x[nodes], ei_sub, pos, heads=H)
+    torch.testing.assert_close(sub, full[rows], rtol=1e-12, atol=1e-12)
