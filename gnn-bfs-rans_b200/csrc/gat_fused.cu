@@ -1,0 +1,488 @@
+// gat_fused.cu — K4f: the attention-weighted neighbour aggregation of GATConv(heads = 4, concat = False)
+// (gnn_model.py:65-68,168) FUSED with the output projection:
+//
+//      out_i = sum_h (sum_j alpha_ijh x_j) Wc_h^T + b = z_i Wc^T + b,      z_i = [sum_j alpha_ij1 x_j | ... | sum_j alpha_ij4 x_j]
+//
+// In the unfused aggregate-first path (gat_rows.cu) z [N, H*F] is written to HBM by gatz_fwd_kernel and read back by the
+// K6 GEMM: 2 x 20.5 GB of the layer's 56 GB at cfg4, for 26 GB of compulsory traffic.  Here z never leaves the SM:
+//
+//   gather warps   compute bf16 tiles of z — 128 target rows x (4 heads x 64 features) per step — straight into the
+//                  128B-swizzled K-major shared-memory layout that tcgen05.mma reads (the layout TMA would produce),
+//   MMA warp       one elected thread issues tcgen05.mma (kind::f16, 128 x 256 x 16) on them against Wc k-blocks streamed
+//                  by TMA (Wc is 512 KB: L2-resident, not shared-memory-resident), fp32 accumulator in TMEM,
+//   epilogue warps tcgen05.ld -> + bias -> bf16 -> 128-byte row stores, overlapped with the next tile (2 accumulators).
+//
+// The softmax is NOT in this kernel: b2g_gat_alpha (below) writes the post-dropout attention weights alpha [nnz, 4] fp32
+// once (1.1 GB at cfg4; the backward pass wants them anyway), and the gather warps read 16 bytes per entry next to the
+// column index.  That keeps the gather loop to: index broadcast, one 16-byte load per lane, 8 unpacks, 16 packed FMAs.
+//
+// K order.  A row's 4 heads x 256 features do not fit shared memory for 128 rows (256 KB), so the reduction is cut by
+// FEATURE: chunk kc = features [64 kc, 64 kc + 64) of all four heads = 256 K-columns = 4 swizzle atoms (one per head).
+// A warp gathers 128-byte pieces of 4 neighbour rows per load instruction (lane = 4 rows x 8 pieces), the same bytes in
+// total as gathering 512-byte rows once.  The host permutes the columns of Wc accordingly:
+//      Wp[c, kc*256 + h*64 + f] = Wc[c, h*256 + kc*64 + f].
+//
+// Also the transposed use (backward): y_j = [sum_i alpha_ijh g_i]_h over the source-major CSR followed by the dgrad GEMM is
+// the same computation (perm maps a transposed-CSR position to its alpha entry).
+#include "rows.cuh"
+#include "tc_ptx.cuh"
+
+namespace b2g {
+
+constexpr int GF_BM = 128;                       // target rows per tile == UMMA_M
+constexpr int GF_BN = 256;                       // UMMA_N; C_out <= 256
+constexpr int GF_H = 4;                          // heads
+constexpr int GF_KCH = 4;                        // feature chunks of 64 (F = 256 bf16 = 512-byte rows)
+constexpr int GF_GW = 16;                        // gather warps
+constexpr int GF_THREADS = 32 * (8 + GF_GW);     // warp 0 TMA, 1 MMA, 2-3 idle (warpgroup padding), 4-7 epilogue, 8.. gather
+constexpr int GF_A_REGION = GF_BM * 128;         // 16 KB: 128 rows x 64 bf16 (one head of one chunk), SWIZZLE_128B K-major
+constexpr int GF_A_CHUNK = GF_H * GF_A_REGION;   // 64 KB
+constexpr int GF_W_STAGE = GF_BN * 128;          // 32 KB: 256 rows of Wp x 64 k
+constexpr int GF_W_STAGES = 2;
+constexpr int GF_STG = 4 * 32 * 128;             // epilogue staging: 32 rows x 128 B per epilogue warp
+constexpr int GF_WST_WARP = 2 * 4 * 8 * 16;      // per gather warp: 2 units x 4 rows x 8 entries x float4 weights = 1 KB
+constexpr int GF_WST = GF_GW * GF_WST_WARP;
+constexpr int GF_BAR = 256;
+constexpr int GF_SMEM = 2 * GF_A_CHUNK + GF_W_STAGES * GF_W_STAGE + GF_STG + GF_WST + GF_BAR;
+static_assert(GF_SMEM + 1024 <= 232448, "fused GAT shared-memory plan exceeds 227 KB");
+
+struct GfArgs {
+  const char* x; uint32_t xrow_bytes;            // gathered rows, bf16 [*, 256]
+  const int32_t* rowptr; const int32_t* col; const int32_t* perm;
+  const float* alpha;                            // fp32 [nnz, 4]: weight of (entry, head); entry = perm[pos] or pos
+  const float* bias;                             // fp32 [m] or NULL
+  __nv_bfloat16* out; int64_t ldo;
+  uint32_t n_rows; int m;
+  RowSched ord;                                  // chunk_rows = GF_BM
+};
+
+__device__ __forceinline__ uint4 gf_ldg_if(const char* p, bool pred) {
+  uint4 u;
+  asm volatile(
+      "{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n"
+      " mov.b32 %0, 0;\n mov.b32 %1, 0;\n mov.b32 %2, 0;\n mov.b32 %3, 0;\n"
+      " @q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
+      : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+      : "l"(p), "r"((uint32_t)pred));
+  return u;
+}
+
+// acc[h][0..8) += w[h] * (8 bf16 of u)
+__device__ __forceinline__ void gf_fma(float (&acc)[GF_H][8], const float4& w, const uint4& u) {
+  float f[8];
+  unpack_row16(u, f, __nv_bfloat16());
+  const float wv[GF_H] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int h = 0; h < GF_H; ++h)
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) ffma2_acc(acc[h][k], acc[h][k + 1], wv[h], f[k], f[k + 1]);
+}
+
+// the first K (<= 8) entries of the 4 rows of a unit: K loads in flight per lane, then K x (LDS.128 weights, FMA)
+template <int K>
+__device__ __forceinline__ void gf_gather(float (&acc)[GF_H][8], const char* xk, uint32_t xrow_bytes, int cl, int len,
+                                          int grp_lane0, const float4* wrow) {
+  uint4 buf[K];
+#pragma unroll
+  for (int t = 0; t < K; ++t) {
+    const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, grp_lane0 + t);
+    buf[t] = gf_ldg_if(xk + (uint64_t)c * xrow_bytes, t < len);
+  }
+#pragma unroll
+  for (int t = 0; t < K; ++t) gf_fma(acc, wrow[t], buf[t]);
+}
+
+__global__ void __launch_bounds__(GF_THREADS, 1)
+gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  if (smem_base & 1023u) __trap();
+  const uint32_t abuf0 = smem_base;                                   // 2 x 64 KB z chunks
+  const uint32_t wring = abuf0 + 2 * GF_A_CHUNK;                      // 2 x 32 KB W stages
+  const uint32_t stg = wring + GF_W_STAGES * GF_W_STAGE;              // epilogue staging
+  const uint32_t wst = stg + GF_STG;                                  // gather-weight staging
+  const uint32_t bars = wst + GF_WST;
+  auto full_w = [&](int s) { return bars + 8u * s; };
+  auto empty_w = [&](int s) { return bars + 8u * (2 + s); };
+  auto full_a = [&](int b) { return bars + 8u * (4 + b); };
+  auto empty_a = [&](int b) { return bars + 8u * (6 + b); };
+  auto tfull = [&](int t) { return bars + 8u * (8 + t); };
+  auto tempty = [&](int t) { return bars + 8u * (10 + t); };
+  const uint32_t tmem_slot = bars + 8u * 12;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_w(s), 1);
+      mbar_init(empty_w(s), 1);
+      mbar_init(full_a(s), GF_GW);       // one arrive per gather warp
+      mbar_init(empty_a(s), 1);
+      mbar_init(tfull(s), 1);
+      mbar_init(tempty(s), 4);           // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      // ===================================================== TMA producer: Wp k-blocks, 16 per tile
+      int stage = 0;
+      uint32_t phase = 0;
+      for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
+        uint32_t rows;
+        a.ord.chunk(q, a.n_rows, rows);
+        if (rows == 0) continue;
+        for (int kb = 0; kb < GF_KCH * GF_H; ++kb) {
+          mbar_wait(empty_w(stage), phase ^ 1);
+          mbar_expect_tx(full_w(stage), GF_W_STAGE);
+          tma_load_2d(wring + stage * GF_W_STAGE, &map_w, full_w(stage), kb * 64, 0);
+          if (++stage == GF_W_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ===================================================== MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(GF_BM, GF_BN);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0, g = 0;          // g = z chunks consumed so far (buffer g & 1, phase (g >> 1) & 1)
+      for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
+        uint32_t rows;
+        a.ord.chunk(q, a.n_rows, rows);
+        if (rows == 0) continue;
+        mbar_wait(tempty(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * GF_BN);
+        for (int kc = 0; kc < GF_KCH; ++kc, ++g) {
+          const int ab = g & 1;
+          mbar_wait(full_a(ab), (g >> 1) & 1);
+          tc_fence_after();
+          for (int h = 0; h < GF_H; ++h) {
+            mbar_wait(full_w(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = abuf0 + ab * GF_A_CHUNK + h * GF_A_REGION;
+            const uint32_t sb = wring + stage * GF_W_STAGE;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc_mma_bf16(d_tmem, make_smem_desc(sa + ks * 32), make_smem_desc(sb + ks * 32), idesc, (kc | h | ks) ? 1u : 0u);
+            tc_commit(empty_w(stage));
+            if (++stage == GF_W_STAGES) { stage = 0; phase ^= 1; }
+          }
+          tc_commit(empty_a(ab));                         // the z chunk may be overwritten once these MMAs retire
+        }
+        tc_commit(tfull(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================================================== epilogue warps 4..7 (TMEM lane quadrant = warp & 3)
+    const int qd = warp & 3;
+    uint8_t* my_stg = smem_raw + (stg - smem_base) + qd * 32 * 128;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
+      uint32_t rows;
+      const uint32_t c0 = a.ord.chunk(q, a.n_rows, rows);
+      if (rows == 0) continue;
+      mbar_wait(tfull(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t row0 = c0 + qd * 32;
+      const uint32_t rend = c0 + rows;
+#pragma unroll 1
+      for (int c = 0; c < a.m; c += 64) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * GF_BN + c);
+#pragma unroll
+        for (int hlf = 0; hlf < 2; ++hlf) {
+          uint32_t r[32];
+          tc_ld32(taddr + hlf * 32, r);
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[j + k]);
+            if (a.bias) {
+              const int cg = c + hlf * 32 + j;             // m % 64 == 0 (launcher): always in range
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cg));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cg + 4));
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+              v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            Vec<__nv_bfloat16> o;
+            o.from_float(v);
+            *reinterpret_cast<uint4*>(my_stg + lane * 128 + (((hlf * 4 + (j >> 3)) ^ (lane & 7)) << 4)) = o.v;
+          }
+        }
+        __syncwarp();
+        const int piece = lane & 7;
+#pragma unroll
+        for (int r4 = 0; r4 < 32; r4 += 4) {
+          const int rr = r4 + (lane >> 3);
+          if (row0 + rr < rend) {
+            const uint4 val = *reinterpret_cast<const uint4*>(my_stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
+            __nv_bfloat16* dst = a.out + (int64_t)(row0 + rr) * a.ldo + c + piece * 8;
+            asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(val.x), "r"(val.y),
+                         "r"(val.z), "r"(val.w)
+                         : "memory");
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===================================================== gather warps 8..: z chunks into the swizzled A operand
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    const int gw = warp - 8;
+    const int r4 = lane >> 3, p = lane & 7;
+    float4* wrow_base = reinterpret_cast<float4*>(smem_raw + (wst - smem_base) + gw * GF_WST_WARP);   // [unit][r4][entry]
+    const char* xl = a.x + p * 16;
+    uint32_t g = 0;
+    for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
+      uint32_t rows;
+      const uint32_t c0 = a.ord.chunk(q, a.n_rows, rows);
+      if (rows == 0) continue;
+      // ---- per tile: this lane's entry (row r4 of the unit, entry p) of both units: column index + 4 head weights
+      int cl[2], len[2], b0[2], mlen[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const uint32_t rl = (uint32_t)(gw + GF_GW * u) * 4u + r4;          // row inside the tile
+        const bool valid = rl < rows;
+        const uint32_t row = valid ? c0 + rl : c0;
+        const int b = __ldg(a.rowptr + row), e = __ldg(a.rowptr + row + 1);
+        len[u] = valid ? e - b : 0;
+        b0[u] = b;
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const bool has = p < len[u];
+        const int pos = b0[u] + (has ? p : 0);
+        int c = 0, pi = pos;
+        float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has) {
+          c = __ldg(a.col + pos);
+          if (a.perm) pi = __ldg(a.perm + pos);
+          w4 = __ldg(reinterpret_cast<const float4*>(a.alpha) + pi);
+        }
+        cl[u] = c;
+        wrow_base[(u * 4 + r4) * 8 + p] = w4;
+        int ml = len[u];
+        ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, 8));
+        ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, 16));
+        mlen[u] = ml;
+      }
+      __syncwarp();
+      for (int kc = 0; kc < GF_KCH; ++kc, ++g) {
+        const int ab = g & 1;
+        mbar_wait(empty_a(ab), ((g >> 1) & 1) ^ 1);
+        const char* xk = xl + kc * 128;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float acc[GF_H][8];
+#pragma unroll
+          for (int h = 0; h < GF_H; ++h)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[h][k] = 0.f;
+          const float4* wrow = wrow_base + (u * 4 + r4) * 8;
+          const int g0 = lane & 24;
+          switch (min(mlen[u], 8)) {                                      // warp-uniform
+#define B2G_CASE(KK) case KK: gf_gather<KK>(acc, xk, a.xrow_bytes, cl[u], len[u], g0, wrow); break;
+            B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4) B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
+#undef B2G_CASE
+            default: break;
+          }
+          for (int t = 8; t < mlen[u]; ++t) {                             // rows longer than 8 entries (cold on meshes)
+            const bool has = t < len[u];
+            float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (has) {
+              const int pos = b0[u] + t;
+              const int c = __ldg(a.col + pos);
+              const int pi = a.perm ? __ldg(a.perm + pos) : pos;
+              w4 = __ldg(reinterpret_cast<const float4*>(a.alpha) + pi);
+              v = ldg_row16(xk + (uint64_t)(uint32_t)c * a.xrow_bytes);
+            }
+            gf_fma(acc, w4, v);
+          }
+          const uint32_t rl = (uint32_t)(gw + GF_GW * u) * 4u + r4;
+          const uint32_t dst = abuf0 + ab * GF_A_CHUNK + rl * 128u + (uint32_t)((p ^ (rl & 7)) << 4);
+#pragma unroll
+          for (int h = 0; h < GF_H; ++h) {
+            Vec<__nv_bfloat16> o;
+            o.from_float(acc[h]);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst + h * GF_A_REGION), "r"(o.v.x), "r"(o.v.y),
+                         "r"(o.v.z), "r"(o.v.w)
+                         : "memory");
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full_a(ab));
+      }
+      __syncwarp();                                                        // weight staging is rewritten by the next tile
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ attention weights
+// alpha[p, h] for every entry p of the target-major CSR: exact max-subtracted segment softmax of
+// leaky_relu(a_src[col_p, h] + a_dst[i, h]) (+ edge term) over the entries of row i (PyG softmax: denominator + 1e-16),
+// times the attention-dropout keep scale.  One thread per (row, head); rows of <= 8 entries keep their scores in registers.
+struct AlphaArgs {
+  const float* a; uint32_t lda;              // fp32 [N, >= 8]: a_src | a_dst
+  const int32_t* rowptr; const int32_t* col;
+  const float* ebias;                        // fp32 [nnz, 4] added to the logits before the LeakyReLU (edge features) or NULL
+  float* alpha;                              // [nnz, 4]
+  float* smax; float* ssum;                  // [N, 4] or NULL
+  uint32_t n_rows;
+  float slope, p_drop;
+  uint64_t seed; const uint64_t* epoch;
+};
+
+__device__ __forceinline__ float gf_lrelu(float s, float slope) { return s > 0.f ? s : s * slope; }
+
+__global__ void __launch_bounds__(256) gat_alpha_kernel(const AlphaArgs a) {
+  const uint64_t total = (uint64_t)a.n_rows * GF_H;
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t i = (uint32_t)(t >> 2);
+    const int h = (int)(t & 3);
+    const int b = __ldg(a.rowptr + i), e = __ldg(a.rowptr + i + 1);
+    const int len = e - b;
+    const float ad = __ldg(a.a + (uint64_t)i * a.lda + GF_H + h);
+    float m = -INFINITY, zs = 0.f;
+    if (len <= 8) {
+      float s[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s[k] = -INFINITY;
+        if (k < len) {
+          const uint32_t c = (uint32_t)__ldg(a.col + b + k);
+          float v = __ldg(a.a + (uint64_t)c * a.lda + h) + ad;
+          if (a.ebias) v += __ldg(a.ebias + (uint64_t)(b + k) * GF_H + h);
+          s[k] = gf_lrelu(v, a.slope);
+          m = fmaxf(m, s[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s[k] = k < len ? __expf(s[k] - m) : 0.f;
+        zs += s[k];
+      }
+      zs += 1e-16f;
+      const float inv = 1.0f / zs;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < len) {
+          float w = s[k] * inv;
+          if (a.p_drop > 0.f) {
+            float sc[4];
+            dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)(b + k), a.p_drop, sc);
+            w *= (h == 0 ? sc[0] : (h == 1 ? sc[1] : (h == 2 ? sc[2] : sc[3])));
+          }
+          a.alpha[(uint64_t)(b + k) * GF_H + h] = w;
+        }
+    } else {
+      auto score = [&](int pos) {
+        const uint32_t c = (uint32_t)__ldg(a.col + pos);
+        float v = __ldg(a.a + (uint64_t)c * a.lda + h) + ad;
+        if (a.ebias) v += __ldg(a.ebias + (uint64_t)pos * GF_H + h);
+        return gf_lrelu(v, a.slope);
+      };
+      for (int pos = b; pos < e; ++pos) m = fmaxf(m, score(pos));
+      for (int pos = b; pos < e; ++pos) zs += __expf(score(pos) - m);
+      zs += 1e-16f;
+      const float inv = 1.0f / zs;
+      for (int pos = b; pos < e; ++pos) {
+        float w = __expf(score(pos) - m) * inv;
+        if (a.p_drop > 0.f) {
+          float sc[4];
+          dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)pos, a.p_drop, sc);
+          w *= (h == 0 ? sc[0] : (h == 1 ? sc[1] : (h == 2 ? sc[2] : sc[3])));
+        }
+        a.alpha[(uint64_t)pos * GF_H + h] = w;
+      }
+    }
+    if (a.smax) {
+      a.smax[(uint64_t)i * GF_H + h] = len > 0 ? m : 0.f;
+      a.ssum[(uint64_t)i * GF_H + h] = len > 0 ? zs : 1e-16f;
+    }
+  }
+}
+
+}  // namespace b2g
+
+using namespace b2g;
+
+extern "C" {
+
+int b2g_gatw_gemm_supported(int64_t n, int H, int F, int C, int dt) {
+  return (dt == B2G_BF16 && H == GF_H && F == 256 && C >= 64 && C <= GF_BN && (C % 64) == 0 && n >= 1 &&
+          n < (1ll << 32) - (1ll << 25)) ? 1 : 0;
+}
+
+int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                  const float* alpha, const void* wp, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t n_rows,
+                  int H, int F, int C, int dt, int64_t band, void* stream) {
+  if (n_rows < 0) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (!b2g_gatw_gemm_supported(n_rows, H, F, C, dt)) return B2G_E_UNSUPPORTED;
+  if (!x || !rowptr || !col || !alpha || !wp || !out) return B2G_E_ARG;
+  if (!aligned16(x) || !aligned16(alpha) || !aligned16(wp) || !aligned16(out) || (bias && !aligned16(bias)) || (ldx * 2) % 16 ||
+      (ldw * 2) % 16 || (ldo * 2) % 16 || ldx * 2 >= (1ll << 32))
+    return B2G_E_ALIGN;
+  static bool attr_set[64] = {false};
+  const int dev = current_device_slot();
+  if (!attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gatw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    attr_set[dev] = true;
+  }
+  GfArgs a{};
+  if (!make_row_sched(n_rows, band, a.ord, GF_BM, 8192)) return B2G_E_UNSUPPORTED;
+  CUtensorMap map_w;
+  if (!tc_make_map_bf16(&map_w, wp, C, (int64_t)H * F, ldw, GF_BN)) return B2G_E_UNSUPPORTED;
+  a.x = static_cast<const char*>(x); a.xrow_bytes = (uint32_t)(ldx * 2);
+  a.rowptr = rowptr; a.col = col; a.perm = perm; a.alpha = alpha; a.bias = bias;
+  a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.n_rows = (uint32_t)n_rows; a.m = C;
+  const unsigned grid = a.ord.n_chunks < (uint32_t)B2G_NUM_SMS ? a.ord.n_chunks : (unsigned)B2G_NUM_SMS;
+  gatw_gemm_kernel<<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, a);
+  count_launch();
+  return cuda_status();
+}
+
+int b2g_gat_alpha(const float* a_srcdst, int64_t lda, const int32_t* rowptr, const int32_t* col, const float* edge_bias,
+                  int64_t n, int H, float slope, float p_drop, uint64_t seed, float* alpha, float* smax, float* ssum,
+                  void* stream) {
+  if (n < 0 || H != GF_H) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  if (!a_srcdst || !rowptr || !col || !alpha || (smax == nullptr) != (ssum == nullptr)) return B2G_E_ARG;
+  if (lda < 2 * GF_H || lda >= (1ll << 32) || n >= (1ll << 32)) return B2G_E_SHAPE;
+  AlphaArgs a{a_srcdst, (uint32_t)lda, rowptr, col, edge_bias, alpha, smax, ssum, (uint32_t)n, slope, p_drop, seed,
+              dropout_epoch_ptr()};
+  const int64_t want = ceil_div(n * GF_H, 256);
+  const int64_t cap = (int64_t)B2G_NUM_SMS * 16;
+  gat_alpha_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(a);
+  count_launch();
+  return cuda_status();
+}
+
+}  // extern "C"
