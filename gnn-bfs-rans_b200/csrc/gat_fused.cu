@@ -135,7 +135,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0 && lane == 0) {
       // ===================================================== TMA producer: Wp k-blocks, 16 per tile
       int stage = 0;
@@ -244,7 +244,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
     }
   } else {
     // ===================================================== gather warps 8..: z chunks into the swizzled A operand
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int gw = warp - 8;
     const int r4 = lane >> 3, p = lane & 7;
     float4* wrow_base = reinterpret_cast<float4*>(smem_raw + (wst - smem_base) + gw * GF_WST_WARP);   // [unit][r4][entry]

@@ -111,13 +111,20 @@ struct GatzArgs {
   const float* alpha_in;                     // TransformerConv backward: the forward pass's (pre-dropout) alpha [nnz, H]
   const float* ebias;                        // TransformerConv with edge features (edge_dim): per-(entry, head) term added to
                                              // the logits (forward) / to d alpha (backward), fp32 [nnz, H] target-major; or NULL
-  float* d_a; uint32_t ldda;                 // [N, >= 2H]
+  float* d_a; uint32_t ldda;                 // [N, >= 2H] (row stride in ELEMENTS of its type)
+  int da_bf16;                               // d_a holds bf16 (a column block of the bf16 dgrad operand) instead of fp32
   uint32_t n_rows;
   float slope, p_drop;
   uint64_t seed;
   const uint64_t* epoch;                     // dropout epoch word (common.cuh), mixed into seed
   RowSched ord;
 };
+
+// d a[i, k] = v, in the buffer's type (fp32, or bf16 when the caller hands the column block of a bf16 GEMM operand)
+__device__ __forceinline__ void store_da(const GatzArgs& a, uint64_t i, int k, float v) {
+  if (a.da_bf16) reinterpret_cast<__nv_bfloat16*>(a.d_a)[i * a.ldda + k] = __float2bfloat16_rn(v);
+  else a.d_a[i * a.ldda + k] = v;
+}
 
 #ifndef B2G_GATZ_BU
 #define B2G_GATZ_BU 8
@@ -602,7 +609,7 @@ __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int
   }
   if (!kT) {
     warp_sum4(dad[0], dad[1], dad[2], dad[3]);
-    if (lane < GH) a.d_a[(uint64_t)i * a.ldda + GH + lane] = pick4(dad, lane);
+    if (lane < GH) store_da(a, i, GH + lane, pick4(dad, lane));
   } else if (a.z) {
     gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)i * a.zrow_bytes, du, lane);
   }
@@ -697,7 +704,7 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
       }
       if (!kT) {
         const float dad = head_sum8(de);
-        if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + GH + lane] = dad;
+        if (lane < GH) store_da(a, r.i, GH + lane, dad);
       } else {
         float du[GH][VPL][VN];
 #pragma unroll
@@ -737,7 +744,7 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
       gatz_bwd_finish<T, VPL>(a, r.b, len, lane, alpha, dal, sraw, mask, t, dad, de);
       if (!kT) {
         warp_sum4(dad[0], dad[1], dad[2], dad[3]);
-        if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + GH + lane] = pick4(dad, lane);
+        if (lane < GH) store_da(a, r.i, GH + lane, pick4(dad, lane));
       } else if (a.z) {                          // du_i = sum_j de_ij x_j (rows of 9..32 entries, or VPL = 2: second gather)
         float du[GH][VPL][VN];
 #pragma unroll
@@ -1051,7 +1058,7 @@ __global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_bwd_src_kernel(const 
     }
     if (a.d_a) {
       warp_sum4(das[0], das[1], das[2], das[3]);
-      if (lane < GH) a.d_a[(uint64_t)r.i * a.ldda + lane] = pick4(das, lane);
+      if (lane < GH) store_da(a, r.i, lane, pick4(das, lane));
     }
     gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, acc, lane);
     if (!r.shift()) break;
@@ -1270,10 +1277,11 @@ int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda,
 int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, const void* dz, int64_t lddz,
                      int64_t n, int H, int F, int dt, float slope, const int32_t* rowptr, const int32_t* col,
                      const float* smax, const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* de_e,
-                     float* d_a, int64_t ldda, int64_t band, void* stream) {
+                     void* d_a, int64_t ldda, int d_a_dt, int64_t band, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
+  if (d_a_dt != B2G_F32 && d_a_dt != B2G_BF16) return B2G_E_ARG;
   if (!x || !a_srcdst || !dz || !rowptr || !col || !smax || !ssum || !alpha_e || !de_e || !d_a) return B2G_E_ARG;
   if (!aligned16(x) || !aligned16(dz) || !aligned16(a_srcdst) || !aligned16(smax) || !aligned16(ssum) || !aligned16(alpha_e) ||
       !aligned16(de_e) || (ldx * es) % 16 || (lddz * es) % 16 || lda % 4 || lda < 2 * GH || ldda < 2 * GH)
@@ -1284,16 +1292,18 @@ int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t 
   if (rc) return rc;
   a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.a = a_srcdst; a.lda = (uint32_t)lda; a.dz = dz; a.dzrow_bytes = (uint32_t)(lddz * es);
   a.rowptr = rowptr; a.col = col; a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum);
-  a.slope = slope; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.alpha_e = alpha_e; a.de_e = de_e; a.d_a = d_a; a.ldda = (uint32_t)ldda;
+  a.slope = slope; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.alpha_e = alpha_e; a.de_e = de_e; a.d_a = static_cast<float*>(d_a); a.ldda = (uint32_t)ldda;
+  a.da_bf16 = d_a_dt == B2G_BF16;
   return gatz_dispatch(1, dt, F * es, a, (cudaStream_t)stream);
 }
 
 int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const float* de_e, void* y, int64_t ldy,
-                     float* d_a, int64_t ldda, int64_t n, int H, int C, int dt, const int32_t* rowptr_t,
+                     void* d_a, int64_t ldda, int d_a_dt, int64_t n, int H, int C, int dt, const int32_t* rowptr_t,
                      const int32_t* col_t, const int32_t* perm, int64_t band, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
+  if (d_a && d_a_dt != B2G_F32 && d_a_dt != B2G_BF16) return B2G_E_ARG;
   if (!g || !alpha_e || !de_e || !y || !rowptr_t || !col_t) return B2G_E_ARG;     // perm NULL = identity, d_a NULL = not wanted
   if (!aligned16(g) || !aligned16(y) || !aligned16(alpha_e) || !aligned16(de_e) || (ldg * es) % 16 || (ldy * es) % 16 ||
       (d_a && ldda < GH))
@@ -1304,7 +1314,7 @@ int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const flo
   if (rc) return rc;
   a.x = g; a.xrow_bytes = (uint32_t)(ldg * es); a.z = y; a.zrow_bytes = (uint32_t)(ldy * es);
   a.rowptr = rowptr_t; a.col = col_t; a.perm = perm; a.alpha_e = const_cast<float*>(alpha_e); a.de_e = const_cast<float*>(de_e);
-  a.d_a = d_a; a.ldda = (uint32_t)ldda;
+  a.d_a = static_cast<float*>(d_a); a.ldda = (uint32_t)ldda; a.da_bf16 = d_a && d_a_dt == B2G_BF16;
   return gatz_dispatch(2, dt, C * es, a, (cudaStream_t)stream);
 }
 

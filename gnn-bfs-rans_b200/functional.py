@@ -169,59 +169,68 @@ class GATFn(torch.autograd.Function):
 
 
 class GATZFn(torch.autograd.Function):
-    """GATConv(heads=4, concat=False) core, aggregate-first (csrc/gat_rows.cu): a = x V^T, z = per-head attention-
-    weighted sums of the F-wide rows of x, out = z Wc^T + b with Wc[c, hF+f] = W[hC+c, f] / H.  `wc` and `v` are
-    assembled (differentiably) by the module from lin.weight / att_src / att_dst, which get their gradients through
-    them.  4x fewer gathered bytes than projecting first (the [N, H*C] matrix is never gathered)."""
+    """GATConv(heads=4, concat=False) core, aggregate-first: a = x V^T, z = per-head attention-weighted sums of the F-wide
+    rows of x, out = z Wc^T + b with Wc[c, hF+f] = W[hC+c, f] / H.  `wc` and `v` are assembled (differentiably) by the module
+    from lin.weight / att_src / att_dst, which get their gradients through them.  4x fewer gathered bytes than projecting
+    first (the [N, H*C] matrix is never gathered).
+
+    Forward, two implementations of the same arithmetic:
+      fused   (bf16, F = 256; csrc/gat_fused.cu): attention weights alpha [nnz, H] by one thin kernel, then ONE kernel whose
+              gather warps write z tiles straight into the shared-memory A operand of a tcgen05 GEMM — z never touches HBM;
+      unfused (csrc/gat_rows.cu): gatz_fwd writes z [N, H*F], the K6 GEMM reads it back.  B2G_GAT_PATH=unfused selects it.
+    Backward needs no z either way: dWc_h = (sum_j y_jh x_j^T) with y = the alpha-weighted sums of g over the transposed
+    CSR that the dx GEMM consumes anyway."""
 
     @staticmethod
     def forward(ctx, x, wc, v, bias, graph: Graph, H: int, slope: float, p_drop: float):
         csr = graph.csr("sl", False)
         need_grad = x.requires_grad or wc.requires_grad or v.requires_grad
         seed = _next_seed() if p_drop > 0 else 0
+        N, F = x.shape
+        C = wc.shape[0]
         a = ops.rowdot8(x, v)
-        z, smax, ssum = ops.gatz_fwd(x, a, H, slope, csr.rowptr, csr.col, p_drop, seed, need_grad, band=graph.band())
-        out, _ = ops.linear_fwd(z, wc, bias.float() if bias is not None else None)
+        fused = os.environ.get("B2G_GAT_PATH", "") != "unfused" and ops.gatw_gemm_supported(N, H, F, C, x.dtype)
+        if fused:
+            alpha, smax, ssum = ops.gat_alpha(a, csr.rowptr, csr.col, H, slope, p_drop, seed, need_grad)
+            wp = wc.view(C, H, F // 64, 64).permute(0, 2, 1, 3).reshape(C, H * F)     # K order (chunk, head, 64 features)
+            out = ops.gatw_gemm(x, csr.rowptr, csr.col, None, alpha, wp, bias, N, H, band=graph.band())
+            del alpha
+        else:
+            z, smax, ssum = ops.gatz_fwd(x, a, H, slope, csr.rowptr, csr.col, p_drop, seed, need_grad, band=graph.band())
+            out, _ = ops.linear_fwd(z, wc, bias.float() if bias is not None else None)
         if need_grad:
-            # B2G_RECOMPUTE=1: do not keep z [N, H*F] (25.6 GB per layer at 12.5 M cells, cfg5) for the weight gradient;
-            # the backward pass re-runs the aggregation (same seed -> same dropout mask -> same bits)
-            recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"
-            ctx.save_for_backward(x, wc, v, None if recompute else z, a, smax, ssum)
+            ctx.save_for_backward(x, wc, v, a, smax, ssum)
             ctx.cfg = (graph, H, slope, p_drop, seed, bias is not None)
             ctx.ei_keepalive = graph.edge_index
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, wc, v, z, a, smax, ssum = ctx.saved_tensors
+        x, wc, v, a, smax, ssum = ctx.saved_tensors
         graph, H, slope, p_drop, seed, has_bias = ctx.cfg
         N, F = x.shape
         C = wc.shape[0]
         g = g.contiguous()
         csr, csr_t, perm = graph.csr("sl", False), graph.csr("sl", True), graph.perm("sl")
-        if z is None and ctx.needs_input_grad[1]:
-            z, _, _ = ops.gatz_fwd(x, a, H, slope, csr.rowptr, csr.col, p_drop, seed, False, band=graph.band())
         gwc = gv = gx = None
-        if ctx.needs_input_grad[1]:
-            dw, _ = ops.linear_wgrad(g, z, want_bias=False)                 # dWc = g^T z  [C, H*F]
-            gwc = _cast_like(dw, wc)
-        del z
         dz, _ = ops.linear_fwd(g, wc.t().contiguous(), None)                # dz = g Wc    [N, H*F]
         # [y | d a] so that dx = y (W/H) + d a V is ONE GEMM against [Wc_src ; V]
         ka = H * C + 2 * H
         y_aug = ops.empty_rows(N, ka, x.dtype, x.device)
-        d_a = ops.gatz_bwd(x, a, dz, g, H, slope, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
-                           y_aug[:, :H * C], band=graph.band())
+        ops.gatz_bwd(x, a, dz, g, H, slope, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
+                     y_aug[:, :H * C], band=graph.band(), d_a_out=y_aug[:, H * C:])
         del dz
-        y_aug[:, H * C:] = d_a
+        if ctx.needs_input_grad[1]:
+            # dWc[c, hF+f] = sum_j y_j[hC+c] x_j[f]  (y_jh = sum_i alpha_ijh g_i): one wgrad GEMM [H*C, F], no z needed
+            dw, _ = ops.linear_wgrad(y_aug[:, :H * C], x, want_bias=False)
+            gwc = _cast_like(dw.view(H, C, F).permute(1, 0, 2).reshape(C, H * F), wc)
         if ctx.needs_input_grad[0]:
             # Wc[c, hF+f] = W[hC+c, f]/H  ->  (W/H)[hC+c, f] = Wc[c, hF+f]: rows of the [H*C, F] matrix
             w_src = wc.view(C, H, F).permute(1, 0, 2).reshape(H * C, F)
             w_aug = torch.cat([w_src, v.to(wc.dtype)], dim=0)               # [H*C + 2H, F]
             gx = ops.linear_dgrad(y_aug, w_aug)
         if ctx.needs_input_grad[2]:
-            da_t = d_a.to(x.dtype) if x.dtype != torch.float32 else d_a
-            dv, _ = ops.linear_wgrad(da_t, x, want_bias=False)              # dV = d a^T x [2H, F]
+            dv, _ = ops.linear_wgrad(y_aug[:, H * C:], x, want_bias=False)  # dV = d a^T x [2H, F]
             gv = _cast_like(dv, v)
         gb = ops.colsum(g) if (has_bias and ctx.needs_input_grad[3]) else None
         return gx, gwc, gv, gb, None, None, None, None
@@ -440,7 +449,7 @@ class TConvZFn(torch.autograd.Function):
         o_dr = o_du + HF
         o_g = o_dr + E4
         big = ops.empty_rows(N, o_g + C, x.dtype, x.device)
-        t_rows = torch.zeros((N, 8), dtype=torch.float32, device=x.device)
+        big[:, o_t + H:o_t + 8].zero_()                                       # padding of the t block (8 - H columns)
         fuse_du = os.environ.get("B2G_TZ_FUSE_DU", "1") != "0"
         alpha_e, de_e = ops.tz_bwd_dst(x, dz_aug, alpha, H, csr.rowptr, csr.col, p_drop, seed,
                                        big[:, o_du:o_du + HF] if fuse_du else None,
@@ -451,9 +460,8 @@ class TConvZFn(torch.autograd.Function):
         if ea is not None:
             ops.edge_wsum4(de_e, ea, csr.rowptr, H, big[:, o_dr:o_dr + E4])
         ops.seg_wsum4(g, alpha_e, csr_t.rowptr, csr_t.col, perm, big[:, o_y:o_y + H * C], band=band)
-        ops.seg_wsum4(x, de_e, csr_t.rowptr, csr_t.col, perm, big[:, o_w:o_w + HF], d_a=t_rows, band=band)
-        del alpha_e, de_e
-        big[:, o_t:o_t + 8] = t_rows
+        ops.seg_wsum4(x, de_e, csr_t.rowptr, csr_t.col, perm, big[:, o_w:o_w + HF], d_a=big[:, o_t:o_t + 8], band=band)
+        del alpha_e, de_e                                                   # t_jh written in place (columns o_t .. o_t + H)
         big[:, o_g:] = g
         du = big[:, o_du:o_du + HF + E4]
         gmq = gcq = gx = None

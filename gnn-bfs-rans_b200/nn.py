@@ -71,6 +71,24 @@ class Linear(tnn.Module):
         return f'{self.in_channels}, {self.out_channels}, bias={self.bias is not None}'
 
 
+def _cached_fold(mod, tag, params, dtype, make):
+    """Derived weights (folded / concatenated / cast) of a layer.  When a gradient may flow into the parameters they are
+    rebuilt (differentiably) on every forward; otherwise — inference, frozen layers — they are built once and reused until a
+    parameter changes (optimizer step, load_state_dict and .to() all change the (storage, version) key): the shipped 12 k-cell
+    case is launch-bound, and the einsum / cat / cast kernels of the fold were ~10 extra launches per attention layer."""
+    params = [q for q in params if q is not None]
+    if torch.is_grad_enabled() and any(q.requires_grad for q in params):
+        return make()
+    key = (tag, dtype, tuple((q.data_ptr(), q._version) for q in params))
+    hit = mod.__dict__.get('_fold_cache', {}).get(tag)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    with torch.no_grad():
+        val = make()
+    mod.__dict__.setdefault('_fold_cache', {})[tag] = (key, val)
+    return val
+
+
 def _check_x(x, edge_index):
     if not isinstance(x, torch.Tensor):
         raise NotImplementedError("b2g: bipartite (x_src, x_dst) inputs are not supported")
@@ -180,11 +198,12 @@ class GATConv(MessagePassing):
         _check_x(x, edge_index)
         g = graph_of(edge_index, x.shape[0])
         p = self.dropout if self.training else 0.0
+        ps = (self.lin.weight, self.att_src, self.att_dst)
         if self._aggregate_first(x):
-            wc, v = self._wc_v(x.dtype)
+            wc, v = _cached_fold(self, 'wc_v', ps, x.dtype, lambda: self._wc_v(x.dtype))
             return Fn.GATZFn.apply(x, wc, v, self.bias, g, self.heads, self.negative_slope, p)
-        return Fn.GATFn.apply(x, self._w_aug(x.dtype), self.bias, g, self.heads, self.out_channels, self.concat,
-                              self.negative_slope, p)
+        w_aug = _cached_fold(self, 'w_aug', ps, x.dtype, lambda: self._w_aug(x.dtype))
+        return Fn.GATFn.apply(x, w_aug, self.bias, g, self.heads, self.out_channels, self.concat, self.negative_slope, p)
 
     def _aggregate_first(self, x) -> bool:
         """heads averaged (concat=False, the reference's configuration) and 512 / 1024-byte feature rows: aggregate the
@@ -313,20 +332,22 @@ class TransformerConv(MessagePassing):
             if not self._aggregate_first(x):
                 raise NotImplementedError("b2g TransformerConv(edge_dim): needs 512 / 1024-byte feature rows (the "
                                           "aggregate-first kernels)")
-            mq, cq, w_out, b_out = self._folded(x.dtype, with_edge=True)
+            mq, cq, w_out, b_out = _cached_fold(self, 'folded_e', self._fold_params(), x.dtype,
+                                                lambda: self._folded(x.dtype, with_edge=True))
             return Fn.TConvZFn.apply(x, mq, cq, w_out, b_out, g, self.heads, p, g.edge_rows("raw", edge_attr))
         if self._aggregate_first(x):
-            mq, cq, w_out, b_out = self._folded(x.dtype)
+            mq, cq, w_out, b_out = _cached_fold(self, 'folded', self._fold_params(), x.dtype, lambda: self._folded(x.dtype))
             return Fn.TConvZFn.apply(x, mq, cq, w_out, b_out, g, self.heads, p)
-        ws = [self.lin_query.weight, self.lin_key.weight, self.lin_value.weight]
-        bs = [self.lin_query.bias, self.lin_key.bias, self.lin_value.bias]
-        if self.root_weight:
-            ws.append(self.lin_skip.weight)
-            sb = self.lin_skip.bias
-            bs.append(sb if sb is not None else torch.zeros(self.lin_skip.out_channels, device=x.device))
-        w_cat = torch.cat(ws, 0).to(x.dtype)
-        b_cat = torch.cat(bs, 0).float()
-        p = self.dropout if self.training else 0.0
+
+        def cat():
+            ws = [self.lin_query.weight, self.lin_key.weight, self.lin_value.weight]
+            bs = [self.lin_query.bias, self.lin_key.bias, self.lin_value.bias]
+            if self.root_weight:
+                ws.append(self.lin_skip.weight)
+                sb = self.lin_skip.bias
+                bs.append(sb if sb is not None else torch.zeros(self.lin_skip.out_channels, device=x.device))
+            return torch.cat(ws, 0).to(x.dtype), torch.cat(bs, 0).float()
+        w_cat, b_cat = _cached_fold(self, 'cat', self._fold_params(), x.dtype, cat)
         return Fn.TConvFn.apply(x, w_cat, b_cat, g, self.heads, self.out_channels, self.concat, p, self.root_weight)
 
     def _aggregate_first(self, x) -> bool:
@@ -339,6 +360,15 @@ class TransformerConv(MessagePassing):
         from . import ops
         return x.shape[0] >= 1 and ops.gatz_supported(x.shape[0], self.heads, self.in_channels, x.dtype) and \
             ops.gatz_supported(x.shape[0], self.heads, self.out_channels, x.dtype)
+
+    def _fold_params(self):
+        ps = [self.lin_query.weight, self.lin_query.bias, self.lin_key.weight, self.lin_key.bias, self.lin_value.weight,
+              self.lin_value.bias]
+        if self.root_weight:
+            ps += [self.lin_skip.weight, self.lin_skip.bias]
+        if self.lin_edge is not None:
+            ps.append(self.lin_edge.weight)
+        return ps
 
     def _folded(self, dtype, with_edge: bool = False):
         """(mq [H*F, F], cq [H*F], w_out [C, H*F + 8 + F], b_out [C]) from the q/k/v/skip parameters (differentiable).
@@ -392,7 +422,10 @@ class BatchNorm(tnn.Module):
         from . import ops
         if ops.bn_supported(x):
             return Fn.batch_norm(x, None, self.module)            # csrc/bn.cu
-        return self.module(x)                                      # host tensors / odd widths: torch's own BatchNorm1d
+        if not x.is_cuda:
+            raise RuntimeError("b2g: BatchNorm needs a CUDA tensor (B200 path, no CPU fallback)")
+        return self.module(x)                                      # CUDA tensors of widths the kernels do not cover (rows
+        #                                                            that are not 16-byte multiples, > 4 KB): torch's CUDA BatchNorm1d
 
     def __repr__(self):
         return f'{self.__class__.__name__}({self.module.num_features})'

@@ -388,8 +388,43 @@ def gatz_fwd(x, a, H, slope, rowptr, col, p_drop, seed, save_stats, band=0, out=
     return z, smax, ssum
 
 
-def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, y_out, band=0):
-    """-> d_a fp32 [N, 2H]; writes y = [sum_i alpha_ij1 g_i | ...] into y_out (a [N, H*C] view, any row stride)."""
+def gatw_gemm_supported(n: int, H: int, F: int, C: int, dtype) -> bool:
+    dt = F32 if dtype == torch.float32 else (BF16 if dtype == torch.bfloat16 else -1)
+    return dt >= 0 and bool(_lib.load().b2g_gatw_gemm_supported(int(max(n, 1)), int(H), int(F), int(C), dt))
+
+
+def gat_alpha(a, rowptr, col, H, slope, p_drop, seed, save_stats, edge_bias=None):
+    """Post-dropout attention weights alpha fp32 [nnz, H] in target-major CSR order (+ softmax max / sum [N, H] | None)
+    from a = [a_src | a_dst] fp32 [N, 2H]  (csrc/gat_fused.cu gat_alpha_kernel)."""
+    _cuda(a, rowptr, col)
+    N = a.shape[0]
+    alpha = torch.empty((max(col.numel(), 1), H), dtype=torch.float32, device=a.device)
+    smax = torch.empty((N, H), dtype=torch.float32, device=a.device) if save_stats else None
+    ssum = torch.empty((N, H), dtype=torch.float32, device=a.device) if save_stats else None
+    _lib.check(_lib.load().b2g_gat_alpha(_p(a), a.stride(0), _p(rowptr), _p(col), _p(edge_bias), N, H, float(slope),
+                                         float(p_drop), int(seed), _p(alpha), _p(smax), _p(ssum), _stream()), "gat_alpha")
+    return alpha, smax, ssum
+
+
+def gatw_gemm(x, rowptr, col, perm, alpha, wp, bias, n_rows, H, band=0, out=None):
+    """out [n_rows, C] = (per-head alpha-weighted sums of the rows of x over the CSR) @ Wc^T + bias in ONE kernel
+    (csrc/gat_fused.cu); wp = Wc with columns permuted by 64-feature chunk (see include/b2g.h)."""
+    _cuda(x, wp, alpha)
+    x, wp = _rows(x), _rows(wp)
+    C = wp.shape[0]
+    F = x.shape[1]
+    if out is None:
+        out = torch.empty((n_rows, C), dtype=x.dtype, device=x.device)
+    b = bias.float().contiguous() if bias is not None else None
+    _lib.check(_lib.load().b2g_gatw_gemm(_p(x), _ld(x), _p(rowptr), _p(col), _p(perm), _p(alpha), _p(wp), _ld(wp), _p(b),
+                                         _p(out), _ld(out), n_rows, H, F, C, _dt(x), int(band), _stream()), "gatw_gemm")
+    return out
+
+
+def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, y_out, band=0, d_a_out=None):
+    """Writes y = [sum_i alpha_ij1 g_i | ...] into y_out (a [N, H*C] view, any row stride) and the logit gradients
+    d a = [d a_src | d a_dst] into d_a_out (a [N, 2H] view of dtype fp32 or x.dtype, any row stride; default: a new fp32
+    tensor).  Returns d a."""
     lib = _lib.load()
     x, dz, g = _rows(x), _rows(dz), _rows(g)
     N, F = x.shape
@@ -398,26 +433,27 @@ def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, 
     nnz = csr[1].numel()
     alpha_e = torch.empty((max(nnz, 1), H), dtype=torch.float32, device=dev)
     de_e = torch.empty((max(nnz, 1), H), dtype=torch.float32, device=dev)
-    d_a = torch.empty((N, 2 * H), dtype=torch.float32, device=dev)
+    d_a = d_a_out if d_a_out is not None else torch.empty((N, 2 * H), dtype=torch.float32, device=dev)
+    assert d_a.shape == (N, 2 * H) and d_a.stride(1) == 1 and d_a.dtype in (torch.float32, torch.bfloat16)
     st = _stream()
     _lib.check(lib.b2g_gatz_bwd_dst(_p(x), _ld(x), _p(a), a.stride(0), _p(dz), _ld(dz), N, H, F, _dt(x), float(slope),
                                     _p(csr[0]), _p(csr[1]), _p(smax), _p(ssum), float(p_drop), int(seed), _p(alpha_e),
-                                    _p(de_e), _p(d_a), 2 * H, int(band), st), "gatz_bwd_dst")
-    _lib.check(lib.b2g_gatz_bwd_src(_p(g), _ld(g), _p(alpha_e), _p(de_e), _p(y_out), _ld(y_out), _p(d_a), 2 * H, N, H, C,
-                                    _dt(x), _p(csr_t[0]), _p(csr_t[1]), _p(perm), int(band), st), "gatz_bwd_src")
+                                    _p(de_e), _p(d_a), _ld(d_a), _dt(d_a), int(band), st), "gatz_bwd_dst")
+    _lib.check(lib.b2g_gatz_bwd_src(_p(g), _ld(g), _p(alpha_e), _p(de_e), _p(y_out), _ld(y_out), _p(d_a), _ld(d_a), _dt(d_a),
+                                    N, H, C, _dt(x), _p(csr_t[0]), _p(csr_t[1]), _p(perm), int(band), st), "gatz_bwd_src")
     return d_a
 
 
 def seg_wsum4(x, w_e, rowptr, col, perm, out, d_a=None, band=0):
     """out[i] = [sum_t w_e[p_t,0] x[col_t] | ... | sum_t w_e[p_t,3] x[col_t]] over row i of (rowptr, col), p_t = perm[t] or t
-    (gat_rows.cu gatz_bwd_src_kernel).  d_a (optional, fp32 [N, >= 4]) receives the row sums of w_e's companion."""
+    (gat_rows.cu gatz_bwd_src_kernel).  d_a (optional, [N, >= 4] view, fp32 or bf16) receives the row sums of w_e's companion."""
     lib = _lib.load()
     x = _rows(x)
     N = out.shape[0]
     C = x.shape[1]
     _lib.check(lib.b2g_gatz_bwd_src(_p(x), _ld(x), _p(w_e), _p(w_e), _p(out), _ld(out), _p(d_a),
-                                    d_a.stride(0) if d_a is not None else 0, N, 4, C, _dt(x), _p(rowptr), _p(col), _p(perm),
-                                    int(band), _stream()), "seg_wsum4")
+                                    d_a.stride(0) if d_a is not None else 0, _dt(d_a) if d_a is not None else 0, N, 4, C,
+                                    _dt(x), _p(rowptr), _p(col), _p(perm), int(band), _stream()), "seg_wsum4")
     return out
 
 

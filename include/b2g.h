@@ -204,12 +204,14 @@ int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda,
 int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, const void* dz, int64_t lddz,
                      int64_t n, int H, int F, int dt, float slope, const int32_t* rowptr, const int32_t* col,
                      const float* smax, const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* de_e,
-                     float* d_a, int64_t ldda, int64_t band, void* stream);
-/* Source side: over the transposed CSR (rowptr_t, col_t, perm = position of each entry in the target-major CSR)
+                     void* d_a, int64_t ldda, int d_a_dt, int64_t band, void* stream);
+/* d_a / d_a_dt: the [n, >= 2H] logit-gradient block, fp32 (B2G_F32) or bf16 (B2G_BF16: the column block of the bf16 dgrad
+ * operand [y | d a], written in place); ldda = its row stride in elements of that type.
+ * Source side: over the transposed CSR (rowptr_t, col_t, perm = position of each entry in the target-major CSR)
  * y[j] = [sum_i alpha_ij1 g_i | ... | sum_i alpha_ijH g_i] ([n, H*C], g = d out [*, C]) and d a_src into columns
  * 0..H-1 of d_a. */
 int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const float* de_e, void* y, int64_t ldy,
-                     float* d_a, int64_t ldda, int64_t n, int H, int C, int dt, const int32_t* rowptr_t,
+                     void* d_a, int64_t ldda, int d_a_dt, int64_t n, int H, int C, int dt, const int32_t* rowptr_t,
                      const int32_t* col_t, const int32_t* perm, int64_t band, void* stream);
 
 /* TransformerConv(heads = 4, concat = False) (gnn_model.py:77-80,170), aggregate-first (gat_rows.cu): the logits are
@@ -242,6 +244,26 @@ int b2g_edge_dot4(const float* v, int64_t ldv, const float* ea_csr, const int32_
                   void* stream);
 int b2g_edge_wsum4(const float* w, const float* ea_csr, const int32_t* rowptr, int64_t n, int H, float p_drop, uint64_t seed,
                    void* out, int64_t ldo, int dt, void* stream);
+
+/* ===================================================================================== K4f (fused)
+ * GATConv(heads = 4, concat = False), bf16, F = 256: the attention-weighted aggregation FUSED with the output projection
+ * (csrc/gat_fused.cu) — z [n, H*F] never exists in HBM.  Replaces, like K4, PyG's softmax + [E,H,C] messages + scatter
+ *  and the projection (row 10) of gnn_model.py:65-68,168.
+ *
+ * b2g_gat_alpha: alpha[p, h] (fp32 [nnz, 4], target-major CSR order) = dropout(segment_softmax(leaky_relu(a_src[col_p, h]
+ *   + a_dst[i, h] (+ edge_bias[p, h])))) with PyG's max-subtraction and + 1e-16; a_srcdst fp32 [n, lda >= 8] = [a_src | a_dst];
+ *   smax / ssum (fp32 [n, 4], both or neither) receive the softmax statistics the backward kernels read.
+ * b2g_gatw_gemm: out[i, :] = sum_h (sum_{p in row i} alpha[q(p), h] x[col_p, :]) Wc_h^T + bias, q(p) = perm ? perm[p] : p.
+ *   x: bf16 [*, F] (row stride ldx); wp: bf16 [C, H*F] = Wc with its columns permuted by 64-feature chunk:
+ *   wp[c, kc*256 + h*64 + f] = Wc[c, h*256 + kc*64 + f]; out: bf16 [n_rows, C]; C a multiple of 64, <= 256.
+ *   With the source-major CSR, perm and g in place of x it is the backward's y-aggregation + dgrad GEMM. */
+int b2g_gatw_gemm_supported(int64_t n, int H, int F, int C, int dt);
+int b2g_gat_alpha(const float* a_srcdst, int64_t lda, const int32_t* rowptr, const int32_t* col, const float* edge_bias,
+                  int64_t n, int H, float slope, float p_drop, uint64_t seed, float* alpha, float* smax, float* ssum,
+                  void* stream);
+int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                  const float* alpha, const void* wp, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t n_rows,
+                  int H, int F, int C, int dt, int64_t band, void* stream);
 
 /* ===================================================================================== K5
  * TransformerConv (gnn_model.py:77-80,170) fused q.k score + segment-softmax + aggregate +

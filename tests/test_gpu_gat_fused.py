@@ -1,0 +1,213 @@
+"""K4f (csrc/gat_fused.cu): the fused attention-weighted aggregation + output projection of GATConv(heads=4, concat=False)
+and its attention-weight kernel, through the C ABI (b2g_gat_alpha / b2g_gatw_gemm).
+  * kernel level: arbitrary CSRs (empty rows, rows of 1..8, 9..32 and > 32 entries, partial tiles, C = 64 / 128 / 256, the
+    perm indirection of the transposed use) against an fp64 torch reference of the same contraction;
+  * alpha against the fp64 segment softmax PyG defines (oracle/layers_oracle.py segment_softmax);
+  * layer level: GATConv forward + gradients vs the fp64 oracle on meshes large enough for the panel row order, and the
+    fused path against the unfused one (same arithmetic, z rounded to bf16 in both) incl. attention dropout (same mask)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+H = 4
+
+
+def _random_csr(N, n_src, seed, max_len=12, hubs=True):
+    rng = np.random.default_rng(seed)
+    deg = rng.integers(0, max_len + 1, size=N)
+    deg[rng.integers(0, N, size=max(N // 10, 1))] = 0                      # empty rows
+    if hubs and N > 40:
+        deg[3] = 45
+        deg[N // 2] = 33
+        deg[N - 1] = 9
+    rowptr = np.zeros(N + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(deg)
+    col = rng.integers(0, n_src, size=int(rowptr[-1]))
+    return torch.from_numpy(rowptr).int().cuda(), torch.from_numpy(col).int().cuda(), torch.from_numpy(deg).cuda()
+
+
+def _ref_out(x, rowptr, col, alpha_of_pos, wc, bias, N, F):
+    """fp64: out = z Wc^T + b with z_i = [sum_p alpha[p, h] x[col_p]]_h."""
+    deg = (rowptr[1:] - rowptr[:-1]).long()
+    rows = torch.repeat_interleave(torch.arange(N, device=x.device), deg)
+    xs = x.double()[col.long()]                                             # [nnz, F]
+    z = torch.zeros(N, H, F, dtype=torch.float64, device=x.device)
+    z.index_add_(0, rows, alpha_of_pos.double().unsqueeze(-1) * xs.unsqueeze(1))
+    out = z.reshape(N, H * F) @ wc.double().t()
+    return out + bias.double() if bias is not None else out
+
+
+@pytest.mark.parametrize("C", [64, 128, 256])
+@pytest.mark.parametrize("N", [1, 5, 127, 128, 129, 1000, 4100])
+def test_gatw_gemm_kernel_vs_fp64(N, C):
+    from gnn_bfs_rans_b200 import ops
+    F = 256
+    n_src = N + 37                                                          # gathered rows may lie beyond the target rows (ghosts)
+    rowptr, col, _ = _random_csr(N, n_src, seed=N * 7 + C)
+    nnz = col.numel()
+    torch.manual_seed(N + C)
+    x = torch.randn(n_src, F, device="cuda").bfloat16()
+    alpha = torch.rand(max(nnz, 1), H, device="cuda")
+    wc = (torch.randn(C, H * F, device="cuda") / 16).bfloat16()
+    bias = torch.randn(C, device="cuda")
+    wp = wc.view(C, H, F // 64, 64).permute(0, 2, 1, 3).reshape(C, H * F).contiguous()
+    assert ops.gatw_gemm_supported(N, H, F, C, torch.bfloat16)
+    out = torch.full((N, C), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gatw_gemm(x, rowptr, col, None, alpha, wp, bias, N, H, out=out)
+    ref = _ref_out(x, rowptr, col, alpha[:nnz], wc, bias, N, F)
+    err = float((out.double() - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    assert err < 2e-2, err
+    # rows without entries are exactly the bias
+    empty = (rowptr[1:] == rowptr[:-1])
+    if bool(empty.any()):
+        assert torch.equal(out[empty], bias.bfloat16().expand(int(empty.sum()), C))
+    # deterministic: a second launch gives the same bits
+    out2 = torch.empty_like(out)
+    ops.gatw_gemm(x, rowptr, col, None, alpha, wp, bias, N, H, out=out2)
+    assert torch.equal(out, out2)
+    # perm indirection (transposed use): alpha stored in another order
+    if nnz:
+        perm = torch.randperm(nnz, device="cuda").int()
+        alpha_p = torch.empty_like(alpha)
+        alpha_p[perm.long()] = alpha[:nnz]
+        out3 = torch.empty_like(out)
+        ops.gatw_gemm(x, rowptr, col, perm, alpha_p, wp, None, N, H, out=out3)
+        ref3 = _ref_out(x, rowptr, col, alpha[:nnz], wc, None, N, F)
+        assert float((out3.double() - ref3).abs().max() / ref3.abs().max().clamp_min(1e-30)) < 2e-2
+
+
+def test_gatw_gemm_panel_order_and_band():
+    """A band-structured mesh large enough for the panel row order (band >= 4 panels): every row computed exactly once."""
+    from gnn_bfs_rans_b200 import ops
+    from gnn_bfs_rans_b200.graph import Graph
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    nx, ny, nz = 40, 30, 70                                                 # 84 000 rows, band = 1200 ... use the z-stride
+    N = nx * ny * nz
+    o, n = hex_mesh_faces(nx, ny, nz, device="cuda")
+    ei = ops.build_graph_edges(o, n, 1, None, N, N)
+    g = Graph(ei, N)
+    csr = g.csr("sl", False)
+    torch.manual_seed(0)
+    x = torch.randn(N, 256, device="cuda").bfloat16()
+    alpha = torch.rand(csr.nnz, H, device="cuda")
+    wc = (torch.randn(256, 1024, device="cuda") / 16).bfloat16()
+    wp = wc.view(256, H, 4, 64).permute(0, 2, 1, 3).reshape(256, 1024).contiguous()
+    outs = []
+    for band in (0, g.band(), 40000):
+        out = torch.full((N, 256), float("nan"), device="cuda", dtype=torch.bfloat16)
+        ops.gatw_gemm(x, csr.rowptr, csr.col, None, alpha, wp, None, N, H, band=band, out=out)
+        assert bool(torch.isfinite(out.float()).all())
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    rows = torch.randint(0, N, (3000,), device="cuda")
+    ref = _ref_out(x, csr.rowptr, csr.col, alpha, wc, None, N, 256)[rows]
+    assert float((outs[0][rows].double() - ref).abs().max() / ref.abs().max()) < 2e-2
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.3])
+def test_gat_alpha_is_pygs_segment_softmax(p_drop):
+    from gnn_bfs_rans_b200 import ops
+    from oracle import layers_oracle as lo
+    N = 3000
+    rowptr, col, deg = _random_csr(N, N, seed=11, max_len=10)
+    nnz = col.numel()
+    torch.manual_seed(3)
+    a = torch.randn(N, 2 * H, device="cuda") * 2
+    alpha, smax, ssum = ops.gat_alpha(a, rowptr, col, H, 0.2, p_drop, 1234, True)
+    rows = torch.repeat_interleave(torch.arange(N, device="cuda"), deg.long())
+    s = torch.nn.functional.leaky_relu(a.double()[col.long(), :H] + a.double()[rows, H:], 0.2)
+    ref = lo.segment_softmax(s.cpu(), rows.cpu(), N)
+    got = alpha[:nnz].double().cpu()
+    if p_drop == 0.0:
+        assert float((got - ref).abs().max()) < 1e-5
+    else:
+        keep = got != 0
+        frac = float(keep.double().mean())
+        assert abs(frac - (1 - p_drop)) < 0.02, frac
+        assert float((got[keep] * (1 - p_drop) - ref[keep]).abs().max()) < 1e-5      # kept entries scaled by 1/(1-p)
+        again, _, _ = ops.gat_alpha(a, rowptr, col, H, 0.2, p_drop, 1234, False)
+        assert torch.equal(again, alpha)                                               # same seed -> same mask
+        other, _, _ = ops.gat_alpha(a, rowptr, col, H, 0.2, p_drop, 99, False)
+        assert not torch.equal(other, alpha)
+    # statistics the backward kernels read: max of the scores and the sum of exp (+ 1e-16) per (row, head)
+    nz = deg > 0
+    mref = torch.zeros(N, H, dtype=torch.float64).scatter_reduce_(0, rows.cpu().view(-1, 1).expand(-1, H), s.cpu(), "amax", include_self=False)
+    assert float((smax.double().cpu() - mref)[nz.cpu()].abs().max()) < 1e-5
+    zref = torch.zeros(N, H, dtype=torch.float64).index_add_(0, rows.cpu(), (s.cpu() - mref[rows.cpu()]).exp())
+    assert float(((ssum.double().cpu() - zref) / zref.clamp_min(1e-30))[nz.cpu()].abs().max()) < 1e-5
+
+
+def _layer(C=256):
+    import gnn_bfs_rans_b200 as b2g
+    torch.manual_seed(1234)
+    m = b2g.nn.GATConv(256, C, heads=4, concat=False, dropout=0.2)
+    with torch.no_grad():
+        m.bias.uniform_(-0.5, 0.5)
+    return m.cuda().bfloat16()
+
+
+@pytest.mark.parametrize("C", [128, 256])
+def test_gatconv_fused_equals_unfused_and_oracle(C, monkeypatch):
+    from gnn_bfs_rans_b200 import ops
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    from oracle import layers_oracle as lo
+    nx, ny, nz = 24, 20, 18
+    N = nx * ny * nz
+    o, n = hex_mesh_faces(nx, ny, nz, device="cuda")
+    ei = ops.build_graph_edges(o, n, 1, None, N, N)
+    extra = torch.stack([torch.randint(0, N, (60,), device="cuda"), torch.full((60,), 17, device="cuda")])   # a hub target
+    ei = torch.cat([ei, extra], 1)
+    m = _layer(C).eval()
+    torch.manual_seed(5)
+    x = torch.randn(N, 256, device="cuda").bfloat16()
+    gout = torch.randn(N, C, device="cuda").bfloat16()
+    res = {}
+    for path in ("fused", "unfused"):
+        monkeypatch.setenv("B2G_GAT_PATH", "" if path == "fused" else "unfused")
+        xg = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        out = m(xg, ei)
+        out.backward(gout)
+        res[path] = (out.detach(), xg.grad, {k: p.grad.clone() for k, p in m.named_parameters()})
+    p = {k: v.detach().double().cpu().requires_grad_(True) for k, v in m.state_dict().items()}
+    x64 = x.double().cpu().requires_grad_(True)
+    ref = lo.gat_conv(x64, ei.cpu(), p["lin.weight"], p["att_src"], p["att_dst"], p["bias"], heads=4)
+    ref.backward(gout.double().cpu())
+    rel = lambda a_, b_: float((a_.double().cpu() - b_).abs().max() / b_.abs().max().clamp_min(1e-30))
+    assert rel(res["fused"][0], ref.detach()) < 2e-2
+    assert rel(res["unfused"][0], ref.detach()) < 2e-2
+    assert rel(res["fused"][0], res["unfused"][0].double().cpu()) < 1.2e-2      # two bf16 roundings of the same value
+    for path in ("fused", "unfused"):                                            # same backward kernels either way
+        assert float((res[path][1].double().cpu() - x64.grad).norm() / x64.grad.norm()) < 4e-2, path
+        for k in ("lin.weight", "bias"):
+            assert float((res[path][2][k].double().cpu() - p[k].grad).norm() / p[k].grad.norm()) < 4e-2, (path, k)
+
+
+def test_gatconv_fused_dropout_uses_the_mask_the_backward_regenerates(monkeypatch):
+    """Training mode: the fused forward draws its attention-dropout mask in b2g_gat_alpha with the (seed, position) key the
+    backward kernels regenerate it from; under the same torch seed fused and unfused runs see the same mask."""
+    from gnn_bfs_rans_b200 import ops
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    nx, ny, nz = 16, 14, 12
+    N = nx * ny * nz
+    o, n = hex_mesh_faces(nx, ny, nz, device="cuda")
+    ei = ops.build_graph_edges(o, n, 1, None, N, N)
+    m = _layer().train()
+    x = torch.randn(N, 256, device="cuda").bfloat16()
+    res = {}
+    for path in ("fused", "unfused"):
+        monkeypatch.setenv("B2G_GAT_PATH", "" if path == "fused" else "unfused")
+        torch.manual_seed(77)
+        xg = x.clone().requires_grad_(True)
+        out = m(xg, ei)
+        out.float().square().mean().backward()
+        res[path] = (out.detach().float(), xg.grad.float())
+    scale = res["unfused"][0].abs().max()
+    assert float((res["fused"][0] - res["unfused"][0]).abs().max() / scale) < 1.2e-2
+    assert float((res["fused"][1] - res["unfused"][1]).norm() / res["unfused"][1].norm()) < 2e-2
+    m.eval()
+    with torch.no_grad():
+        ev = m(x, ei).float()
+    assert float((res["fused"][0] - ev).abs().max() / scale) > 5e-2           # the mask is really applied

@@ -24,32 +24,60 @@ def rel_l2(a, b):
     return float((a.double().cpu() - b).norm() / b.norm().clamp_min(1e-30))
 
 
+def _rows_max(d):
+    return d.reshape(d.shape[0], -1).max(1).values if d.dim() > 1 else d
+
+
 def check_grads(pairs, dtype, pairs_bf16_oracle=None):
     """pairs: name -> (mine, fp64 truth).
-    fp32 gate: max-abs error <= 1e-5 x max-abs reference, per tensor.  A tensor whose exact gradient is
-    zero by symmetry (TransformerConv lin_key.bias: a constant added to every key leaves the softmax
-    unchanged, so the fp64 reference is ~1e-17 while any fp32 sum of its O(1) summands carries ~1e-6
-    of rounding noise) is gauged against 5% of the layer's largest gradient, the size of its summands.
-    bf16 gate: rounding xw / pre-activations to bf16 flips the sign of near-zero (leaky-)ReLU inputs,
-    which moves gradient entries by O(1) terms in ANY bf16 implementation (relative L2 ~ sqrt(flip
-    fraction) ~ 3-5%), so 2e-2 cannot be met against exact arithmetic by the reference either.  The
-    gate is therefore: relative L2 error vs the fp64 truth <= max(2e-2, 2 x the error of the SAME
-    oracle executed in bf16 on the CPU (= what PyG does in bf16) + 1e-2), i.e. the same order of error as
-    the reference implementation shows in this dtype (the factor covers the independent kink flips)."""
+    fp32 gate: max-abs error <= 1e-5 x max-abs reference, per tensor.  A tensor whose exact gradient is zero by symmetry
+    (TransformerConv lin_key.bias: a constant added to every key leaves the softmax unchanged, so the fp64 reference is
+    ~1e-17 while any fp32 sum of its O(1) summands carries ~1e-6 of rounding noise) is gauged against 5% of the layer's
+    largest gradient, the size of its summands.
+
+    bf16 gate = the north-star's 2e-2 (relative L2 AND max-norm), per tensor.  Measured on the B200
+    (scripts/grad_err_probe.py, profiles/r02_grad_err_probe.txt): GCNConv and TransformerConv gradients sit at 2-4e-3; the
+    tensors behind a (Leaky)ReLU kink or a softmax cancellation (GATConv att_*, lin.weight, x; the first Linear of the GIN
+    MLP) do not reach 2e-2 in ANY bf16 arithmetic — the reference's own dispatch executed in bf16 on the CPU (the same oracle
+    in bf16) is 1.4-20e-2 off on exactly those tensors.  A tensor may therefore miss the strict gate only if
+      (1) the bf16 CPU oracle misses 1e-2 on it as well (evidence that the tensor, not the kernel, is the problem), and
+      (2a) for per-node gradients (x): the rows deviating by more than 2e-2 of the tensor's max are COUNTED — at most
+           max(3%, 2 x the bf16 oracle's own share + 1%) — and all other rows agree to 2e-2 in relative L2;
+      (2b) for parameter gradients (sums over all nodes): relative L2 <= 2 x the bf16 oracle's + 1e-2 and max-norm <= 2 x the
+           bf16 oracle's + 2e-2."""
     scale = max(float(r.abs().max()) for _, r in pairs.values())
     for name, (mine, ref) in pairs.items():
         ref = ref.double().cpu()
-        err = float((mine.double().cpu() - ref).abs().max())
+        mine = mine.double().cpu()
+        d = (mine - ref).abs()
+        err = float(d.max())
         gauge = max(float(ref.abs().max()), 5e-2 * scale, 1e-30)
         if dtype == torch.float32:
             assert err / gauge < 1e-5, f"grad {name}: {err / gauge:.3e}"
+            continue
+        if float(ref.abs().max()) <= 5e-2 * scale:               # (near-)zero exact gradient: gauge = the layer's gradient scale
+            assert err / gauge < 2e-2, f"grad {name}: max-norm {err / gauge:.3e} of the layer's gradient scale"
+            continue
+        l2 = rel_l2(mine, ref)
+        if l2 < 2e-2 and err / gauge < 2e-2:
+            continue                                             # strict gate met
+        assert pairs_bf16_oracle is not None and name in pairs_bf16_oracle, \
+            f"grad {name}: rel L2 {l2:.3e}, max-norm {err / gauge:.3e} (strict 2e-2 gate)"
+        ob = pairs_bf16_oracle[name].double().cpu()
+        od = (ob - ref).abs()
+        o_l2, o_max = rel_l2(ob, ref), float(od.max()) / gauge
+        assert max(o_l2, o_max) > 1e-2, \
+            f"grad {name}: rel L2 {l2:.3e} / max {err / gauge:.3e} although the bf16 oracle holds {o_l2:.3e} / {o_max:.3e}"
+        if name == "x":
+            bad = _rows_max(d) > 2e-2 * gauge
+            o_bad = _rows_max(od) > 2e-2 * gauge
+            share, o_share = float(bad.double().mean()), float(o_bad.double().mean())
+            assert share <= max(0.03, 2 * o_share + 0.01), f"grad x: {share:.3%} of the rows off by > 2e-2 (bf16 oracle: {o_share:.3%})"
+            rest = float((mine - ref)[~bad].norm() / ref[~bad].norm().clamp_min(1e-30))
+            assert rest < 2e-2, f"grad x: rows outside the counted ones: rel L2 {rest:.3e}"
         else:
-            if float(ref.abs().max()) > 5e-2 * scale:
-                bound = 2e-2
-                if pairs_bf16_oracle is not None and name in pairs_bf16_oracle:
-                    bound = max(bound, 2.0 * rel_l2(pairs_bf16_oracle[name], ref) + 1e-2)
-                assert rel_l2(mine, ref) < bound, f"grad {name}: rel L2 {rel_l2(mine, ref):.3e} (bound {bound:.3e})"
-            assert err / gauge < 0.25, f"grad {name}: max-norm {err / gauge:.3e}"
+            assert l2 < 2 * o_l2 + 1e-2, f"grad {name}: rel L2 {l2:.3e} (bf16 oracle {o_l2:.3e})"
+            assert err / gauge < 2 * o_max + 2e-2, f"grad {name}: max-norm {err / gauge:.3e} (bf16 oracle {o_max:.3e})"
 
 
 def multigraph(N, E, seed, with_isolated=True):

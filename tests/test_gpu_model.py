@@ -190,3 +190,61 @@ def test_cuda_graph_train_step(layer_type):
     gd = b2g.graphs.GraphedTrainStep(m_d, o_d, loss_fn, xs[0], ys[0], ei, warmup=2)
     l1 = float(gd.step(xs[0], ys[0])); l2 = float(gd.step(xs[0], ys[0]))
     assert l1 != l2 and abs(l1 - l2) < 0.5 * abs(l1)
+
+
+@pytest.mark.parametrize("layer_type", ["GCN", "GAT"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("training", [False, True])
+def test_flowgnn_on_the_shipped_graph_cfg1_cfg2(layer_type, dtype, training, golden_dir):
+    """BASELINE cfg1 / cfg2 as configured: the shipped BFS case's train graph (12 225 cells, mode A), FlowGNN hidden 128,
+    L = 4, GCN and GAT (4 heads), eval and train mode (batch statistics), fp32 and bf16, against oracle.flow_gnn_forward in
+    fp64 on identical weights and inputs.
+    fp32: forward <= 2e-5 (four layers + BatchNorm + head compound the per-layer 1e-5); input gradients: rows touched by a
+    ReLU that flips between fp32 and fp64 are counted (<= 5 %), every other row agrees to 1e-4 in relative L2.
+    bf16: forward <= 2e-2, or — train mode, where BatchNorm divides by the batch standard deviation of channels that the
+    rank-3 input leaves almost constant — <= 1.5 x the error the SAME oracle makes when executed in bf16 on the CPU (measured:
+    8e-2 GCN / 2.2e-1 GAT for the CPU bf16 oracle, 7e-2 / 2.2e-1 for the kernels)."""
+    import os
+    from gnn_bfs_rans_b200.flow_model import FlowGNN
+    from gnn_bfs_rans_b200 import GraphConstructor
+    from oracle import layers_oracle as lo
+    z = np.load(os.path.join(golden_dir, "shipped_mesh.npz"))
+    mesh = dict(owner=z['owner'], neighbour=z['neighbour'], cell_centers=z['cell_centers'], n_cells=int(z['n_cells']))
+    g = GraphConstructor(mesh).build_graph(node_features=mesh['cell_centers'], filter_internal=True, n_internal_cells=12225)
+    assert g.num_nodes == 12225 and g.edge_index.shape[1] == 48330
+    torch.manual_seed(0)
+    model = FlowGNN(3, 128, 7, 4, layer_type, dropout=0.0).cuda().to(dtype)
+    model.train(training)
+    x = g.x.to(dtype)
+    xg = x.cuda().requires_grad_(True)
+    out = model(xg, g.edge_index.cuda(), g.edge_attr.cuda())
+    out.float().square().mean().backward()
+    pn = {k for k, _ in model.named_parameters()}
+    sd = model.state_dict()
+    p = {k: v.detach().double().cpu().requires_grad_(k in pn) for k, v in sd.items()}
+    x64 = x.double().requires_grad_(True)
+    ref = lo.flow_gnn_forward(x64, g.edge_index, p, layer_type, training=training)
+    ref.square().mean().backward()
+    e_fwd = rel(out.detach(), ref.detach())
+    if dtype == torch.float32:
+        assert e_fwd < 2e-5, e_fwd
+        gx, gr = xg.grad.double().cpu(), x64.grad
+        bad = (gx - gr).abs().max(1).values > 1e-4 * gr.abs().max()
+        assert int(bad.sum()) <= (5 * gx.shape[0]) // 100, int(bad.sum())
+        assert float((gx - gr)[~bad].norm() / gr[~bad].norm()) < 1e-4
+        scale = max(float(p[n].grad.abs().max()) for n in pn if p[n].grad is not None)
+        for name, par in model.named_parameters():
+            if par.grad is not None and p[name].grad is not None:
+                err = float((par.grad.double().cpu() - p[name].grad).abs().max())
+                # gauge: 1e-3 of the model's largest gradient for the tensors whose exact gradient is zero (biases in front
+                # of a train-mode BatchNorm); a flipped ReLU enters every parameter sum of the layers below it
+                assert err / max(float(p[name].grad.abs().max()), 1e-3 * scale) < 1.5e-2, (name, err)
+    else:
+        bound = 2e-2
+        if training:
+            with torch.no_grad():
+                pb = {k: v.detach().cpu() for k, v in sd.items()}
+                ob = lo.flow_gnn_forward(x, g.edge_index, pb, layer_type, training=True)
+            bound = max(bound, 1.5 * rel(ob, ref.detach()))
+        assert e_fwd < bound, (e_fwd, bound)
+        assert bool(torch.isfinite(xg.grad.float()).all())
