@@ -428,6 +428,36 @@ __global__ void __launch_bounds__(256) gat_alpha_kernel(const AlphaArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ GATConv(edge_dim) edge rows
+// PyG GATConv with edge_dim: remove_self_loops drops the given loops WITH their attributes, add_self_loops(fill_value =
+// 'mean') gives every node's new loop the mean attribute of its incoming (non-loop) edges, 0 without any.  Output: the
+// attributes in the order of the self-loop-replaced target-major CSR.  eid[p] < E: input edge eid[p]; eid[p] >= E: the new
+// loop of this row.  The mean is sum / count in fp32 in edge order (the CSR is a stable sort: PyG's CPU scatter order).
+__global__ void __launch_bounds__(256) edge_rows_sl_kernel(const float* __restrict__ ea, const int32_t* __restrict__ eid,
+                                                           const int32_t* __restrict__ rowptr, int64_t n, int64_t E,
+                                                           float* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = rowptr[i], e = rowptr[i + 1];
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0, loop_pos = -1;
+    for (int p = b; p < e; ++p) {
+      const int64_t id = eid[p];
+      if (id < E) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(ea) + id);
+        reinterpret_cast<float4*>(out)[p] = v;
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        ++cnt;
+      } else {
+        loop_pos = p;
+      }
+    }
+    if (loop_pos >= 0) {
+      const float c = (float)(cnt > 0 ? cnt : 1);
+      reinterpret_cast<float4*>(out)[loop_pos] = make_float4(sum.x / c, sum.y / c, sum.z / c, sum.w / c);
+    }
+  }
+}
+
 }  // namespace b2g
 
 using namespace b2g;
@@ -481,6 +511,19 @@ int b2g_gat_alpha(const float* a_srcdst, int64_t lda, const int32_t* rowptr, con
   const int64_t want = ceil_div(n * GF_H, 256);
   const int64_t cap = (int64_t)B2G_NUM_SMS * 16;
   gat_alpha_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(a);
+  count_launch();
+  return cuda_status();
+}
+
+int b2g_edge_rows_sl(const float* edge_attr, int64_t E, const int32_t* eid, const int32_t* rowptr, int64_t n, float* out,
+                     void* stream) {
+  if (n < 0 || E < 0) return B2G_E_ARG;
+  if (n == 0) return B2G_OK;
+  if (!eid || !rowptr || !out || (E > 0 && !edge_attr)) return B2G_E_ARG;
+  if ((edge_attr && !aligned16(edge_attr)) || !aligned16(out)) return B2G_E_ALIGN;
+  const int64_t want = ceil_div(n, 256);
+  const int64_t cap = (int64_t)B2G_NUM_SMS * 16;
+  edge_rows_sl_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, (cudaStream_t)stream>>>(edge_attr, eid, rowptr, n, E, out);
   count_launch();
   return cuda_status();
 }

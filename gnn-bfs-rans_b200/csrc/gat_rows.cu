@@ -464,13 +464,18 @@ __device__ __forceinline__ void gatz_bwd_window(const GatzArgs& a, const float (
   gatz_dalpha8<T, VPL>(dal, dzf, xb, a.xrow_bytes, cl, 0, lane, first);
   for (int j = 8; j < n; j += 8) gatz_dalpha8<T, VPL>(dal, dzf, xb, a.xrow_bytes, cl, j, lane, []() {});
   const float in[GH] = {in4.x, in4.y, in4.z, in4.w};
+  float eb[GH] = {0.f, 0.f, 0.f, 0.f};          // GATConv(edge_dim): edge term of the logit, in front of the LeakyReLU
+  if (!kT && a.ebias && lane < n) {
+    const float4 b4 = ldg_f4(a.ebias + (uint64_t)(p0 + lane) * GH);
+    eb[0] = b4.x; eb[1] = b4.y; eb[2] = b4.z; eb[3] = b4.w;
+  }
 #pragma unroll
   for (int h = 0; h < GH; ++h) {
     if (kT) {
       sraw[h] = 1.0f;
       alpha[h] = lane < n ? in[h] : 0.f;
     } else {
-      sraw[h] = in[h] + ad[h];
+      sraw[h] = in[h] + ad[h] + eb[h];
       alpha[h] = lane < n ? __expf(lrelu(sraw[h], a.slope) - sm[h]) * rinv[h] : 0.f;
     }
     mask[h] = 1.0f;
@@ -595,7 +600,11 @@ __device__ __noinline__ void gatz_bwd_dst_long(const GatzArgs a, uint32_t i, int
       for (int h = 0; h < GH; ++h) { sraw[h] = 1.0f; alpha[h] = lane < n ? al[h] : 0.f; }
     } else {
       const float4 as4 = ldg_f4(a.a + (uint64_t)(uint32_t)cl * a.lda);
-      const float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+      float as[GH] = {as4.x, as4.y, as4.z, as4.w};
+      if (a.ebias && lane < n) {
+        const float4 b4 = ldg_f4(a.ebias + (uint64_t)(p0 + lane) * GH);
+        as[0] += b4.x; as[1] += b4.y; as[2] += b4.z; as[3] += b4.w;
+      }
 #pragma unroll
       for (int h = 0; h < GH; ++h) {
         sraw[h] = as[h] + ad[h];
@@ -692,6 +701,7 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
         alpha = u < len ? in0 : 0.f;
       } else {
         sraw = in0 + in1;
+        if (a.ebias && u < len) sraw += __ldg(a.ebias + (uint64_t)(r.b + u) * GH + h);
         alpha = u < len ? __expf(lrelu(sraw, a.slope) - in2) * (1.0f / in3) : 0.f;
       }
       const float mask = a.p_drop > 0.f ? packed_keep_scale(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + u), a.p_drop, h) : 1.0f;
@@ -1277,11 +1287,12 @@ int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda,
 int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, const void* dz, int64_t lddz,
                      int64_t n, int H, int F, int dt, float slope, const int32_t* rowptr, const int32_t* col,
                      const float* smax, const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* de_e,
-                     void* d_a, int64_t ldda, int d_a_dt, int64_t band, void* stream) {
+                     void* d_a, int64_t ldda, int d_a_dt, const float* edge_bias, int64_t band, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
   if (d_a_dt != B2G_F32 && d_a_dt != B2G_BF16) return B2G_E_ARG;
+  if (edge_bias && !aligned16(edge_bias)) return B2G_E_ALIGN;
   if (!x || !a_srcdst || !dz || !rowptr || !col || !smax || !ssum || !alpha_e || !de_e || !d_a) return B2G_E_ARG;
   if (!aligned16(x) || !aligned16(dz) || !aligned16(a_srcdst) || !aligned16(smax) || !aligned16(ssum) || !aligned16(alpha_e) ||
       !aligned16(de_e) || (ldx * es) % 16 || (lddz * es) % 16 || lda % 4 || lda < 2 * GH || ldda < 2 * GH)
@@ -1294,6 +1305,7 @@ int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t 
   a.rowptr = rowptr; a.col = col; a.smax = const_cast<float*>(smax); a.ssum = const_cast<float*>(ssum);
   a.slope = slope; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.alpha_e = alpha_e; a.de_e = de_e; a.d_a = static_cast<float*>(d_a); a.ldda = (uint32_t)ldda;
   a.da_bf16 = d_a_dt == B2G_BF16;
+  a.ebias = edge_bias;
   return gatz_dispatch(1, dt, F * es, a, (cudaStream_t)stream);
 }
 
@@ -1327,8 +1339,8 @@ int b2g_edge_dot4(const float* v, int64_t ldv, const float* ea_csr, const int32_
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   if (!v || !ea_csr || !rowptr || !out) return B2G_E_ARG;
-  if (!aligned16(v) || !aligned16(ea_csr) || !aligned16(out) || ldv % 4 || ldv < 4 * GH) return B2G_E_ALIGN;
-  const int64_t blocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)B2G_NUM_SMS * 16);
+  if (!aligned16(v) || !aligned16(ea_csr) || !aligned16(out) || ldv % 4 || (ldv != 0 && ldv < 4 * GH)) return B2G_E_ALIGN;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n, 256), (int64_t)B2G_NUM_SMS * 16);   // ldv == 0: one v row for all nodes
   edge_dot4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(v, ldv, ea_csr, rowptr, n, out);
   count_launch();
   return cuda_status();

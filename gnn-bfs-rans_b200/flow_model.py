@@ -22,7 +22,7 @@ def _make_layer(layer_type: str, width: int, dropout: float, edge_dim=None):
     if layer_type == 'GCN':
         return gnn.GCNConv(width, width)                                           # gnn_model.py:63
     if layer_type == 'GAT':
-        return gnn.GATConv(width, width, heads=4, concat=False, dropout=dropout)   # :65-68
+        return gnn.GATConv(width, width, heads=4, concat=False, dropout=dropout, edge_dim=edge_dim)   # :65-68
     if layer_type == 'GIN':
         return gnn.GINConv(tnn.Sequential(tnn.Linear(width, width), tnn.ReLU(), tnn.Linear(width, width)))  # :70-75
     if layer_type == 'Transformer':
@@ -43,11 +43,11 @@ class FlowGNN(tnn.Module):
         # opt-in: residual add + BatchNorm + ReLU + dropout (:184-192) as the two passes of csrc/bn.cu
         # instead of four torch ops.  Same arithmetic; the dropout mask comes from the library's Philox stream.
         self.fused_glue = fused_glue
-        # opt-in: edge_dim=4 builds the Transformer layers with PyG's lin_edge so that the edge_attr the
-        # reference already passes (:170) is consumed — "Transformer with edge features" (THEORY_AND_METHODS.md:165-166).
+        # opt-in: edge_dim=4 builds the Transformer (or GAT) layers with PyG's lin_edge so that the edge_attr the
+        # reference already passes (:170) is consumed — attention over edge features (THEORY_AND_METHODS.md:165-166).
         # None = the reference's constructor call (:77-80), where the attribute cannot be used.
-        if edge_dim is not None and layer_type != 'Transformer':
-            raise ValueError("edge_dim is an option of layer_type='Transformer'")
+        if edge_dim is not None and layer_type not in ('Transformer', 'GAT'):
+            raise ValueError("edge_dim is an option of layer_type='Transformer' / 'GAT'")
         self.edge_dim = edge_dim
         self.input_proj = tnn.Linear(input_dim, hidden_dim)
         self.gnn_layers = tnn.ModuleList(_make_layer(layer_type, hidden_dim, dropout, edge_dim) for _ in range(num_layers))
@@ -81,8 +81,8 @@ class FlowGNN(tnn.Module):
         h = self.input_proj(x)
         for i, layer in enumerate(self.gnn_layers):
             try:
-                if self.layer_type == 'Transformer':
-                    h_new = layer(h, edge_index, edge_attr=edge_attr)              # :170
+                if self.layer_type == 'Transformer' or (self.layer_type == 'GAT' and self.edge_dim is not None):
+                    h_new = layer(h, edge_index, edge_attr=edge_attr)              # :170 (GAT: only with the edge_dim opt-in)
                 else:
                     h_new = layer(h, edge_index)                                   # :166,168
             except RuntimeError as e:                                              # :173-181

@@ -182,44 +182,60 @@ class GATZFn(torch.autograd.Function):
     CSR that the dx GEMM consumes anyway."""
 
     @staticmethod
-    def forward(ctx, x, wc, v, bias, graph: Graph, H: int, slope: float, p_drop: float):
+    def forward(ctx, x, wc, v, bias, graph: Graph, H: int, slope: float, p_drop: float, ve=None, ea=None):
+        """ve fp32 [H, 4] / ea fp32 [nnz, 4] (GATConv(edge_dim=4)): PyG adds (lin_edge(e_ij) . att_edge)_h to the
+        logit in front of the LeakyReLU; by linearity that is ve_h . e_ij with ve_h = We_h^T att_edge_h (4 numbers per head, not
+        per node), so the [E, H*C] edge embedding never exists.  ea = the attributes in the order of the self-loop-replaced
+        CSR with mean-filled loops (graph.edge_rows("sl", ...)); the messages stay x_j W."""
         csr = graph.csr("sl", False)
-        need_grad = x.requires_grad or wc.requires_grad or v.requires_grad
+        need_grad = x.requires_grad or wc.requires_grad or v.requires_grad or (ve is not None and ve.requires_grad)
         seed = _next_seed() if p_drop > 0 else 0
         N, F = x.shape
         C = wc.shape[0]
         a = ops.rowdot8(x, v)
+        eb = None
+        if ve is not None:
+            eb = ops.edge_dot4(ve.detach().float().reshape(1, 4 * H).expand(N, 4 * H), ea, csr.rowptr, H)   # [nnz, H]
         fused = os.environ.get("B2G_GAT_PATH", "") != "unfused" and ops.gatw_gemm_supported(N, H, F, C, x.dtype)
+        if fused or eb is not None:
+            alpha, smax, ssum = ops.gat_alpha(a, csr.rowptr, csr.col, H, slope, p_drop, seed, need_grad, edge_bias=eb)
         if fused:
-            alpha, smax, ssum = ops.gat_alpha(a, csr.rowptr, csr.col, H, slope, p_drop, seed, need_grad)
             wp = wc.view(C, H, F // 64, 64).permute(0, 2, 1, 3).reshape(C, H * F)     # K order (chunk, head, 64 features)
             out = ops.gatw_gemm(x, csr.rowptr, csr.col, None, alpha, wp, bias, N, H, band=graph.band())
-            del alpha
         else:
-            z, smax, ssum = ops.gatz_fwd(x, a, H, slope, csr.rowptr, csr.col, p_drop, seed, need_grad, band=graph.band())
+            if eb is not None:                 # weights already known: the plain 4-head weighted row sum (gatz_bwd_src kernel)
+                z = ops.seg_wsum4(x, alpha, csr.rowptr, csr.col, None, torch.empty((N, H * F), dtype=x.dtype, device=x.device),
+                                  band=graph.band())
+            else:
+                z, smax, ssum = ops.gatz_fwd(x, a, H, slope, csr.rowptr, csr.col, p_drop, seed, need_grad, band=graph.band())
             out, _ = ops.linear_fwd(z, wc, bias.float() if bias is not None else None)
         if need_grad:
-            ctx.save_for_backward(x, wc, v, a, smax, ssum)
-            ctx.cfg = (graph, H, slope, p_drop, seed, bias is not None)
+            ctx.save_for_backward(x, wc, v, a, smax, ssum, eb, ea)
+            ctx.cfg = (graph, H, slope, p_drop, seed, bias is not None, ve is not None)
             ctx.ei_keepalive = graph.edge_index
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, wc, v, a, smax, ssum = ctx.saved_tensors
-        graph, H, slope, p_drop, seed, has_bias = ctx.cfg
+        x, wc, v, a, smax, ssum, eb, ea = ctx.saved_tensors
+        graph, H, slope, p_drop, seed, has_bias, has_edge = ctx.cfg
         N, F = x.shape
         C = wc.shape[0]
         g = g.contiguous()
         csr, csr_t, perm = graph.csr("sl", False), graph.csr("sl", True), graph.perm("sl")
-        gwc = gv = gx = None
+        gwc = gv = gx = gve = None
         dz, _ = ops.linear_fwd(g, wc.t().contiguous(), None)                # dz = g Wc    [N, H*F]
         # [y | d a] so that dx = y (W/H) + d a V is ONE GEMM against [Wc_src ; V]
         ka = H * C + 2 * H
         y_aug = ops.empty_rows(N, ka, x.dtype, x.device)
-        ops.gatz_bwd(x, a, dz, g, H, slope, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
-                     y_aug[:, :H * C], band=graph.band(), d_a_out=y_aug[:, H * C:])
+        _, de_e = ops.gatz_bwd(x, a, dz, g, H, slope, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
+                               y_aug[:, :H * C], band=graph.band(), d_a_out=y_aug[:, H * C:], edge_bias=eb, want_de=True)
         del dz
+        if has_edge and ctx.needs_input_grad[8]:
+            # d ve_h = sum_p de[p, h] e_p: per-row partial sums (edge_wsum4), then one column sum
+            part = ops.edge_wsum4(de_e, ea, csr.rowptr, H, torch.empty((N, 4 * H), dtype=torch.float32, device=x.device))
+            gve = ops.colsum(part).view(H, 4)
+        del de_e
         if ctx.needs_input_grad[1]:
             # dWc[c, hF+f] = sum_j y_j[hC+c] x_j[f]  (y_jh = sum_i alpha_ijh g_i): one wgrad GEMM [H*C, F], no z needed
             dw, _ = ops.linear_wgrad(y_aug[:, :H * C], x, want_bias=False)
@@ -233,7 +249,7 @@ class GATZFn(torch.autograd.Function):
             dv, _ = ops.linear_wgrad(y_aug[:, H * C:], x, want_bias=False)  # dV = d a^T x [2H, F]
             gv = _cast_like(dv, v)
         gb = ops.colsum(g) if (has_bias and ctx.needs_input_grad[3]) else None
-        return gx, gwc, gv, gb, None, None, None, None
+        return gx, gwc, gv, gb, None, None, None, None, gve, None
 
 
 class TConvFn(torch.autograd.Function):

@@ -118,12 +118,15 @@ class Graph:
 
     def edge_rows(self, variant: str, edge_attr: torch.Tensor) -> torch.Tensor:
         """Per-edge rows (e.g. edge_attr [E, 4]) as fp32 in the order of the target-major CSR of `variant`; cached for the
-        tensor last passed (the reference hands the same edge_attr to every layer, gnn_model.py:170).  "raw" only: the
-        self-loop-replaced list has entries without an input edge."""
-        if variant != "raw":
-            raise NotImplementedError("edge_rows: only the raw edge list has one input edge per CSR entry")
+        tensor last passed (the reference hands the same edge_attr to every layer, gnn_model.py:170)."""
         if not edge_attr.is_cuda:
             raise RuntimeError("b2g: CUDA tensor required (this is the B200 path; there is no CPU fallback)")
+        if variant == "sl":
+            # GATConv(edge_dim): dropped loops lose their attributes, the new loops get the mean attribute of the row's other
+            # entries (PyG fill_value='mean') — csrc/gat_fused.cu edge_rows_sl_kernel
+            c = self.csr("sl", False)
+            return identity_cached(self.__dict__, "_edge_rows_sl", edge_attr,
+                                   lambda: ops.edge_rows_sl(edge_attr, c.eid, c.rowptr, self.N))
         return identity_cached(self.__dict__, "_edge_rows", edge_attr,
                                lambda: edge_attr.detach().float().index_select(0, self.csr("raw", False).eid.long()).contiguous())
 

@@ -151,8 +151,11 @@ class GATConv(MessagePassing):
                  negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
                  edge_dim: Optional[int] = None, fill_value='mean', bias: bool = True, **kwargs):
         super().__init__(aggr='add')
-        if not add_self_loops or edge_dim is not None:
-            raise NotImplementedError("b2g GATConv: only add_self_loops=True, edge_dim=None")
+        if not add_self_loops:
+            raise NotImplementedError("b2g GATConv: only add_self_loops=True")
+        if edge_dim is not None and (edge_dim != 4 or concat or heads != 4 or fill_value != 'mean'):
+            raise NotImplementedError("b2g GATConv: edge_dim is built for edge_dim=4 (graph_constructor.py:58-90), heads=4, "
+                                      "concat=False, fill_value='mean'")
         if not isinstance(in_channels, int):
             raise NotImplementedError("b2g GATConv: bipartite in_channels are not supported")
         self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
@@ -161,6 +164,13 @@ class GATConv(MessagePassing):
         self.lin = Linear(in_channels, heads * out_channels, bias=False, weight_initializer='glorot')
         self.att_src = tnn.Parameter(torch.empty(1, heads, out_channels))
         self.att_dst = tnn.Parameter(torch.empty(1, heads, out_channels))
+        if edge_dim is not None:           # PyG: lin_edge (no bias, glorot) + att_edge; SURVEY §8f-2
+            self.lin_edge = Linear(edge_dim, heads * out_channels, bias=False, weight_initializer='glorot')
+            self.att_edge = tnn.Parameter(torch.empty(1, heads, out_channels))
+        else:
+            self.lin_edge = None
+            self.register_parameter('att_edge', None)
+        self._warned_edge_attr = False
         if bias:
             self.bias = tnn.Parameter(torch.empty(heads * out_channels if concat else out_channels))
         else:
@@ -171,6 +181,9 @@ class GATConv(MessagePassing):
         self.lin.reset_parameters()
         glorot(self.att_src)
         glorot(self.att_dst)
+        if self.lin_edge is not None:
+            self.lin_edge.reset_parameters()
+        glorot(self.att_edge)
         zeros(self.bias)
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
@@ -193,12 +206,26 @@ class GATConv(MessagePassing):
     def forward(self, x, edge_index, edge_attr=None, size=None, return_attention_weights=None):
         if return_attention_weights:
             raise NotImplementedError("b2g GATConv: return_attention_weights is not supported")
-        if edge_attr is not None:
-            raise NotImplementedError("b2g GATConv: edge_attr needs edge_dim (not supported)")
+        if edge_attr is not None and self.lin_edge is None and not self._warned_edge_attr:
+            # PyG's edge_update only looks at edge_attr when lin_edge exists (edge_dim given): the attribute is ignored
+            warnings.warn("b2g GATConv: edge_attr ignored because edge_dim=None")
+            self._warned_edge_attr = True
         _check_x(x, edge_index)
         g = graph_of(edge_index, x.shape[0])
         p = self.dropout if self.training else 0.0
         ps = (self.lin.weight, self.att_src, self.att_dst)
+        if self.lin_edge is not None and edge_attr is not None:
+            # GATConv(edge_dim=4): logit_ijh += (lin_edge(e_ij)_h . att_edge_h) = ve_h . e_ij, self loops with the mean attribute
+            if edge_attr.dim() != 2 or edge_attr.shape != (edge_index.shape[1], self.edge_dim):
+                raise ValueError(f"edge_attr must be [{edge_index.shape[1]}, {self.edge_dim}], got {tuple(edge_attr.shape)}")
+            if not self._aggregate_first(x):
+                raise NotImplementedError("b2g GATConv(edge_dim): needs 512 / 1024-byte feature rows (the aggregate-first kernels)")
+            wc, v = _cached_fold(self, 'wc_v', ps, x.dtype, lambda: self._wc_v(x.dtype))
+            H, C, D = self.heads, self.out_channels, self.edge_dim
+            ve = _cached_fold(self, 've', (self.lin_edge.weight, self.att_edge), torch.float32,
+                              lambda: torch.einsum('hcd,hc->hd', self.lin_edge.weight.view(H, C, D).float(),
+                                                   self.att_edge[0].float()))
+            return Fn.GATZFn.apply(x, wc, v, self.bias, g, self.heads, self.negative_slope, p, ve, g.edge_rows("sl", edge_attr))
         if self._aggregate_first(x):
             wc, v = _cached_fold(self, 'wc_v', ps, x.dtype, lambda: self._wc_v(x.dtype))
             return Fn.GATZFn.apply(x, wc, v, self.bias, g, self.heads, self.negative_slope, p)

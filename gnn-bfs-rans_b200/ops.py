@@ -421,7 +421,18 @@ def gatw_gemm(x, rowptr, col, perm, alpha, wp, bias, n_rows, H, band=0, out=None
     return out
 
 
-def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, y_out, band=0, d_a_out=None):
+def edge_rows_sl(edge_attr, eid, rowptr, n_rows):
+    """GATConv(edge_dim): fp32 [nnz, 4] edge attributes in the order of the self-loop-replaced target-major CSR, the new
+    self loops filled with the mean attribute of the row's other entries (PyG fill_value='mean')."""
+    _cuda(edge_attr, eid, rowptr)
+    ea = edge_attr.detach().float().contiguous()
+    out = torch.empty((max(eid.numel(), 1), 4), dtype=torch.float32, device=eid.device)
+    _lib.check(_lib.load().b2g_edge_rows_sl(_p(ea), ea.shape[0], _p(eid), _p(rowptr), n_rows, _p(out), _stream()), "edge_rows_sl")
+    return out
+
+
+def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, y_out, band=0, d_a_out=None, edge_bias=None,
+             want_de=False):
     """Writes y = [sum_i alpha_ij1 g_i | ...] into y_out (a [N, H*C] view, any row stride) and the logit gradients
     d a = [d a_src | d a_dst] into d_a_out (a [N, 2H] view of dtype fp32 or x.dtype, any row stride; default: a new fp32
     tensor).  Returns d a."""
@@ -438,10 +449,10 @@ def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, 
     st = _stream()
     _lib.check(lib.b2g_gatz_bwd_dst(_p(x), _ld(x), _p(a), a.stride(0), _p(dz), _ld(dz), N, H, F, _dt(x), float(slope),
                                     _p(csr[0]), _p(csr[1]), _p(smax), _p(ssum), float(p_drop), int(seed), _p(alpha_e),
-                                    _p(de_e), _p(d_a), _ld(d_a), _dt(d_a), int(band), st), "gatz_bwd_dst")
+                                    _p(de_e), _p(d_a), _ld(d_a), _dt(d_a), _p(edge_bias), int(band), st), "gatz_bwd_dst")
     _lib.check(lib.b2g_gatz_bwd_src(_p(g), _ld(g), _p(alpha_e), _p(de_e), _p(y_out), _ld(y_out), _p(d_a), _ld(d_a), _dt(d_a),
                                     N, H, C, _dt(x), _p(csr_t[0]), _p(csr_t[1]), _p(perm), int(band), st), "gatz_bwd_src")
-    return d_a
+    return (d_a, de_e) if want_de else d_a                 # de_e: gradient of the logits in front of the LeakyReLU, [nnz, H]
 
 
 def seg_wsum4(x, w_e, rowptr, col, perm, out, d_a=None, band=0):
@@ -487,7 +498,7 @@ def edge_dot4(v, ea_csr, rowptr, H):
     """out[p, h] = v[i(p), 4h..4h+3] . ea_csr[p]: v fp32 [N, >= 4H] (any row stride), ea_csr fp32 [nnz, 4] -> fp32 [nnz, H]."""
     _cuda(v, ea_csr, rowptr)
     assert v.dtype == torch.float32 and ea_csr.dtype == torch.float32 and v.stride(1) == 1 and ea_csr.is_contiguous()
-    N = v.shape[0]
+    N = v.shape[0]                                          # v.stride(0) == 0 (an expanded [1, 4H] row): the same v for all nodes
     out = torch.empty((max(ea_csr.shape[0], 1), H), dtype=torch.float32, device=v.device)
     _lib.check(_lib.load().b2g_edge_dot4(_p(v), v.stride(0), _p(ea_csr), _p(rowptr), N, H, _p(out), _stream()), "edge_dot4")
     return out

@@ -204,8 +204,10 @@ int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda,
 int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, const void* dz, int64_t lddz,
                      int64_t n, int H, int F, int dt, float slope, const int32_t* rowptr, const int32_t* col,
                      const float* smax, const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* de_e,
-                     void* d_a, int64_t ldda, int d_a_dt, int64_t band, void* stream);
-/* d_a / d_a_dt: the [n, >= 2H] logit-gradient block, fp32 (B2G_F32) or bf16 (B2G_BF16: the column block of the bf16 dgrad
+                     void* d_a, int64_t ldda, int d_a_dt, const float* edge_bias, int64_t band, void* stream);
+/* edge_bias (may be NULL): GATConv(edge_dim) — fp32 [nnz, H], the edge term of the logits (added in front of the LeakyReLU,
+ * as b2g_gat_alpha does); de_e is then also the gradient of that term.
+ * d_a / d_a_dt: the [n, >= 2H] logit-gradient block, fp32 (B2G_F32) or bf16 (B2G_BF16: the column block of the bf16 dgrad
  * operand [y | d a], written in place); ldda = its row stride in elements of that type.
  * Source side: over the transposed CSR (rowptr_t, col_t, perm = position of each entry in the target-major CSR)
  * y[j] = [sum_i alpha_ij1 g_i | ... | sum_i alpha_ijH g_i] ([n, H*C], g = d out [*, C]) and d a_src into columns
@@ -264,6 +266,13 @@ int b2g_gat_alpha(const float* a_srcdst, int64_t lda, const int32_t* rowptr, con
 int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                   const float* alpha, const void* wp, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t n_rows,
                   int H, int F, int C, int dt, int64_t band, void* stream);
+
+/* GATConv(edge_dim = 4): edge attributes fp32 [E, 4] -> fp32 [nnz, 4] in the order of the self-loop-replaced
+ * target-major CSR (eid from b2g_csr_fill): dropped loops lose their attributes, every node's new loop gets the mean
+ * attribute of its incoming edges (PyG fill_value = 'mean'; 0 without any).  The logit term is then
+ * b2g_edge_dot4(v = We_h^T att_edge_h with ldv = 0, ...) -> the edge_bias input of b2g_gat_alpha / b2g_gatz_bwd_dst. */
+int b2g_edge_rows_sl(const float* edge_attr, int64_t E, const int32_t* eid, const int32_t* rowptr, int64_t n, float* out,
+                     void* stream);
 
 /* ===================================================================================== K5
  * TransformerConv (gnn_model.py:77-80,170) fused q.k score + segment-softmax + aggregate +

@@ -82,7 +82,7 @@ def gat_conv(x, edge_index, weight, att_src, att_dst, bias=None, heads=4, concat
     the self loops are dropped WITH their attributes, every node's new loop gets the mean attribute of its incoming edges
     (fill_value='mean'; 0 for a node without one), and alpha_edge = (lin_edge(edge_attr).view(-1,H,C) * att_edge).sum(-1)
     joins a_src[j] + a_dst[i] in front of the LeakyReLU.  The messages stay x_j W (no edge term).
-    (Oracle for the next step of SURVEY §8f-2: the product's GATConv raises NotImplementedError for edge_dim.)"""
+    (the product: nn.GATConv(edge_dim=4) -> functional.GATZFn with ve / ea.)"""
     N = x.shape[0]
     H = heads
     C = weight.shape[0] // H
@@ -174,7 +174,9 @@ def flow_gnn_forward(x, edge_index, params, layer_type, training=False, edge_att
         if layer_type == 'GCN':
             hn = gcn_conv(h, edge_index, p[g + 'lin.weight'], p[g + 'bias'])
         elif layer_type == 'GAT':
-            hn = gat_conv(h, edge_index, p[g + 'lin.weight'], p[g + 'att_src'], p[g + 'att_dst'], p[g + 'bias'])
+            hn = gat_conv(h, edge_index, p[g + 'lin.weight'], p[g + 'att_src'], p[g + 'att_dst'], p[g + 'bias'],
+                          edge_attr=edge_attr if (g + 'lin_edge.weight') in p else None,
+                          we=p.get(g + 'lin_edge.weight'), att_edge=p.get(g + 'att_edge'))
         elif layer_type == 'GIN':
             hn = gin_conv(h, edge_index, gin_mlp(p[g + 'nn.0.weight'], p[g + 'nn.0.bias'],
                                                  p[g + 'nn.2.weight'], p[g + 'nn.2.bias']))

@@ -42,7 +42,8 @@ def check_grads(pairs, dtype, pairs_bf16_oracle=None):
     in bf16) is 1.4-20e-2 off on exactly those tensors.  A tensor may therefore miss the strict gate only if
       (1) the bf16 CPU oracle misses 1e-2 on it as well (evidence that the tensor, not the kernel, is the problem), and
       (2a) for per-node gradients (x): the rows deviating by more than 2e-2 of the tensor's max are COUNTED — at most
-           max(3%, 2 x the bf16 oracle's own share + 1%) — and all other rows agree to 2e-2 in relative L2;
+           max(3%, 2 x the bf16 oracle's own share + 1%) — and all other rows agree to 2e-2 in relative L2 (or to what the
+           bf16 oracle's uncounted rows reach, if that is more);
       (2b) for parameter gradients (sums over all nodes): relative L2 <= 2 x the bf16 oracle's + 1e-2 and max-norm <= 2 x the
            bf16 oracle's + 2e-2."""
     scale = max(float(r.abs().max()) for _, r in pairs.values())
@@ -55,9 +56,10 @@ def check_grads(pairs, dtype, pairs_bf16_oracle=None):
         if dtype == torch.float32:
             assert err / gauge < 1e-5, f"grad {name}: {err / gauge:.3e}"
             continue
-        if float(ref.abs().max()) <= 5e-2 * scale:               # (near-)zero exact gradient: gauge = the layer's gradient scale
+        if float(ref.abs().max()) <= 1e-3 * scale:               # (near-)zero exact gradient: gauge = the layer's gradient scale
             assert err / gauge < 2e-2, f"grad {name}: max-norm {err / gauge:.3e} of the layer's gradient scale"
             continue
+        gauge = float(ref.abs().max())                           # every other tensor is measured against its own max
         l2 = rel_l2(mine, ref)
         if l2 < 2e-2 and err / gauge < 2e-2:
             continue                                             # strict gate met
@@ -74,7 +76,10 @@ def check_grads(pairs, dtype, pairs_bf16_oracle=None):
             share, o_share = float(bad.double().mean()), float(o_bad.double().mean())
             assert share <= max(0.03, 2 * o_share + 0.01), f"grad x: {share:.3%} of the rows off by > 2e-2 (bf16 oracle: {o_share:.3%})"
             rest = float((mine - ref)[~bad].norm() / ref[~bad].norm().clamp_min(1e-30))
-            assert rest < 2e-2, f"grad x: rows outside the counted ones: rel L2 {rest:.3e}"
+            o_rest = float((ob - ref)[~o_bad].norm() / ref[~o_bad].norm().clamp_min(1e-30))
+            # (GINConv: a flipped ReLU of the MLP moves its node's row by ~1/sqrt(width) of the row, below the counting
+            #  threshold but on many rows; the bf16 oracle's uncounted rows carry the same residue)
+            assert rest < max(2e-2, o_rest), f"grad x: rows outside the counted ones: rel L2 {rest:.3e} (bf16 oracle {o_rest:.3e})"
         else:
             assert l2 < 2 * o_l2 + 1e-2, f"grad {name}: rel L2 {l2:.3e} (bf16 oracle {o_l2:.3e})"
             assert err / gauge < 2 * o_max + 2e-2, f"grad {name}: max-norm {err / gauge:.3e} (bf16 oracle {o_max:.3e})"
@@ -353,3 +358,79 @@ def test_transformer_edge_features_argument_errors():
     m32 = b2g.nn.TransformerConv(32, 32, heads=4, concat=False, edge_dim=4).cuda()      # 128-byte rows: no aggregate-first kernel
     with pytest.raises(NotImplementedError):
         m32(torch.randn(50, 32, device="cuda"), ei, edge_attr=torch.randn(200, 4, device="cuda"))
+
+
+@pytest.mark.parametrize("dtype,F", [(torch.float32, 128), (torch.float32, 256), (torch.bfloat16, 256)])
+@pytest.mark.parametrize("N,E", [(300, 2500), (1000, 3000), (2000, 30000), (40, 0)])
+def test_gat_edge_features_forward_and_grads(dtype, F, N, E):
+    """GATConv(edge_dim=4): (lin_edge(edge_attr) . att_edge) joins the logits in front of the LeakyReLU, given
+    self loops are dropped with their attributes and every node's new loop carries the mean attribute of its incoming edges
+    (PyG fill_value='mean').  Computed as ve_h . e_ij with ve_h = We_h^T att_edge_h (b2g_edge_rows_sl, b2g_edge_dot4,
+    b2g_gat_alpha; bf16 F = 256 also through the fused b2g_gatw_gemm).  Rows of every length class incl. a hub target and
+    nodes whose only incoming edge is a dropped loop."""
+    import gnn_bfs_rans_b200 as b2g
+    from oracle import layers_oracle as lo
+    ei = multigraph(N, E, N + E) if E else torch.zeros((2, 0), dtype=torch.long)
+    torch.manual_seed(4321)
+    m = b2g.nn.GATConv(F, F, heads=4, concat=False, dropout=0.1, edge_dim=4)
+    with torch.no_grad():
+        m.bias.uniform_(-0.5, 0.5)
+    m = m.cuda().to(dtype).eval()
+    assert set(m.state_dict().keys()) == {"att_src", "att_dst", "att_edge", "bias", "lin.weight", "lin_edge.weight"}
+    torch.manual_seed(11)
+    x = torch.randn(N, F).to(dtype)
+    ea = torch.randn(ei.shape[1], 4).to(dtype)
+    xg = x.cuda().requires_grad_(True)
+    out = m(xg, ei.cuda(), edge_attr=ea.cuda())
+    assert out.dtype == dtype and out.shape == (N, F)
+    gout = torch.randn(out.shape).to(dtype)
+    out.backward(gout.cuda())
+
+    def oracle(dt, xin):
+        p = {k: v.detach().cpu().to(dt).requires_grad_(True) for k, v in m.state_dict().items()}
+        o = lo.gat_conv(xin, ei, p["lin.weight"], p["att_src"], p["att_dst"], p["bias"], heads=4, concat=False,
+                        edge_attr=ea.to(dt), we=p["lin_edge.weight"], att_edge=p["att_edge"])
+        return o, p
+
+    x64 = x.double().requires_grad_(True)
+    ref, p = oracle(torch.float64, x64)
+    ref.backward(gout.double())
+    assert rel(out.detach(), ref.detach()) < TOL[dtype], "forward"
+    pairs = {"x": (xg.grad, x64.grad)}
+    for name, par in m.named_parameters():
+        if par.grad is None:
+            assert p[name].grad is None or float(p[name].grad.abs().max()) == 0.0, name
+            continue
+        pairs[name] = (par.grad, p[name].grad)
+    if E:
+        for k in ("lin_edge.weight", "att_edge"):
+            assert k in pairs and float(pairs[k][0].abs().max()) > 0, k
+    pb = None
+    if dtype == torch.bfloat16:
+        xb = x.clone().requires_grad_(True)
+        refb, pbp = oracle(torch.bfloat16, xb)
+        refb.backward(gout)
+        pb = {"x": xb.grad}
+        pb.update({n: pbp[n].grad for n in pbp if pbp[n].grad is not None})
+    check_grads(pairs, dtype, pb)
+    if E:                                   # the edge terms matter; edge_attr=None is the plain layer
+        with torch.no_grad():
+            plain = m(x.cuda(), ei.cuda())
+        assert rel(out.detach(), plain.double().cpu()) > 1e-3
+
+
+def test_gat_edge_features_argument_errors():
+    import gnn_bfs_rans_b200 as b2g
+    with pytest.raises(NotImplementedError):
+        b2g.nn.GATConv(128, 128, heads=4, concat=False, edge_dim=3)
+    with pytest.raises(NotImplementedError):
+        b2g.nn.GATConv(128, 128, heads=2, concat=True, edge_dim=4)
+    m = b2g.nn.GATConv(128, 128, heads=4, concat=False, edge_dim=4).cuda()
+    ei = multigraph(50, 200, 1).cuda()
+    x = torch.randn(50, 128, device="cuda")
+    with pytest.raises(ValueError):
+        m(x, ei, edge_attr=torch.randn(199, 4, device="cuda"))
+    plain = b2g.nn.GATConv(128, 128, heads=4, concat=False).cuda()
+    with pytest.warns(UserWarning):
+        a = plain(x, ei, edge_attr=torch.randn(200, 4, device="cuda"))       # edge_dim=None: PyG ignores the attribute
+    assert torch.equal(a, plain(x, ei))

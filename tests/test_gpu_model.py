@@ -20,7 +20,7 @@ def grid_graph(nx, ny):
     return o[order].astype(np.int32), n[order].astype(np.int32)
 
 
-@pytest.mark.parametrize("layer_type", ["GCN", "GAT", "GIN", "Transformer", "Transformer+edge"])
+@pytest.mark.parametrize("layer_type", ["GCN", "GAT", "GIN", "Transformer", "Transformer+edge", "GAT+edge"])
 @pytest.mark.parametrize("training", [False, True])
 def test_flowgnn_matches_oracle(layer_type, training):
     # "Transformer+edge": FlowGNN(edge_dim=4), the Transformer layers consume the edge_attr the reference passes (§8f-2)
@@ -49,6 +49,7 @@ def test_flowgnn_matches_oracle(layer_type, training):
     ref.square().mean().backward()
     if edge_dim:
         assert model.gnn_layers[0].lin_edge.weight.grad is not None and 'gnn_layers.0.lin_edge.weight' in p
+        assert float(model.gnn_layers[0].lin_edge.weight.grad.abs().max()) > 0
     # whole-model gate: L layers + BatchNorm + head in fp32 (torch ops of the caller included), so the
     # per-layer 1e-5 compounds; gradients are gauged against the largest gradient of the model because
     # several (biases in front of a BatchNorm) are zero in exact arithmetic.
@@ -200,7 +201,7 @@ def test_flowgnn_on_the_shipped_graph_cfg1_cfg2(layer_type, dtype, training, gol
     L = 4, GCN and GAT (4 heads), eval and train mode (batch statistics), fp32 and bf16, against oracle.flow_gnn_forward in
     fp64 on identical weights and inputs.
     fp32: forward <= 2e-5 (four layers + BatchNorm + head compound the per-layer 1e-5); input gradients: rows touched by a
-    ReLU that flips between fp32 and fp64 are counted (<= 5 %), every other row agrees to 1e-4 in relative L2.
+    ReLU that flips between fp32 and fp64 are counted (<= 5 %), every other row agrees to 1e-4 (eval) / 3e-4 (train) in relative L2.
     bf16: forward <= 2e-2, or — train mode, where BatchNorm divides by the batch standard deviation of channels that the
     rank-3 input leaves almost constant — <= 1.5 x the error the SAME oracle makes when executed in bf16 on the CPU (measured:
     8e-2 GCN / 2.2e-1 GAT for the CPU bf16 oracle, 7e-2 / 2.2e-1 for the kernels)."""
@@ -231,7 +232,8 @@ def test_flowgnn_on_the_shipped_graph_cfg1_cfg2(layer_type, dtype, training, gol
         gx, gr = xg.grad.double().cpu(), x64.grad
         bad = (gx - gr).abs().max(1).values > 1e-4 * gr.abs().max()
         assert int(bad.sum()) <= (5 * gx.shape[0]) // 100, int(bad.sum())
-        assert float((gx - gr)[~bad].norm() / gr[~bad].norm()) < 1e-4
+        # train mode: 1 / sqrt(batch variance) of the almost-constant channels amplifies fp32 rounding (forward 4e-6 -> 1e-4 here)
+        assert float((gx - gr)[~bad].norm() / gr[~bad].norm()) < (3e-4 if training else 1e-4)
         scale = max(float(p[n].grad.abs().max()) for n in pn if p[n].grad is not None)
         for name, par in model.named_parameters():
             if par.grad is not None and p[name].grad is not None:
