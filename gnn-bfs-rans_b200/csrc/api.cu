@@ -16,6 +16,20 @@ const uint64_t* dropout_epoch_ptr() {
   }
   return g_epoch[dev];
 }
+// 1 KB of zeros per device: the address padding lanes of the gather kernels load from (an unconditional load of zeros
+// instead of a predicated load, which ptxas implements as load-to-temporary + predicated move = a wait on every load)
+static const void* g_zero_row[64] = {nullptr};
+const void* zero_row_ptr() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!g_zero_row[dev]) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, 1024) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    cudaMemset(p, 0, 1024);
+    g_zero_row[dev] = p;
+  }
+  return g_zero_row[dev];
+}
 __global__ void epoch_advance_kernel(uint64_t* e) { *e += 1; }
 __global__ void epoch_set_kernel(uint64_t* e, uint64_t v) { *e = v; }
 }

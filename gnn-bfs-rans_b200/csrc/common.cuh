@@ -322,6 +322,7 @@ __device__ __forceinline__ void warp_sum4(float& a, float& b, float& c, float& d
 // b2g_dropout_epoch_advance (one tiny launch, captured at the top of a training-step graph) increments it.  The epoch is 0
 // until advanced, so eager runs draw exactly the masks their seeds define; forward and backward of one step see the
 // same epoch.
+const void* zero_row_ptr();                   // host: 1 KB of zeros on this device (allocated on first use), api.cu
 const uint64_t* dropout_epoch_ptr();          // host: this device's epoch word (allocated on first use), api.cu
 __device__ __forceinline__ uint64_t mix_epoch(uint64_t seed, const uint64_t* epoch) {
   return epoch ? seed ^ (__ldg(epoch) * 0xD1B54A32D192ED03ull) : seed;

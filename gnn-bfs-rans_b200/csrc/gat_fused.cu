@@ -51,19 +51,21 @@ struct GfArgs {
   const int32_t* rowptr; const int32_t* col; const int32_t* perm;
   const float* alpha;                            // fp32 [nnz, 4]: weight of (entry, head); entry = perm[pos] or pos
   const float* bias;                             // fp32 [m] or NULL
+  const char* zero;                              // >= 512 bytes of zeros (padding lanes load from here)
   __nv_bfloat16* out; int64_t ldo;
   uint32_t n_rows; int m;
   RowSched ord;                                  // chunk_rows = GF_BM
 };
 
-__device__ __forceinline__ uint4 gf_ldg_if(const char* p, bool pred) {
+// Load of entry t of a row, or of zeros when the row has no entry t.  NOT a predicated load: ptxas turns `@p ld` with a
+// zero-initialised destination into load-to-temporary + predicated move, and that move waits for the load right behind it
+// (ncu on the first versions: every gather load was followed by a long-scoreboard stall = one load in flight per warp).
+// The padding lanes load from a zero row instead (always an L1 hit), so the load is unconditional and nothing depends on it
+// until the FMAs consume it.
+__device__ __forceinline__ uint4 gf_ldg_sel(const char* p, const char* zero, bool valid) {
+  const char* q = valid ? p : zero;
   uint4 u;
-  asm volatile(
-      "{\n .reg .pred q;\n setp.ne.b32 q, %5, 0;\n"
-      " mov.b32 %0, 0;\n mov.b32 %1, 0;\n mov.b32 %2, 0;\n mov.b32 %3, 0;\n"
-      " @q ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];\n}"
-      : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-      : "l"(p), "r"((uint32_t)pred));
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(q));
   return u;
 }
 
@@ -81,15 +83,15 @@ __device__ __forceinline__ void gf_fma(float (&acc)[GF_H][8], const float4& w, c
 // the first K (<= 8) entries of the 4 rows of a unit: K loads in flight per lane, then K x (LDS.128 weights, FMA)
 template <int K>
 __device__ __forceinline__ void gf_gather(float (&acc)[GF_H][8], const char* xk, uint32_t xrow_bytes, int cl, int len,
-                                          int grp_lane0, const float4* wrow) {
+                                          int grp_lane0, const float4* wrow, const char* zero) {
   uint4 buf[K];
 #pragma unroll
   for (int t = 0; t < K; ++t) {
     const uint32_t c = (uint32_t)__shfl_sync(0xffffffffu, cl, grp_lane0 + t);
-    buf[t] = gf_ldg_if(xk + (uint64_t)c * xrow_bytes, t < len);
+    buf[t] = gf_ldg_sel(xk + (uint64_t)c * xrow_bytes, zero, t < len);
   }
 #pragma unroll
-  for (int t = 0; t < K; ++t) gf_fma(acc, wrow[t], buf[t]);
+  for (int t = 0; t < K; ++t) gf_fma(acc, wrow[t * 4], buf[t]);   // staged [entry][row]: the 4 rows of a warp read 64 contiguous bytes
 }
 
 __global__ void __launch_bounds__(GF_THREADS, 1)
@@ -247,8 +249,9 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
     const int gw = warp - 8;
     const int r4 = lane >> 3, p = lane & 7;
-    float4* wrow_base = reinterpret_cast<float4*>(smem_raw + (wst - smem_base) + gw * GF_WST_WARP);   // [unit][r4][entry]
+    float4* wrow_base = reinterpret_cast<float4*>(smem_raw + (wst - smem_base) + gw * GF_WST_WARP);   // [unit][entry][r4]
     const char* xl = a.x + p * 16;
+    const char* zl = a.zero + p * 16;
     uint32_t g = 0;
     for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
       uint32_t rows;
@@ -277,7 +280,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
           w4 = __ldg(reinterpret_cast<const float4*>(a.alpha) + pi);
         }
         cl[u] = c;
-        wrow_base[(u * 4 + r4) * 8 + p] = w4;
+        wrow_base[(u * 8 + p) * 4 + r4] = w4;             // [unit][entry][row]: conflict-free LDS.128 in the FMA loop
         int ml = len[u];
         ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, 8));
         ml = max(ml, __shfl_xor_sync(0xffffffffu, ml, 16));
@@ -295,10 +298,10 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
           for (int h = 0; h < GF_H; ++h)
 #pragma unroll
             for (int k = 0; k < 8; ++k) acc[h][k] = 0.f;
-          const float4* wrow = wrow_base + (u * 4 + r4) * 8;
+          const float4* wrow = wrow_base + u * 32 + r4;
           const int g0 = lane & 24;
           switch (min(mlen[u], 8)) {                                      // warp-uniform
-#define B2G_CASE(KK) case KK: gf_gather<KK>(acc, xk, a.xrow_bytes, cl[u], len[u], g0, wrow); break;
+#define B2G_CASE(KK) case KK: gf_gather<KK>(acc, xk, a.xrow_bytes, cl[u], len[u], g0, wrow, zl); break;
             B2G_CASE(1) B2G_CASE(2) B2G_CASE(3) B2G_CASE(4) B2G_CASE(5) B2G_CASE(6) B2G_CASE(7) B2G_CASE(8)
 #undef B2G_CASE
             default: break;
@@ -492,6 +495,8 @@ int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32
   if (!tc_make_map_bf16(&map_w, wp, C, (int64_t)H * F, ldw, GF_BN)) return B2G_E_UNSUPPORTED;
   a.x = static_cast<const char*>(x); a.xrow_bytes = (uint32_t)(ldx * 2);
   a.rowptr = rowptr; a.col = col; a.perm = perm; a.alpha = alpha; a.bias = bias;
+  a.zero = static_cast<const char*>(zero_row_ptr());
+  if (!a.zero) return B2G_E_UNSUPPORTED;
   a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.n_rows = (uint32_t)n_rows; a.m = C;
   const unsigned grid = a.ord.n_chunks < (uint32_t)B2G_NUM_SMS ? a.ord.n_chunks : (unsigned)B2G_NUM_SMS;
   gatw_gemm_kernel<<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, a);
