@@ -215,6 +215,44 @@ def halo_check(b2g, layer, layer_name, world, rank, dev, dtype, tol):
             "max_rel_all_rows": mx, "max_rel_cut_planes": mxc, "rows_not_bit_equal": int(allr[:, 2].sum()), "tol": tol,
             "ok": bool(mx < tol), "compares": "partitioned (wrap_forward + NCCL halo exchange) vs monolithic, same kernels"}
 
+def run_strong_scaling(b2g, ops, layer, layer_name, world, rank, dev, dtype, timed, steps):
+    """BASELINE cfg4 as written: ONE 250x200x200 (10 M-cell) mesh cut by recursive coordinate bisection of the cell centres
+    into `world` parts (2x2x2 blocks of 125x100x100 at 8), general partitioner (distributed.rcb_partition + build_partition:
+    every rank derives its share and the halo plan from the global edge list, no communication), one halo exchange per
+    layer over NCCL.  Fixed total work: "scaling": "strong"."""
+    import torch
+    import torch.distributed as dist
+    from gnn_bfs_rans_b200.distributed import build_partition, rcb_partition
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    ng = NX * NY * NZ
+    o, n = hex_mesh_faces(NX, NY, NZ, device=dev)
+    ei = ops.build_graph_edges(o, n, 1, None, ng, ng)
+    del o, n
+    ids = torch.arange(ng, device=dev)
+    centers = torch.stack([(ids % NX).float(), ((ids // NX) % NY).float(), (ids // (NX * NY)).float()], dim=1) + 0.5
+    del ids
+    t0 = time.perf_counter()
+    pv = rcb_partition(centers, world)
+    part = build_partition(ei, pv, rank, world, device=dev)
+    torch.cuda.synchronize()
+    t_part = time.perf_counter() - t0
+    del ei, pv, centers
+    torch.cuda.empty_cache()
+    torch.manual_seed(4321 + rank)
+    x = torch.randn(part.n_local, F, device=dev).to(dtype)
+    fwd = part.wrap_forward(layer)
+    ms = timed(lambda: fwd(x, part.edge_index), steps, 3)
+    t = torch.tensor([part.aggregated_edges(layer_name), part.n_owned, part.n_ghost], device=dev, dtype=torch.int64)
+    mx = t.clone()
+    dist.all_reduce(t)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    return {"scaling": "strong", "mesh": f"{NX}x{NY}x{NZ} hex = {ng} cells in total", "partition": f"RCB into {world} parts "
+            "(distributed.rcb_partition + build_partition), 1-ring halo exchange per layer (NCCL)", "n_gpus": world,
+            "layer": f"{layer_name}Conv({F},{F}) forward", "cells_per_gpu_max": int(mx[1]), "ghost_rows_per_gpu_max": int(mx[2]),
+            "edges_per_step": int(t[0]), "ms_per_step": ms, "edges_per_sec": int(t[0]) / (ms * 1e-3),
+            "partition_build_s": t_part}
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     args = parse()
@@ -458,12 +496,26 @@ def main():
         extras = run_extras(b2g, ops, part, dev, timed)
         extras.update(run_mesh_ingest(b2g, dev, timed, (nx, ny, nz)))
 
-    # ---- opt-in: cfg5-shaped train step, partitioned (halo exchange per layer, synchronised BatchNorm, gradient all-reduce)
+    # ---- BASELINE cfg4 as a strong-scaling problem (one 10 M-cell mesh, RCB), N > 1
+    strong = None
+    if world > 1 and not args.no_extras:
+        try:
+            del x
+            torch.cuda.empty_cache()
+            strong = run_strong_scaling(b2g, ops, layer, args.layer, world, rank, dev, dtype, timed, args.steps)
+        except Exception as e:
+            strong = {"error": str(e)[:200]}
+        x = None
+
+    # ---- cfg5-shaped train step, partitioned (halo exchange per layer, synchronised BatchNorm, gradient all-reduce):
+    # part of the default line at N = 8 (BASELINE cfg5: 100 M cells = 12.5 M per GPU, GAT L = 6, F = 256, bf16); opt-in elsewhere
     train_line = None
+    if world == 8 and not args.no_extras and not args.train_step:
+        args.train_step, args.train_checkpoint, args.train_cells = True, True, 12500000
     if args.train_step:
         from gnn_bfs_rans_b200.distributed import flow_forward_partitioned, allreduce_gradients
         from gnn_bfs_rans_b200.flow_model import FlowGNN
-        del x
+        x = None
         torch.cuda.empty_cache()
         nzs = max(2, args.train_cells // (nx * ny))
         tpart = slab_partition_hex(nx, ny, nzs, world, rank, dev)
@@ -520,6 +572,8 @@ def main():
                            "cache_policy": "inputs (>5 GB) larger than the 126 MB L2; CSR cached across steps in `value`"},
                 "parity_check": parity, "halo_check": halo, "clocks": clk, "e2e": e2e, "gpu_launches": int(round(launches_per_step * args.steps)),
                 "gpu_launches_per_step": launches_per_step, "roofline": roof, "cpu_baseline": cb, "extras": extras}
+        if strong is not None:
+            line["strong_scaling_cfg4"] = strong
         if train_line is not None:
             line["train_step_partitioned"] = train_line
         print(json.dumps(line))

@@ -159,10 +159,10 @@ class Partition:
             return lambda x, ei: layer(x, ei)
         holder = {}
         from .nn import GCNConv
-        # opt-in: measured at N = 2 on cfg4 it changes nothing (4.54 ms against 4.50 ms with the blocking exchange: the
-        # 9.6 MB exchange is not what the N = 2 step loses against N = 1), so the blocking path stays the default
+        # GCNConv inference: the exchange (pack + NCCL send/recv on a side stream) runs behind the projection of the owned
+        # rows; bit-equal with the blocking path (2-GPU test).  B2G_HALO_OVERLAP=0 selects the blocking exchange for A/B runs.
         overlapped = (self._gcn_forward_overlapped(layer, holder)
-                      if isinstance(layer, GCNConv) and os.environ.get("B2G_HALO_OVERLAP", "0") == "1" else None)
+                      if isinstance(layer, GCNConv) and os.environ.get("B2G_HALO_OVERLAP", "1") != "0" else None)
 
         def fwd(x, ei):
             if overlapped is not None and x.is_cuda and not (torch.is_grad_enabled() and (
