@@ -779,10 +779,23 @@ def run_extras(b2g, ops, part, dev, timed):
                     del gts, opt_c
                 except Exception as e:
                     ms_tg = "error: " + str(e)[:120]
+                ms_tf = None
+                if dt_name == "fp32":
+                    try:                # + the reference's criterion and clip + Adam as fused kernels (training.py), fused glue
+                        torch.manual_seed(0)
+                        mf = FlowGNN(3, 128, 7, 4, lt, dropout=0.1, fused_glue=True).to(dev).train()
+                        crit = b2g.training.WeightedMSELoss()
+                        opt_f = b2g.training.FusedClipAdam(mf.parameters(), lr=3e-4, weight_decay=1e-5, max_grad_norm=1.0)
+                        gtf = b2g.graphs.GraphedTrainStep(mf, opt_f, lambda o, t: crit(o, t, pressure_ref_weight=0.1), xin, y, ei2)
+                        ms_tf = timed_grad(lambda: gtf.step(xin, y), 50, 5)
+                        del gtf, opt_f, mf
+                    except Exception as e:
+                        ms_tf = "error: " + str(e)[:120]
                 out[f"cfg2_shipped_BFS_FlowGNN_{lt}_L4_F128_{dt_name}"] = {"cells": n2, "edges": int(ei2.shape[1]),
                                                                            "forward_ms": ms_f, "forward_cuda_graph_ms": ms_g,
                                                                            "train_step_ms": ms_t,
-                                                                           "train_step_cuda_graph_ms": ms_tg}
+                                                                           "train_step_cuda_graph_ms": ms_tg,
+                                                                           "train_step_cuda_graph_fused_loss_adam_ms": ms_tf}
                 del model, opt
     except Exception as e:
         out["cfg2_shipped_BFS"] = {"error": str(e)[:200]}

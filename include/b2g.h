@@ -384,6 +384,30 @@ int b2g_mesh_cell_centers(const double* points, int64_t n_points, const int32_t*
 int b2g_mesh_internal_cells(const int32_t* owner, int64_t n_owner, const int32_t* neighbour, int64_t n_nb, int64_t n_cells,
                             uint8_t* mask, int64_t* n_bad_out, void* ws, void* stream);
 
+/* ===================================================================================== training glue
+ * Device side of torch_geometric.data.Batch.from_data_list (train.py:155): after the B samples' edge_index blocks have been
+ * copied into place ([2, e_tot] row-major, sample s at columns edge_ptr[s]..edge_ptr[s+1]), add sample s's node offset
+ * node_ptr[s] to its entries and write the per-node graph id vector batch[n_tot] (batch may be NULL).  edge_ptr / node_ptr:
+ * int64 [B + 1] on the device. */
+int b2g_batch_finalize(int64_t* edge_index, int64_t e_tot, const int64_t* edge_ptr, const int64_t* node_ptr, int n_graphs,
+                       int64_t* batch, int64_t n_tot, void* stream);
+
+/* The reference's field-wise weighted MSE loss (normalization.py:177-236, use_fieldwise=True): columns U(3) p k epsilon nut,
+ * loss = sum_f w_f mean_f((pred - target)^2) + w_p * prw * (mean pred_p - mean target_p)^2.  field_weights: fp32 [5] (device);
+ * loss: fp32 [1]; coef: fp32 [8] handed to b2g_wmse_bwd, which writes d loss / d pred * grad_out[0] (grad_out NULL = 1). */
+int64_t b2g_wmse_workspace_bytes(void);
+int b2g_wmse_fwd(const void* pred, int64_t ldp, const void* target, int64_t ldt, int64_t n, int dt, const float* field_weights,
+                 float pressure_ref_weight, float* loss, float* coef, void* ws, void* stream);
+int b2g_wmse_bwd(const void* pred, int64_t ldp, const void* target, int64_t ldt, int64_t n, int dt, const float* coef,
+                 const float* grad_out, void* dpred, int64_t ldd, void* stream);
+
+/* clip_grad_norm_(max_norm) + torch.optim.Adam(lr, betas, eps, weight_decay).step() (train.py:188-189) over ONE flat fp32
+ * parameter / gradient / moment buffer: gradient norm (two-stage, deterministic), clip coefficient, Adam update, step counter.
+ * state: fp32 [2] on the device = (steps taken, gradient norm of the last step); max_norm <= 0 = no clipping. */
+int64_t b2g_adam_workspace_bytes(void);
+int b2g_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm, float lr,
+                       float beta1, float beta2, float eps, float weight_decay, float* state, void* ws, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
