@@ -447,11 +447,8 @@ def main():
                 ei_keep = part.edge_index
             elif world == 1:
                 def e2e_step():
-                    dx = hx.to(dev, non_blocking=True)
-                    dei = hei.to(dev, non_blocking=True)
-                    o = layer(dx, dei)
-                    hout.copy_(o, non_blocking=True)
-                e2e_api = "layer(x.to(dev), edge_index.to(dev)) -> pinned host copy"
+                    b2g.streaming.forward_host(layer, hx, hei, hout)
+                e2e_api = "gnn_bfs_rans_b200.streaming.forward_host(layer, x_host, edge_index_host, out_host)"
             else:
                 ei_keep = part.edge_index
 
@@ -680,6 +677,34 @@ def run_extras(b2g, ops, part, dev, timed):
             except Exception as e:  # an extra must never take the headline down
                 out[key] = {"error": str(e)[:200]}
             torch.cuda.empty_cache()
+
+    # host-buffer (e2e) entry for the other layer types: streaming.forward_host from pinned host buffers, copies in the timed region
+    try:
+        hei = torch.empty(tuple(ei.shape), dtype=torch.int64, pin_memory=True)
+        hei.copy_(ei)
+        hx = torch.empty((N, F), dtype=torch.bfloat16, pin_memory=True).normal_()
+        hout = torch.empty((N, F), dtype=torch.bfloat16, pin_memory=True)
+        for lt in ("GAT", "GIN", "Transformer"):
+            torch.manual_seed(0)
+            layer = mk(lt).to(dev).to(torch.bfloat16).eval()
+            for _ in range(2):
+                b2g.streaming.forward_host(layer, hx, hei, hout)
+            torch.cuda.synchronize()
+            import time as _t
+            t0 = _t.perf_counter()
+            for _ in range(3):
+                b2g.streaming.forward_host(layer, hx, hei, hout)
+            torch.cuda.synchronize()
+            ms = (_t.perf_counter() - t0) / 3 * 1e3
+            e_agg = part.aggregated_edges(lt)
+            out[f"{lt}_bf16_e2e_host"] = {"ms": ms, "edges_per_sec": e_agg / (ms * 1e-3),
+                                          "h2d_bytes": hx.numel() * 2 + hei.numel() * 8, "d2h_bytes": hout.numel() * 2,
+                                          "api": "streaming.forward_host"}
+            del layer
+        del hx, hei, hout
+    except Exception as e:
+        out["e2e_host_layers"] = {"error": str(e)[:200]}
+    torch.cuda.empty_cache()
 
     # TransformerConv(edge_dim=4): the same layer consuming [dir, dist] edge attributes of the mesh
     try:

@@ -356,7 +356,7 @@ struct AlphaArgs {
   const float* ebias;                        // fp32 [nnz, 4] added to the logits before the LeakyReLU (edge features) or NULL
   float* alpha;                              // [nnz, 4]
   float* smax; float* ssum;                  // [N, 4] or NULL
-  uint32_t n_rows;
+  uint32_t n_rows, row0;                     // rows [row0, row0 + n_rows) of the problem (all arrays are indexed globally)
   float slope, p_drop;
   uint64_t seed; const uint64_t* epoch;
 };
@@ -366,7 +366,7 @@ __device__ __forceinline__ float gf_lrelu(float s, float slope) { return s > 0.f
 __global__ void __launch_bounds__(256) gat_alpha_kernel(const AlphaArgs a) {
   const uint64_t total = (uint64_t)a.n_rows * GF_H;
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (uint64_t)gridDim.x * blockDim.x) {
-    const uint32_t i = (uint32_t)(t >> 2);
+    const uint32_t i = a.row0 + (uint32_t)(t >> 2);
     const int h = (int)(t & 3);
     const int b = __ldg(a.rowptr + i), e = __ldg(a.rowptr + i + 1);
     const int len = e - b;
@@ -505,13 +505,13 @@ int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32
 }
 
 int b2g_gat_alpha(const float* a_srcdst, int64_t lda, const int32_t* rowptr, const int32_t* col, const float* edge_bias,
-                  int64_t n, int H, float slope, float p_drop, uint64_t seed, float* alpha, float* smax, float* ssum,
+                  int64_t row0, int64_t n, int H, float slope, float p_drop, uint64_t seed, float* alpha, float* smax, float* ssum,
                   void* stream) {
-  if (n < 0 || H != GF_H) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n < 0 || row0 < 0 || row0 + n >= (1ll << 32) || H != GF_H) return (n < 0 || row0 < 0) ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   if (!a_srcdst || !rowptr || !col || !alpha || (smax == nullptr) != (ssum == nullptr)) return B2G_E_ARG;
   if (lda < 2 * GF_H || lda >= (1ll << 32) || n >= (1ll << 32)) return B2G_E_SHAPE;
-  AlphaArgs a{a_srcdst, (uint32_t)lda, rowptr, col, edge_bias, alpha, smax, ssum, (uint32_t)n, slope, p_drop, seed,
+  AlphaArgs a{a_srcdst, (uint32_t)lda, rowptr, col, edge_bias, alpha, smax, ssum, (uint32_t)n, (uint32_t)row0, slope, p_drop, seed,
               dropout_epoch_ptr()};
   const int64_t want = ceil_div(n * GF_H, 256);
   const int64_t cap = (int64_t)B2G_NUM_SMS * 16;

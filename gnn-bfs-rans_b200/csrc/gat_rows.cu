@@ -102,6 +102,8 @@ __device__ __forceinline__ void ld16_rows(const char* p, float (&f)[Vec<T>::N]) 
 
 struct GatzArgs {
   const void* x; uint32_t xrow_bytes;        // gathered rows [*, F] (fwd / bwd_dst: x; bwd_src: g = d out)
+  const void* x_self;                        // tz_fwd: the target rows' own features (row i of THIS call); == x unless the call
+                                             // covers a row range of a larger problem (streaming.py)
   const float* a; uint32_t lda;              // fp32 [N, >= 2H]: columns 0..H-1 a_src, H..2H-1 a_dst (stride in floats)
   void* z; uint32_t zrow_bytes;              // fwd: z [N, H*F];  bwd_src: y [N, H*C]
   const void* dz; uint32_t dzrow_bytes;      // bwd_dst: dz [N, H*F]
@@ -806,7 +808,7 @@ __device__ __forceinline__ void tz_store_tail(const GatzArgs& a, uint32_t i, int
     o.from_float(f);
     *reinterpret_cast<uint4*>(zrow + lane * 16) = *reinterpret_cast<uint4*>(&o.v);
   }
-  const char* xi = reinterpret_cast<const char*>(a.x) + (uint64_t)i * a.xrow_bytes + lane * 16;
+  const char* xi = reinterpret_cast<const char*>(a.x_self) + (uint64_t)i * a.xrow_bytes + lane * 16;
 #pragma unroll
   for (int v = 0; v < VPL; ++v)
     __stcs(reinterpret_cast<uint4*>(zrow + 8 * sizeof(T) + v * 512 + lane * 16), ldg_row16(xi + 512 * v));
@@ -1366,9 +1368,9 @@ int b2g_edge_wsum4(const float* w, const float* ea_csr, const int32_t* rowptr, i
 }
 
 /* TransformerConv, aggregate-first (see tz_fwd_kernel).  u [n, H*F] = x Mq + cq; z_aug [n, H*F + 8 + F]. */
-int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_aug, int64_t ldz, int64_t n, int H, int F,
-               int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, const float* edge_bias, float p_drop,
-               uint64_t seed, int64_t band, void* stream) {
+int b2g_tz_fwd(const void* x, int64_t ldx, const void* x_self, const void* u, int64_t ldu, void* z_aug, int64_t ldz, int64_t n,
+               int H, int F, int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, const float* edge_bias,
+               float p_drop, uint64_t seed, int64_t band, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
@@ -1381,7 +1383,8 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_a
   GatzArgs a{};
   const int rc = gatz_common(a, n, F, dt, band);
   if (rc) return rc;
-  a.x = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = u; a.dzrow_bytes = (uint32_t)(ldu * es); a.z = z_aug;
+  if (x_self && !aligned16(x_self)) return B2G_E_ALIGN;
+  a.x = x; a.x_self = x_self ? x_self : x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = u; a.dzrow_bytes = (uint32_t)(ldu * es); a.z = z_aug;
   a.zrow_bytes = (uint32_t)(ldz * es); a.rowptr = rowptr; a.col = col; a.alpha_e = alpha_e; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   a.ebias = edge_bias;
   return gatz_dispatch(3, dt, F * es, a, (cudaStream_t)stream);

@@ -393,15 +393,16 @@ def gatw_gemm_supported(n: int, H: int, F: int, C: int, dtype) -> bool:
     return dt >= 0 and bool(_lib.load().b2g_gatw_gemm_supported(int(max(n, 1)), int(H), int(F), int(C), dt))
 
 
-def gat_alpha(a, rowptr, col, H, slope, p_drop, seed, save_stats, edge_bias=None):
+def gat_alpha(a, rowptr, col, H, slope, p_drop, seed, save_stats, edge_bias=None, rows=None, alpha_out=None):
     """Post-dropout attention weights alpha fp32 [nnz, H] in target-major CSR order (+ softmax max / sum [N, H] | None)
     from a = [a_src | a_dst] fp32 [N, 2H]  (csrc/gat_fused.cu gat_alpha_kernel)."""
     _cuda(a, rowptr, col)
     N = a.shape[0]
-    alpha = torch.empty((max(col.numel(), 1), H), dtype=torch.float32, device=a.device)
+    r0, n = (0, rowptr.numel() - 1) if rows is None else (rows[0], rows[1] - rows[0])      # rows = (r0, r1): a row range
+    alpha = alpha_out if alpha_out is not None else torch.empty((max(col.numel(), 1), H), dtype=torch.float32, device=a.device)
     smax = torch.empty((N, H), dtype=torch.float32, device=a.device) if save_stats else None
     ssum = torch.empty((N, H), dtype=torch.float32, device=a.device) if save_stats else None
-    _lib.check(_lib.load().b2g_gat_alpha(_p(a), a.stride(0), _p(rowptr), _p(col), _p(edge_bias), N, H, float(slope),
+    _lib.check(_lib.load().b2g_gat_alpha(_p(a), a.stride(0), _p(rowptr), _p(col), _p(edge_bias), r0, n, H, float(slope),
                                          float(p_drop), int(seed), _p(alpha), _p(smax), _p(ssum), _stream()), "gat_alpha")
     return alpha, smax, ssum
 
@@ -468,14 +469,15 @@ def seg_wsum4(x, w_e, rowptr, col, perm, out, d_a=None, band=0):
     return out
 
 
-def tz_fwd(x, u, H, rowptr, col, p_drop, seed, save_alpha, band=0, edge_bias=None, extra_cols=0):
+def tz_fwd(x, u, H, rowptr, col, p_drop, seed, save_alpha, band=0, edge_bias=None, extra_cols=0, x_self=None, alpha_out=None):
     """z_aug [N, H*F + 8 + F (+ extra_cols, left for the caller to fill)] (see include/b2g.h b2g_tz_fwd) and the
     pre-dropout attention weights [nnz, H] | None.  edge_bias: fp32 [nnz, H] added to the logits (edge features)."""
     x, u = _rows(x), _rows(u)
-    N, F = x.shape
+    N, F = u.shape[0], x.shape[1]                      # rows of this call = rows of u (a row range when x_self is given)
     z = empty_rows(N, H * F + 8 + F + extra_cols, x.dtype, x.device)
-    alpha = torch.empty((max(col.numel(), 1), H), dtype=torch.float32, device=x.device) if save_alpha else None
-    _lib.check(_lib.load().b2g_tz_fwd(_p(x), _ld(x), _p(u), _ld(u), _p(z), _ld(z), N, H, F, _dt(x), _p(rowptr), _p(col),
+    alpha = alpha_out if alpha_out is not None else (
+        torch.empty((max(col.numel(), 1), H), dtype=torch.float32, device=x.device) if save_alpha else None)
+    _lib.check(_lib.load().b2g_tz_fwd(_p(x), _ld(x), _p(x_self), _p(u), _ld(u), _p(z), _ld(z), N, H, F, _dt(x), _p(rowptr), _p(col),
                                       _p(alpha), _p(edge_bias), float(p_drop), int(seed), int(band), _stream()), "tz_fwd")
     return z, alpha
 

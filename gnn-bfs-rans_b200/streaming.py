@@ -21,7 +21,7 @@ import torch
 
 from . import ops
 from .graph import Graph
-from .nn import GCNConv
+from .nn import GATConv, GCNConv, GINConv, TransformerConv, _cached_fold
 
 _STREAMS = {}
 
@@ -182,4 +182,181 @@ def gcn_forward_host(layer: GCNConv, x_host: torch.Tensor, edge_index_host: torc
     cur.wait_stream(s_out)
     cur.wait_stream(s_cmp)
     s_out.synchronize()                        # the result is host memory: return only when it is complete
+    return out_host
+
+
+# ------------------------------------------------------------------------------------------ all four layer types
+class _Stages:
+    """What a layer type does per row chunk of the host pipeline: `project(r0, r1)` as soon as the chunk of x has landed,
+    `finish(r0, r1) -> rows [r0, r1) of the output` once every neighbour row of the chunk is projected.  Same kernels and
+    arithmetic as the layer's forward on the whole graph; the CSR positions, the attention weights and every gathered
+    matrix are indexed globally, only the target rows are a range."""
+    variant = "sl"
+
+    def __init__(self, layer, dx, g: Graph):
+        self.layer, self.dx, self.g = layer, dx, g
+        self.csr = g.csr(self.variant, False)
+        self.N = dx.shape[0]
+
+    def project(self, r0, r1):
+        pass
+
+
+class _GINStages(_Stages):
+    variant = "raw"
+
+    def finish(self, r0, r1):
+        L = self.layer
+        eps = float(L.eps.item()) if not hasattr(self, "_eps") else self._eps
+        self._eps = eps
+        h = ops.seg_sum(self.dx, self.csr.rowptr[r0:r1 + 1], self.csr.col, r1 - r0, None, None, 1.0 + eps, self.dx[r0:r1], None)
+        return L._mlp(h)
+
+
+class _GATStages(_Stages):
+    def __init__(self, layer, dx, g):
+        super().__init__(layer, dx, g)
+        L = layer
+        H, C, F = L.heads, L.out_channels, L.in_channels
+        if L.concat or H != 4 or not ops.gatw_gemm_supported(self.N, H, F, C, dx.dtype):
+            raise NotImplementedError
+        ps = (L.lin.weight, L.att_src, L.att_dst)
+        wc, self.v = _cached_fold(L, 'wc_v', ps, dx.dtype, lambda: L._wc_v(dx.dtype))
+        self.wp = wc.view(C, H, F // 64, 64).permute(0, 2, 1, 3).reshape(C, H * F).contiguous()
+        self.a = torch.empty((self.N, 8), dtype=torch.float32, device=dx.device)
+        self.alpha = torch.empty((max(self.csr.nnz, 1), H), dtype=torch.float32, device=dx.device)
+        self.H = H
+
+    def project(self, r0, r1):
+        self.a[r0:r1] = ops.rowdot8(self.dx[r0:r1], self.v)
+
+    def finish(self, r0, r1):
+        L = self.layer
+        ops.gat_alpha(self.a, self.csr.rowptr, self.csr.col, self.H, L.negative_slope, 0.0, 0, False, rows=(r0, r1),
+                      alpha_out=self.alpha)
+        return ops.gatw_gemm(self.dx, self.csr.rowptr[r0:r1 + 1], self.csr.col, None, self.alpha, self.wp, L.bias, r1 - r0,
+                             self.H, band=0)
+
+
+class _TConvStages(_Stages):
+    variant = "raw"
+
+    def __init__(self, layer, dx, g):
+        super().__init__(layer, dx, g)
+        L = layer
+        if not L._aggregate_first(dx) or L.lin_edge is not None:
+            raise NotImplementedError
+        self.mq, self.cq, self.w_out, self.b_out = _cached_fold(L, 'folded', L._fold_params(), dx.dtype, lambda: L._folded(dx.dtype))
+        self.H = L.heads
+        self.u = torch.empty((self.N, self.H * dx.shape[1]), dtype=dx.dtype, device=dx.device)
+
+    def project(self, r0, r1):
+        ops.linear_fwd(self.dx[r0:r1], self.mq, self.cq, out=self.u[r0:r1])
+
+    def finish(self, r0, r1):
+        z_aug, _ = ops.tz_fwd(self.dx, self.u[r0:r1], self.H, self.csr.rowptr[r0:r1 + 1], self.csr.col, 0.0, 0, False, band=0,
+                              x_self=self.dx[r0:r1])
+        out, _ = ops.linear_fwd(z_aug, self.w_out, self.b_out)
+        return out
+
+
+@torch.no_grad()
+def forward_host(layer, x_host: torch.Tensor, edge_index_host: torch.Tensor, out_host: Optional[torch.Tensor] = None,
+                 rows_per_chunk: int = 1 << 18, partition=None) -> torch.Tensor:
+    """`layer(x, edge_index)` (gnn_model.py:166-170) for host-resident x [N, F] / edge_index [2, E] and a host result, for
+    GCNConv / GATConv / GINConv / TransformerConv in eval mode: the reference's `batch.to(device)` ... `.cpu()` round trip
+    (train.py:167, inference.py:87) with the host->device copy, the kernels and the device->host copy pipelined over row
+    chunks (see the module docstring; GCNConv: `gcn_forward_host`).  Inference only.  Layer configurations without a
+    row-range pipeline (project-first attention paths, edge features, fp32 GAT) copy everything, run the layer and copy
+    the result back — still through pinned buffers on the copy streams."""
+    if isinstance(layer, GCNConv):
+        return gcn_forward_host(layer, x_host, edge_index_host, out_host, rows_per_chunk, partition)
+    if partition is not None and partition.world > 1:
+        raise NotImplementedError("b2g.streaming: the partitioned host pipeline exists for GCNConv")
+    if not isinstance(layer, (GATConv, GINConv, TransformerConv)):
+        raise NotImplementedError(f"b2g.streaming: no host pipeline for {type(layer).__name__}")
+    if layer.training:
+        raise RuntimeError("b2g.streaming: inference only (layer.eval())")
+    par = next(layer.parameters())
+    if not par.is_cuda:
+        raise RuntimeError("b2g.streaming: the layer must live on a CUDA device (no CPU fallback)")
+    dev = par.device
+    if x_host.dim() != 2 or edge_index_host.dim() != 2 or edge_index_host.shape[0] != 2:
+        raise ValueError("x must be [N,F] and edge_index [2,E]")
+    if x_host.dtype not in (torch.float32, torch.bfloat16):
+        raise RuntimeError(f"b2g: x dtype {x_host.dtype} not supported (float32 / bfloat16)")
+    hx = _pinned(x_host.contiguous(), "x")
+    hei = _pinned(edge_index_host.long().contiguous(), "edge_index")
+    N = hx.shape[0]
+    F_out = layer.nn[-1].out_features if isinstance(layer, GINConv) else layer.out_channels * (layer.heads if layer.concat else 1)
+    if out_host is None:
+        out_host = torch.empty((N, F_out), dtype=hx.dtype).pin_memory()
+    elif out_host.is_cuda or not out_host.is_pinned() or out_host.shape != (N, F_out) or out_host.dtype != hx.dtype:
+        raise ValueError("out_host must be a pinned host tensor [N, out_channels] of x's dtype")
+    if N == 0:
+        return out_host
+    s_in, s_cmp, s_out = _streams(dev)
+    cur = torch.cuda.current_stream(dev)
+    for st in (s_in, s_cmp, s_out):
+        st.wait_stream(cur)
+    R = max(1024, int(rows_per_chunk))
+    bounds = [(r0, min(r0 + R, N)) for r0 in range(0, N, R)]
+    with torch.cuda.stream(s_in):
+        dei = torch.empty(hei.shape, dtype=torch.int64, device=dev)
+        dei.copy_(hei, non_blocking=True)
+        ev_ei = torch.cuda.Event()
+        ev_ei.record(s_in)
+        dx = torch.empty(tuple(hx.shape), dtype=hx.dtype, device=dev)
+        ev_x = []
+        for r0, r1 in bounds:
+            dx[r0:r1].copy_(hx[r0:r1], non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(s_in)
+            ev_x.append(e)
+    with torch.cuda.stream(s_cmp):
+        for t in (dei, dx):
+            t.record_stream(s_cmp)
+        s_cmp.wait_event(ev_ei)
+        g = Graph(dei, N)
+        cls = _GINStages if isinstance(layer, GINConv) else (_GATStages if isinstance(layer, GATConv) else _TConvStages)
+        try:
+            stages = cls(layer, dx, g)
+        except NotImplementedError:
+            stages = None
+        if stages is None:                      # no row-range pipeline for this configuration: whole-graph call
+            s_cmp.wait_event(ev_x[-1])
+            out = layer(dx, dei)
+            out.record_stream(s_out)
+            e = torch.cuda.Event()
+            e.record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e)
+                out_host.copy_(out, non_blocking=True)
+        else:
+            band = int((dei[0] - dei[1]).abs().max()) if dei.shape[1] else 0          # one reduction + host sync; copies are queued
+            done_rows, pending = 0, list(range(len(bounds)))
+
+            def finish_ready():
+                for c in list(pending):
+                    r0, r1 = bounds[c]
+                    if min(r1 + band, N) > done_rows:
+                        continue
+                    o = stages.finish(r0, r1)
+                    o.record_stream(s_out)
+                    e = torch.cuda.Event()
+                    e.record(s_cmp)
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(e)
+                        out_host[r0:r1].copy_(o, non_blocking=True)
+                    pending.remove(c)
+
+            for c, (r0, r1) in enumerate(bounds):
+                s_cmp.wait_event(ev_x[c])
+                stages.project(r0, r1)
+                done_rows = r1
+                finish_ready()
+            finish_ready()
+    cur.wait_stream(s_out)
+    cur.wait_stream(s_cmp)
+    s_out.synchronize()
     return out_host

@@ -223,9 +223,12 @@ int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const flo
  * NULL) receives the pre-dropout attention weights [nnz, H] for the backward pass.  edge_bias (may be NULL): fp32
  * [nnz, H] in target-major CSR order, added to the logits — the edge-feature term of TransformerConv(edge_dim)
  * (b2g_edge_dot4 below). */
-int b2g_tz_fwd(const void* x, int64_t ldx, const void* u, int64_t ldu, void* z_aug, int64_t ldz, int64_t n, int H, int F,
-               int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, const float* edge_bias, float p_drop,
-               uint64_t seed, int64_t band, void* stream);
+int b2g_tz_fwd(const void* x, int64_t ldx, const void* x_self, const void* u, int64_t ldu, void* z_aug, int64_t ldz, int64_t n,
+               int H, int F, int dt, const int32_t* rowptr, const int32_t* col, float* alpha_e, const float* edge_bias,
+               float p_drop, uint64_t seed, int64_t band, void* stream);
+/* x_self (NULL = x): the matrix whose row i is target row i's own feature row (copied into z_aug).  It differs from x — the
+ * matrix the column indices address — when the call covers a row range [r0, r1) of a larger problem (rowptr + r0, u + r0 rows,
+ * z_aug + r0 rows, x_self = x + r0 rows): the host-buffer pipeline of streaming.py. */
 /* Target side of its backward pass: dz_aug [n, >= H*F + 8] (columns H*F .. H*F+H-1 = d s), alpha_in = the forward
  * pass's alpha_e; writes alpha_e (after dropout) and de_e [nnz, H] (gradients of the logits), target-major.  The
  * `du` (may be NULL) [n, H*F] receives d u_i = [sum_j de_ij1 x_j | ...] from the same gather.  The sums over the
@@ -261,8 +264,8 @@ int b2g_edge_wsum4(const float* w, const float* ea_csr, const int32_t* rowptr, i
  *   With the source-major CSR, perm and g in place of x it is the backward's y-aggregation + dgrad GEMM. */
 int b2g_gatw_gemm_supported(int64_t n, int H, int F, int C, int dt);
 int b2g_gat_alpha(const float* a_srcdst, int64_t lda, const int32_t* rowptr, const int32_t* col, const float* edge_bias,
-                  int64_t n, int H, float slope, float p_drop, uint64_t seed, float* alpha, float* smax, float* ssum,
-                  void* stream);
+                  int64_t row0, int64_t n, int H, float slope, float p_drop, uint64_t seed, float* alpha, float* smax, float* ssum,
+                  void* stream);   /* rows [row0, row0 + n); every array is indexed by the global row / CSR position */
 int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                   const float* alpha, const void* wp, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t n_rows,
                   int H, int F, int C, int dt, int64_t band, void* stream);

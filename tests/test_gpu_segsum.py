@@ -166,3 +166,37 @@ def test_host_pipelined_gcn_equals_device_forward(dtype, rows_per_chunk):
             ref = layer(x.cuda(), ei).cpu()
         out = b2g.streaming.gcn_forward_host(layer, x, ei.cpu(), rows_per_chunk=rows_per_chunk)
         assert out.is_pinned() and torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("kind", ["GAT", "GIN", "Transformer"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_host_pipeline_all_layer_types(kind, dtype):
+    """streaming.forward_host for GATConv / GINConv / TransformerConv: the row-chunked host pipeline (or, for configurations
+    without one — fp32 GATConv — the whole-graph call between pinned copies) against layer(x.cuda(), ei.cuda()).cpu().  The
+    chunked kernels do the same arithmetic per row; bf16 GAT goes through the fused kernel in both (bit-equal), the others
+    may differ in the last bit where a GEMM tile boundary moves (tolerance 1e-6 fp32 / 1 bf16 ulp)."""
+    import gnn_bfs_rans_b200 as b2g
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    from gnn_bfs_rans_b200 import ops
+    torch.manual_seed(0)
+    F = 256
+    layer = {"GAT": lambda: b2g.nn.GATConv(F, F, heads=4, concat=False),
+             "GIN": lambda: b2g.nn.GINConv(torch.nn.Sequential(torch.nn.Linear(F, F), torch.nn.ReLU(), torch.nn.Linear(F, F))),
+             "Transformer": lambda: b2g.nn.TransformerConv(F, F, heads=4, concat=False)}[kind]().cuda().to(dtype).eval()
+    nx, ny, nz = 40, 30, 20
+    N = nx * ny * nz
+    o, n = hex_mesh_faces(nx, ny, nz, device='cuda')
+    ei_mesh = ops.build_graph_edges(o, n, 1, None, N, N)
+    ei_rand = torch.cat([torch.randint(0, N, (2, 5 * N), device='cuda'), torch.stack([torch.randint(0, N, (50,), device='cuda'),
+                                                                                     torch.full((50,), 7, device='cuda')])], 1)
+    for ei in (ei_mesh, ei_rand):
+        x = torch.randn(N, F).to(dtype)
+        with torch.no_grad():
+            ref = layer(x.cuda(), ei).cpu()
+        for rpc in (2048, 1 << 19):
+            out = b2g.streaming.forward_host(layer, x, ei.cpu(), rows_per_chunk=rpc)
+            assert out.is_pinned() and out.shape == ref.shape
+            err = float((out.double() - ref.double()).abs().max() / ref.double().abs().max())
+            assert err <= (1e-6 if dtype == torch.float32 else 8e-3), (kind, rpc, err)
+    with pytest.raises(RuntimeError):
+        b2g.streaming.forward_host(layer.train(), x, ei.cpu())
