@@ -382,12 +382,21 @@ def main():
             if args.layer == "GAT":
                 csr = g.csr("sl", False)
                 xin = torch.randn(part.n_local, F, device=dev).to(dtype)
-                a = torch.randn(part.n_local, 2 * H, device=dev)
-                zbuf = torch.empty(N, H * F, device=dev, dtype=dtype)
-                kfn = lambda: ops.gatz_fwd(xin, a, H, 0.2, csr.rowptr, csr.col, 0.0, 0, False, band=g.band(), out=zbuf)
-                # aggregate-first kernel: read x once, a [N,2H] fp32, indices; write z [N, H*F]
-                alg = N * F * s + N * H * F * s + 2 * 4 * N * H + 4 * csr.nnz + 4 * (N + 1)
-                kname = "gatz_fwd_kernel (K4 aggregate-first, gat_rows.cu)"
+                if ops.gatw_gemm_supported(N, H, F, F, dtype):
+                    # fused aggregation + projection (gat_fused.cu): reads x once, col + alpha [nnz, 4]; writes out [N, C]
+                    alpha = torch.rand(max(csr.nnz, 1), H, device=dev)
+                    wp = torch.randn(F, H * F, device=dev).to(dtype) / 16
+                    obuf = torch.empty(N, F, device=dev, dtype=dtype)
+                    kfn = lambda: ops.gatw_gemm(xin, csr.rowptr, csr.col, None, alpha, wp, None, N, H, band=g.band(), out=obuf)
+                    alg = N * F * s + N * F * s + 16 * csr.nnz + 4 * csr.nnz + 4 * (N + 1)
+                    kname = "gatw_gemm_kernel (K4f fused aggregation + projection, gat_fused.cu)"
+                else:
+                    a = torch.randn(part.n_local, 2 * H, device=dev)
+                    zbuf = torch.empty(N, H * F, device=dev, dtype=dtype)
+                    kfn = lambda: ops.gatz_fwd(xin, a, H, 0.2, csr.rowptr, csr.col, 0.0, 0, False, band=g.band(), out=zbuf)
+                    # aggregate-first kernel: read x once, a [N,2H] fp32, indices; write z [N, H*F]
+                    alg = N * F * s + N * H * F * s + 2 * 4 * N * H + 4 * csr.nnz + 4 * (N + 1)
+                    kname = "gatz_fwd_kernel (K4 aggregate-first, gat_rows.cu)"
                 gather_row_bytes = F * s
             else:
                 csr = g.csr("raw", False)
@@ -407,7 +416,9 @@ def main():
         tfile = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tfile):
             try:
-                roof["traffic"] = json.load(open(tfile)).get(f"{args.layer}_{args.dtype}")
+                tj = json.load(open(tfile))
+                roof["traffic"] = tj.get(f"{args.layer}_{args.dtype}")
+                roof["traffic_source"] = (tj.get("source") or {}).get(f"{args.layer}_{args.dtype}")
             except Exception:
                 pass
 
