@@ -43,8 +43,10 @@ constexpr int GF_STG = 4 * 32 * 128;             // epilogue staging: 32 rows x 
 constexpr int GF_WST_WARP = 2 * 4 * 8 * 16;      // per gather warp: 2 units x 4 rows x 8 entries x float4 weights = 1 KB
 constexpr int GF_WST = GF_GW * GF_WST_WARP;
 constexpr int GF_BAR = 256;
-constexpr int GF_SMEM = 2 * GF_A_CHUNK + GF_W_STAGES * GF_W_STAGE + GF_STG + GF_WST + GF_BAR;
-static_assert(GF_SMEM + 1024 <= 232448, "fused GAT shared-memory plan exceeds 227 KB");
+constexpr int GF_BVH = GF_H * GF_BN * 2;         // TransformerConv: bv_h / H as bf16 [4][256] (exact: the model's weights are bf16)
+constexpr int GF_SMEM = 2 * GF_A_CHUNK + GF_W_STAGES * GF_W_STAGE + GF_STG + GF_WST + GF_BVH + GF_BAR;
+// no static shared memory in this kernel: the dynamic window starts 1024-byte aligned (checked at run time with a trap)
+static_assert(GF_SMEM <= 232448, "fused GAT shared-memory plan exceeds 227 KB");
 
 struct GfArgs {
   const char* x; uint32_t xrow_bytes;            // gathered rows, bf16 [*, 256]
@@ -52,6 +54,10 @@ struct GfArgs {
   const float* alpha;                            // fp32 [nnz, 4]: weight of (entry, head); entry = perm[pos] or pos
   const float* bias;                             // fp32 [m] or NULL
   const char* zero;                              // >= 512 bytes of zeros (padding lanes load from here)
+  // TransformerConv (out = sum_h (z_h Wv_h^T + s_h bv_h) / H + x Ws^T + bs): optional epilogue terms
+  const float* srow;                             // fp32 [n_rows, 4]: per-head weight sums s_ih (post-dropout) or NULL
+  const float* bvh;                              // fp32 [4, m]: bv_h / H; out += sum_h s_ih bvh[h, :]  (needs srow) or NULL
+  const __nv_bfloat16* addend; int64_t ldadd;    // [n_rows, m]: out += addend (the skip projection) or NULL
   __nv_bfloat16* out; int64_t ldo;
   uint32_t n_rows; int m;
   RowSched ord;                                  // chunk_rows = GF_BM
@@ -103,7 +109,8 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
   const uint32_t wring = abuf0 + 2 * GF_A_CHUNK;                      // 2 x 32 KB W stages
   const uint32_t stg = wring + GF_W_STAGES * GF_W_STAGE;              // epilogue staging
   const uint32_t wst = stg + GF_STG;                                  // gather-weight staging
-  const uint32_t bars = wst + GF_WST;
+  const uint32_t sbv = wst + GF_WST;                                  // bv_h / H (bf16 [4][256]) or zeros
+  const uint32_t bars = sbv + GF_BVH;
   auto full_w = [&](int s) { return bars + 8u * s; };
   auto empty_w = [&](int s) { return bars + 8u * (2 + s); };
   auto full_a = [&](int b) { return bars + 8u * (4 + b); };
@@ -115,6 +122,13 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  if (a.bvh) {                                                          // visible to the epilogue warps after the __syncthreads below
+    __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(smem_raw + (sbv - smem_base));
+    for (int t = threadIdx.x; t < GF_H * GF_BN; t += GF_THREADS) {
+      const int h = t / GF_BN, c = t - h * GF_BN;
+      sb[t] = __float2bfloat16_rn(c < a.m ? a.bvh[h * a.m + c] : 0.f);
+    }
+  }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     for (int s = 0; s < 2; ++s) {
@@ -200,11 +214,23 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
       tc_fence_after();
       const uint32_t row0 = c0 + qd * 32;
       const uint32_t rend = c0 + rows;
+      const uint32_t my_row = row0 + lane;                 // the accumulator row this lane holds
+      float4 srow4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.srow && my_row < rend) srow4 = __ldg(reinterpret_cast<const float4*>(a.srow) + my_row);
 #pragma unroll 1
       for (int c = 0; c < a.m; c += 64) {
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * GF_BN + c);
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
+          uint4 adv[4];                                      // this row's 32 addend values, requested before the TMEM read waits
+          if (a.addend) {
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) {
+              adv[k8] = make_uint4(0u, 0u, 0u, 0u);
+              if (my_row < rend)
+                adv[k8] = __ldg(reinterpret_cast<const uint4*>(a.addend + (int64_t)my_row * a.ldadd + c + hlf * 32 + k8 * 8));
+            }
+          }
           uint32_t r[32];
           tc_ld32(taddr + hlf * 32, r);
 #pragma unroll
@@ -212,12 +238,29 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
             float v[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[j + k]);
+            const int cg = c + hlf * 32 + j;               // m % 64 == 0 (launcher): always in range
             if (a.bias) {
-              const int cg = c + hlf * 32 + j;             // m % 64 == 0 (launcher): always in range
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.bias + cg));
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(a.bias + cg + 4));
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (a.bvh) {                                   // + sum_h s_ih bv_h / H: 4 broadcast LDS.128 from shared memory
+              const uint8_t* sb = smem_raw + (sbv - smem_base) + cg * 2;
+#pragma unroll
+              for (int h = 0; h < GF_H; ++h) {
+                const float sh = h == 0 ? srow4.x : (h == 1 ? srow4.y : (h == 2 ? srow4.z : srow4.w));
+                float f[8];
+                unpack_row16(*reinterpret_cast<const uint4*>(sb + h * GF_BN * 2), f, __nv_bfloat16());
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] += sh * f[k];
+              }
+            }
+            if (a.addend) {                                // + the skip projection of this row (prefetched above; zeros past the end)
+              float f[8];
+              unpack_row16(adv[j >> 3], f, __nv_bfloat16());
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] += f[k];
             }
             Vec<__nv_bfloat16> o;
             o.from_float(v);
@@ -472,10 +515,25 @@ int b2g_gatw_gemm_supported(int64_t n, int H, int F, int C, int dt) {
           n < (1ll << 32) - (1ll << 25)) ? 1 : 0;
 }
 
+int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                     const float* alpha, const void* wp, int64_t ldw, const float* bias, const float* srow, const float* bvh,
+                     const void* addend, int64_t ldadd, void* out, int64_t ldo, int64_t n_rows, int H, int F, int C, int dt,
+                     int64_t band, void* stream);
+
 int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                   const float* alpha, const void* wp, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t n_rows,
                   int H, int F, int C, int dt, int64_t band, void* stream) {
+  return b2g_gatw_gemm_ex(x, ldx, rowptr, col, perm, alpha, wp, ldw, bias, nullptr, nullptr, nullptr, 0, out, ldo, n_rows, H, F, C,
+                          dt, band, stream);
+}
+
+int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                     const float* alpha, const void* wp, int64_t ldw, const float* bias, const float* srow, const float* bvh,
+                     const void* addend, int64_t ldadd, void* out, int64_t ldo, int64_t n_rows, int H, int F, int C, int dt,
+                     int64_t band, void* stream) {
   if (n_rows < 0) return B2G_E_ARG;
+  if ((bvh != nullptr) != (srow != nullptr)) return B2G_E_ARG;
+  if ((srow && !aligned16(srow)) || (bvh && !aligned16(bvh)) || (addend && (!aligned16(addend) || (ldadd * 2) % 16))) return B2G_E_ALIGN;
   if (n_rows == 0) return B2G_OK;
   if (!b2g_gatw_gemm_supported(n_rows, H, F, C, dt)) return B2G_E_UNSUPPORTED;
   if (!x || !rowptr || !col || !alpha || !wp || !out) return B2G_E_ARG;
@@ -497,6 +555,7 @@ int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32
   a.rowptr = rowptr; a.col = col; a.perm = perm; a.alpha = alpha; a.bias = bias;
   a.zero = static_cast<const char*>(zero_row_ptr());
   if (!a.zero) return B2G_E_UNSUPPORTED;
+  a.srow = srow; a.bvh = bvh; a.addend = static_cast<const __nv_bfloat16*>(addend); a.ldadd = ldadd;
   a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.n_rows = (uint32_t)n_rows; a.m = C;
   const unsigned grid = a.ord.n_chunks < (uint32_t)B2G_NUM_SMS ? a.ord.n_chunks : (unsigned)B2G_NUM_SMS;
   gatw_gemm_kernel<<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, a);

@@ -114,6 +114,8 @@ struct GatzArgs {
   const float* ebias;                        // TransformerConv with edge features (edge_dim): per-(entry, head) term added to
                                              // the logits (forward) / to d alpha (backward), fp32 [nnz, H] target-major; or NULL
   float* d_a; uint32_t ldda;                 // [N, >= 2H] (row stride in ELEMENTS of its type)
+  int alpha_only;                            // tz_fwd: attention weights only (fused TransformerConv forward): alpha_e = pre-dropout
+                                             // weights, de_e = post-dropout weights (or NULL when p_drop == 0), smax = weight sums
   int da_bf16;                               // d_a holds bf16 (a column block of the bf16 dgrad operand) instead of fp32
   uint32_t n_rows;
   float slope, p_drop;
@@ -878,7 +880,15 @@ __device__ __noinline__ void tz_fwd_long(const GatzArgs a, uint32_t i, int b, in
     warp_sum4(ws[0], ws[1], ws[2], ws[3]);
 #pragma unroll
     for (int h = 0; h < GH; ++h) ssum[h] += ws[h];
+    if (a.alpha_only) {
+      if (a.de_e && lane < n) *reinterpret_cast<float4*>(a.de_e + (uint64_t)(p0 + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
+      continue;
+    }
     for (int j = 0; j < n; j += GatzCfg<VPL>::BU) gatz_gather_fma<T, VPL>(acc, xb, a.xrow_bytes, cl, w, j, []() {});
+  }
+  if (a.alpha_only) {
+    if (a.smax && lane < GH) a.smax[(uint64_t)i * GH + lane] = pick4(ssum, lane);
+    return;
   }
   gatz_store<T, VPL>(reinterpret_cast<char*>(a.z) + (uint64_t)i * a.zrow_bytes, acc, lane);
   tz_store_tail<T, VPL>(a, i, lane, ssum);
@@ -949,6 +959,13 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
       if (a.alpha_e && pu < len) a.alpha_e[(uint64_t)(r.b + pu) * GH + ph] = wp;      // coalesced 4-byte stores
       if (a.p_drop > 0.f) wp *= packed_keep_scale(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + pu), a.p_drop, ph);
       const float ss = head_sum8(wp);                          // per-head weight sums (every lane of the head has it)
+      if (a.alpha_only) {
+        if (a.de_e && pu < len) a.de_e[(uint64_t)(r.b + pu) * GH + ph] = wp;
+        if (a.smax && lane < GH) a.smax[(uint64_t)r.i * GH + lane] = ss;       // lanes 0..3: entry 0, head = lane
+        if (!r.shift()) break;
+        cl = cl2;
+        continue;
+      }
       float ssum[GH];
 #pragma unroll
       for (int h = 0; h < GH; ++h) ssum[h] = __shfl_sync(0xffffffffu, ss, h);
@@ -998,6 +1015,13 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
 #pragma unroll
       for (int h = 0; h < GH; ++h) ssum[h] = w[h];
       warp_sum4(ssum[0], ssum[1], ssum[2], ssum[3]);
+      if (a.alpha_only) {
+        if (a.de_e && lane < len) *reinterpret_cast<float4*>(a.de_e + (uint64_t)(r.b + lane) * GH) = make_float4(w[0], w[1], w[2], w[3]);
+        if (a.smax && lane < GH) a.smax[(uint64_t)r.i * GH + lane] = pick4(ssum, lane);
+        if (!r.shift()) break;
+        cl = cl2;
+        continue;
+      }
       float acc[GH][VPL][VN];
 #pragma unroll
       for (int h = 0; h < GH; ++h)
@@ -1387,6 +1411,29 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* x_self, const void* u, in
   a.x = x; a.x_self = x_self ? x_self : x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = u; a.dzrow_bytes = (uint32_t)(ldu * es); a.z = z_aug;
   a.zrow_bytes = (uint32_t)(ldz * es); a.rowptr = rowptr; a.col = col; a.alpha_e = alpha_e; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr();
   a.ebias = edge_bias;
+  return gatz_dispatch(3, dt, F * es, a, (cudaStream_t)stream);
+}
+
+/* Attention weights only (fused TransformerConv forward, gat_fused.cu): alpha_pre [nnz, H] = softmax_j(u_ih . x_j (+ edge_bias)),
+ * alpha_post (NULL when p_drop == 0: identical) = alpha_pre with the attention-dropout keep scale, ssum [n, H] = per-head sums of
+ * the post-dropout weights.  Same kernel as b2g_tz_fwd without the weighted sums. */
+int b2g_tz_alpha(const void* x, int64_t ldx, const void* u, int64_t ldu, int64_t n, int H, int F, int dt, const int32_t* rowptr,
+                 const int32_t* col, float* alpha_pre, float* alpha_post, float* ssum, const float* edge_bias, float p_drop,
+                 uint64_t seed, int64_t band, void* stream) {
+  if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
+  if (n == 0) return B2G_OK;
+  const int es = esz(dt);
+  if (!x || !u || !rowptr || !col || !alpha_pre || !ssum || (p_drop > 0.f && !alpha_post)) return B2G_E_ARG;
+  if (!aligned16(x) || !aligned16(u) || !aligned16(alpha_pre) || (alpha_post && !aligned16(alpha_post)) || !aligned16(ssum) ||
+      (edge_bias && !aligned16(edge_bias)) || (ldx * es) % 16 || (ldu * es) % 16)
+    return B2G_E_ALIGN;
+  if (!fits32(ldx * es) || !fits32(ldu * es)) return B2G_E_SHAPE;
+  GatzArgs a{};
+  const int rc = gatz_common(a, n, F, dt, band);
+  if (rc) return rc;
+  a.x = x; a.x_self = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = u; a.dzrow_bytes = (uint32_t)(ldu * es);
+  a.rowptr = rowptr; a.col = col; a.alpha_e = alpha_pre; a.de_e = p_drop > 0.f ? alpha_post : nullptr; a.smax = ssum;
+  a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.ebias = edge_bias; a.alpha_only = 1;
   return gatz_dispatch(3, dt, F * es, a, (cudaStream_t)stream);
 }
 

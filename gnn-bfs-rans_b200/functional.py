@@ -417,21 +417,44 @@ class TConvZFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, mq, cq, w_out, b_out, graph: Graph, H: int, p_drop: float, ea=None):
+        """Two implementations of the same arithmetic (B2G_TCONV_PATH=unfused selects the second):
+          fused   (bf16, F = 256, no edge features): attention weights by tz_alpha (logits + softmax only), skip projection by a
+                  plain GEMM, then the fused gather + value-projection kernel of gat_fused.cu with the s.bv and skip terms in
+                  its epilogue — z_aug [N, H*F + 8 + F] (26 GB at cfg4) is neither written nor read;
+          unfused tz_fwd writes z_aug, one k = H*F + 8 + F GEMM reads it back."""
         need_grad = any(t is not None and t.requires_grad for t in (x, mq, cq, w_out, b_out))
         seed = _next_seed() if p_drop > 0 else 0
-        z_aug, alpha = TConvZFn._forward_z(x, mq, cq, graph, H, p_drop, seed, need_grad, ea)
-        out, _ = ops.linear_fwd(z_aug, w_out, b_out)
+        N, F = x.shape
+        C, HF = w_out.shape[0], H * F
+        fused = (ea is None and os.environ.get("B2G_TCONV_PATH", "") != "unfused"
+                 and ops.gatw_gemm_supported(N, H, F, C, x.dtype))
+        ssum = None
+        if fused:
+            csr = graph.csr("raw", False)
+            u, _ = ops.linear_fwd(x, mq, cq)
+            alpha, a_post, ssum = ops.tz_alpha(x, u, H, csr.rowptr, csr.col, p_drop, seed, band=graph.band())
+            del u
+            skip, _ = ops.linear_fwd(x, w_out[:, HF + 8:HF + 8 + F].contiguous(), b_out)
+            wp = w_out[:, :HF].reshape(C, H, F // 64, 64).permute(0, 2, 1, 3).reshape(C, HF)   # K order (chunk, head, 64 features)
+            bvh = w_out[:, HF:HF + H].t().float().contiguous()                                    # [H, C] = bv_h / H
+            out = ops.gatw_gemm(x, csr.rowptr, csr.col, None, a_post if a_post is not None else alpha, wp, None, N, H,
+                                band=graph.band(), srow=ssum, bvh=bvh, addend=skip)
+            z_aug = None
+        else:
+            z_aug, alpha = TConvZFn._forward_z(x, mq, cq, graph, H, p_drop, seed, need_grad, ea)
+            out, _ = ops.linear_fwd(z_aug, w_out, b_out)
         if need_grad:
-            recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"     # see GATZFn: z_aug is re-derived in backward
-            ctx.save_for_backward(x, mq, cq, w_out, None if recompute else z_aug, alpha, ea)
+            recompute = os.environ.get("B2G_RECOMPUTE", "0") == "1"     # unfused path: z_aug is re-derived in backward
+            ctx.save_for_backward(x, mq, cq, w_out, None if recompute else z_aug, alpha, ea, ssum)
             ctx.cfg = (graph, H, p_drop, seed, b_out is not None)
             ctx.ei_keepalive = graph.edge_index
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, mq, cq, w_out, z_aug, alpha, ea = ctx.saved_tensors
+        x, mq, cq, w_out, z_aug, alpha, ea, ssum = ctx.saved_tensors
         graph, H, p_drop, seed, has_bout = ctx.cfg
+        fused = ssum is not None                 # forward ran fused: d W_out comes from y (below), no z_aug anywhere
         N, F = x.shape
         C = w_out.shape[0]
         HF = H * F
@@ -439,10 +462,10 @@ class TConvZFn(torch.autograd.Function):
         g = g.contiguous()
         csr, csr_t, perm = graph.csr("raw", False), graph.csr("raw", True), graph.perm("raw")
         band = graph.band()
-        if z_aug is None and ctx.needs_input_grad[3]:
+        if z_aug is None and ctx.needs_input_grad[3] and not fused:
             z_aug, _ = TConvZFn._forward_z(x, mq, cq, graph, H, p_drop, seed, False, ea)
         gw_out = None
-        if ctx.needs_input_grad[3]:
+        if ctx.needs_input_grad[3] and not fused:
             dw, _ = ops.linear_wgrad(g, z_aug, want_bias=False)               # d W_out = g^T z_aug  [C, H*F + 8 + F (+ 4H)]
             gw_out = _cast_like(dw, w_out)
         del z_aug
@@ -478,6 +501,15 @@ class TConvZFn(torch.autograd.Function):
         ops.seg_wsum4(g, alpha_e, csr_t.rowptr, csr_t.col, perm, big[:, o_y:o_y + H * C], band=band)
         ops.seg_wsum4(x, de_e, csr_t.rowptr, csr_t.col, perm, big[:, o_w:o_w + HF], d_a=big[:, o_t:o_t + 8], band=band)
         del alpha_e, de_e                                                   # t_jh written in place (columns o_t .. o_t + H)
+        if fused and ctx.needs_input_grad[3]:
+            # d W_out without z_aug: value block  sum_i g_i z_ih^T = sum_j y_jh x_j^T  (y is already in `big`), weight-sum
+            # block g^T s, skip block g^T x
+            dwv, _ = ops.linear_wgrad(big[:, o_y:o_y + H * C], x, want_bias=False)            # [H*C, F]
+            s8 = torch.zeros((N, 8), dtype=x.dtype, device=x.device)
+            s8[:, :H] = ssum
+            dws, _ = ops.linear_wgrad(g, s8, want_bias=False)                                 # [C, 8]
+            dwk, _ = ops.linear_wgrad(g, x, want_bias=False)                                  # [C, F]
+            gw_out = _cast_like(torch.cat([dwv.view(H, C, F).permute(1, 0, 2).reshape(C, HF), dws, dwk], dim=1), w_out)
         big[:, o_g:] = g
         du = big[:, o_du:o_du + HF + E4]
         gmq = gcq = gx = None

@@ -407,9 +407,10 @@ def gat_alpha(a, rowptr, col, H, slope, p_drop, seed, save_stats, edge_bias=None
     return alpha, smax, ssum
 
 
-def gatw_gemm(x, rowptr, col, perm, alpha, wp, bias, n_rows, H, band=0, out=None):
+def gatw_gemm(x, rowptr, col, perm, alpha, wp, bias, n_rows, H, band=0, out=None, srow=None, bvh=None, addend=None):
     """out [n_rows, C] = (per-head alpha-weighted sums of the rows of x over the CSR) @ Wc^T + bias in ONE kernel
-    (csrc/gat_fused.cu); wp = Wc with columns permuted by 64-feature chunk (see include/b2g.h)."""
+    (csrc/gat_fused.cu); wp = Wc with columns permuted by 64-feature chunk (see include/b2g.h).
+    TransformerConv terms (optional): + sum_h srow[i, h] bvh[h, :] (fp32 [n_rows, 4] / [4, C]) + addend[i, :] ([n_rows, C])."""
     _cuda(x, wp, alpha)
     x, wp = _rows(x), _rows(wp)
     C = wp.shape[0]
@@ -417,9 +418,32 @@ def gatw_gemm(x, rowptr, col, perm, alpha, wp, bias, n_rows, H, band=0, out=None
     if out is None:
         out = torch.empty((n_rows, C), dtype=x.dtype, device=x.device)
     b = bias.float().contiguous() if bias is not None else None
-    _lib.check(_lib.load().b2g_gatw_gemm(_p(x), _ld(x), _p(rowptr), _p(col), _p(perm), _p(alpha), _p(wp), _ld(wp), _p(b),
-                                         _p(out), _ld(out), n_rows, H, F, C, _dt(x), int(band), _stream()), "gatw_gemm")
+    if srow is None and bvh is None and addend is None:
+        _lib.check(_lib.load().b2g_gatw_gemm(_p(x), _ld(x), _p(rowptr), _p(col), _p(perm), _p(alpha), _p(wp), _ld(wp), _p(b),
+                                             _p(out), _ld(out), n_rows, H, F, C, _dt(x), int(band), _stream()), "gatw_gemm")
+        return out
+    ad = _rows(addend) if addend is not None else None
+    if srow is not None:
+        assert srow.dtype == torch.float32 and srow.is_contiguous() and srow.shape[1] == 4 and bvh.dtype == torch.float32 \
+            and bvh.is_contiguous() and tuple(bvh.shape) == (4, C)
+    _lib.check(_lib.load().b2g_gatw_gemm_ex(_p(x), _ld(x), _p(rowptr), _p(col), _p(perm), _p(alpha), _p(wp), _ld(wp), _p(b),
+                                            _p(srow), _p(bvh), _p(ad), _ld(ad) if ad is not None else 0, _p(out), _ld(out),
+                                            n_rows, H, F, C, _dt(x), int(band), _stream()), "gatw_gemm_ex")
     return out
+
+
+def tz_alpha(x, u, H, rowptr, col, p_drop, seed, band=0, edge_bias=None):
+    """TransformerConv attention weights without the weighted sums (gat_rows.cu tz_fwd_kernel, alpha-only mode):
+    -> (alpha_pre [nnz, H], alpha_post | None (p_drop == 0), ssum fp32 [N, H] = per-head sums of the post-dropout weights)."""
+    x, u = _rows(x), _rows(u)
+    N, F = x.shape
+    nnz = max(col.numel(), 1)
+    a_pre = torch.empty((nnz, H), dtype=torch.float32, device=x.device)
+    a_post = torch.empty((nnz, H), dtype=torch.float32, device=x.device) if p_drop > 0 else None
+    ssum = torch.empty((N, H), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().b2g_tz_alpha(_p(x), _ld(x), _p(u), _ld(u), N, H, F, _dt(x), _p(rowptr), _p(col), _p(a_pre), _p(a_post),
+                                        _p(ssum), _p(edge_bias), float(p_drop), int(seed), int(band), _stream()), "tz_alpha")
+    return a_pre, a_post, ssum
 
 
 def edge_rows_sl(edge_attr, eid, rowptr, n_rows):

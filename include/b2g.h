@@ -229,6 +229,12 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* x_self, const void* u, in
 /* x_self (NULL = x): the matrix whose row i is target row i's own feature row (copied into z_aug).  It differs from x — the
  * matrix the column indices address — when the call covers a row range [r0, r1) of a larger problem (rowptr + r0, u + r0 rows,
  * z_aug + r0 rows, x_self = x + r0 rows): the host-buffer pipeline of streaming.py. */
+/* Attention weights only (first half of b2g_tz_fwd; fused TransformerConv forward): alpha_pre [nnz, H] = softmax over the
+ * entries of a row of u_ih . x_j (+ edge_bias), alpha_post (may be NULL when p_drop == 0: identical) = alpha_pre times the
+ * attention-dropout keep scale, ssum fp32 [n, H] = per-head sums of the post-dropout weights. */
+int b2g_tz_alpha(const void* x, int64_t ldx, const void* u, int64_t ldu, int64_t n, int H, int F, int dt, const int32_t* rowptr,
+                 const int32_t* col, float* alpha_pre, float* alpha_post, float* ssum, const float* edge_bias, float p_drop,
+                 uint64_t seed, int64_t band, void* stream);
 /* Target side of its backward pass: dz_aug [n, >= H*F + 8] (columns H*F .. H*F+H-1 = d s), alpha_in = the forward
  * pass's alpha_e; writes alpha_e (after dropout) and de_e [nnz, H] (gradients of the logits), target-major.  The
  * `du` (may be NULL) [n, H*F] receives d u_i = [sum_j de_ij1 x_j | ...] from the same gather.  The sums over the
@@ -269,6 +275,15 @@ int b2g_gat_alpha(const float* a_srcdst, int64_t lda, const int32_t* rowptr, con
 int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                   const float* alpha, const void* wp, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t n_rows,
                   int H, int F, int C, int dt, int64_t band, void* stream);
+
+/* The same kernel with the epilogue terms of TransformerConv(heads = 4, concat = False), whose output is
+ *   out_i = sum_h (z_ih Wv_h^T + s_ih bv_h) / H + x_i Ws^T + bs:   srow fp32 [n_rows, 4] = s_ih (per-head sums of the post-dropout
+ * attention weights), bvh fp32 [4, C] = bv_h / H (both or neither), addend bf16 [n_rows, C] (row stride ldadd) = the skip
+ * projection; any of them may be NULL.  With b2g_tz_alpha (K5) this is the fused TransformerConv forward: z_aug never exists. */
+int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                     const float* alpha, const void* wp, int64_t ldw, const float* bias, const float* srow, const float* bvh,
+                     const void* addend, int64_t ldadd, void* out, int64_t ldo, int64_t n_rows, int H, int F, int C, int dt,
+                     int64_t band, void* stream);
 
 /* GATConv(edge_dim = 4): edge attributes fp32 [E, 4] -> fp32 [nnz, 4] in the order of the self-loop-replaced
  * target-major CSR (eid from b2g_csr_fill): dropped loops lose their attributes, every node's new loop gets the mean

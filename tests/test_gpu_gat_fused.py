@@ -211,3 +211,59 @@ def test_gatconv_fused_dropout_uses_the_mask_the_backward_regenerates(monkeypatc
     with torch.no_grad():
         ev = m(x, ei).float()
     assert float((res["fused"][0] - ev).abs().max() / scale) > 5e-2           # the mask is really applied
+
+
+@pytest.mark.parametrize("C", [128, 256])
+@pytest.mark.parametrize("train", [False, True])
+def test_transformerconv_fused_equals_unfused_and_oracle(C, train, monkeypatch):
+    """Fused TransformerConv forward (b2g_tz_alpha + b2g_gatw_gemm_ex: value projection, s.bv and skip terms in one kernel, no
+    z_aug) against the unfused aggregate-first path and the fp64 oracle; gradients of both against the oracle (the fused
+    path derives d W_out from y instead of z_aug); with attention dropout both paths draw the same mask."""
+    import gnn_bfs_rans_b200 as b2g
+    from gnn_bfs_rans_b200 import ops
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    from oracle import layers_oracle as lo
+    nx, ny, nz = 24, 20, 18
+    N = nx * ny * nz
+    o, n = hex_mesh_faces(nx, ny, nz, device="cuda")
+    ei = ops.build_graph_edges(o, n, 1, None, N, N)
+    extra = torch.stack([torch.randint(0, N, (60,), device="cuda"), torch.full((60,), 17, device="cuda")])   # a hub target
+    ei = torch.cat([ei, extra], 1)
+    ei = ei[:, ei[1] != 5]                                                  # node 5 has no incoming edge at all
+    torch.manual_seed(1234)
+    m = b2g.nn.TransformerConv(256, C, heads=4, concat=False, dropout=0.2)
+    with torch.no_grad():
+        for p_ in m.parameters():
+            if p_.dim() == 1:
+                p_.uniform_(-0.5, 0.5)
+    m = m.cuda().bfloat16().train(train)
+    torch.manual_seed(5)
+    x = torch.randn(N, 256, device="cuda").bfloat16()
+    gout = torch.randn(N, C, device="cuda").bfloat16()
+    res = {}
+    for path in ("fused", "unfused"):
+        monkeypatch.setenv("B2G_TCONV_PATH", "" if path == "fused" else "unfused")
+        torch.manual_seed(77)
+        xg = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        out = m(xg, ei)
+        out.backward(gout)
+        res[path] = (out.detach(), xg.grad, {k: p.grad.clone() for k, p in m.named_parameters()})
+    rel = lambda a_, b_: float((a_.double().cpu() - b_.double().cpu()).abs().max() / b_.double().abs().max().clamp_min(1e-30))
+    l2 = lambda a_, b_: float((a_.double().cpu() - b_.double().cpu()).norm() / b_.double().norm().clamp_min(1e-30))
+    assert rel(res["fused"][0], res["unfused"][0]) < 1.2e-2
+    assert l2(res["fused"][1], res["unfused"][1]) < 2e-2
+    for k in res["unfused"][2]:
+        if float(res["unfused"][2][k].abs().max()) > 0:
+            assert l2(res["fused"][2][k], res["unfused"][2][k]) < 3e-2 or k == "lin_key.bias", k
+    if not train:
+        p = {k: v.detach().double().cpu().requires_grad_(True) for k, v in m.state_dict().items()}
+        x64 = x.double().cpu().requires_grad_(True)
+        ref = lo.transformer_conv(x64, ei.cpu(), p["lin_query.weight"], p["lin_query.bias"], p["lin_key.weight"], p["lin_key.bias"],
+                                  p["lin_value.weight"], p["lin_value.bias"], p["lin_skip.weight"], p["lin_skip.bias"], heads=4)
+        ref.backward(gout.double().cpu())
+        for path in ("fused", "unfused"):
+            assert rel(res[path][0], ref.detach()) < 2e-2, path
+            assert l2(res[path][1], x64.grad) < 2e-2, path
+            for k in ("lin_value.weight", "lin_value.bias", "lin_skip.weight", "lin_query.weight"):
+                assert l2(res[path][2][k], p[k].grad) < 2e-2, (path, k)
