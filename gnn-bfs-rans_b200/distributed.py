@@ -190,6 +190,28 @@ class Partition:
         from . import ops
         part = self
 
+        def ghost_ranges(g, n0):
+            """Row ranges [0, a) and [b, n0) that contain every owned row reading a ghost row (cached on the graph); None when
+            they are not two thin end ranges (general partitions: the exchange is then waited for before the kernel)."""
+            hit = getattr(g, "_ghost_ranges", False)
+            if hit is not False:
+                return hit
+            csr = g.csr("sl", False)
+            pos = torch.nonzero(csr.col[:int(csr.rowptr[n0])] >= n0).squeeze(1)
+            res = None
+            if pos.numel():
+                rows = torch.unique(torch.searchsorted(csr.rowptr[:n0 + 1].long(), pos, right=True) - 1)
+                mid = n0 // 2
+                lo, hi = rows[rows < mid], rows[rows >= mid]
+                a = int(lo.max()) + 1 if lo.numel() else 0
+                b = int(hi.min()) if hi.numel() else n0
+                if a + (n0 - b) <= n0 // 4:
+                    res = (a, b)
+            else:
+                res = (0, n0)
+            g._ghost_ranges = res
+            return res
+
         def fwd(x, ei):
             n0, nl = part.n_owned, part.n_local
             g = part._graph
@@ -212,6 +234,26 @@ class Partition:
                 done = torch.cuda.Event()
                 done.record(side)
             w = layer.lin.weight if layer.lin.weight.dtype == x.dtype else layer.lin.weight.to(x.dtype)
+            if (os.environ.get("B2G_GCN_PATH", "") == "fused"
+                    and ops.segw_gemm_supported(nl, x.shape[1], layer.out_channels, x.dtype)):
+                # fused aggregation + projection (csrc/gcn_fused.cu) on the raw rows: the interior rows (no ghost sources) run
+                # while the boundary rows of x travel; the two thin end ranges that read ghosts follow the exchange
+                out = x.new_empty((n0, layer.out_channels))
+                rng = ghost_ranges(g, n0)
+
+                def run(r0, r1):
+                    if r1 > r0:
+                        ops.segw_gemm(xf, csr.rowptr[r0:r1 + 1], csr.col, r1 - r0, w, layer.bias, col_scale=dinv,
+                                      row_scale=dinv[r0:r1], band=g.band(), out=out[r0:r1])
+                if rng is None:
+                    cur.wait_event(done)
+                    run(0, n0)
+                else:
+                    run(rng[0], rng[1])
+                    cur.wait_event(done)
+                    run(0, rng[0])
+                    run(rng[1], n0)
+                return out
             xs = x.new_empty((nl, layer.out_channels))
             ops.linear_fwd(xf[:n0], w, None, row_scale=dinv[:n0], out=xs[:n0])
             cur.wait_event(done)

@@ -89,6 +89,18 @@ class GCNFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, graph: Graph):
         csr = graph.csr("sl", False)
         dinv = graph.dinv()
+        if (os.environ.get("B2G_GCN_PATH", "") == "fused"
+                and ops.segw_gemm_supported(graph.N, x.shape[1], weight.shape[0], x.dtype)):
+            # opt-in (bf16, F = 256; csrc/gcn_fused.cu): aggregate the dinv-weighted INPUT rows and project them in one kernel —
+            # out = dinv_i (sum_j dinv_j x_j) W^T + b; the [N, F] intermediate never exists in HBM (10.9 GB instead of 21.5 GB).
+            # Correct and tested, but measured SLOWER than the two-kernel path at cfg4 (5.9 ms against 4.3 ms: 258 warp
+            # instructions per 4-row x 64-feature unit on 16 gather warps, DESIGN §4 point 9), so the default stays unfused.
+            out = ops.segw_gemm(x, csr.rowptr, csr.col, graph.N, weight, bias, col_scale=dinv, row_scale=dinv,
+                                band=graph.band())
+            ctx.save_for_backward(x, weight)
+            ctx.graph, ctx.has_bias = graph, bias is not None
+            ctx.ei_keepalive = graph.edge_index
+            return out
         xs, _ = ops.linear_fwd(x, weight, None, row_scale=dinv)
         out = ops.seg_sum(xs, csr.rowptr, csr.col, graph.N, dinv, None, 0.0, None,
                           bias.float() if bias is not None else None, band=graph.band())

@@ -243,6 +243,28 @@ def seg_sum(x, rowptr, col, n_rows, row_scale=None, col_scale=None, self_coef=0.
     return out
 
 
+def segw_gemm_supported(n: int, F: int, C: int, dtype) -> bool:
+    dt = F32 if dtype == torch.float32 else (BF16 if dtype == torch.bfloat16 else -1)
+    return dt >= 0 and bool(_lib.load().b2g_segw_gemm_supported(int(max(n, 1)), int(F), int(C), dt))
+
+
+def segw_gemm(x, rowptr, col, n_rows, w, bias=None, col_scale=None, row_scale=None, self_coef=0.0, relu=False, band=0, out=None):
+    """out [n_rows, C] = act(row_scale * (sum_j col_scale_j x_j + self_coef x_i) W^T + bias) in ONE kernel (csrc/gcn_fused.cu):
+    the CSR segment-sum feeding a tcgen05 GEMM from shared memory (GCNConv forward; GINConv + first Linear of its MLP)."""
+    _cuda(x, w)
+    x, w = _rows(x), _rows(w)
+    if w.dtype != x.dtype:
+        w = w.to(x.dtype)
+    C, F = w.shape
+    if out is None:
+        out = torch.empty((n_rows, C), dtype=x.dtype, device=x.device)
+    b = bias.float().contiguous() if bias is not None else None
+    _lib.check(_lib.load().b2g_segw_gemm(_p(x), _ld(x), _p(rowptr), _p(col), _p(col_scale), _p(row_scale), float(self_coef),
+                                         _p(w), _ld(w), _p(b), int(relu), _p(out), _ld(out), n_rows, F, C, _dt(x), int(band),
+                                         _stream()), "segw_gemm")
+    return out
+
+
 def colsum(x) -> torch.Tensor:
     _cuda(x)
     lib = _lib.load()

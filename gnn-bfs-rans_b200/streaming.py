@@ -117,7 +117,7 @@ def gcn_forward_host(layer: GCNConv, x_host: torch.Tensor, edge_index_host: torc
         dei.copy_(hei, non_blocking=True)
         ev_ei = torch.cuda.Event()
         ev_ei.record(s_in)
-        dx = torch.empty((N, F_in), dtype=hx.dtype, device=dev)
+        dx = torch.empty((n_local, F_in), dtype=hx.dtype, device=dev)      # [owned | ghost rows (fused path: filled by the exchange)]
         ev_x = []
         for r0, r1 in bounds:
             dx[r0:r1].copy_(hx[r0:r1], non_blocking=True)
@@ -148,15 +148,23 @@ def gcn_forward_host(layer: GCNConv, x_host: torch.Tensor, edge_index_host: torc
         band = int(torch.where(dsrc < N, (dsrc - ddst).abs(), torch.zeros_like(dsrc)).max()) if dei.shape[1] else 0
         wt = w if w.dtype == hx.dtype else w.to(hx.dtype)
         bias = layer.bias.float() if layer.bias is not None else None
-        xs = torch.empty((n_local, F_out), dtype=hx.dtype, device=dev)
+        import os
+        # opt-in B2G_GCN_PATH=fused (bf16, F = 256; csrc/gcn_fused.cu): every chunk is ONE kernel on the raw rows of x (aggregation + projection), the
+        # same arithmetic as GCNConv.forward on the whole graph; otherwise project each chunk as it lands, aggregate when ready
+        fused = (os.environ.get("B2G_GCN_PATH", "") == "fused" and ops.segw_gemm_supported(n_local, F_in, F_out, hx.dtype))
+        xs = dx if fused else torch.empty((n_local, F_out), dtype=hx.dtype, device=dev)
         out = torch.empty((N, F_out), dtype=hx.dtype, device=dev)
         out.record_stream(s_out)
         done_rows, pending = 0, list(range(len(bounds)))           # rows projected so far / chunks not yet aggregated
 
         def aggregate(c):
             r0, r1 = bounds[c]
-            ops.seg_sum(xs, csr.rowptr[r0:r1 + 1], csr.col, r1 - r0, dinv[r0:r1], None, 0.0, None, bias,
-                        out=out[r0:r1], band=g.band())
+            if fused:
+                ops.segw_gemm(xs, csr.rowptr[r0:r1 + 1], csr.col, r1 - r0, wt, bias, col_scale=dinv, row_scale=dinv[r0:r1],
+                              out=out[r0:r1])
+            else:
+                ops.seg_sum(xs, csr.rowptr[r0:r1 + 1], csr.col, r1 - r0, dinv[r0:r1], None, 0.0, None, bias,
+                            out=out[r0:r1], band=g.band())
             e = torch.cuda.Event()
             e.record(s_cmp)
             with torch.cuda.stream(s_out):
@@ -173,11 +181,12 @@ def gcn_forward_host(layer: GCNConv, x_host: torch.Tensor, edge_index_host: torc
 
         for c, (r0, r1) in enumerate(bounds):
             s_cmp.wait_event(ev_x[c])
-            ops.linear_fwd(dx[r0:r1], wt, None, row_scale=dinv[r0:r1], out=xs[r0:r1])
+            if not fused:
+                ops.linear_fwd(dx[r0:r1], wt, None, row_scale=dinv[r0:r1], out=xs[r0:r1])
             done_rows = r1
             aggregate_ready(False)
         if multi:
-            partition.exchange(xs)             # projected (and dinv-scaled) boundary rows -> the neighbours' ghost rows
+            partition.exchange(xs)             # boundary rows (projected + dinv-scaled, or raw when fused) -> the neighbours' ghost rows
         aggregate_ready(True)
     cur.wait_stream(s_out)
     cur.wait_stream(s_cmp)

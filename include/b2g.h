@@ -153,6 +153,19 @@ int b2g_seg_sum_tuned(const void* x, int64_t ldx, const void* x_self, int64_t ld
                       float self_coef, const float* bias, int relu, int64_t band, int64_t max_row_len, int impl,
                       int chunk_rows, int panel_rows, void* stream);
 
+/* ===================================================================================== K2f (fused)
+ * The CSR segment-sum FUSED with the layer's (first) Linear, bf16, F = 256 (csrc/gcn_fused.cu): the aggregated rows go from the
+ * gather warps into the shared-memory A operand of a tcgen05 GEMM against W (resident in shared memory); the [n, F]
+ * intermediate of the unfused K6 + K2 pair never exists in HBM.
+ *   out[i, :] = act( row_scale[i] * ( sum_{p in row i} col_scale[col_p] x[col_p, :] + self_coef x[i, :] ) W^T + bias )
+ * GCNConv (gnn_model.py:63,166): col_scale = row_scale = deg^-1/2 over the self-loop-replaced list, self_coef = 0;
+ * GINConv + the first Linear / ReLU of its MLP (gnn_model.py:70-75,166; inference): scales NULL, self_coef = 1 + eps, relu = 1.
+ * x: bf16 [*, F]; w: bf16 [C, F]; out: bf16 [n_rows, C]; C a multiple of 64, <= 256. */
+int b2g_segw_gemm_supported(int64_t n, int F, int C, int dt);
+int b2g_segw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const float* col_scale,
+                  const float* row_scale, float self_coef, const void* w, int64_t ldw, const float* bias, int relu, void* out,
+                  int64_t ldo, int64_t n_rows, int F, int C, int dt, int64_t band, void* stream);
+
 /* ===================================================================================== K4
  * GATConv (gnn_model.py:65-68,168) fused edge-score + segment-softmax + aggregate + head-mean +
  * bias.  xw: [N, H*C] (= lin(x)); a_src/a_dst: fp32 [N,H] with row stride
