@@ -45,7 +45,7 @@ SIGNATURES = {
     "b2g_segw_gemm": (i32, [vp, i64, vp, vp, vp, vp, f32, vp, i64, vp, i32, vp, i64, i64, i32, i32, i32, i64, vp]),
     "b2g_edge_rows_sl": (i32, [vp, i64, vp, vp, i64, vp, vp]),
     "b2g_gatw_gemm_ex": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp, i64, i64, i32, i32, i32, i32, i64, vp]),
-    "b2g_tz_alpha": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, f32, u64, i64, vp]),
+    "b2g_tz_alpha": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp, vp, f32, u64, i64, i32, vp]),
     "b2g_batch_finalize": (i32, [vp, i64, vp, vp, i32, vp, i64, vp]),
     "b2g_wmse_workspace_bytes": (i64, []),
     "b2g_wmse_fwd": (i32, [vp, i64, vp, i64, i64, i32, vp, f32, vp, vp, vp, vp]),

@@ -1038,6 +1038,95 @@ __global__ void __launch_bounds__(256, 2) tz_fwd_kernel(const GatzArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------ attention weights on the tensor cores
+// tz_alpha for bf16 rows of 512 bytes (F = 256, H = 4): the logits of a target row are the 8 x 4 matrix
+//     L[e, h] = sum_f x_{j(e)}[f] * u_ih[f]         (u already carries 1/sqrt(C), see tz_fwd_kernel)
+// = one m16n8k16 tile product chain (rows 8..15 and columns 4..7 are padding) with K = 256 in 16 steps.  The SIMT version
+// spent 592 warp instructions per row on it (unpack + packed FMAs + a 31-shuffle transposed reduction; ncu: issue 43 % at
+// 16 warps per SM, 12.3 ms at cfg4 for 30 GB = 2.4 TB/s); here it is 16 HMMAs on operands that are ALREADY in fragment layout:
+// the order of k is free in a dot product, so lane (g, q) = (entry, quarter) simply loads the 16-byte pieces q, q + 4, ...
+// of row x_{j(g)} (A fragment: a0 / a2 of step s = registers 2s, 2s + 1 of those 32) and of u_i's head g & 3 (B fragment),
+// 64 contiguous bytes per row and instruction.  The accumulator fragment leaves entry g / heads 2q, 2q + 1 in lanes q < 2;
+// two shuffles bring them to the packed (entry, head) = lane layout of the softmax (head_max8).
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  const uint32_t zero = 0u;                       // rows 8..15 of the A tile
+  asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(zero), "r"(a2), "r"(zero), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2) tz_alpha_mma_kernel(const GatzArgs a) {
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const char* xb = reinterpret_cast<const char*>(a.x) + q * 16;
+  const char* ub = reinterpret_cast<const char*>(a.dz) + (g & 3) * 512 + q * 16;
+  asm volatile("" : "+l"(xb));
+  asm volatile("" : "+l"(ub));
+  WarpRows r;
+  if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
+  // entry g of the 8-entry window at p0 (lanes past the row's end repeat its last entry: a valid address, logit masked)
+  auto entry = [&](int p0, int e_) -> int { return ldg_i32_ordered(a.col + max(min(p0 + g, e_ - 1), 0)); };
+  int cl = entry(r.b, r.e);
+  while (true) {
+    const int cl2 = entry(r.b2, r.e2);
+    r.look_ahead(a.ord, wi, a.rowptr);
+    const int len = r.e - r.b;
+    uint4 U[8];
+    {
+      const char* pu = ub + (uint64_t)r.i * a.dzrow_bytes;
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(U[m].x), "=r"(U[m].y), "=r"(U[m].z), "=r"(U[m].w) : "l"(pu + 64 * m));
+    }
+    // logit (+ edge term) of entry p0 + g, head q, for the window whose entry-g column index is c; -inf past the row's end
+    auto window_logit = [&](int c, int p0) -> float {
+      uint4 X[8];
+      const char* px = xb + (uint64_t)(uint32_t)c * a.xrow_bytes;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) X[m] = ldg_row16(px + 64 * m);
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};     // two chains: the HMMA latencies overlap
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        mma_bf16_16816(c0, X[m].x, X[m].y, U[m].x, U[m].y);
+        mma_bf16_16816(c1, X[m].z, X[m].w, U[m].z, U[m].w);
+      }
+      const float l0 = c0[0] + c1[0], l1 = c0[1] + c1[1];          // lane (g, q < 2): entry g, heads 2q and 2q + 1
+      const int src = (lane & ~3) | (q >> 1);
+      const float v0 = __shfl_sync(0xffffffffu, l0, src), v1 = __shfl_sync(0xffffffffu, l1, src);
+      float s = (q & 1) ? v1 : v0;                                  // lane 4g + h: logit of entry g, head h
+      const bool in = p0 + g < r.e;
+      if (a.ebias && in) s += __ldg(a.ebias + (uint64_t)(p0 + g) * GH + q);
+      return in ? s : -INFINITY;
+    };
+    // weights w of the window at p0 (0 past the end): alpha_e, dropout, de_e; returns the per-head sum of what was kept
+    auto emit = [&](float w, int p0) -> float {
+      const bool in = p0 + g < r.e;
+      if (a.alpha_e && in) a.alpha_e[(uint64_t)(p0 + g) * GH + q] = w;            // coalesced 4-byte stores
+      if (a.p_drop > 0.f) w *= packed_keep_scale(mix_epoch(a.seed, a.epoch), (uint64_t)(p0 + g), a.p_drop, q);
+      if (a.de_e && in) a.de_e[(uint64_t)(p0 + g) * GH + q] = w;
+      return head_sum8(w);
+    };
+    float ss = 0.f;
+    if (len > 0 && len <= 8) {                                      // every mesh row
+      const float sc = window_logit(cl, r.b);
+      const float m = head_max8(sc);
+      float w = __expf(sc - m);                                     // exp(-inf) = 0 past the end
+      w *= 1.0f / (head_sum8(w) + 1e-16f);
+      ss = emit(w, r.b);
+    } else if (len > 8) {                                           // cold: three sweeps over the 8-entry windows
+      float m = -INFINITY, zs = 0.f;
+      for (int p0 = r.b; p0 < r.e; p0 += 8) m = fmaxf(m, head_max8(window_logit(entry(p0, r.e), p0)));
+      for (int p0 = r.b; p0 < r.e; p0 += 8) zs += head_sum8(__expf(window_logit(entry(p0, r.e), p0) - m));
+      const float inv = 1.0f / (zs + 1e-16f);
+      for (int p0 = r.b; p0 < r.e; p0 += 8) ss += emit(__expf(window_logit(entry(p0, r.e), p0) - m) * inv, p0);
+    }
+    if (a.smax && lane < GH) a.smax[(uint64_t)r.i * GH + lane] = ss;          // lanes 0..3: head = lane
+    if (!r.shift()) break;
+    cl = cl2;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ backward, source side
 // Row j of the TRANSPOSED CSR: entries (i = col[t], p = perm[t] = the edge's position in the target-major CSR).
 //   y_j[h] = sum_t alpha_e[p, h] * g_i,   d a_src[j, h] = sum_t de_e[p, h]
@@ -1416,10 +1505,11 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* x_self, const void* u, in
 
 /* Attention weights only (fused TransformerConv forward, gat_fused.cu): alpha_pre [nnz, H] = softmax_j(u_ih . x_j (+ edge_bias)),
  * alpha_post (NULL when p_drop == 0: identical) = alpha_pre with the attention-dropout keep scale, ssum [n, H] = per-head sums of
- * the post-dropout weights.  Same kernel as b2g_tz_fwd without the weighted sums. */
+ * the post-dropout weights.  impl 0: bf16 rows of 512 bytes take tz_alpha_mma_kernel (logits by mma.sync), everything else
+ * b2g_tz_fwd's kernel without the weighted sums; impl 1: always the latter (A/B runs, tests). */
 int b2g_tz_alpha(const void* x, int64_t ldx, const void* u, int64_t ldu, int64_t n, int H, int F, int dt, const int32_t* rowptr,
                  const int32_t* col, float* alpha_pre, float* alpha_post, float* ssum, const float* edge_bias, float p_drop,
-                 uint64_t seed, int64_t band, void* stream) {
+                 uint64_t seed, int64_t band, int impl, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
@@ -1434,6 +1524,11 @@ int b2g_tz_alpha(const void* x, int64_t ldx, const void* u, int64_t ldu, int64_t
   a.x = x; a.x_self = x; a.xrow_bytes = (uint32_t)(ldx * es); a.dz = u; a.dzrow_bytes = (uint32_t)(ldu * es);
   a.rowptr = rowptr; a.col = col; a.alpha_e = alpha_pre; a.de_e = p_drop > 0.f ? alpha_post : nullptr; a.smax = ssum;
   a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.ebias = edge_bias; a.alpha_only = 1;
+  if (impl != 1 && dt == B2G_BF16 && F * es == 512) {               // logits on the tensor cores (tz_alpha_mma_kernel)
+    tz_alpha_mma_kernel<<<(unsigned)gatz_blocks(tz_alpha_mma_kernel, a.ord), 256, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    return cuda_status();
+  }
   return gatz_dispatch(3, dt, F * es, a, (cudaStream_t)stream);
 }
 

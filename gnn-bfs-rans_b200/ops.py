@@ -454,17 +454,18 @@ def gatw_gemm(x, rowptr, col, perm, alpha, wp, bias, n_rows, H, band=0, out=None
     return out
 
 
-def tz_alpha(x, u, H, rowptr, col, p_drop, seed, band=0, edge_bias=None):
-    """TransformerConv attention weights without the weighted sums (gat_rows.cu tz_fwd_kernel, alpha-only mode):
+def tz_alpha(x, u, H, rowptr, col, p_drop, seed, band=0, edge_bias=None, impl=0):
+    """TransformerConv attention weights without the weighted sums (gat_rows.cu: tz_alpha_mma_kernel for bf16 F = 256 — the
+    logits as m16n8k16 tile products —, else / impl=1 tz_fwd_kernel in alpha-only mode):
     -> (alpha_pre [nnz, H], alpha_post | None (p_drop == 0), ssum fp32 [N, H] = per-head sums of the post-dropout weights)."""
     x, u = _rows(x), _rows(u)
-    N, F = x.shape
+    N, F = u.shape[0], x.shape[1]               # target rows = rows of u; x may hold more rows (sources that are not targets)
     nnz = max(col.numel(), 1)
     a_pre = torch.empty((nnz, H), dtype=torch.float32, device=x.device)
     a_post = torch.empty((nnz, H), dtype=torch.float32, device=x.device) if p_drop > 0 else None
     ssum = torch.empty((N, H), dtype=torch.float32, device=x.device)
     _lib.check(_lib.load().b2g_tz_alpha(_p(x), _ld(x), _p(u), _ld(u), N, H, F, _dt(x), _p(rowptr), _p(col), _p(a_pre), _p(a_post),
-                                        _p(ssum), _p(edge_bias), float(p_drop), int(seed), int(band), _stream()), "tz_alpha")
+                                        _p(ssum), _p(edge_bias), float(p_drop), int(seed), int(band), int(impl), _stream()), "tz_alpha")
     return a_pre, a_post, ssum
 
 

@@ -244,10 +244,11 @@ int b2g_tz_fwd(const void* x, int64_t ldx, const void* x_self, const void* u, in
  * z_aug + r0 rows, x_self = x + r0 rows): the host-buffer pipeline of streaming.py. */
 /* Attention weights only (first half of b2g_tz_fwd; fused TransformerConv forward): alpha_pre [nnz, H] = softmax over the
  * entries of a row of u_ih . x_j (+ edge_bias), alpha_post (may be NULL when p_drop == 0: identical) = alpha_pre times the
- * attention-dropout keep scale, ssum fp32 [n, H] = per-head sums of the post-dropout weights. */
+ * attention-dropout keep scale, ssum fp32 [n, H] = per-head sums of the post-dropout weights.  impl 0 = default (bf16,
+ * F = 256: the logits on the tensor cores), 1 = the SIMT dot products for every shape (A/B runs). */
 int b2g_tz_alpha(const void* x, int64_t ldx, const void* u, int64_t ldu, int64_t n, int H, int F, int dt, const int32_t* rowptr,
                  const int32_t* col, float* alpha_pre, float* alpha_post, float* ssum, const float* edge_bias, float p_drop,
-                 uint64_t seed, int64_t band, void* stream);
+                 uint64_t seed, int64_t band, int impl, void* stream);
 /* Target side of its backward pass: dz_aug [n, >= H*F + 8] (columns H*F .. H*F+H-1 = d s), alpha_in = the forward
  * pass's alpha_e; writes alpha_e (after dropout) and de_e [nnz, H] (gradients of the logits), target-major.  The
  * `du` (may be NULL) [n, H*F] receives d u_i = [sum_j de_ij1 x_j | ...] from the same gather.  The sums over the

@@ -37,6 +37,9 @@ for path in os.environ.get("PATHS", "aggregate,project").split(","):
     with torch.no_grad():
         outs[path] = layer(x, ei)
         ms = timeit(lambda: layer(x, ei))
+    if os.environ.get("FWD_ONLY"):
+        print(f"{dtype} {path:9s}: fwd {ms:.2f} ms", flush=True)
+        continue
     xg = x.clone().requires_grad_(True)
 
     def fb():

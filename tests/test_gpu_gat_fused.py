@@ -267,3 +267,58 @@ def test_transformerconv_fused_equals_unfused_and_oracle(C, train, monkeypatch):
             assert l2(res[path][1], x64.grad) < 2e-2, path
             for k in ("lin_value.weight", "lin_value.bias", "lin_skip.weight", "lin_query.weight"):
                 assert l2(res[path][2][k], p[k].grad) < 2e-2, (path, k)
+
+
+@pytest.mark.parametrize("N", [1, 37, 1000, 5000])
+@pytest.mark.parametrize("p_drop", [0.0, 0.3])
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_tz_alpha_tensor_core_logits_vs_simt_and_fp64(N, p_drop, with_bias):
+    """b2g_tz_alpha, bf16 F = 256: the m16n8k16 tile-product kernel (impl 0) against the SIMT dot products (impl 1) and an fp64
+    softmax of u_ih . x_j over random CSRs with empty rows, rows of 1..8, 9..31 and > 32 entries; same dropout mask."""
+    from gnn_bfs_rans_b200 import ops
+    import numpy as np
+    rng = np.random.default_rng(N + 7)
+    deg = rng.integers(0, 10, size=N)
+    if N > 30:
+        deg[4] = 70
+        deg[9] = 21
+        deg[N - 1] = 33
+        deg[7] = 0
+    rowptr = np.zeros(N + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(deg)
+    nnz = int(rowptr[-1])
+    n_src = N + 11
+    col = torch.from_numpy(rng.integers(0, n_src, size=max(nnz, 1))).int().cuda()[:nnz] if nnz else torch.zeros(0, dtype=torch.int32, device="cuda")
+    rp = torch.from_numpy(rowptr).int().cuda()
+    torch.manual_seed(N)
+    x = torch.randn(n_src, 256, device="cuda").bfloat16()
+    u = (torch.randn(N, 1024, device="cuda") / 16).bfloat16()
+    eb = torch.randn(max(nnz, 1), 4, device="cuda") if with_bias else None
+    res = {}
+    for impl in (0, 1):
+        res[impl] = ops.tz_alpha(x, u, 4, rp, col, p_drop, 99, band=0, edge_bias=eb, impl=impl)
+    if nnz:
+        rows = torch.repeat_interleave(torch.arange(N, device="cuda"), torch.from_numpy(deg).cuda())
+        logit = (u.double().view(N, 4, 256)[rows] * x.double()[col.long()].unsqueeze(1)).sum(-1)
+        if with_bias:
+            logit = logit + eb[:nnz].double()
+        mx = torch.full((N, 4), -float("inf"), dtype=torch.float64, device="cuda").scatter_reduce(0, rows[:, None].expand(-1, 4), logit, "amax")
+        ex = (logit - mx[rows]).exp()
+        den = torch.zeros(N, 4, dtype=torch.float64, device="cuda").index_add_(0, rows, ex)
+        ref = ex / (den[rows] + 1e-16)
+        for impl in (0, 1):
+            assert float((res[impl][0][:nnz].double() - ref).abs().max()) < 2e-5, impl
+        assert float((res[0][0][:nnz] - res[1][0][:nnz]).abs().max()) < 2e-6         # same products, another summation order
+        if p_drop > 0:
+            keep0, keep1 = res[0][1][:nnz] != 0, res[1][1][:nnz] != 0
+            assert torch.equal(keep0 | (res[0][0][:nnz] == 0), keep1 | (res[1][0][:nnz] == 0))   # the same Philox mask
+            assert float((res[0][1][:nnz] - res[1][1][:nnz]).abs().max()) < 4e-6
+            post = res[0][1][:nnz]
+        else:
+            assert res[0][1] is None
+            post = res[0][0][:nnz]
+        ssum = torch.zeros(N, 4, device="cuda").index_add_(0, rows, post)
+        assert float((res[0][2] - ssum).abs().max()) < 1e-5
+    empty = torch.from_numpy(deg == 0).cuda()
+    if bool(empty.any()):
+        assert float(res[0][2][empty].abs().max()) == 0.0
