@@ -15,6 +15,7 @@
 // warps 2..9 = epilogue (TMEM lane quadrant = warp_idx % 4; the two warps of a quadrant take alternate
 // 64-column chunks).  The epilogue is instruction-bound with one warp per scheduler, hence eight warps
 // and a specialised chunk body per (row-scale, bias, ReLU) combination.
+#include <cstdlib>
 #include "tc_ptx.cuh"
 
 namespace b2g {
@@ -29,16 +30,19 @@ constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;   // 32 KB
 constexpr int TC_TMEM_COLS = 512; // two 256-column fp32 accumulators
 constexpr int TC_STG_PITCH = 128; // epilogue staging: 32 rows x 128 B per warp, 16-byte pieces XOR-swizzled by row
 constexpr int TC_STG_BYTES = TC_EPI_WARPS * 32 * TC_STG_PITCH;   // 32 KB: a private 32-row x 128-byte buffer per epilogue warp
+                                                                  // (the streaming plan holds two per warp: the TMA store of one
+                                                                  // chunk reads its buffer while the next chunk is packed)
 constexpr int TC_BAR_BYTES = 128;                     // (2*5 + 6) x 8 bytes
 // Two shared-memory plans (227 KB = 232448 B per CTA on sm_100):
-//  kBRes = true  (m <= 256, k <= 256: GCNConv / GINConv / plain Linear): W is loaded ONCE per CTA and stays
-//                resident (k/64 x 32 KB); only X tiles stream through a 4-deep ring of 16 KB stages.
+//  kBRes = true  (k <= 256: GCNConv / GINConv / plain Linear, and the wide outputs of the attention layers, one 256-row
+//                block of W per CTA group): the W block is loaded ONCE per CTA and stays resident (k/64 x 32 KB); only X
+//                tiles stream through a 4-deep ring of 16 KB stages.
 //  kBRes = false (wide fused outputs: GAT 4F+8, Transformer 13F): a 4-deep ring of (X 16 KB + W 32 KB) stages.
 constexpr int TC_RES_STAGES = 4;
-constexpr int TC_STR_STAGES = 4;
+constexpr int TC_STR_STAGES = 3;
 constexpr int TC_RES_KB_MAX = 4;
 constexpr int TC_SMEM_RES = TC_RES_KB_MAX * TC_B_BYTES + TC_RES_STAGES * TC_A_BYTES + TC_STG_BYTES + TC_BAR_BYTES;   // 229504
-constexpr int TC_SMEM_STR = TC_STR_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_STG_BYTES + TC_BAR_BYTES;                  // 213120
+constexpr int TC_SMEM_STR = TC_STR_STAGES * (TC_A_BYTES + TC_B_BYTES) + 2 * TC_STG_BYTES + TC_BAR_BYTES;              // 213120
 static_assert(TC_SMEM_RES + 1024 <= 232448 && TC_SMEM_STR + 1024 <= 232448, "shared-memory plan exceeds 227 KB (1 KB is charged for the 1024-byte alignment)");
 
 // One 32-column slice of the accumulator row held by this lane: fused row-scale / bias / ReLU, pack to
@@ -81,11 +85,13 @@ struct TcParams {
   float* aux;
   int64_t ldaux;
   int act;
+  int tma_store;   // full 64-column chunks leave through map_y (cp.async.bulk.tensor stores) instead of LDS + 128-byte row stores
 };
 
 template <bool kBRes>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ CUtensorMap map_y, const TcParams p) {
   constexpr int STAGES = kBRes ? TC_RES_STAGES : TC_STR_STAGES;
   constexpr int STAGE_BYTES = kBRes ? TC_A_BYTES : (TC_A_BYTES + TC_B_BYTES);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -94,7 +100,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const uint32_t bres = smem_base;                          // resident W (kBRes only)
   const uint32_t ring = smem_base + (kBRes ? TC_RES_KB_MAX * TC_B_BYTES : 0);
   const uint32_t stg = ring + STAGES * STAGE_BYTES;
-  const uint32_t bars = stg + TC_STG_BYTES;
+  constexpr int NBUF = kBRes ? 1 : 2;                       // staging buffers per epilogue warp
+  const uint32_t bars = stg + NBUF * TC_STG_BYTES;
   // barrier slots (8 bytes each): full[S], empty[S], tmem_full[2], tmem_empty[2], b_full; then the TMEM base word
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -109,6 +116,32 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   const int col_tiles = (p.m + TC_BN - 1) / TC_BN;
   const int64_t tiles = row_tiles * col_tiles;
   const int kblocks = (p.k + TC_BK - 1) / TC_BK;
+  // j-th tile of this CTA.  With at least one row tile per CTA a CTA takes ALL column tiles of a row tile back to back: the
+  // X tile is then read from DRAM once and from L2 for the other column tiles (interleaved over CTAs the 256 -> 1024 GEMM
+  // read x twice: ncu 9.9 GB for 5.1 GB).  Small problems keep the interleaved order so that every SM gets a tile.
+  const bool row_major = row_tiles >= (int64_t)gridDim.x;
+  // Resident plan (k <= 256): the grid is col_tiles groups of CTAs; a CTA keeps ONE 256-row block of W in shared memory and
+  // sweeps the row tiles of its group, so a tile costs 64 KB of TMA traffic (X) instead of 192 KB (X + the W block again):
+  // the streamed 256 -> 1024 GEMM moved 60 GB from L2 to the SMs for 25.6 GB of HBM traffic.  The groups walk the rows in
+  // step, so the col_tiles reads of an X tile meet in L2.
+  const int my_ct = kBRes ? (int)(blockIdx.x % (unsigned)col_tiles) : 0;
+  auto tile_at = [&](int64_t j, int64_t& rt, int& ct) -> bool {
+    if (kBRes) {
+      rt = (int64_t)(blockIdx.x / (unsigned)col_tiles) + j * (int64_t)(gridDim.x / (unsigned)col_tiles);
+      ct = my_ct;
+      return rt < row_tiles;
+    }
+    if (row_major) {
+      const int64_t g = j / col_tiles;
+      rt = blockIdx.x + g * gridDim.x;
+      ct = (int)(j - g * col_tiles);
+      return rt < row_tiles;
+    }
+    const int64_t t = blockIdx.x + j * gridDim.x;
+    rt = t / col_tiles;
+    ct = (int)(t - rt * col_tiles);
+    return t < tiles;
+  };
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -138,13 +171,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       if (kBRes) {                                           // W: loaded once, resident for every tile of this CTA
         mbar_expect_tx(bfull_bar, (uint32_t)kblocks * TC_B_BYTES);
-        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(bres + kb * TC_B_BYTES, &map_b, bfull_bar, kb * TC_BK, 0);
+        for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(bres + kb * TC_B_BYTES, &map_b, bfull_bar, kb * TC_BK, my_ct * TC_BN);
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int64_t rt = t / col_tiles;
-        const int ct = (int)(t - rt * col_tiles);
+      for (int64_t j = 0;; ++j) {
+        int64_t rt;
+        int ct;
+        if (!tile_at(j, rt, ct)) break;
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = ring + stage * STAGE_BYTES;
@@ -167,7 +201,10 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(bfull_bar, 0);
         tc_fence_after();
       }
-      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      for (int64_t j = 0;; ++j) {
+        int64_t rt;
+        int ct;
+        if (!tile_at(j, rt, ct)) break;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
@@ -193,14 +230,16 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // ===================================================== epilogue warps 2..9
     const int q = warp & 3;                                   // TMEM lane quadrant this warp may read
     const int half = (warp - 2) >> 2;                         // which of the quadrant's two warps
-    uint8_t* my_stg = smem_raw + (stg - smem_base) + (warp - 2) * 32 * TC_STG_PITCH;
+    uint8_t* const my_stg0 = smem_raw + (stg - smem_base) + (warp - 2) * NBUF * 32 * TC_STG_PITCH;
+    uint32_t sbuf = 0;                                        // staging buffer of the next chunk
     const bool vec_ok = (p.m_main % 8) == 0;                  // 16-byte pieces never straddle the Y / aux split
     const int flags = (p.row_scale ? 1 : 0) | (p.bias ? 2 : 0) | (p.act == 1 ? 4 : 0);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int64_t rt = t / col_tiles;
-      const int ct = (int)(t - rt * col_tiles);
+    for (int64_t j = 0;; ++j) {
+      int64_t rt;
+      int ct;
+      if (!tile_at(j, rt, ct)) break;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int64_t row0 = rt * TC_BM + q * 32;
@@ -214,11 +253,23 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_BN + c);
         const int cg0 = col0 + c;
         if (vec_ok && cg0 + 64 <= p.m_main) {
-          // ---- fast path: 64 full columns -> bf16 -> swizzled staging -> 128-byte row stores
+          // ---- fast path: 64 full columns -> bf16 -> swizzled staging -> one TMA tile store (or 128-byte row stores).
+          // ncu on the 256 -> 1024 GEMM (write-heavy): the LSU data pipe was 81 % busy with STS + LDS + STG of every output
+          // byte; the staging buffer IS the SWIZZLE_128B image of a 32-row x 64-column box, so the copy-out is one bulk store.
+          uint8_t* const my_stg = my_stg0 + sbuf * (32 * TC_STG_PITCH);
+          uint32_t r2[2][32];
+          tc_ld32_issue(taddr, r2[0]);                        // both halves in flight: one TMEM latency per chunk
+          tc_ld32_issue(taddr + 32, r2[1]);
+          if (p.tma_store) {
+            if (lane == 0) {                                  // the store that last read THIS buffer has finished reading
+              if (NBUF == 2) tma_store_wait_read1(); else tma_store_wait_read();
+            }
+            __syncwarp();
+          }
+          tc_wait_ld();
 #pragma unroll
           for (int hlf = 0; hlf < 2; ++hlf) {
-            uint32_t r[32];
-            tc_ld32(taddr + hlf * 32, r);
+            const uint32_t (&r)[32] = r2[hlf];
             switch (flags) {   // warp-uniform; each case is a straight-line body without per-element predicates
               case 0: epi_pack<false, false, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
               case 1: epi_pack<true, false, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
@@ -229,6 +280,13 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               case 6: epi_pack<false, true, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
               default: epi_pack<true, true, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
             }
+          }
+          if (p.tma_store) {
+            fence_proxy_async_smem();                         // generic-proxy STS -> visible to the async proxy
+            __syncwarp();
+            if (lane == 0 && row0 < p.n) tma_store_2d(&map_y, smem_u32(my_stg), cg0, (int)row0);   // rows >= n are clipped
+            sbuf = (sbuf + 1) & (NBUF - 1);
+            continue;
           }
           __syncwarp();
           const int piece = lane & 7;                         // 16-byte piece inside the 128-byte row segment
@@ -273,6 +331,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && lane == 0) tma_store_wait_all();       // shared memory stays valid until the last store has read it
   }
 
   tc_fence_before();
@@ -818,6 +877,9 @@ static int tc_linear_fwd_tf32x3(const void* X, int64_t ldx, const void* W, int64
   return cuda_status();
 }
 
+// B2G_TC_TMA_STORE=0 in the environment at first use selects the LDS + row-store epilogue (A/B runs); read once, never written
+static const int g_tma_store = [] { const char* e = getenv("B2G_TC_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
+
 int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                   const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n, int m,
                   int m_main, int k, int dt, int act, void* ws, cudaStream_t st) {
@@ -839,13 +901,19 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   TcParams p;
   p.n = n; p.m = m; p.m_main = m_main; p.k = k; p.bias = bias; p.row_scale = row_scale;
   p.Y = static_cast<__nv_bfloat16*>(Y); p.ldy = ldy; p.aux = aux; p.ldaux = ldaux; p.act = act;
-  const int64_t tiles = ceil_div(n, TC_BM) * ceil_div(m, TC_BN);
+  CUtensorMap map_y = map_a;                                  // placeholder when the row-store epilogue is used
+  p.tma_store = (g_tma_store && m_main >= 64 && (m_main % 8) == 0 && make_map(&map_y, Y, n, m_main, ldy, 32)) ? 1 : 0;
+  const int64_t row_tiles = ceil_div(n, TC_BM), col_tiles = ceil_div(m, TC_BN);
+  const int64_t tiles = row_tiles * col_tiles;
   int sms = B2G_NUM_SMS;
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  if (m <= TC_BN && k <= TC_RES_KB_MAX * TC_BK)
-    tc_linear_kernel<true><<<grid, TC_THREADS, TC_SMEM_RES, st>>>(map_a, map_b, p);
-  else
-    tc_linear_kernel<false><<<grid, TC_THREADS, TC_SMEM_STR, st>>>(map_a, map_b, p);
+  if (k <= TC_RES_KB_MAX * TC_BK && col_tiles <= sms) {
+    int64_t per = sms / col_tiles;                            // CTAs per column group
+    if (per > row_tiles) per = row_tiles;
+    tc_linear_kernel<true><<<(unsigned)(per * col_tiles), TC_THREADS, TC_SMEM_RES, st>>>(map_a, map_b, map_y, p);
+  } else {
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    tc_linear_kernel<false><<<grid, TC_THREADS, TC_SMEM_STR, st>>>(map_a, map_b, map_y, p);
+  }
   count_launch();
   return cuda_status();
 }
