@@ -56,10 +56,10 @@ SIGNATURES = {
     "b2g_gatw_gemm": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, i32, i64, vp]),
     "b2g_rowdot8": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp]),
     "b2g_gatz_fwd": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, f32, vp, vp, vp, vp, f32, u64, i64, vp]),
-    "b2g_gatz_bwd_dst": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, f32, vp, vp, vp, vp, f32, u64, vp, vp, vp, i64, i32, vp, i64, vp]),
+    "b2g_gatz_bwd_dst": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, f32, vp, vp, vp, vp, f32, u64, vp, vp, vp, i64, i32, vp, i64, i64, vp]),
     "b2g_gatz_bwd_src": (i32, [vp, i64, vp, vp, vp, i64, vp, i64, i32, i64, i32, i32, i32, vp, vp, vp, i64, vp]),
     "b2g_tz_fwd": (i32, [vp, i64, vp, vp, i64, vp, i64, i64, i32, i32, i32, vp, vp, vp, vp, f32, u64, i64, vp]),
-    "b2g_tz_bwd_dst": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, f32, u64, vp, vp, vp, i64, vp, i64, vp]),
+    "b2g_tz_bwd_dst": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, f32, u64, vp, vp, vp, i64, vp, i64, i64, vp]),
     "b2g_edge_dot4": (i32, [vp, i64, vp, vp, i64, i32, vp, vp]),
     "b2g_edge_wsum4": (i32, [vp, vp, vp, i64, i32, f32, u64, vp, i64, i32, vp]),
     "b2g_tconv_fwd": (i32, [vp, vp, vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp, f32, u64, vp]),

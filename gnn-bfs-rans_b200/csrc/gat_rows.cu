@@ -17,6 +17,7 @@
 //   K6 GEMM           dx = [y | d a] [W/H ; V]                   (one GEMM, k = H*C + 2H)
 // Deterministic: fp32 accumulation in CSR (= edge) order; attention dropout is the same counter-based Philox stream as
 // attention.cu (keyed by the target-major edge position), regenerated in backward.
+#include <cstdlib>
 #include "rows.cuh"
 
 namespace b2g {
@@ -117,6 +118,7 @@ struct GatzArgs {
   int alpha_only;                            // tz_fwd: attention weights only (fused TransformerConv forward): alpha_e = pre-dropout
                                              // weights, de_e = post-dropout weights (or NULL when p_drop == 0), smax = weight sums
   int da_bf16;                               // d_a holds bf16 (a column block of the bf16 dgrad operand) instead of fp32
+  int only_long;                             // bwd_dst: rows of <= 8 entries were done by gatz_bwd_dst_mma_kernel: skip them
   uint32_t n_rows;
   float slope, p_drop;
   uint64_t seed;
@@ -641,7 +643,9 @@ __global__ void __launch_bounds__(256, 2) gatz_bwd_dst_kernel(const GatzArgs a) 
     const int cl2 = window_entry(a.col, r.b2, r.e2, lane);
     r.look_ahead(a.ord, wi, a.rowptr);
     const int len = r.e - r.b;
-    if (len > 32) {
+    if (a.only_long && len <= 8) {
+      // done by gatz_bwd_dst_mma_kernel
+    } else if (len > 32) {
       gatz_bwd_dst_long<T, VPL, kT>(a, r.i, r.b, r.e);
     } else if (VPL == 1 && len > 0 && len <= 8 && (!kT || a.z)) {
       // every mesh row, packed (entry, head)-per-lane layout (see head_max8): ONE gather serves the d alpha dots and -
@@ -1191,6 +1195,226 @@ __global__ void __launch_bounds__(256, B2G_GATZ_MINB) gatz_bwd_src_kernel(const 
   }
 }
 
+// ------------------------------------------------------------------------------------------ weighted row sums on the tensor cores
+// y[h][f] = sum_e w[e][h] * x_e[f] for the <= 8 entries of a window is a (heads x entries) . (entries x features) product:
+// m16n8k8 tiles with A = the weights and B = 8 entries x 8 features.  The gathered rows arrive in the layout of
+// tz_alpha_mma_kernel (lane (g, q) = entry g, 16-byte pieces q, q + 4, ...: the A-fragment layout of an entries x features
+// matrix); one movmatrix (8x8 b16 transpose inside the warp) per register turns it into the B fragment: entries 2q, 2q + 1 of
+// the two features that lane (., q)'s register holds, so the accumulator fragment of thread (g, q) is y[head g] at exactly the
+// features of its own registers.  The weights keep fp32 accuracy: rows 0..3 of A carry their bf16 heads, rows 8..11 the bf16
+// remainders (w = hi + lo to 2^-17), and the two halves of the accumulator are added.  Per 8-entry window: 32 movmatrix + 32
+// HMMA + 64 FADD instead of 8 x (4 SHFL + 8 unpack + 16 packed FMA) = 224 instructions.
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t v) {
+  uint32_t d;
+  asm("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(v));
+  return d;
+}
+__device__ __forceinline__ void mma_bf16_1688(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, float c0, float c1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%8,%9,%10};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(b0), "f"(c0), "f"(c1), "f"(0.f), "f"(0.f));
+}
+// A fragment from the packed weights wp (lane 4u + h: weight of entry u, head h; 0 past the row's end)
+__device__ __forceinline__ void wsum_afrag(float wp, int g, int q, uint32_t& a0, uint32_t& a1) {
+  const float w0 = __shfl_sync(0xffffffffu, wp, 8 * q + (g & 3)), w1 = __shfl_sync(0xffffffffu, wp, 8 * q + 4 + (g & 3));
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(w0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(w1 - __bfloat162float(h1));
+  a0 = g < 4 ? ((uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16)) : 0u;
+  a1 = g < 4 ? ((uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16)) : 0u;
+}
+// single window (rows of <= 8 entries): products straight to the output row, no accumulators held
+__device__ __forceinline__ void wsum_mma8_store(char* yrow, const uint4 (&X)[8], uint32_t a0, uint32_t a1, int g, int q) {
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const uint32_t xr[4] = {X[m].x, X[m].y, X[m].z, X[m].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int r4 = 0; r4 < 4; ++r4) {
+      float d[4];
+      mma_bf16_1688(d, a0, a1, movmatrix_trans(xr[r4]), 0.f, 0.f);
+      o[r4] = pack_bf16x2(d[0] + d[2], d[1] + d[3]);
+    }
+    if (g < 4) __stcs(reinterpret_cast<uint4*>(yrow + g * 512 + (q + 4 * m) * 16), make_uint4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// gatz_bwd_dst for bf16 rows of 512 bytes, rows of <= 8 entries (every mesh row; longer rows are left to the SIMT kernel's
+// only_long pass): d alpha_eh = dz_ih . x_e as in tz_alpha_mma_kernel (16 HMMAs instead of ~380 instructions of unpack /
+// packed FMA / transposed reduction), the softmax backward in the packed (entry, head) = lane layout, and - TransformerConv -
+// du_i = sum_e de_eh x_e from the SAME registers through movmatrix + m16n8k8 (wsum_mma8_store).
+template <bool kT>
+__global__ void __launch_bounds__(256, 2) gatz_bwd_dst_mma_kernel(const GatzArgs a) {
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const char* xb = reinterpret_cast<const char*>(a.x) + q * 16;
+  const char* ub = reinterpret_cast<const char*>(a.dz) + (g & 3) * 512 + q * 16;
+  asm volatile("" : "+l"(xb));
+  asm volatile("" : "+l"(ub));
+  WarpRows r;
+  if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
+  auto entry = [&](int b_, int e_) -> int { return ldg_i32_ordered(a.col + max(min(b_ + g, e_ - 1), 0)); };
+  int cl = entry(r.b, r.e);
+  while (true) {
+    const int cl2 = entry(r.b2, r.e2);
+    r.look_ahead(a.ord, wi, a.rowptr);
+    const int len = r.e - r.b;
+    if (len == 0) {
+      if (!kT) {
+        if (lane < GH) store_da(a, r.i, GH + lane, 0.f);
+      } else if (a.z && g < 4) {
+        char* zrow = reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) __stcs(reinterpret_cast<uint4*>(zrow + g * 512 + (q + 4 * m) * 16), make_uint4(0u, 0u, 0u, 0u));
+      }
+    } else if (len <= 8) {
+      uint4 X[8], U[8];
+      const char* px = xb + (uint64_t)(uint32_t)cl * a.xrow_bytes;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) X[m] = ldg_row16(px + 64 * m);
+      const char* pu = ub + (uint64_t)r.i * a.dzrow_bytes;
+#pragma unroll
+      for (int m = 0; m < 8; ++m)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(U[m].x), "=r"(U[m].y), "=r"(U[m].z), "=r"(U[m].w) : "l"(pu + 64 * m));
+      // per-(entry, head) side inputs, requested before anything consumes the gathers
+      const bool in = g < len;
+      const uint64_t pos = (uint64_t)(r.b + min(g, len - 1));
+      float in0 = 0.f, in1 = 0.f, in2 = 0.f, in3 = 0.f, eb = 0.f;
+      if (kT) {
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in0) : "l"(a.alpha_in + pos * GH + q));                 // alpha (forward)
+        // d s_alpha of the row: bf16 columns H*F .. H*F+3 of dz_aug
+        unsigned short raw;
+        asm volatile("ld.global.nc.u16 %0, [%1];" : "=h"(raw)
+                     : "l"(reinterpret_cast<const char*>(a.dz) + (uint64_t)r.i * a.dzrow_bytes + GH * 512 + q * 2));
+        in1 = __uint_as_float((uint32_t)raw << 16);
+      } else {
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in0) : "l"(a.a + (uint64_t)(uint32_t)cl * a.lda + q));  // a_src
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in1) : "l"(a.a + (uint64_t)r.i * a.lda + GH + q));      // a_dst
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in2) : "l"(a.smax + (uint64_t)r.i * GH + q));
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(in3) : "l"(a.ssum + (uint64_t)r.i * GH + q));
+      }
+      if (a.ebias) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(eb) : "l"(a.ebias + pos * GH + q));
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        mma_bf16_16816(c0, X[m].x, X[m].y, U[m].x, U[m].y);
+        mma_bf16_16816(c1, X[m].z, X[m].w, U[m].z, U[m].w);
+      }
+      const float l0 = c0[0] + c1[0], l1 = c0[1] + c1[1];
+      const int src = (lane & ~3) | (q >> 1);
+      const float v0 = __shfl_sync(0xffffffffu, l0, src), v1 = __shfl_sync(0xffffffffu, l1, src);
+      float dal = (q & 1) ? v1 : v0;                               // lane 4g + h: dz_ih . x_g
+      float alpha, sraw = 1.0f;
+      if (kT) {
+        dal += in1;
+        if (in) dal += eb;
+        alpha = in ? in0 : 0.f;
+      } else {
+        sraw = in0 + in1;
+        if (in) sraw += eb;
+        alpha = in ? __expf(lrelu(sraw, a.slope) - in2) * (1.0f / in3) : 0.f;
+      }
+      const float mask = a.p_drop > 0.f ? packed_keep_scale(mix_epoch(a.seed, a.epoch), (uint64_t)(r.b + g), a.p_drop, q) : 1.0f;
+      dal *= mask;
+      const float t = head_sum8(alpha * dal);
+      const float de = alpha * (dal - t) * (sraw > 0.f ? 1.0f : a.slope);
+      if (in) {
+        a.alpha_e[(uint64_t)(r.b + g) * GH + q] = alpha * mask;
+        a.de_e[(uint64_t)(r.b + g) * GH + q] = de;
+      }
+      if (!kT) {
+        const float dad = head_sum8(de);
+        if (lane < GH) store_da(a, r.i, GH + lane, dad);
+      } else if (a.z) {
+        uint32_t a0, a1;
+        wsum_afrag(de, g, q, a0, a1);                               // de = 0 past the row's end (alpha = 0)
+        wsum_mma8_store(reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes, X, a0, a1, g, q);
+      }
+    }
+    if (!r.shift()) break;
+    cl = cl2;
+  }
+}
+
+// gatz_bwd_src for bf16 rows of 512 bytes: y_j = [sum_t alpha_e[p_t, h] g_{i_t}]_h, d a_src[j, h] = sum_t de_e[p_t, h]
+__global__ void __launch_bounds__(256, 2) gatz_bwd_src_mma_kernel(const GatzArgs a) {
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const char* xb = reinterpret_cast<const char*>(a.x) + q * 16;
+  asm volatile("" : "+l"(xb));
+  WarpRows r;
+  if (!r.begin(a.ord, a.n_rows, wi, a.rowptr)) return;
+  auto entry_c = [&](int p0, int e_) -> int { return ldg_i32_ordered(a.col + max(min(p0 + g, e_ - 1), 0)); };
+  auto entry_p = [&](int p0, int e_) -> int {                  // perm == NULL: the weights are in this CSR's order
+    const int t = max(min(p0 + g, e_ - 1), 0);
+    return a.perm ? ldg_i32_ordered(a.perm + t) : t;
+  };
+  int cl = entry_c(r.b, r.e), pl = entry_p(r.b, r.e);
+  while (true) {
+    const int cl2 = entry_c(r.b2, r.e2), pl2 = entry_p(r.b2, r.e2);
+    r.look_ahead(a.ord, wi, a.rowptr);
+    char* yrow = reinterpret_cast<char*>(a.z) + (uint64_t)r.i * a.zrow_bytes;
+    float das = 0.f;
+    // the window at p0 with entry-g indices (c, p): gathered rows, A fragment of the weights, d a_src partial sum
+    auto window = [&](int c, int p, int p0, uint4 (&X)[8], uint32_t& a0, uint32_t& a1) {
+      const char* px = xb + (uint64_t)(uint32_t)c * a.xrow_bytes;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) X[m] = ldg_row16(px + 64 * m);
+      float wv, dv = 0.f;
+      asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(wv) : "l"(a.alpha_e + (uint64_t)(uint32_t)p * GH + q));
+      if (a.d_a) asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(dv) : "l"(a.de_e + (uint64_t)(uint32_t)p * GH + q));
+      const bool in = p0 + g < r.e;
+      wsum_afrag(in ? wv : 0.f, g, q, a0, a1);
+      if (a.d_a) das += head_sum8(in ? dv : 0.f);
+    };
+    if (r.e == r.b) {                                               // no entries: zeros (and no gather through an index
+      if (g < 4) {                                                  // that belongs to no row: col may be a dummy when nnz = 0)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) __stcs(reinterpret_cast<uint4*>(yrow + g * 512 + (q + 4 * m) * 16), make_uint4(0u, 0u, 0u, 0u));
+      }
+    } else if (r.e - r.b <= 8) {                                    // every mesh row
+      uint4 X[8];
+      uint32_t a0, a1;
+      window(cl, pl, r.b, X, a0, a1);
+      wsum_mma8_store(yrow, X, a0, a1, g, q);
+    } else {                                                        // cold: piece by piece, accumulating over the 8-entry
+#pragma unroll 1                                                    // windows (8 accumulators instead of 64: no spills)
+      for (int m = 0; m < 8; ++m) {
+        float acc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 1
+        for (int p0 = r.b; p0 < r.e; p0 += 8) {
+          const int c = entry_c(p0, r.e), p = entry_p(p0, r.e);
+          const uint4 x4 = ldg_row16(xb + (uint64_t)(uint32_t)c * a.xrow_bytes + 64 * m);
+          const bool in = p0 + g < r.e;
+          const float wv = __ldg(a.alpha_e + (uint64_t)(uint32_t)p * GH + q);
+          if (m == 0 && a.d_a) das += head_sum8(in ? __ldg(a.de_e + (uint64_t)(uint32_t)p * GH + q) : 0.f);
+          uint32_t a0, a1;
+          wsum_afrag(in ? wv : 0.f, g, q, a0, a1);
+          const uint32_t xr[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+          for (int r4 = 0; r4 < 4; ++r4) {
+            float d[4];
+            mma_bf16_1688(d, a0, a1, movmatrix_trans(xr[r4]), acc[r4][0], acc[r4][1]);
+            acc[r4][0] = d[0] + d[2];
+            acc[r4][1] = d[1] + d[3];
+          }
+        }
+        if (g < 4)
+          __stcs(reinterpret_cast<uint4*>(yrow + g * 512 + (q + 4 * m) * 16),
+                 make_uint4(pack_bf16x2(acc[0][0], acc[0][1]), pack_bf16x2(acc[1][0], acc[1][1]),
+                            pack_bf16x2(acc[2][0], acc[2][1]), pack_bf16x2(acc[3][0], acc[3][1])));
+      }
+    }
+    if (a.d_a && lane < GH) store_da(a, r.i, lane, das);
+    if (!r.shift()) break;
+    cl = cl2; pl = pl2;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ a = x V^T
 // Warp per row, 4 consecutive rows per step: 32 partial dot products reduced with one transposed reduction; lane
 // 8r + m ends up with a[row r, m] -> one coalesced 128-byte store per step when lda = 8.
@@ -1274,6 +1498,8 @@ static int gatz_dispatch(int which, int dt, int row_bytes, const GatzArgs& a, cu
 
 static inline int esz(int dt) { return dt == B2G_F32 ? 4 : 2; }
 static inline bool fits32(int64_t v) { return v >= 0 && v < (1ll << 32); }
+// B2G_ATTN_MMA=0 in the environment at load time keeps the SIMT kernels for bf16 F = 256 (A/B runs); read once, never written
+static const int g_attn_mma = [] { const char* e = getenv("B2G_ATTN_MMA"); return (e && e[0] == '0') ? 0 : 1; }();
 
 // ------------------------------------------------------------------------------------------ edge features (edge_dim)
 // TransformerConv(edge_dim = 4) in the aggregate-first form: with e_ijh = We_h a_ij (lin_edge, no bias) PyG
@@ -1402,7 +1628,8 @@ int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda,
 int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, const void* dz, int64_t lddz,
                      int64_t n, int H, int F, int dt, float slope, const int32_t* rowptr, const int32_t* col,
                      const float* smax, const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* de_e,
-                     void* d_a, int64_t ldda, int d_a_dt, const float* edge_bias, int64_t band, void* stream) {
+                     void* d_a, int64_t ldda, int d_a_dt, const float* edge_bias, int64_t band, int64_t max_row_len,
+                     void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
@@ -1421,6 +1648,12 @@ int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t 
   a.slope = slope; a.p_drop = p_drop; a.seed = seed; a.epoch = dropout_epoch_ptr(); a.alpha_e = alpha_e; a.de_e = de_e; a.d_a = static_cast<float*>(d_a); a.ldda = (uint32_t)ldda;
   a.da_bf16 = d_a_dt == B2G_BF16;
   a.ebias = edge_bias;
+  if (g_attn_mma && dt == B2G_BF16 && F * es == 512) {              // rows of <= 8 entries on the tensor cores, the rest after
+    gatz_bwd_dst_mma_kernel<false><<<(unsigned)gatz_blocks(gatz_bwd_dst_mma_kernel<false>, a.ord), 256, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    if (max_row_len > 0 && max_row_len <= 8) return cuda_status();
+    a.only_long = 1;
+  }
   return gatz_dispatch(1, dt, F * es, a, (cudaStream_t)stream);
 }
 
@@ -1442,6 +1675,11 @@ int b2g_gatz_bwd_src(const void* g, int64_t ldg, const float* alpha_e, const flo
   a.x = g; a.xrow_bytes = (uint32_t)(ldg * es); a.z = y; a.zrow_bytes = (uint32_t)(ldy * es);
   a.rowptr = rowptr_t; a.col = col_t; a.perm = perm; a.alpha_e = const_cast<float*>(alpha_e); a.de_e = const_cast<float*>(de_e);
   a.d_a = static_cast<float*>(d_a); a.ldda = (uint32_t)ldda; a.da_bf16 = d_a && d_a_dt == B2G_BF16;
+  if (g_attn_mma && dt == B2G_BF16 && C * es == 512) {              // weighted sums as m16n8k8 tile products
+    gatz_bwd_src_mma_kernel<<<(unsigned)gatz_blocks(gatz_bwd_src_mma_kernel, a.ord), 256, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    return cuda_status();
+  }
   return gatz_dispatch(2, dt, C * es, a, (cudaStream_t)stream);
 }
 
@@ -1536,7 +1774,7 @@ int b2g_tz_alpha(const void* x, int64_t ldx, const void* u, int64_t ldu, int64_t
  * the forward pass's alpha [nnz,H]; writes alpha_e (after dropout) and de_e [nnz,H] in target-major CSR order. */
 int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz, const float* alpha_in, int64_t n, int H,
                    int F, int dt, const int32_t* rowptr, const int32_t* col, float p_drop, uint64_t seed, float* alpha_e,
-                   float* de_e, void* du, int64_t lddu, const float* edge_bias, int64_t band, void* stream) {
+                   float* de_e, void* du, int64_t lddu, const float* edge_bias, int64_t band, int64_t max_row_len, void* stream) {
   if (n < 0 || H != GH) return n < 0 ? B2G_E_ARG : B2G_E_UNSUPPORTED;
   if (n == 0) return B2G_OK;
   const int es = esz(dt);
@@ -1555,6 +1793,12 @@ int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz,
     if (!aligned16(du) || (lddu * es) % 16 || lddu < (int64_t)H * F) return B2G_E_ALIGN;
     if (!fits32(lddu * es)) return B2G_E_SHAPE;
     a.z = du; a.zrow_bytes = (uint32_t)(lddu * es);
+  }
+  if (g_attn_mma && dt == B2G_BF16 && F * es == 512) {
+    gatz_bwd_dst_mma_kernel<true><<<(unsigned)gatz_blocks(gatz_bwd_dst_mma_kernel<true>, a.ord), 256, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    if (max_row_len > 0 && max_row_len <= 8) return cuda_status();
+    a.only_long = 1;
   }
   return gatz_dispatch(4, dt, F * es, a, (cudaStream_t)stream);
 }

@@ -241,7 +241,8 @@ class GATZFn(torch.autograd.Function):
         ka = H * C + 2 * H
         y_aug = ops.empty_rows(N, ka, x.dtype, x.device)
         _, de_e = ops.gatz_bwd(x, a, dz, g, H, slope, csr.pair(), csr_t.pair(), perm, smax, ssum, p_drop, seed,
-                               y_aug[:, :H * C], band=graph.band(), d_a_out=y_aug[:, H * C:], edge_bias=eb, want_de=True)
+                               y_aug[:, :H * C], band=graph.band(), d_a_out=y_aug[:, H * C:], edge_bias=eb, want_de=True,
+                               max_row_len=graph.max_degree("sl"))
         del dz
         if has_edge and ctx.needs_input_grad[8]:
             # d ve_h = sum_p de[p, h] e_p: per-row partial sums (edge_wsum4), then one column sum
@@ -504,7 +505,8 @@ class TConvZFn(torch.autograd.Function):
         fuse_du = os.environ.get("B2G_TZ_FUSE_DU", "1") != "0"
         alpha_e, de_e = ops.tz_bwd_dst(x, dz_aug, alpha, H, csr.rowptr, csr.col, p_drop, seed,
                                        big[:, o_du:o_du + HF] if fuse_du else None,
-                                       band=band, edge_bias=dab)          # du comes out of the same gather as d alpha
+                                       band=band, edge_bias=dab,          # du comes out of the same gather as d alpha
+                                       max_row_len=graph.max_degree("raw"))
         del dz_aug, dab
         if not fuse_du:
             ops.seg_wsum4(x, de_e, csr.rowptr, csr.col, None, big[:, o_du:o_du + HF], band=band)

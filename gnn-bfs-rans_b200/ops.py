@@ -480,7 +480,7 @@ def edge_rows_sl(edge_attr, eid, rowptr, n_rows):
 
 
 def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, y_out, band=0, d_a_out=None, edge_bias=None,
-             want_de=False):
+             want_de=False, max_row_len=0):
     """Writes y = [sum_i alpha_ij1 g_i | ...] into y_out (a [N, H*C] view, any row stride) and the logit gradients
     d a = [d a_src | d a_dst] into d_a_out (a [N, 2H] view of dtype fp32 or x.dtype, any row stride; default: a new fp32
     tensor).  Returns d a."""
@@ -497,7 +497,8 @@ def gatz_bwd(x, a, dz, g, H, slope, csr, csr_t, perm, smax, ssum, p_drop, seed, 
     st = _stream()
     _lib.check(lib.b2g_gatz_bwd_dst(_p(x), _ld(x), _p(a), a.stride(0), _p(dz), _ld(dz), N, H, F, _dt(x), float(slope),
                                     _p(csr[0]), _p(csr[1]), _p(smax), _p(ssum), float(p_drop), int(seed), _p(alpha_e),
-                                    _p(de_e), _p(d_a), _ld(d_a), _dt(d_a), _p(edge_bias), int(band), st), "gatz_bwd_dst")
+                                    _p(de_e), _p(d_a), _ld(d_a), _dt(d_a), _p(edge_bias), int(band), int(max_row_len), st),
+               "gatz_bwd_dst")
     _lib.check(lib.b2g_gatz_bwd_src(_p(g), _ld(g), _p(alpha_e), _p(de_e), _p(y_out), _ld(y_out), _p(d_a), _ld(d_a), _dt(d_a),
                                     N, H, C, _dt(x), _p(csr_t[0]), _p(csr_t[1]), _p(perm), int(band), st), "gatz_bwd_src")
     return (d_a, de_e) if want_de else d_a                 # de_e: gradient of the logits in front of the LeakyReLU, [nnz, H]
@@ -529,7 +530,7 @@ def tz_fwd(x, u, H, rowptr, col, p_drop, seed, save_alpha, band=0, edge_bias=Non
     return z, alpha
 
 
-def tz_bwd_dst(x, dz_aug, alpha, H, rowptr, col, p_drop, seed, du_out, band=0, edge_bias=None):
+def tz_bwd_dst(x, dz_aug, alpha, H, rowptr, col, p_drop, seed, du_out, band=0, edge_bias=None, max_row_len=0):
     """-> (alpha_e after dropout, de_e) fp32 [nnz, H], target-major; writes du = [sum_j de_ijh x_j]_h into du_out
     (a [N, H*F] view, any row stride) from the same gather.  edge_bias: fp32 [nnz, H] added to d alpha' (edge features)."""
     x, dz_aug = _rows(x), _rows(dz_aug)
@@ -538,7 +539,8 @@ def tz_bwd_dst(x, dz_aug, alpha, H, rowptr, col, p_drop, seed, du_out, band=0, e
     de_e = torch.empty_like(alpha)
     _lib.check(_lib.load().b2g_tz_bwd_dst(_p(x), _ld(x), _p(dz_aug), _ld(dz_aug), _p(alpha), N, H, F, _dt(x), _p(rowptr),
                                           _p(col), float(p_drop), int(seed), _p(alpha_e), _p(de_e), _p(du_out),
-                                          _ld(du_out) if du_out is not None else 0, _p(edge_bias), int(band), _stream()),
+                                          _ld(du_out) if du_out is not None else 0, _p(edge_bias), int(band), int(max_row_len),
+                                          _stream()),
                "tz_bwd_dst")
     return alpha_e, de_e
 

@@ -213,11 +213,13 @@ int b2g_gatz_fwd(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda,
                  float p_drop, uint64_t seed, int64_t band, void* stream);
 /* Target side of the backward pass: given dz [n, H*F] writes the per-edge attention weights alpha_e [nnz,H] (after
  * dropout), the per-edge logit gradients de_e [nnz,H] (both in target-major CSR order) and d a_dst into columns
- * H..2H-1 of d_a (row stride ldda floats). */
+ * H..2H-1 of d_a (row stride ldda floats).  max_row_len: the longest row of (rowptr, col) when the caller knows it (0 = not
+ * known): bf16 F = 256 runs rows of <= 8 entries on the tensor cores and needs the second pass over the longer rows only when
+ * there are any. */
 int b2g_gatz_bwd_dst(const void* x, int64_t ldx, const float* a_srcdst, int64_t lda, const void* dz, int64_t lddz,
                      int64_t n, int H, int F, int dt, float slope, const int32_t* rowptr, const int32_t* col,
                      const float* smax, const float* ssum, float p_drop, uint64_t seed, float* alpha_e, float* de_e,
-                     void* d_a, int64_t ldda, int d_a_dt, const float* edge_bias, int64_t band, void* stream);
+                     void* d_a, int64_t ldda, int d_a_dt, const float* edge_bias, int64_t band, int64_t max_row_len, void* stream);
 /* edge_bias (may be NULL): GATConv(edge_dim) — fp32 [nnz, H], the edge term of the logits (added in front of the LeakyReLU,
  * as b2g_gat_alpha does); de_e is then also the gradient of that term.
  * d_a / d_a_dt: the [n, >= 2H] logit-gradient block, fp32 (B2G_F32) or bf16 (B2G_BF16: the column block of the bf16 dgrad
@@ -256,7 +258,7 @@ int b2g_tz_alpha(const void* x, int64_t ldx, const void* u, int64_t ldu, int64_t
  * the CSR passed in, d_a == NULL skips the logit-gradient row sums. */
 int b2g_tz_bwd_dst(const void* x, int64_t ldx, const void* dz_aug, int64_t lddz, const float* alpha_in, int64_t n, int H,
                    int F, int dt, const int32_t* rowptr, const int32_t* col, float p_drop, uint64_t seed, float* alpha_e,
-                   float* de_e, void* du, int64_t lddu, const float* edge_bias, int64_t band, void* stream);
+                   float* de_e, void* du, int64_t lddu, const float* edge_bias, int64_t band, int64_t max_row_len, void* stream);
 /* Edge features of TransformerConv(edge_dim = 4) (PyG: key_j + lin_edge(edge_attr), value_j + the same),
  * aggregate-first: with r_ih = We_h^T q_ih / sqrt(C) (16 more columns of the u GEMM) the logit term is r_ih . a_ij, and
  * sum_j alpha'_ijh We_h a_ij = We_h m_ih with m_ih = sum_j alpha'_ijh a_ij (16 more columns of the output GEMM): the

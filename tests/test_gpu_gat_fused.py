@@ -322,3 +322,51 @@ def test_tz_alpha_tensor_core_logits_vs_simt_and_fp64(N, p_drop, with_bias):
     empty = torch.from_numpy(deg == 0).cuda()
     if bool(empty.any()):
         assert float(res[0][2][empty].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N", [1, 37, 1000, 5000])
+@pytest.mark.parametrize("use_perm", [False, True])
+def test_weighted_row_sums_tensor_core_vs_fp64(N, use_perm):
+    """b2g_gatz_bwd_src for bf16 rows of 512 bytes (gatz_bwd_src_mma_kernel: the 4-head weighted sums as m16n8k8 tile products,
+    weights split into bf16 head + remainder) against fp64 on random CSRs with empty rows and rows of 1..8, 9..31, > 32 entries;
+    the companion row sums (d a_src)."""
+    from gnn_bfs_rans_b200 import ops
+    import numpy as np
+    rng = np.random.default_rng(N + 3)
+    deg = rng.integers(0, 10, size=N)
+    if N > 30:
+        deg[4] = 70
+        deg[9] = 21
+        deg[N - 1] = 33
+        deg[7] = 0
+    rowptr = np.zeros(N + 1, dtype=np.int64)
+    rowptr[1:] = np.cumsum(deg)
+    nnz = int(rowptr[-1])
+    n_src = N + 13
+    col = torch.from_numpy(rng.integers(0, n_src, size=max(nnz, 1))).int().cuda()
+    perm = torch.from_numpy(rng.permutation(max(nnz, 1))).int().cuda() if use_perm else None
+    rp = torch.from_numpy(rowptr).int().cuda()
+    torch.manual_seed(N)
+    x = torch.randn(n_src, 256, device="cuda").bfloat16()
+    w = torch.randn(max(nnz, 1), 4, device="cuda")
+    out = torch.full((N, 1024), float("nan"), device="cuda", dtype=torch.bfloat16)
+    d_a = torch.full((N, 8), float("nan"), device="cuda")
+    ops.seg_wsum4(x, w, rp, col, perm, out, d_a=d_a)
+    rows = torch.repeat_interleave(torch.arange(N, device="cuda"), torch.from_numpy(deg).cuda())
+    wp = w[perm.long()[:nnz]] if use_perm else w[:nnz]
+    ref = torch.zeros(N, 4, 256, dtype=torch.float64, device="cuda")
+    if nnz:
+        ref.index_add_(0, rows, wp.double().unsqueeze(2) * x.double()[col.long()[:nnz]].unsqueeze(1))
+    err = float((out.double().view(N, 4, 256) - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+    assert err < 6e-3, err                                                   # bf16 rounding of the output only
+    sums = torch.zeros(N, 4, dtype=torch.float64, device="cuda")
+    if nnz:
+        sums.index_add_(0, rows, wp.double())
+    assert float((d_a[:, :4].double() - sums).abs().max()) < 1e-4
+    # the weights keep fp32 accuracy: the error is the bf16 rounding of the result (2^-8 |y|) plus 1e-5 of sum |w| |x| — weights
+    # rounded to bf16 would show 2^-9 of that sum
+    mag = torch.zeros(N, 4, 256, dtype=torch.float64, device="cuda")
+    if nnz:
+        mag.index_add_(0, rows, wp.double().abs().unsqueeze(2) * x.double()[col.long()[:nnz]].abs().unsqueeze(1))
+    excess = (out.double().view(N, 4, 256) - ref).abs() - (2.0 ** -8) * ref.abs() - 1e-5 * mag
+    assert float(excess.max()) <= 0.0
