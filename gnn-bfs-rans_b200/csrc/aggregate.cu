@@ -203,7 +203,8 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const T* __restrict__ 
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = t / nvec;
     const int v = (int)(t - r * nvec);
-    stg_vec<T>(out + r * ldo + v * VN, ldg_vec<T>(x + (int64_t)__ldg(idx + r) * ldx + v * VN));
+    const int64_t src = idx ? (int64_t)__ldg(idx + r) : r;      // idx == NULL: identity (a strided row copy)
+    stg_vec<T>(out + r * ldo + v * VN, ldg_vec<T>(x + src * ldx + v * VN));
   }
 }
 template <typename T>
@@ -377,7 +378,7 @@ int b2g_rows_gather(const void* x, int64_t ldx, const int32_t* idx, int64_t n_id
                     int64_t ldo, int F, int dt, void* stream) {
   if (n_idx < 0 || F <= 0 || (dt != B2G_F32 && dt != B2G_BF16)) return B2G_E_ARG;
   if (n_idx == 0) return B2G_OK;
-  if (!x || !idx || !out) return B2G_E_ARG;
+  if (!x || !out) return B2G_E_ARG;                            // idx == NULL: rows 0 .. n_idx-1 (copy into a column block)
   if ((F * elem_size(dt)) % 16 != 0) return B2G_E_SHAPE;
   if (!row_ok(x, ldx, dt) || !row_ok(out, ldo, dt)) return B2G_E_ALIGN;
   const int nvec = F * elem_size(dt) / 16;

@@ -43,6 +43,8 @@ constexpr int TC_STR_STAGES = 3;
 constexpr int TC_RES_KB_MAX = 4;
 constexpr int TC_SMEM_RES = TC_RES_KB_MAX * TC_B_BYTES + TC_RES_STAGES * TC_A_BYTES + TC_STG_BYTES + TC_BAR_BYTES;   // 229504
 constexpr int TC_SMEM_STR = TC_STR_STAGES * (TC_A_BYTES + TC_B_BYTES) + 2 * TC_STG_BYTES + TC_BAR_BYTES;              // 213120
+constexpr int TC_SMEM_DUAL = TC_STR_STAGES * (2 * TC_A_BYTES + TC_B_BYTES) + TC_STG_BYTES + TC_BAR_BYTES;                // 229504
+static_assert(TC_SMEM_DUAL + 1024 <= 232448, "shared-memory plan 2 exceeds 227 KB");
 static_assert(TC_SMEM_RES + 1024 <= 232448 && TC_SMEM_STR + 1024 <= 232448, "shared-memory plan exceeds 227 KB (1 KB is charged for the 1024-byte alignment)");
 
 // One 32-column slice of the accumulator row held by this lane: fused row-scale / bias / ReLU, pack to
@@ -88,19 +90,26 @@ struct TcParams {
   int tma_store;   // full 64-column chunks leave through map_y (cp.async.bulk.tensor stores) instead of LDS + 128-byte row stores
 };
 
-template <bool kBRes>
+// kPlan: 0 = streaming (X + W k-blocks through the ring), 1 = resident W block (k <= 256), 2 = streaming with TWO row tiles per
+// W k-block (m <= 256, long k: the dgrad GEMMs of the attention layers, k = 1032 .. 3336).  Plan 0 re-reads the whole W (up to
+// 1.7 MB) from L2 for every 128 rows: ncu on the k = 3336 dgrad showed 69 GB of DRAM reads at 3.9 TB/s with ~200 GB of L2 -> SM
+// traffic.  Plan 2 multiplies each W k-block with two X tiles into the two TMEM accumulators (no accumulator double buffering:
+// the epilogue of a pair is 3 us against a 40 us main loop), which halves the W traffic per row.
+template <int kPlan>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_y, const TcParams p) {
+  constexpr bool kBRes = kPlan == 1, kDual = kPlan == 2;
   constexpr int STAGES = kBRes ? TC_RES_STAGES : TC_STR_STAGES;
-  constexpr int STAGE_BYTES = kBRes ? TC_A_BYTES : (TC_A_BYTES + TC_B_BYTES);
+  constexpr int STAGE_BYTES = kBRes ? TC_A_BYTES : ((kDual ? 2 : 1) * TC_A_BYTES + TC_B_BYTES);
+  constexpr int B_OFF = (kDual ? 2 : 1) * TC_A_BYTES;       // W block inside a streaming stage
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();                          // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t bres = smem_base;                          // resident W (kBRes only)
   const uint32_t ring = smem_base + (kBRes ? TC_RES_KB_MAX * TC_B_BYTES : 0);
   const uint32_t stg = ring + STAGES * STAGE_BYTES;
-  constexpr int NBUF = kBRes ? 1 : 2;                       // staging buffers per epilogue warp
+  constexpr int NBUF = kPlan == 0 ? 2 : 1;                  // staging buffers per epilogue warp
   const uint32_t bars = stg + NBUF * TC_STG_BYTES;
   // barrier slots (8 bytes each): full[S], empty[S], tmem_full[2], tmem_empty[2], b_full; then the TMEM base word
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -129,6 +138,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (kBRes) {
       rt = (int64_t)(blockIdx.x / (unsigned)col_tiles) + j * (int64_t)(gridDim.x / (unsigned)col_tiles);
       ct = my_ct;
+      return rt < row_tiles;
+    }
+    if (kDual) {                                             // tiles 2P, 2P + 1 of pair P = blockIdx.x + (j / 2) * gridDim.x
+      rt = 2 * ((int64_t)blockIdx.x + (j >> 1) * (int64_t)gridDim.x) + (j & 1);
+      ct = 0;
       return rt < row_tiles;
     }
     if (row_major) {
@@ -175,7 +189,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t j = 0;; ++j) {
+      for (int64_t j = 0;; j += kDual ? 2 : 1) {
         int64_t rt;
         int ct;
         if (!tile_at(j, rt, ct)) break;
@@ -184,7 +198,8 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t sa = ring + stage * STAGE_BYTES;
           mbar_expect_tx(full_bar(stage), STAGE_BYTES);
           tma_load_2d(sa, &map_a, full_bar(stage), kb * TC_BK, (int)(rt * TC_BM));
-          if (!kBRes) tma_load_2d(sa + TC_A_BYTES, &map_b, full_bar(stage), kb * TC_BK, ct * TC_BN);
+          if (kDual) tma_load_2d(sa + TC_A_BYTES, &map_a, full_bar(stage), kb * TC_BK, (int)((rt + 1) * TC_BM));   // rows >= n: zeros
+          if (!kBRes) tma_load_2d(sa + B_OFF, &map_b, full_bar(stage), kb * TC_BK, ct * TC_BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -201,29 +216,41 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(bfull_bar, 0);
         tc_fence_after();
       }
-      for (int64_t j = 0;; ++j) {
+      for (int64_t j = 0;; j += kDual ? 2 : 1) {
         int64_t rt;
         int ct;
         if (!tile_at(j, rt, ct)) break;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);          // epilogue has drained this accumulator
+        if (kDual) mbar_wait(tempty_bar(1), acc_phase ^ 1); // (acc == 0 here: a pair takes both)
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TC_BN);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);                 // TMA bytes have landed
           tc_fence_after();
           const uint32_t sa = ring + stage * STAGE_BYTES;
-          const uint32_t sb = kBRes ? (bres + kb * TC_B_BYTES) : (sa + TC_A_BYTES);
+          const uint32_t sb = kBRes ? (bres + kb * TC_B_BYTES) : (sa + B_OFF);
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 16; ++ks) {          // UMMA_K = 16 bf16 = 32 bytes inside the swizzle row
             const uint64_t ad = make_smem_desc(sa + ks * 32);
             const uint64_t bd = make_smem_desc(sb + ks * 32);
             tc_mma_bf16(d_tmem, ad, bd, idesc, (kb | ks) ? 1u : 0u);
           }
+          if (kDual) {
+#pragma unroll
+            for (int ks = 0; ks < TC_BK / 16; ++ks) {        // the second row tile against the same W k-block
+              const uint64_t ad = make_smem_desc(sa + TC_A_BYTES + ks * 32);
+              const uint64_t bd = make_smem_desc(sb + ks * 32);
+              tc_mma_bf16(tmem_base + (uint32_t)TC_BN, ad, bd, idesc, (kb | ks) ? 1u : 0u);
+            }
+          }
           tc_commit(empty_bar(stage));                       // frees the smem slot when these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar(acc));                           // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (kDual) {
+          tc_commit(tfull_bar(1));
+          acc_phase ^= 1;
+        } else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
@@ -878,6 +905,7 @@ static int tc_linear_fwd_tf32x3(const void* X, int64_t ldx, const void* W, int64
 }
 
 // B2G_TC_TMA_STORE=0 in the environment at first use selects the LDS + row-store epilogue (A/B runs); read once, never written
+static const int g_dual_plan = [] { const char* e = getenv("B2G_TC_DUAL"); return (e && e[0] == '0') ? 0 : 1; }();   // same, plan 2
 static const int g_tma_store = [] { const char* e = getenv("B2G_TC_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();
 
 int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
@@ -891,8 +919,9 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   static bool attr_set[64] = {false};
   const int dev = current_device_slot();
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_STR);
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_STR);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_DUAL);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
@@ -909,10 +938,12 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   if (k <= TC_RES_KB_MAX * TC_BK && col_tiles <= sms) {
     int64_t per = sms / col_tiles;                            // CTAs per column group
     if (per > row_tiles) per = row_tiles;
-    tc_linear_kernel<true><<<(unsigned)(per * col_tiles), TC_THREADS, TC_SMEM_RES, st>>>(map_a, map_b, map_y, p);
+    tc_linear_kernel<1><<<(unsigned)(per * col_tiles), TC_THREADS, TC_SMEM_RES, st>>>(map_a, map_b, map_y, p);
+  } else if (g_dual_plan && col_tiles == 1 && row_tiles >= 2 * (int64_t)sms) {
+    tc_linear_kernel<2><<<(unsigned)sms, TC_THREADS, TC_SMEM_DUAL, st>>>(map_a, map_b, map_y, p);
   } else {
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    tc_linear_kernel<false><<<grid, TC_THREADS, TC_SMEM_STR, st>>>(map_a, map_b, map_y, p);
+    tc_linear_kernel<0><<<grid, TC_THREADS, TC_SMEM_STR, st>>>(map_a, map_b, map_y, p);
   }
   count_launch();
   return cuda_status();

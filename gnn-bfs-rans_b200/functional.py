@@ -524,7 +524,7 @@ class TConvZFn(torch.autograd.Function):
             dws, _ = ops.linear_wgrad(g, s8, want_bias=False)                                 # [C, 8]
             dwk, _ = ops.linear_wgrad(g, x, want_bias=False)                                  # [C, F]
             gw_out = _cast_like(torch.cat([dwv.view(H, C, F).permute(1, 0, 2).reshape(C, HF), dws, dwk], dim=1), w_out)
-        big[:, o_g:] = g
+        ops.rows_gather(g, None, out=big[:, o_g:])                             # big[:, o_g:] = g in one launch
         du = big[:, o_du:o_du + HF + E4]
         gmq = gcq = gx = None
         if ctx.needs_input_grad[1]:

@@ -599,9 +599,11 @@ def tconv_bwd(q, k, v, gout, H, C, concat, csr, csr_t, perm, smax, ssum, p_drop,
 
 # ------------------------------------------------------------------------------------------ halo
 def rows_gather(x, idx, out=None):
+    """out[r] = x[idx[r]]; idx None: out[r] = x[r] for every row of x (a copy into `out`, e.g. a column block of a wider
+    matrix: torch splits such a copy of > 2^31 elements into ~30 launches at a third of the bandwidth)."""
     lib = _lib.load()
     x = _rows(x)
-    n = idx.numel()
+    n = idx.numel() if idx is not None else x.shape[0]
     if out is None:
         out = torch.empty((n, x.shape[1]), dtype=x.dtype, device=x.device)
     _lib.check(lib.b2g_rows_gather(_p(x), _ld(x), _p(idx), n, _p(out), _ld(out), x.shape[1], _dt(x), _stream()), "rows_gather")

@@ -357,7 +357,8 @@ int b2g_colsum(const void* x, int64_t ldx, int64_t n_rows, int F, int dt, float*
 
 /* ===================================================================================== halo
  * Multi-GPU halo plumbing (no reference counterpart).  pack: out[r,:] = x[idx[r],:];
- * unpack_add: x[idx[r],:] += in[r,:] (idx unique within one call). */
+ * unpack_add: x[idx[r],:] += in[r,:] (idx unique within one call).  b2g_rows_gather with idx == NULL copies rows
+ * 0 .. n_idx-1 (any two row strides: a matrix into a column block of a wider one). */
 int b2g_rows_gather(const void* x, int64_t ldx, const int32_t* idx, int64_t n_idx, void* out,
                     int64_t ldo, int F, int dt, void* stream);
 int b2g_rows_scatter_add(void* x, int64_t ldx, const int32_t* idx, int64_t n_idx, const void* in,

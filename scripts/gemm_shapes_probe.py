@@ -6,11 +6,13 @@ import torch
 from gnn_bfs_rans_b200 import ops
 
 N = int(os.environ.get("ROWS", 10_000_000))
-SHAPES = [(256, 256, True, True), (256, 1024, True, False), (1024, 256, True, False), (256, 128, True, False), (256, 1280, False, False)]
+SHAPES = [(256, 256, True, True), (256, 1024, True, False), (1024, 256, True, False), (256, 128, True, False), (256, 1280, False, False), (1032, 256, False, False), (3336, 256, False, False)]
 if os.environ.get("ONLY"):
     SHAPES = [s_ for s_ in SHAPES if f"{s_[0]}x{s_[1]}" in os.environ["ONLY"].split(",")]
 for (k, m, bias, rs) in SHAPES:
-    x = torch.randn(N, k, device='cuda').bfloat16()
+    x = torch.empty(N, k, device='cuda', dtype=torch.bfloat16)
+    for r0 in range(0, N, 1 << 20):
+        x[r0:r0 + (1 << 20)] = torch.randn(min(1 << 20, N - r0), k, device='cuda').bfloat16()
     w = (torch.randn(m, k, device='cuda') / k ** 0.5).bfloat16()
     b = torch.randn(m, device='cuda') if bias else None
     r = torch.rand(N, device='cuda') if rs else None

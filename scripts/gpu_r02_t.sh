@@ -3,4 +3,5 @@
 mkdir -p gpurun_out
 PATHS=fused timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
   --log-file gpurun_out/r02t_tconv_launches.csv python scripts/tconv_probe.py > gpurun_out/r02t_ncu.log 2>&1; echo "ncu exit $?"
-tail -2 gpurun_out/r02t_ncu.log
+B2G_GAT_PATH= timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
+  --log-file gpurun_out/r02t_gat_launches.csv python scripts/gatf_probe.py > gpurun_out/r02t_ncu2.log 2>&1; echo "ncu exit $?"

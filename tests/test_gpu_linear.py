@@ -88,9 +88,33 @@ def test_colsum_and_rows():
         assert rel(ops.colsum(x), x.double().sum(0)) < 1e-5
         idx = torch.randperm(10007, device='cuda')[:3000].int()
         assert torch.equal(ops.rows_gather(x, idx), x[idx.long()])
+        wide = torch.zeros(10007, 640, device='cuda', dtype=dtype)               # idx None: a copy into a column block
+        ops.rows_gather(x, None, out=wide[:, 128:384])
+        assert torch.equal(wide[:, 128:384], x) and float(wide[:, :128].abs().max()) == 0 and float(wide[:, 384:].abs().max()) == 0
         y = x.clone()
         add = torch.randn(3000, 256, device='cuda').to(dtype)
         ops.rows_scatter_add(y, idx, add)
         ref = x.clone()
         ref[idx.long()] = (x[idx.long()].float() + add.float()).to(dtype)
         assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("n,k,m", [(2 * 148 * 128 + 77, 1032, 256), (2 * 148 * 128 + 128 + 5, 3336, 200), (3 * 148 * 128, 520, 256),
+                                   (40000, 256, 1024), (40000, 256, 1040)])
+def test_linear_large_row_counts_plans(n, k, m):
+    """bf16 tcgen05 Linear at row counts that select the large-problem plans (gemm_tc.cu): two row tiles per W k-block for long
+    reductions (plan 2: odd and even numbers of row tiles, a partial last tile), one resident W block per CTA group for
+    k <= 256 and wide outputs (plan 1, incl. a ragged last column tile), TMA tile stores; every output row against fp64."""
+    from gnn_bfs_rans_b200 import ops
+    torch.manual_seed(k + m)
+    x = torch.randn(n, k, device='cuda').bfloat16()
+    w = (torch.randn(m, k, device='cuda') / k ** 0.5).bfloat16()
+    b = torch.randn(m, device='cuda')
+    rs = torch.rand(n, device='cuda') + 0.5
+    y = torch.full((n, m), float('nan'), device='cuda', dtype=torch.bfloat16)
+    ops.linear_fwd(x, w, b, row_scale=rs, act=1, out=y)
+    for r0 in range(0, n, 8192):
+        xs = x[r0:r0 + 8192].double()
+        ref = torch.relu(rs[r0:r0 + 8192].double()[:, None] * (xs @ w.double().T) + b.double())
+        assert rel(y[r0:r0 + 8192], ref) < 2e-2, r0
+    assert bool(torch.isfinite(y.float()).all())
