@@ -521,47 +521,11 @@ def main():
     if world == 8 and not args.no_extras and not args.train_step:
         args.train_step, args.train_checkpoint, args.train_cells = True, True, 12500000
     if args.train_step:
-        from gnn_bfs_rans_b200.distributed import flow_forward_partitioned, allreduce_gradients
-        from gnn_bfs_rans_b200.flow_model import FlowGNN
         x = None
-        torch.cuda.empty_cache()
-        nzs = max(2, args.train_cells // (nx * ny))
-        tpart = slab_partition_hex(nx, ny, nzs, world, rank, dev)
-        n_glob = tpart.n_owned * world
-        torch.manual_seed(0)
-        tmodel = FlowGNN(3, F, 7, 6, "GAT", dropout=0.1).to(dev).to(torch.bfloat16).train()
-        topt = torch.optim.Adam(tmodel.parameters(), lr=3e-4, weight_decay=1e-5)
-        txin = torch.rand(tpart.n_owned, 3, device=dev, dtype=torch.bfloat16)
-        ty = torch.rand(tpart.n_owned, 7, device=dev, dtype=torch.bfloat16)
-
-        def tstep():
-            topt.zero_grad(set_to_none=True)
-            o = flow_forward_partitioned(tmodel, txin, tpart, checkpoint_layers=args.train_checkpoint)
-            loss = (o - ty).float().square().sum() / (n_glob * 7)
-            loss.backward()
-            allreduce_gradients(list(tmodel.parameters()), world)
-            torch.nn.utils.clip_grad_norm_(tmodel.parameters(), 1.0)
-            topt.step()
-        for _ in range(2):
-            tstep()
-        barrier()
-        torch.cuda.reset_peak_memory_stats()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            tstep()
-        e1.record()
-        barrier()
-        tms = e0.elapsed_time(e1) / 3
-        if world > 1:
-            t = torch.tensor([tms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            tms = float(t)
-        train_line = {"model": "FlowGNN GAT L=6 F=256 bf16 (cfg5 shape), fwd + loss + bwd + gradient all-reduce + clip + Adam",
-                      "cells_per_gpu": tpart.n_owned, "cells_total": n_glob, "ms_per_step": tms,
-                      "cells_per_sec": n_glob / (tms * 1e-3), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
-                      "recompute": os.environ.get("B2G_RECOMPUTE", "0"), "checkpoint_layers": bool(args.train_checkpoint)}
-        del tmodel, topt
+        try:
+            train_line = run_partitioned_train_step(args, b2g, world, rank, dev, F, nx, ny, barrier)
+        except Exception as e:                                   # never lose the headline line to the extra
+            train_line = {"error": str(e)[:300]}
 
     # ---- CPU baseline (rank 0, N=1, bounded sample)
     cb = None
@@ -587,6 +551,55 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_partitioned_train_step(args, b2g, world, rank, dev, F, nx, ny, barrier):
+    """cfg5-shaped train step on this rank's slab (halo exchange per layer, synchronised BatchNorm, gradient all-reduce)."""
+    import torch
+    import torch.distributed as dist
+    from gnn_bfs_rans_b200.distributed import slab_partition_hex
+    from gnn_bfs_rans_b200.distributed import flow_forward_partitioned, allreduce_gradients
+    from gnn_bfs_rans_b200.flow_model import FlowGNN
+    torch.cuda.empty_cache()
+    nzs = max(2, args.train_cells // (nx * ny))
+    tpart = slab_partition_hex(nx, ny, nzs, world, rank, dev)
+    n_glob = tpart.n_owned * world
+    torch.manual_seed(0)
+    tmodel = FlowGNN(3, F, 7, 6, "GAT", dropout=0.1).to(dev).to(torch.bfloat16).train()
+    topt = torch.optim.Adam(tmodel.parameters(), lr=3e-4, weight_decay=1e-5)
+    txin = torch.rand(tpart.n_owned, 3, device=dev, dtype=torch.bfloat16)
+    ty = torch.rand(tpart.n_owned, 7, device=dev, dtype=torch.bfloat16)
+
+    def tstep():
+        topt.zero_grad(set_to_none=True)
+        o = flow_forward_partitioned(tmodel, txin, tpart, checkpoint_layers=args.train_checkpoint)
+        loss = (o - ty).float().square().sum() / (n_glob * 7)
+        loss.backward()
+        allreduce_gradients(list(tmodel.parameters()), world)
+        torch.nn.utils.clip_grad_norm_(tmodel.parameters(), 1.0)
+        topt.step()
+    for _ in range(2):
+        tstep()
+    barrier()
+    torch.cuda.reset_peak_memory_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        tstep()
+    e1.record()
+    barrier()
+    tms = e0.elapsed_time(e1) / 3
+    if world > 1:
+        t = torch.tensor([tms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tms = float(t)
+    train_line = {"model": "FlowGNN GAT L=6 F=256 bf16 (cfg5 shape), fwd + loss + bwd + gradient all-reduce + clip + Adam",
+                  "cells_per_gpu": tpart.n_owned, "cells_total": n_glob, "ms_per_step": tms,
+                  "cells_per_sec": n_glob / (tms * 1e-3), "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9,
+                  "recompute": os.environ.get("B2G_RECOMPUTE", "0"), "checkpoint_layers": bool(args.train_checkpoint)}
+    del tmodel, topt
+    return train_line
+
 
 
 def run_mesh_ingest(b2g, dev, timed, dims):
