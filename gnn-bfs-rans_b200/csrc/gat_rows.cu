@@ -1473,6 +1473,49 @@ __global__ void __launch_bounds__(256, 2) rowdot8_kernel(const RowdotArgs a) {
   }
 }
 
+// a = x V^T for bf16 rows of 512 bytes on mma.sync: 8 rows x 8 vectors per warp step = one m16n8k16 chain over K = 256 with the
+// rows loaded straight into A-fragment layout (lane (g, q): row g, pieces q, q + 4, ...; see tz_alpha_mma_kernel) and V resident
+// in registers as B fragments, split into bf16 head + bf16 remainder so that the fp32 vectors keep their accuracy (2^-17).
+// 16 loads + 32 HMMAs per 8 rows instead of ~70 instructions per row: the kernel streams x at the HBM rate.
+__global__ void __launch_bounds__(256, 2) rowdot8_mma_kernel(const RowdotArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  uint32_t bh[16][2], bl[16][2];               // k-step s = 2m + half: features (q + 4m) * 8 + 4 * half + {0, 1 | 2, 3} of vector g
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    const float4 v4 = __ldg(reinterpret_cast<const float4*>(a.V + (int64_t)g * a.ldv + (q + 4 * (s >> 1)) * 8 + 4 * (s & 1)));
+    const float f[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * j]), h1 = __float2bfloat16_rn(f[2 * j + 1]);
+      bh[s][j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      bl[s][j] = pack_bf16x2(f[2 * j] - __bfloat162float(h0), f[2 * j + 1] - __bfloat162float(h1));
+    }
+  }
+  const uint32_t warps = gridDim.x * 8u, w = blockIdx.x * 8u + (threadIdx.x >> 5);
+  const char* xb = reinterpret_cast<const char*>(a.x) + q * 16;
+  asm volatile("" : "+l"(xb));
+  for (uint32_t i0 = w * 8u; i0 < a.n_rows; i0 += warps * 8u) {
+    const uint32_t i = min(i0 + (uint32_t)g, a.n_rows - 1u);
+    uint4 X[8];
+    const char* px = xb + (uint64_t)i * a.xrow_bytes;
+#pragma unroll
+    for (int m = 0; m < 8; ++m)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(X[m].x), "=r"(X[m].y), "=r"(X[m].z), "=r"(X[m].w) : "l"(px + 64 * m));
+    float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      mma_bf16_16816(c0, X[m].x, X[m].y, bh[2 * m][0], bh[2 * m][1]);
+      mma_bf16_16816(c1, X[m].z, X[m].w, bh[2 * m + 1][0], bh[2 * m + 1][1]);
+      mma_bf16_16816(c0, X[m].x, X[m].y, bl[2 * m][0], bl[2 * m][1]);
+      mma_bf16_16816(c1, X[m].z, X[m].w, bl[2 * m + 1][0], bl[2 * m + 1][1]);
+    }
+    if (i0 + (uint32_t)g < a.n_rows)          // lane (g, q): a[row g][2q, 2q + 1]
+      *reinterpret_cast<float2*>(a.out + (uint64_t)(i0 + g) * a.ldo + 2 * q) = make_float2(c0[0] + c1[0], c0[1] + c1[1]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 template <typename K>
 static inline int64_t gatz_blocks(K kernel, const RowSched& ord) {
@@ -1586,6 +1629,14 @@ int b2g_rowdot8(const void* x, int64_t ldx, const float* V, int64_t ldv, float* 
   RowdotArgs a{x, (uint32_t)(ldx * esz(dt)), V, (int)ldv, out, (uint32_t)ldo, (uint32_t)n};
   const int rb = F * esz(dt);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_attn_mma && dt == B2G_BF16 && rb == 512 && ldv % 4 == 0 && aligned16(V) && ldo % 2 == 0 && ((uintptr_t)out % 8) == 0) {
+    int64_t blocks = resident_ctas(rowdot8_mma_kernel, 256);
+    const int64_t want8 = ceil_div(n, 64);
+    if (want8 < blocks) blocks = want8;
+    rowdot8_mma_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
+    count_launch();
+    return cuda_status();
+  }
   const int64_t want = ceil_div(n, 32);
 #define B2G_RD(T, VPL)                                                                   \
   {                                                                                      \

@@ -910,7 +910,7 @@ static const int g_tma_store = [] { const char* e = getenv("B2G_TC_TMA_STORE"); 
 
 int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                   const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n, int m,
-                  int m_main, int k, int dt, int act, void* ws, cudaStream_t st) {
+                  int m_main, int k, int dt, int act, int reserve_sms, void* ws, cudaStream_t st) {
   if (dt == B2G_F32)
     return tc_linear_fwd_tf32x3(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, act, ws, st);
   if (dt != B2G_BF16) return B2G_E_UNSUPPORTED;
@@ -934,7 +934,8 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   p.tma_store = (g_tma_store && m_main >= 64 && (m_main % 8) == 0 && make_map(&map_y, Y, n, m_main, ldy, 32)) ? 1 : 0;
   const int64_t row_tiles = ceil_div(n, TC_BM), col_tiles = ceil_div(m, TC_BN);
   const int64_t tiles = row_tiles * col_tiles;
-  int sms = B2G_NUM_SMS;
+  int sms = B2G_NUM_SMS - reserve_sms;                        // bf16 kernels only; the fp32 path ignores the hint
+  if (sms < 1) sms = 1;
   if (k <= TC_RES_KB_MAX * TC_BK && col_tiles <= sms) {
     int64_t per = sms / col_tiles;                            // CTAs per column group
     if (per > row_tiles) per = row_tiles;

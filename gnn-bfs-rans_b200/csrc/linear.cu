@@ -11,7 +11,7 @@ int simt_linear_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_
 // gemm_tc.cu
 bool tc_linear_supported(int64_t n, int m, int k, int dt, int which);
 int64_t tc_linear_ws_bytes(int64_t n, int m, int k, int dt, int which);
-int tc_linear_fwd(const void*, int64_t, const void*, int64_t, const float*, const float*, void*, int64_t, float*, int64_t, int64_t, int, int, int, int, int, void*, cudaStream_t);
+int tc_linear_fwd(const void*, int64_t, const void*, int64_t, const float*, const float*, void*, int64_t, float*, int64_t, int64_t, int, int, int, int, int, int, void*, cudaStream_t);
 int64_t tc_wgrad_ws_bytes(int64_t n, int m, int k);
 int tc_linear_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int, int, void*, cudaStream_t);
 }  // namespace b2g
@@ -41,6 +41,10 @@ int b2g_linear_impl(int64_t n, int m, int k, int dt, int which) {
 int b2g_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                    const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n,
                    int m, int m_main, int k, int dt, int act, int impl, void* ws, void* stream) {
+  // bits 8..15 of impl: SMs the persistent tensor-core kernel leaves idle (a collective running on another stream needs SMs:
+  // the GEMM's CTAs hold all of an SM's shared memory, so nothing else is scheduled next to them)
+  const int reserve = (impl >> 8) & 0xff;
+  impl &= 0xff;
   if (n < 0 || m <= 0 || k <= 0 || !dt_ok(dt) || act < 0 || act > 1 || impl < 0 || impl > 2) return B2G_E_ARG;
   if (m_main < 0 || m_main > m || (m_main < m && (!aux || (m_main % 8) != 0))) return B2G_E_ARG;
   if (n == 0) return B2G_OK;
@@ -49,7 +53,7 @@ int b2g_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const
   const bool tc = tc_linear_supported(n, m, k, dt, 0);
   if (impl == 2 && !tc) return B2G_E_UNSUPPORTED;
   if (tc && impl != 1) {
-    const int rc = tc_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, ws, st);
+    const int rc = tc_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, reserve, ws, st);
     // shapes the tensor-core kernels decline at launch time (fp32 aux split with k > 256, tensors TMA cannot map):
     // auto mode falls through to the exact-fp32 SIMT kernel instead of failing the request
     if (rc != B2G_E_UNSUPPORTED || impl == 2) return rc;

@@ -255,7 +255,11 @@ class Partition:
                     run(rng[1], n0)
                 return out
             xs = x.new_empty((nl, layer.out_channels))
-            ops.linear_fwd(xf[:n0], w, None, row_scale=dinv[:n0], out=xs[:n0])
+            # B2G_HALO_RESERVE_SMS=r: the persistent GEMM leaves r SMs to the pack kernel and NCCL's send / recv CTAs on the side
+            # stream (its CTAs take a whole SM's shared memory).  Measured at N = 2: 4.427 (r = 0) / 4.441 (8) / 4.468 ms (16) — the
+            # 25 MB exchange is too short for the reserve to pay, so the default is 0
+            ops.linear_fwd(xf[:n0], w, None, row_scale=dinv[:n0], out=xs[:n0],
+                           reserve_sms=int(os.environ.get("B2G_HALO_RESERVE_SMS", "0")) if part.world > 1 else 0)
             cur.wait_event(done)
             if nl > n0:
                 ops.linear_fwd(xf[n0:], w, None, row_scale=dinv[n0:], out=xs[n0:])

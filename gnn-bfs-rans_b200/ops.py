@@ -280,8 +280,9 @@ def colsum(x) -> torch.Tensor:
 GEMM_IMPL = 0  # 0 auto, 1 SIMT, 2 tcgen05 (tests force one or the other)
 
 
-def linear_fwd(x, w, bias=None, row_scale=None, act=0, m_main=None, out=None):
-    """y = act(row_scale * (x @ w.T) + bias).  Returns (y [n,m_main], aux fp32 [n,m-m_main] | None)."""
+def linear_fwd(x, w, bias=None, row_scale=None, act=0, m_main=None, out=None, reserve_sms=0):
+    """y = act(row_scale * (x @ w.T) + bias).  Returns (y [n,m_main], aux fp32 [n,m-m_main] | None).
+    reserve_sms: SMs the persistent tensor-core kernel leaves to a collective running on another stream."""
     _cuda(x, w)
     lib = _lib.load()
     x = _rows(x)
@@ -299,7 +300,7 @@ def linear_fwd(x, w, bias=None, row_scale=None, act=0, m_main=None, out=None):
     ws = _ws(lib.b2g_linear_workspace_bytes(n, m, k, _dt(x), 0), x.device)
     _lib.check(lib.b2g_linear_fwd(_p(x), _ld(x), _p(w), _ld(w), _p(b), _p(row_scale), _p(y), _ld(y), _p(aux),
                                   (m - m_main) if aux is not None else 0, n, m, m_main, k, _dt(x), int(act),
-                                  GEMM_IMPL, _p(ws), _stream()), "linear_fwd")
+                                  GEMM_IMPL | (max(0, min(int(reserve_sms), 128)) << 8), _p(ws), _stream()), "linear_fwd")
     return y, aux
 
 

@@ -335,7 +335,9 @@ int b2g_tconv_bwd_src(const void* q, int64_t ldq, const void* gout, int64_t ldg,
  *   dgrad: dX[n,k] = sum_m dY[n,m] W[m,k]
  *   wgrad: dW[m,k] = sum_n dY[n,m] X[n,k];  db[m] = sum_n dY[n,m]   (fp32 outputs)
  * X,Y,dX,dY dtype `dt`; W dtype `dt` for fwd/dgrad; accumulate fp32.  act: 0 none, 1 relu.
- * impl: 0 = auto, 1 = SIMT (FFMA) kernel, 2 = tcgen05 tensor-core kernel. */
+ * impl: 0 = auto, 1 = SIMT (FFMA) kernel, 2 = tcgen05 tensor-core kernel.  b2g_linear_fwd: bits 8..15 of impl = the number of
+ * SMs the persistent tensor-core kernel leaves idle (its CTAs hold a whole SM's shared memory; a halo exchange running on another
+ * stream gets no SM otherwise and waits for the GEMM to finish). */
 int64_t b2g_linear_workspace_bytes(int64_t n, int m, int k, int dt, int which /*0 fwd 1 dgrad 2 wgrad*/);
 /* Which kernel impl=0 (auto) picks for this shape: 1 = SIMT, 2 = tcgen05. */
 int b2g_linear_impl(int64_t n, int m, int k, int dt, int which);

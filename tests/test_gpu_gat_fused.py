@@ -370,3 +370,18 @@ def test_weighted_row_sums_tensor_core_vs_fp64(N, use_perm):
         mag.index_add_(0, rows, wp.double().abs().unsqueeze(2) * x.double()[col.long()[:nnz]].abs().unsqueeze(1))
     excess = (out.double().view(N, 4, 256) - ref).abs() - (2.0 ** -8) * ref.abs() - 1e-5 * mag
     assert float(excess.max()) <= 0.0
+
+
+@pytest.mark.parametrize("N", [1, 7, 8, 1000, 4099])
+def test_rowdot8_tensor_core_vs_fp64(N):
+    """b2g_rowdot8 for bf16 rows of 512 bytes (rowdot8_mma_kernel: V as bf16 head + remainder B fragments) against fp64: the fp32
+    vectors keep their accuracy (a bf16-rounded V would show 2^-9)."""
+    from gnn_bfs_rans_b200 import ops
+    torch.manual_seed(N)
+    x = torch.randn(N, 256, device="cuda").bfloat16()
+    v = torch.randn(8, 256, device="cuda")
+    a = ops.rowdot8(x, v)
+    ref = x.double() @ v.double().T
+    mag = x.double().abs() @ v.double().abs().T
+    assert a.shape == (N, 8)
+    assert float(((a.double() - ref).abs() / mag).max()) < 2e-5
