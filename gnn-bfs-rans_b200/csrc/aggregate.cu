@@ -199,11 +199,21 @@ __global__ void __launch_bounds__(256) rows_gather_kernel(const T* __restrict__ 
                                                           T* __restrict__ out, int64_t ldo, int nvec) {
   constexpr int VN = Vec<T>::N;
   const int64_t total = n_idx * nvec;
+  if (total < (1ll << 32)) {                                    // 32-bit index arithmetic (the 64-bit division below ran the
+    const uint32_t tot = (uint32_t)total, step = gridDim.x * blockDim.x, nv = (uint32_t)nvec;   // identity copy at 3.5 TB/s)
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < tot; t += step) {
+      const uint32_t r = t / nv, v = t - r * nv;
+      const int64_t src = idx ? (int64_t)__ldg(idx + r) : (int64_t)r;   // idx == NULL: identity (a strided row copy)
+      stg_vec<T>(out + (int64_t)r * ldo + v * VN, ldg_vec<T>(x + src * ldx + v * VN));
+      if (t + step < t) break;                                  // uint32 wrap
+    }
+    return;
+  }
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = t / nvec;
     const int v = (int)(t - r * nvec);
-    const int64_t src = idx ? (int64_t)__ldg(idx + r) : r;      // idx == NULL: identity (a strided row copy)
+    const int64_t src = idx ? (int64_t)__ldg(idx + r) : r;
     stg_vec<T>(out + r * ldo + v * VN, ldg_vec<T>(x + src * ldx + v * VN));
   }
 }

@@ -25,6 +25,7 @@
 // Also the transposed use (backward): y_j = [sum_i alpha_ijh g_i]_h over the source-major CSR followed by the dgrad GEMM is
 // the same computation (perm maps a transposed-CSR position to its alpha entry).
 #include "rows.cuh"
+#include <cstdlib>
 #include "tc_ptx.cuh"
 
 namespace b2g {
@@ -39,6 +40,12 @@ constexpr int GF_A_REGION = GF_BM * 128;         // 16 KB: 128 rows x 64 bf16 (o
 constexpr int GF_A_CHUNK = GF_H * GF_A_REGION;   // 64 KB
 constexpr int GF_W_STAGE = GF_BN * 128;          // 32 KB: 256 rows of Wp x 64 k
 constexpr int GF_W_STAGES = 2;
+// CTA-pair variant (kPair, tcgen05 cta_group::2): each CTA of a cluster of two gathers its own 128-row tile, the leader issues ONE
+// M = 256 MMA per k-step, and each CTA holds only HALF of every Wp k-block (128 of its 256 rows): the TMA writes of Wp and the
+// tensor core's B-operand reads per SM halve — the two biggest items of the shared-memory traffic that bounds this kernel
+// (DESIGN §4 point 7).  Same 64 KB ring: 4 stages of 16 KB.
+constexpr int GF_W_HALF = (GF_BN / 2) * 128;     // 16 KB
+constexpr int GF_W_STAGES_PAIR = 4;
 constexpr int GF_STG = 4 * 32 * 128;             // epilogue staging: 32 rows x 128 B per epilogue warp
 constexpr int GF_WST_WARP = 2 * 4 * 8 * 16;      // per gather warp: 2 units x 4 rows x 8 entries x float4 weights = 1 KB
 constexpr int GF_WST = GF_GW * GF_WST_WARP;
@@ -100,8 +107,23 @@ __device__ __forceinline__ void gf_gather(float (&acc)[GF_H][8], const char* xk,
   for (int t = 0; t < K; ++t) gf_fma(acc, wrow[t * 4], buf[t]);   // staged [entry][row]: the 4 rows of a warp read 64 contiguous bytes
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(GF_THREADS, 1)
 gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
+  constexpr int W_STAGES = kPair ? GF_W_STAGES_PAIR : GF_W_STAGES;
+  constexpr int W_BYTES = kPair ? GF_W_HALF : GF_W_STAGE;
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;                // CTA of the pair; rank 0 = leader (issues the MMAs)
+  const uint32_t ngrp = kPair ? gridDim.x / 2 : gridDim.x;             // tile groups in flight: pairs or single CTAs
+  const uint32_t gid = kPair ? blockIdx.x / 2 : blockIdx.x;
+  // step t of this CTA's group: chunk q = 2t + rank (pair) or t; a pair runs the step when chunk 2t exists, a CTA whose own chunk
+  // does not exist (or is empty) takes part with zero rows so that the pair's barriers stay in step
+  auto my_tile = [&](uint32_t t, uint32_t& c0, uint32_t& rows) -> int {    // -1: done, 0: skip (single CTA, empty chunk), 1: run
+    if ((kPair ? 2 * t : t) >= a.ord.n_chunks) return -1;
+    const uint32_t q = kPair ? 2 * t + rank : t;
+    rows = 0; c0 = 0;
+    if (q < a.ord.n_chunks) c0 = a.ord.chunk(q, a.n_rows, rows);
+    return (!kPair && rows == 0) ? 0 : 1;
+  };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();
@@ -112,12 +134,14 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
   const uint32_t sbv = wst + GF_WST;                                  // bv_h / H (bf16 [4][256]) or zeros
   const uint32_t bars = sbv + GF_BVH;
   auto full_w = [&](int s) { return bars + 8u * s; };
-  auto empty_w = [&](int s) { return bars + 8u * (2 + s); };
-  auto full_a = [&](int b) { return bars + 8u * (4 + b); };
-  auto empty_a = [&](int b) { return bars + 8u * (6 + b); };
-  auto tfull = [&](int t) { return bars + 8u * (8 + t); };
-  auto tempty = [&](int t) { return bars + 8u * (10 + t); };
-  const uint32_t tmem_slot = bars + 8u * 12;
+  auto empty_w = [&](int s) { return bars + 8u * (4 + s); };
+  auto full_a = [&](int b) { return bars + 8u * (8 + b); };
+  auto empty_a = [&](int b) { return bars + 8u * (10 + b); };
+  auto tfull = [&](int t) { return bars + 8u * (12 + t); };
+  auto tempty = [&](int t) { return bars + 8u * (14 + t); };
+  const uint32_t tmem_slot = bars + 8u * 16;
+  // pair: full_w / full_a / tempty are waited on by the leader's MMA thread and receive arrivals from both CTAs (the leader's copy
+  // is the one in use); empty_w / empty_a / tfull are per CTA and get the leader's multicast commits
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,22 +155,30 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
   }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < W_STAGES; ++s) {
       mbar_init(full_w(s), 1);
       mbar_init(empty_w(s), 1);
-      mbar_init(full_a(s), GF_GW);       // one arrive per gather warp
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_a(s), (kPair ? 2 : 1) * GF_GW);       // one arrive per gather warp (of both CTAs)
       mbar_init(empty_a(s), 1);
       mbar_init(tfull(s), 1);
-      mbar_init(tempty(s), 4);           // one arrive per epilogue warp
+      mbar_init(tempty(s), (kPair ? 2 : 1) * 4);           // one arrive per epilogue warp (of both CTAs)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();           // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -156,47 +188,58 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
       // ===================================================== TMA producer: Wp k-blocks, 16 per tile
       int stage = 0;
       uint32_t phase = 0;
-      for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
-        uint32_t rows;
-        a.ord.chunk(q, a.n_rows, rows);
-        if (rows == 0) continue;
+      for (uint32_t t = gid;; t += ngrp) {
+        uint32_t c0, rows;
+        const int run = my_tile(t, c0, rows);
+        if (run < 0) break;
+        if (run == 0) continue;
         for (int kb = 0; kb < GF_KCH * GF_H; ++kb) {
           mbar_wait(empty_w(stage), phase ^ 1);
-          mbar_expect_tx(full_w(stage), GF_W_STAGE);
-          tma_load_2d(wring + stage * GF_W_STAGE, &map_w, full_w(stage), kb * 64, 0);
-          if (++stage == GF_W_STAGES) { stage = 0; phase ^= 1; }
+          if (kPair) {
+            // both halves are counted on the leader's barrier (a complete_tx that lands before the leader's expect_tx is legal: the
+            // phase cannot complete without the leader's arrival)
+            if (rank == 0) mbar_expect_tx(full_w(stage), 2 * GF_W_HALF);
+            tma_load_2d_pair(wring + stage * GF_W_HALF, &map_w, mapa_u32(full_w(stage), 0), kb * 64, (int)rank * (GF_BN / 2));
+          } else {
+            mbar_expect_tx(full_w(stage), GF_W_STAGE);
+            tma_load_2d(wring + stage * GF_W_STAGE, &map_w, full_w(stage), kb * 64, 0);
+          }
+          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (warp == 1 && lane == 0) {
-      // ===================================================== MMA issuer
-      constexpr uint32_t idesc = make_idesc_bf16(GF_BM, GF_BN);
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      // ===================================================== MMA issuer (pair: the leader CTA only, M = 256 over both CTAs)
+      constexpr uint32_t idesc = make_idesc_bf16(kPair ? 2 * GF_BM : GF_BM, GF_BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0, g = 0;          // g = z chunks consumed so far (buffer g & 1, phase (g >> 1) & 1)
-      for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
-        uint32_t rows;
-        a.ord.chunk(q, a.n_rows, rows);
-        if (rows == 0) continue;
-        mbar_wait(tempty(acc), acc_phase ^ 1);
+      for (uint32_t t = gid;; t += ngrp) {
+        uint32_t c0, rows;
+        const int run = my_tile(t, c0, rows);
+        if (run < 0) break;
+        if (run == 0) continue;
+        if (kPair) mbar_wait_cluster(tempty(acc), acc_phase ^ 1); else mbar_wait(tempty(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * GF_BN);
         for (int kc = 0; kc < GF_KCH; ++kc, ++g) {
           const int ab = g & 1;
-          mbar_wait(full_a(ab), (g >> 1) & 1);
+          if (kPair) mbar_wait_cluster(full_a(ab), (g >> 1) & 1); else mbar_wait(full_a(ab), (g >> 1) & 1);
           tc_fence_after();
           for (int h = 0; h < GF_H; ++h) {
             mbar_wait(full_w(stage), phase);
             tc_fence_after();
             const uint32_t sa = abuf0 + ab * GF_A_CHUNK + h * GF_A_REGION;
-            const uint32_t sb = wring + stage * GF_W_STAGE;
+            const uint32_t sb = wring + stage * W_BYTES;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              tc_mma_bf16(d_tmem, make_smem_desc(sa + ks * 32), make_smem_desc(sb + ks * 32), idesc, (kc | h | ks) ? 1u : 0u);
-            tc_commit(empty_w(stage));
-            if (++stage == GF_W_STAGES) { stage = 0; phase ^= 1; }
+            for (int ks = 0; ks < 4; ++ks) {
+              if (kPair) tc_mma_bf16_pair(d_tmem, make_smem_desc(sa + ks * 32), make_smem_desc(sb + ks * 32), idesc, (kc | h | ks) ? 1u : 0u);
+              else tc_mma_bf16(d_tmem, make_smem_desc(sa + ks * 32), make_smem_desc(sb + ks * 32), idesc, (kc | h | ks) ? 1u : 0u);
+            }
+            if (kPair) tc_commit_pair(empty_w(stage)); else tc_commit(empty_w(stage));
+            if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
           }
-          tc_commit(empty_a(ab));                         // the z chunk may be overwritten once these MMAs retire
+          if (kPair) tc_commit_pair(empty_a(ab)); else tc_commit(empty_a(ab));   // the z chunk may be overwritten once these MMAs retire
         }
-        tc_commit(tfull(acc));
+        if (kPair) tc_commit_pair(tfull(acc)); else tc_commit(tfull(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -206,10 +249,11 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
     uint8_t* my_stg = smem_raw + (stg - smem_base) + qd * 32 * 128;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
-      uint32_t rows;
-      const uint32_t c0 = a.ord.chunk(q, a.n_rows, rows);
-      if (rows == 0) continue;
+    for (uint32_t t = gid;; t += ngrp) {
+      uint32_t c0, rows;
+      const int run = my_tile(t, c0, rows);
+      if (run < 0) break;
+      if (run == 0) continue;
       mbar_wait(tfull(acc), acc_phase);
       tc_fence_after();
       const uint32_t row0 = c0 + qd * 32;
@@ -284,7 +328,9 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty(acc));
+      if (lane == 0) {                                       // pair: the leader's MMA thread waits for both CTAs' epilogues
+        if (kPair) mbar_arrive_cluster(mapa_u32(tempty(acc), 0)); else mbar_arrive(tempty(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
@@ -296,10 +342,11 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
     const char* xl = a.x + p * 16;
     const char* zl = a.zero + p * 16;
     uint32_t g = 0;
-    for (uint32_t q = blockIdx.x; q < a.ord.n_chunks; q += gridDim.x) {
-      uint32_t rows;
-      const uint32_t c0 = a.ord.chunk(q, a.n_rows, rows);
-      if (rows == 0) continue;
+    for (uint32_t t = gid;; t += ngrp) {
+      uint32_t c0, rows;
+      const int run = my_tile(t, c0, rows);
+      if (run < 0) break;
+      if (run == 0) continue;
       // ---- per tile: this lane's entry (row r4 of the unit, entry p) of both units: column index + 4 head weights
       int cl[2], len[2], b0[2], mlen[2];
 #pragma unroll
@@ -375,7 +422,9 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05.mma
         __syncwarp();
-        if (lane == 0) mbar_arrive(full_a(ab));
+        if (lane == 0) {                                                   // pair: release at cluster scope to the leader's MMA thread
+          if (kPair) mbar_arrive_cluster(mapa_u32(full_a(ab), 0)); else mbar_arrive(full_a(ab));
+        }
       }
       __syncwarp();                                                        // weight staging is rewritten by the next tile
     }
@@ -383,9 +432,11 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
 
   tc_fence_before();
   __syncthreads();
+  if (kPair) cluster_sync_all();           // no CTA leaves (or frees TMEM) while its peer may still signal or read it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -515,6 +566,9 @@ int b2g_gatw_gemm_supported(int64_t n, int H, int F, int C, int dt) {
           n < (1ll << 32) - (1ll << 25)) ? 1 : 0;
 }
 
+// B2G_GATW_PAIR in the environment at load time: 1 = CTA pairs whenever there are two tiles, 0 = never, unset = large problems
+static const int g_gatw_pair = [] { const char* e = getenv("B2G_GATW_PAIR"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
+
 int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                      const float* alpha, const void* wp, int64_t ldw, const float* bias, const float* srow, const float* bvh,
                      const void* addend, int64_t ldadd, void* out, int64_t ldo, int64_t n_rows, int H, int F, int C, int dt,
@@ -543,22 +597,42 @@ int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const in
   static bool attr_set[64] = {false};
   const int dev = current_device_slot();
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gatw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gatw_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gatw_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
   GfArgs a{};
   if (!make_row_sched(n_rows, band, a.ord, GF_BM, 8192)) return B2G_E_UNSUPPORTED;
+  // CTA pairs for problems with at least two tiles per SM (B2G_GATW_PAIR=0/1 in the environment at load time overrides: A/B runs)
+  const bool pair = g_gatw_pair >= 0 ? (g_gatw_pair == 1 && a.ord.n_chunks >= 2) : false;
   CUtensorMap map_w;
-  if (!tc_make_map_bf16(&map_w, wp, C, (int64_t)H * F, ldw, GF_BN)) return B2G_E_UNSUPPORTED;
+  if (!tc_make_map_bf16(&map_w, wp, C, (int64_t)H * F, ldw, pair ? GF_BN / 2 : GF_BN)) return B2G_E_UNSUPPORTED;
   a.x = static_cast<const char*>(x); a.xrow_bytes = (uint32_t)(ldx * 2);
   a.rowptr = rowptr; a.col = col; a.perm = perm; a.alpha = alpha; a.bias = bias;
   a.zero = static_cast<const char*>(zero_row_ptr());
   if (!a.zero) return B2G_E_UNSUPPORTED;
   a.srow = srow; a.bvh = bvh; a.addend = static_cast<const __nv_bfloat16*>(addend); a.ldadd = ldadd;
   a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.n_rows = (uint32_t)n_rows; a.m = C;
-  const unsigned grid = a.ord.n_chunks < (uint32_t)B2G_NUM_SMS ? a.ord.n_chunks : (unsigned)B2G_NUM_SMS;
-  gatw_gemm_kernel<<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, a);
+  if (pair) {
+    const unsigned pairs_wanted = (a.ord.n_chunks + 1) / 2;
+    const unsigned pairs = pairs_wanted < (unsigned)(B2G_NUM_SMS / 2) ? pairs_wanted : (unsigned)(B2G_NUM_SMS / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(GF_THREADS);
+    cfg.dynamicSmemBytes = GF_SMEM;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gatw_gemm_kernel<true>, map_w, a);
+    if (e != cudaSuccess) return (int)e;
+  } else {
+    const unsigned grid = a.ord.n_chunks < (uint32_t)B2G_NUM_SMS ? a.ord.n_chunks : (unsigned)B2G_NUM_SMS;
+    gatw_gemm_kernel<false><<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, a);
+  }
   count_launch();
   return cuda_status();
 }
