@@ -67,6 +67,7 @@ struct GfArgs {
   const __nv_bfloat16* addend; int64_t ldadd;    // [n_rows, m]: out += addend (the skip projection) or NULL
   __nv_bfloat16* out; int64_t ldo;
   uint32_t n_rows; int m;
+  int tma_store;                                 // full 32-row x 64-column blocks leave through map_o (one bulk tensor store)
   RowSched ord;                                  // chunk_rows = GF_BM
 };
 
@@ -109,7 +110,7 @@ __device__ __forceinline__ void gf_gather(float (&acc)[GF_H][8], const char* xk,
 
 template <bool kPair>
 __global__ void __launch_bounds__(GF_THREADS, 1)
-gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
+gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_o, const GfArgs a) {
   constexpr int W_STAGES = kPair ? GF_W_STAGES_PAIR : GF_W_STAGES;
   constexpr int W_BYTES = kPair ? GF_W_HALF : GF_W_STAGE;
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;                // CTA of the pair; rank 0 = leader (issues the MMAs)
@@ -261,9 +262,16 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
       const uint32_t my_row = row0 + lane;                 // the accumulator row this lane holds
       float4 srow4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.srow && my_row < rend) srow4 = __ldg(reinterpret_cast<const float4*>(a.srow) + my_row);
+      // a block whose 32 rows all belong to this chunk leaves as ONE TMA tile store from the swizzled staging buffer (as in
+      // gemm_tc.cu); partial blocks (chunk ends) keep the row stores — the rows past `rend` belong to another chunk
+      const bool blk_tma = a.tma_store && row0 + 32 <= rend;
 #pragma unroll 1
       for (int c = 0; c < a.m; c += 64) {
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * GF_BN + c);
+        if (a.tma_store) {
+          if (lane == 0) tma_store_wait_read();             // the previous block's store has read the staging buffer
+          __syncwarp();
+        }
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
           uint4 adv[4];                                      // this row's 32 addend values, requested before the TMEM read waits
@@ -311,6 +319,12 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
             *reinterpret_cast<uint4*>(my_stg + lane * 128 + (((hlf * 4 + (j >> 3)) ^ (lane & 7)) << 4)) = o.v;
           }
         }
+        if (blk_tma) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&map_o, smem_u32(my_stg), c, (int)row0);
+          continue;
+        }
         __syncwarp();
         const int piece = lane & 7;
 #pragma unroll
@@ -333,6 +347,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const GfArgs a) {
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (a.tma_store && lane == 0) tma_store_wait_all();      // shared memory stays valid until the last store has read it
   } else {
     // ===================================================== gather warps 8..: z chunks into the swizzled A operand
     asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
@@ -567,6 +582,7 @@ int b2g_gatw_gemm_supported(int64_t n, int H, int F, int C, int dt) {
 }
 
 // B2G_GATW_PAIR in the environment at load time: 1 = CTA pairs whenever there are two tiles, 0 = never, unset = large problems
+static const int g_gatw_tma_store = [] { const char* e = getenv("B2G_GATW_TMA_STORE"); return (e && e[0] == '0') ? 0 : 1; }();   // A/B
 static const int g_gatw_pair = [] { const char* e = getenv("B2G_GATW_PAIR"); return !e ? -1 : (e[0] == '0' ? 0 : 1); }();
 
 int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
@@ -614,6 +630,8 @@ int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const in
   if (!a.zero) return B2G_E_UNSUPPORTED;
   a.srow = srow; a.bvh = bvh; a.addend = static_cast<const __nv_bfloat16*>(addend); a.ldadd = ldadd;
   a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.n_rows = (uint32_t)n_rows; a.m = C;
+  CUtensorMap map_o = map_w;                                   // placeholder when the row-store epilogue is used
+  a.tma_store = (g_gatw_tma_store && tc_make_map_bf16(&map_o, out, n_rows, C, ldo, 32)) ? 1 : 0;
   if (pair) {
     const unsigned pairs_wanted = (a.ord.n_chunks + 1) / 2;
     const unsigned pairs = pairs_wanted < (unsigned)(B2G_NUM_SMS / 2) ? pairs_wanted : (unsigned)(B2G_NUM_SMS / 2);
@@ -627,11 +645,11 @@ int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const in
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, gatw_gemm_kernel<true>, map_w, a);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gatw_gemm_kernel<true>, map_w, map_o, a);
     if (e != cudaSuccess) return (int)e;
   } else {
     const unsigned grid = a.ord.n_chunks < (uint32_t)B2G_NUM_SMS ? a.ord.n_chunks : (unsigned)B2G_NUM_SMS;
-    gatw_gemm_kernel<false><<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, a);
+    gatw_gemm_kernel<false><<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, map_o, a);
   }
   count_launch();
   return cuda_status();
