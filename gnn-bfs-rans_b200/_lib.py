@@ -53,6 +53,8 @@ SIGNATURES = {
     "b2g_adam_workspace_bytes": (i64, []),
     "b2g_clip_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, vp, vp]),
     "b2g_gat_alpha": (i32, [vp, i64, vp, vp, vp, i64, i64, i32, f32, f32, u64, vp, vp, vp, vp]),
+    "b2g_gatw_gemm_sm": (i32, [vp, i64, vp, vp, vp, vp, i64, vp, f32, f32, u64, vp, vp, vp, i64, vp, vp, i64, i64, i64, i32, i32, i32, i32,
+                                i64, vp]),
     "b2g_gatw_gemm": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, i32, i64, vp]),
     "b2g_rowdot8": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, vp]),
     "b2g_gatz_fwd": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, f32, vp, vp, vp, vp, f32, u64, i64, vp]),

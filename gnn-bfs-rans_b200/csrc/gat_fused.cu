@@ -68,6 +68,13 @@ struct GfArgs {
   __nv_bfloat16* out; int64_t ldo;
   uint32_t n_rows; int m;
   int tma_store;                                 // full 32-row x 64-column blocks leave through map_o (one bulk tensor store)
+  // softmax inside the kernel (alpha == NULL; every row has <= 8 entries): the gather warps derive the attention weights of
+  // their rows in the per-tile prologue from a_src / a_dst — no [nnz, 4] alpha round trip through HBM, no separate kernel
+  const float* a_src; const float* a_dst; uint32_t lda;   // fp32: a_src[c * lda + h] (global node c), a_dst[r * lda + h] (row r of this call)
+  const float* ebias;                            // fp32 [nnz, 4] added to the logits (edge features) or NULL
+  float* smax; float* ssum;                      // fp32 [n_rows, 4] softmax statistics for the backward pass, or NULL
+  float slope, p_drop;
+  uint64_t seed; const uint64_t* epoch;
   RowSched ord;                                  // chunk_rows = GF_BM
 };
 
@@ -82,6 +89,8 @@ __device__ __forceinline__ uint4 gf_ldg_sel(const char* p, const char* zero, boo
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(q));
   return u;
 }
+
+__device__ __forceinline__ float gf_lrelu(float s, float slope) { return s > 0.f ? s : s * slope; }
 
 // acc[h][0..8) += w[h] * (8 bf16 of u)
 __device__ __forceinline__ void gf_fma(float (&acc)[GF_H][8], const float4& w, const uint4& u) {
@@ -379,10 +388,59 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         const int pos = b0[u] + (has ? p : 0);
         int c = 0, pi = pos;
         float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has) {
-          c = __ldg(a.col + pos);
-          if (a.perm) pi = __ldg(a.perm + pos);
-          w4 = __ldg(reinterpret_cast<const float4*>(a.alpha) + pi);
+        if (a.alpha) {
+          if (has) {
+            c = __ldg(a.col + pos);
+            if (a.perm) pi = __ldg(a.perm + pos);
+            w4 = __ldg(reinterpret_cast<const float4*>(a.alpha) + pi);
+          }
+        } else {
+          // exact max-subtracted softmax over the (<= 8) entries of row r4: the 8 lanes of a row are lanes r4 * 8 .. r4 * 8 + 7.
+          // (Same box: 9.91 ms layer forward against 10.32 with the separate b2g_gat_alpha kernel.  A software pipeline that
+          // requested rowptr two tiles and col one tile ahead to shorten this prologue's rowptr -> col -> a_src chain made the
+          // kernel 1 ms SLOWER — 8 more live registers spilled at the 80-register ceiling of a 768-thread CTA — and was dropped.)
+          const uint32_t rl_ = (uint32_t)(gw + GF_GW * u) * 4u + r4;
+          const uint32_t row = rl_ < rows ? c0 + rl_ : c0;
+          float s4[GF_H] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          if (has) {
+            c = __ldg(a.col + pos);
+            const float4 as4 = __ldg(reinterpret_cast<const float4*>(a.a_src + (uint64_t)(uint32_t)c * a.lda));
+            const float4 ad4 = __ldg(reinterpret_cast<const float4*>(a.a_dst + (uint64_t)row * a.lda));
+            float4 eb4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.ebias) eb4 = __ldg(reinterpret_cast<const float4*>(a.ebias) + pos);
+            s4[0] = gf_lrelu(as4.x + ad4.x + eb4.x, a.slope); s4[1] = gf_lrelu(as4.y + ad4.y + eb4.y, a.slope);
+            s4[2] = gf_lrelu(as4.z + ad4.z + eb4.z, a.slope); s4[3] = gf_lrelu(as4.w + ad4.w + eb4.w, a.slope);
+          }
+          float m4[GF_H], z4[GF_H], wv[GF_H];
+#pragma unroll
+          for (int h = 0; h < GF_H; ++h) {
+            float m = s4[h];
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+            m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+            const float ex = has ? __expf(s4[h] - m) : 0.f;
+            float z = ex;
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            z += __shfl_xor_sync(0xffffffffu, z, 2);
+            z += __shfl_xor_sync(0xffffffffu, z, 4);
+            z += 1e-16f;
+            m4[h] = m; z4[h] = z;
+            wv[h] = ex * (1.0f / z);
+          }
+          if (a.p_drop > 0.f && has) {
+            float sc[4];
+            dropout_scale4(mix_epoch(a.seed, a.epoch), (uint64_t)pos, a.p_drop, sc);
+#pragma unroll
+            for (int h = 0; h < GF_H; ++h) wv[h] *= sc[h];
+          }
+          w4 = make_float4(wv[0], wv[1], wv[2], wv[3]);
+          if (a.smax && p == 0 && rl_ < rows) {                  // same statistics as gat_alpha_kernel (empty row: 0 / 1e-16)
+            const bool any = len[u] > 0;
+            *reinterpret_cast<float4*>(a.smax + (uint64_t)row * GF_H) =
+                any ? make_float4(m4[0], m4[1], m4[2], m4[3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(a.ssum + (uint64_t)row * GF_H) =
+                any ? make_float4(z4[0], z4[1], z4[2], z4[3]) : make_float4(1e-16f, 1e-16f, 1e-16f, 1e-16f);
+          }
         }
         cl[u] = c;
         wrow_base[(u * 8 + p) * 4 + r4] = w4;             // [unit][entry][row]: conflict-free LDS.128 in the FMA loop
@@ -469,8 +527,6 @@ struct AlphaArgs {
   float slope, p_drop;
   uint64_t seed; const uint64_t* epoch;
 };
-
-__device__ __forceinline__ float gf_lrelu(float s, float slope) { return s > 0.f ? s : s * slope; }
 
 __global__ void __launch_bounds__(256) gat_alpha_kernel(const AlphaArgs a) {
   const uint64_t total = (uint64_t)a.n_rows * GF_H;
@@ -597,17 +653,57 @@ int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32
                           dt, band, stream);
 }
 
+// softmax inside the kernel (sm != NULL, alpha == NULL): see GfArgs
+struct GfSoftmax {
+  const float* a_src; const float* a_dst; int64_t lda; const float* ebias; float* smax; float* ssum;
+  float slope, p_drop; uint64_t seed;
+};
+
+static int gatw_launch(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                       const float* alpha, const GfSoftmax* sm, const void* wp, int64_t ldw, const float* bias, const float* srow,
+                       const float* bvh, const void* addend, int64_t ldadd, void* out, int64_t ldo, int64_t n_rows, int H, int F,
+                       int C, int dt, int64_t band, void* stream);
+
 int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                      const float* alpha, const void* wp, int64_t ldw, const float* bias, const float* srow, const float* bvh,
                      const void* addend, int64_t ldadd, void* out, int64_t ldo, int64_t n_rows, int H, int F, int C, int dt,
                      int64_t band, void* stream) {
+  if (!alpha && n_rows > 0) return B2G_E_ARG;
+  return gatw_launch(x, ldx, rowptr, col, perm, alpha, nullptr, wp, ldw, bias, srow, bvh, addend, ldadd, out, ldo, n_rows, H, F, C,
+                     dt, band, stream);
+}
+
+/* GATConv forward with the segment softmax INSIDE the fused kernel (rows of <= 8 entries): a_src fp32 indexed by global source
+ * node (row stride lda), a_dst fp32 indexed by the rows of this call (same stride), edge_bias fp32 [nnz, 4] or NULL, smax / ssum
+ * fp32 [n_rows, 4] (both or neither: statistics for the backward pass); dropout as b2g_gat_alpha.  max_row_len must be the longest
+ * row of (rowptr, col) and <= 8, else B2G_E_UNSUPPORTED (use b2g_gat_alpha + b2g_gatw_gemm). */
+int b2g_gatw_gemm_sm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const float* a_src, const float* a_dst,
+                     int64_t lda, const float* edge_bias, float slope, float p_drop, uint64_t seed, float* smax, float* ssum,
+                     const void* wp, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t n_rows, int64_t max_row_len,
+                     int H, int F, int C, int dt, int64_t band, void* stream) {
+  if (n_rows < 0 || (smax == nullptr) != (ssum == nullptr)) return B2G_E_ARG;
+  if (n_rows == 0) return B2G_OK;
+  if (max_row_len < 1 || max_row_len > 8) return B2G_E_UNSUPPORTED;
+  if (!a_src || !a_dst) return B2G_E_ARG;
+  if (!aligned16(a_src) || !aligned16(a_dst) || lda % 4 || lda < GF_H || lda >= (1ll << 32) || (edge_bias && !aligned16(edge_bias)) ||
+      (smax && (!aligned16(smax) || !aligned16(ssum))))
+    return B2G_E_ALIGN;
+  const GfSoftmax sm{a_src, a_dst, lda, edge_bias, smax, ssum, slope, p_drop, seed};
+  return gatw_launch(x, ldx, rowptr, col, nullptr, nullptr, &sm, wp, ldw, bias, nullptr, nullptr, nullptr, 0, out, ldo, n_rows, H, F, C,
+                     dt, band, stream);
+}
+
+static int gatw_launch(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
+                       const float* alpha, const GfSoftmax* sm, const void* wp, int64_t ldw, const float* bias, const float* srow,
+                       const float* bvh, const void* addend, int64_t ldadd, void* out, int64_t ldo, int64_t n_rows, int H, int F,
+                       int C, int dt, int64_t band, void* stream) {
   if (n_rows < 0) return B2G_E_ARG;
   if ((bvh != nullptr) != (srow != nullptr)) return B2G_E_ARG;
   if ((srow && !aligned16(srow)) || (bvh && !aligned16(bvh)) || (addend && (!aligned16(addend) || (ldadd * 2) % 16))) return B2G_E_ALIGN;
   if (n_rows == 0) return B2G_OK;
   if (!b2g_gatw_gemm_supported(n_rows, H, F, C, dt)) return B2G_E_UNSUPPORTED;
-  if (!x || !rowptr || !col || !alpha || !wp || !out) return B2G_E_ARG;
-  if (!aligned16(x) || !aligned16(alpha) || !aligned16(wp) || !aligned16(out) || (bias && !aligned16(bias)) || (ldx * 2) % 16 ||
+  if (!x || !rowptr || !col || (!alpha && !sm) || !wp || !out) return B2G_E_ARG;
+  if (!aligned16(x) || (alpha && !aligned16(alpha)) || !aligned16(wp) || !aligned16(out) || (bias && !aligned16(bias)) || (ldx * 2) % 16 ||
       (ldw * 2) % 16 || (ldo * 2) % 16 || ldx * 2 >= (1ll << 32))
     return B2G_E_ALIGN;
   static bool attr_set[64] = {false};
@@ -628,6 +724,10 @@ int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const in
   a.rowptr = rowptr; a.col = col; a.perm = perm; a.alpha = alpha; a.bias = bias;
   a.zero = static_cast<const char*>(zero_row_ptr());
   if (!a.zero) return B2G_E_UNSUPPORTED;
+  if (sm) {
+    a.a_src = sm->a_src; a.a_dst = sm->a_dst; a.lda = (uint32_t)sm->lda; a.ebias = sm->ebias; a.smax = sm->smax; a.ssum = sm->ssum;
+    a.slope = sm->slope; a.p_drop = sm->p_drop; a.seed = sm->seed; a.epoch = dropout_epoch_ptr();
+  }
   a.srow = srow; a.bvh = bvh; a.addend = static_cast<const __nv_bfloat16*>(addend); a.ldadd = ldadd;
   a.out = static_cast<__nv_bfloat16*>(out); a.ldo = ldo; a.n_rows = (uint32_t)n_rows; a.m = C;
   CUtensorMap map_o = map_w;                                   // placeholder when the row-store epilogue is used

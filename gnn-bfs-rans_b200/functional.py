@@ -209,11 +209,17 @@ class GATZFn(torch.autograd.Function):
         if ve is not None:
             eb = ops.edge_dot4(ve.detach().float().reshape(1, 4 * H).expand(N, 4 * H), ea, csr.rowptr, H)   # [nnz, H]
         fused = os.environ.get("B2G_GAT_PATH", "") != "unfused" and ops.gatw_gemm_supported(N, H, F, C, x.dtype)
-        if fused or eb is not None:
+        # rows of <= 8 entries (every mesh): the softmax runs inside the fused kernel's per-tile prologue, no alpha in HBM
+        fused_sm = fused and os.environ.get("B2G_GAT_SOFTMAX", "") != "separate" and 1 <= graph.max_degree("sl") <= 8
+        if (fused and not fused_sm) or (not fused and eb is not None):
             alpha, smax, ssum = ops.gat_alpha(a, csr.rowptr, csr.col, H, slope, p_drop, seed, need_grad, edge_bias=eb)
         if fused:
             wp = wc.view(C, H, F // 64, 64).permute(0, 2, 1, 3).reshape(C, H * F)     # K order (chunk, head, 64 features)
-            out = ops.gatw_gemm(x, csr.rowptr, csr.col, None, alpha, wp, bias, N, H, band=graph.band())
+            if fused_sm:
+                out, smax, ssum = ops.gatw_gemm_sm(x, a, csr.rowptr, csr.col, wp, bias, N, H, slope, p_drop, seed, need_grad,
+                                                   graph.max_degree("sl"), band=graph.band(), edge_bias=eb)
+            else:
+                out = ops.gatw_gemm(x, csr.rowptr, csr.col, None, alpha, wp, bias, N, H, band=graph.band())
         else:
             if eb is not None:                 # weights already known: the plain 4-head weighted row sum (gatz_bwd_src kernel)
                 z = ops.seg_wsum4(x, alpha, csr.rowptr, csr.col, None, torch.empty((N, H * F), dtype=x.dtype, device=x.device),

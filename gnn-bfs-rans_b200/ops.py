@@ -455,6 +455,28 @@ def gatw_gemm(x, rowptr, col, perm, alpha, wp, bias, n_rows, H, band=0, out=None
     return out
 
 
+def gatw_gemm_sm(x, a, rowptr, col, wp, bias, n_rows, H, slope, p_drop, seed, save_stats, max_row_len, band=0, out=None,
+                 edge_bias=None, row0=0):
+    """GATConv forward with the softmax inside the fused kernel (every row <= 8 entries; csrc/gat_fused.cu): a = [a_src | a_dst]
+    fp32 [N, 2H] indexed globally, rows [row0, row0 + n_rows) of it are this call's targets (rowptr is their slice).
+    -> (out [n_rows, C], smax, ssum fp32 [n_rows, H] | None)."""
+    _cuda(x, wp, a)
+    x, wp = _rows(x), _rows(wp)
+    C, F = wp.shape[0], x.shape[1]
+    if out is None:
+        out = torch.empty((n_rows, C), dtype=x.dtype, device=x.device)
+    b = bias.float().contiguous() if bias is not None else None
+    smax = torch.empty((n_rows, H), dtype=torch.float32, device=x.device) if save_stats else None
+    ssum = torch.empty((n_rows, H), dtype=torch.float32, device=x.device) if save_stats else None
+    assert a.dtype == torch.float32 and a.stride(1) == 1 and a.shape[1] >= 2 * H
+    a_dst = a[row0:, H:]
+    _lib.check(_lib.load().b2g_gatw_gemm_sm(_p(x), _ld(x), _p(rowptr), _p(col), _p(a), _p(a_dst), a.stride(0), _p(edge_bias),
+                                            float(slope), float(p_drop), int(seed), _p(smax), _p(ssum), _p(wp), _ld(wp), _p(b),
+                                            _p(out), _ld(out), n_rows, int(max_row_len), H, F, C, _dt(x), int(band), _stream()),
+               "gatw_gemm_sm")
+    return out, smax, ssum
+
+
 def tz_alpha(x, u, H, rowptr, col, p_drop, seed, band=0, edge_bias=None, impl=0):
     """TransformerConv attention weights without the weighted sums (gat_rows.cu: tz_alpha_mma_kernel for bf16 F = 256 — the
     logits as m16n8k16 tile products —, else / impl=1 tz_fwd_kernel in alpha-only mode):

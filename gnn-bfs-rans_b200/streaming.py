@@ -241,6 +241,9 @@ class _GATStages(_Stages):
 
     def finish(self, r0, r1):
         L = self.layer
+        if 1 <= self.g.max_degree("sl") <= 8:                   # softmax inside the fused kernel
+            return ops.gatw_gemm_sm(self.dx, self.a, self.csr.rowptr[r0:r1 + 1], self.csr.col, self.wp, L.bias, r1 - r0, self.H,
+                                    L.negative_slope, 0.0, 0, False, self.g.max_degree("sl"), band=0, row0=r0)[0]
         ops.gat_alpha(self.a, self.csr.rowptr, self.csr.col, self.H, L.negative_slope, 0.0, 0, False, rows=(r0, r1),
                       alpha_out=self.alpha)
         return ops.gatw_gemm(self.dx, self.csr.rowptr[r0:r1 + 1], self.csr.col, None, self.alpha, self.wp, L.bias, r1 - r0,

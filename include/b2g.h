@@ -296,6 +296,15 @@ int b2g_gatw_gemm(const void* x, int64_t ldx, const int32_t* rowptr, const int32
  *   out_i = sum_h (z_ih Wv_h^T + s_ih bv_h) / H + x_i Ws^T + bs:   srow fp32 [n_rows, 4] = s_ih (per-head sums of the post-dropout
  * attention weights), bvh fp32 [4, C] = bv_h / H (both or neither), addend bf16 [n_rows, C] (row stride ldadd) = the skip
  * projection; any of them may be NULL.  With b2g_tz_alpha (K5) this is the fused TransformerConv forward: z_aug never exists. */
+/* GATConv forward with the segment softmax INSIDE the fused kernel (every row <= 8 entries): the gather warps derive the attention
+ * weights of their rows from a_src (fp32, indexed by global source node, row stride lda) and a_dst (fp32, indexed by the rows of
+ * this call, same stride) in the per-tile prologue — no alpha round trip through HBM, no b2g_gat_alpha launch.  edge_bias fp32
+ * [nnz, 4] or NULL; smax / ssum fp32 [n_rows, 4] (both or neither): the statistics b2g_gatz_bwd_dst needs; dropout as
+ * b2g_gat_alpha.  max_row_len = the longest row of (rowptr, col); > 8 (or unknown, 0) -> B2G_E_UNSUPPORTED. */
+int b2g_gatw_gemm_sm(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const float* a_src, const float* a_dst,
+                     int64_t lda, const float* edge_bias, float slope, float p_drop, uint64_t seed, float* smax, float* ssum,
+                     const void* wp, int64_t ldw, const float* bias, void* out, int64_t ldo, int64_t n_rows, int64_t max_row_len,
+                     int H, int F, int C, int dt, int64_t band, void* stream);
 int b2g_gatw_gemm_ex(const void* x, int64_t ldx, const int32_t* rowptr, const int32_t* col, const int32_t* perm,
                      const float* alpha, const void* wp, int64_t ldw, const float* bias, const float* srow, const float* bvh,
                      const void* addend, int64_t ldadd, void* out, int64_t ldo, int64_t n_rows, int H, int F, int C, int dt,

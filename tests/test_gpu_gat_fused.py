@@ -385,3 +385,37 @@ def test_rowdot8_tensor_core_vs_fp64(N):
     mag = x.double().abs() @ v.double().abs().T
     assert a.shape == (N, 8)
     assert float(((a.double() - ref).abs() / mag).max()) < 2e-5
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_gatconv_softmax_inside_the_fused_kernel_equals_separate_kernel(train, monkeypatch):
+    """Rows of <= 8 entries: b2g_gatw_gemm_sm (softmax in the gather warps' per-tile prologue) against b2g_gat_alpha +
+    b2g_gatw_gemm: same formulas, the 8-term sums in another order -> outputs equal to bf16 rounding, the statistics for the
+    backward pass to fp32 rounding, gradients alike; with dropout both draw the same mask."""
+    import gnn_bfs_rans_b200 as b2g
+    from gnn_bfs_rans_b200 import ops
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    from gnn_bfs_rans_b200.graph import graph_of
+    nx, ny, nz = 30, 20, 25
+    N = nx * ny * nz
+    o, n = hex_mesh_faces(nx, ny, nz, device="cuda")
+    ei = ops.build_graph_edges(o, n, 1, None, N, N)
+    assert graph_of(ei, N).max_degree("sl") <= 8
+    torch.manual_seed(3)
+    m = b2g.nn.GATConv(256, 256, heads=4, concat=False, dropout=0.3).cuda().bfloat16().train(train)
+    x = torch.randn(N, 256, device="cuda").bfloat16()
+    gout = torch.randn(N, 256, device="cuda").bfloat16()
+    res = {}
+    for mode in ("", "separate"):
+        monkeypatch.setenv("B2G_GAT_SOFTMAX", mode)
+        torch.manual_seed(11)
+        xg = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        out = m(xg, ei)
+        out.backward(gout)
+        res[mode] = (out.detach().float(), xg.grad.float(), m.att_src.grad.float().clone())
+    scale = res["separate"][0].abs().max()
+    assert float((res[""][0] - res["separate"][0]).abs().max() / scale) < 8e-3          # one bf16 ulp at most
+    assert float((res[""][0] != res["separate"][0]).float().mean()) < 1e-2              # ... and on few elements
+    assert float((res[""][1] - res["separate"][1]).norm() / res["separate"][1].norm()) < 5e-3
+    assert float((res[""][2] - res["separate"][2]).norm() / res["separate"][2].norm()) < 5e-3
