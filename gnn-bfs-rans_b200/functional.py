@@ -453,11 +453,18 @@ class TConvZFn(torch.autograd.Function):
             u, _ = ops.linear_fwd(x, mq, cq)
             alpha, a_post, ssum = ops.tz_alpha(x, u, H, csr.rowptr, csr.col, p_drop, seed, band=graph.band())
             del u
-            skip, _ = ops.linear_fwd(x, w_out[:, HF + 8:HF + 8 + F].contiguous(), b_out)
             wp = w_out[:, :HF].reshape(C, H, F // 64, 64).permute(0, 2, 1, 3).reshape(C, HF)   # K order (chunk, head, 64 features)
             bvh = w_out[:, HF:HF + H].t().float().contiguous()                                    # [H, C] = bv_h / H
-            out = ops.gatw_gemm(x, csr.rowptr, csr.col, None, a_post if a_post is not None else alpha, wp, None, N, H,
-                                band=graph.band(), srow=ssum, bvh=bvh, addend=skip)
+            if p_drop == 0 and graph.min_degree("raw") >= 1:
+                # no attention dropout and no empty row: every s_ih = sum_j alpha_ijh = 1, so sum_h s_ih bv_h / H is ONE vector:
+                # it joins the bias of the skip GEMM and the fused kernel's epilogue only adds the skip rows
+                sb = bvh.sum(0) if b_out is None else bvh.sum(0) + b_out.float()
+                skip, _ = ops.linear_fwd(x, w_out[:, HF + 8:HF + 8 + F].contiguous(), sb)
+                out = ops.gatw_gemm(x, csr.rowptr, csr.col, None, alpha, wp, None, N, H, band=graph.band(), addend=skip)
+            else:
+                skip, _ = ops.linear_fwd(x, w_out[:, HF + 8:HF + 8 + F].contiguous(), b_out)
+                out = ops.gatw_gemm(x, csr.rowptr, csr.col, None, a_post if a_post is not None else alpha, wp, None, N, H,
+                                    band=graph.band(), srow=ssum, bvh=bvh, addend=skip)
             z_aug = None
         else:
             z_aug, alpha = TConvZFn._forward_z(x, mq, cq, graph, H, p_drop, seed, need_grad, ea)

@@ -82,6 +82,14 @@ class Graph:
             setattr(self, key, int((rp[1:] - rp[:-1]).max()) if self.N > 0 else 0)
         return getattr(self, key)
 
+    def min_degree(self, variant: str) -> int:
+        """Shortest row of the target-major CSR (one device reduction per graph, cached)."""
+        key = "_mindeg_" + variant
+        if not hasattr(self, key):
+            rp = self.csr(variant, False).rowptr
+            setattr(self, key, int((rp[1:] - rp[:-1]).min()) if self.N > 0 else 0)
+        return getattr(self, key)
+
     def band(self) -> int:
         """max |source - target| over the edge list (one device reduction per graph, cached): the hint that lets
         the aggregation kernels sweep band-structured meshes panel by panel (aggregate.cu RowOrder)."""

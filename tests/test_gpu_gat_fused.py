@@ -419,3 +419,39 @@ def test_gatconv_softmax_inside_the_fused_kernel_equals_separate_kernel(train, m
     assert float((res[""][0] != res["separate"][0]).float().mean()) < 1e-2              # ... and on few elements
     assert float((res[""][1] - res["separate"][1]).norm() / res["separate"][1].norm()) < 5e-3
     assert float((res[""][2] - res["separate"][2]).norm() / res["separate"][2].norm()) < 5e-3
+
+
+def test_transformerconv_fused_eval_without_empty_rows_folds_the_value_bias(monkeypatch):
+    """No attention dropout and every row non-empty: s_ih = 1, so sum_h s_ih bv_h / H joins the bias of the skip GEMM and the fused
+    kernel runs without the per-row s.bv term; against the unfused path and the fp64 oracle, with large value biases."""
+    import gnn_bfs_rans_b200 as b2g
+    from gnn_bfs_rans_b200 import ops
+    from gnn_bfs_rans_b200.graph import graph_of
+    from gnn_bfs_rans_b200.synthetic import hex_mesh_faces
+    from oracle import layers_oracle as lo
+    nx, ny, nz = 22, 18, 16
+    N = nx * ny * nz
+    o, n = hex_mesh_faces(nx, ny, nz, device="cuda")
+    ei = ops.build_graph_edges(o, n, 1, None, N, N)
+    assert graph_of(ei, N).min_degree("raw") >= 1
+    torch.manual_seed(21)
+    m = b2g.nn.TransformerConv(256, 256, heads=4, concat=False)
+    with torch.no_grad():
+        for p_ in m.parameters():
+            if p_.dim() == 1:
+                p_.uniform_(-2.0, 2.0)
+    m = m.cuda().bfloat16().eval()
+    x = torch.randn(N, 256, device="cuda").bfloat16()
+    outs = {}
+    for path in ("", "unfused"):
+        monkeypatch.setenv("B2G_TCONV_PATH", path)
+        with torch.no_grad():
+            outs[path] = m(x, ei).double().cpu()
+    p = {k: v.detach().double().cpu() for k, v in m.state_dict().items()}
+    ref = lo.transformer_conv(x.double().cpu(), ei.cpu(), p["lin_query.weight"], p["lin_query.bias"], p["lin_key.weight"],
+                              p["lin_key.bias"], p["lin_value.weight"], p["lin_value.bias"], p["lin_skip.weight"], p["lin_skip.bias"],
+                              heads=4)
+    scale = ref.abs().max()
+    for path in ("", "unfused"):
+        assert float((outs[path] - ref).abs().max() / scale) < 2e-2, path
+    assert float((outs[""] - outs["unfused"]).abs().max() / scale) < 1.2e-2
