@@ -387,8 +387,9 @@ def test_rowdot8_tensor_core_vs_fp64(N):
     assert float(((a.double() - ref).abs() / mag).max()) < 2e-5
 
 
+@pytest.mark.parametrize("edge", [False, True])
 @pytest.mark.parametrize("train", [False, True])
-def test_gatconv_softmax_inside_the_fused_kernel_equals_separate_kernel(train, monkeypatch):
+def test_gatconv_softmax_inside_the_fused_kernel_equals_separate_kernel(train, edge, monkeypatch):
     """Rows of <= 8 entries: b2g_gatw_gemm_sm (softmax in the gather warps' per-tile prologue) against b2g_gat_alpha +
     b2g_gatw_gemm: same formulas, the 8-term sums in another order -> outputs equal to bf16 rounding, the statistics for the
     backward pass to fp32 rounding, gradients alike; with dropout both draw the same mask."""
@@ -402,8 +403,9 @@ def test_gatconv_softmax_inside_the_fused_kernel_equals_separate_kernel(train, m
     ei = ops.build_graph_edges(o, n, 1, None, N, N)
     assert graph_of(ei, N).max_degree("sl") <= 8
     torch.manual_seed(3)
-    m = b2g.nn.GATConv(256, 256, heads=4, concat=False, dropout=0.3).cuda().bfloat16().train(train)
+    m = b2g.nn.GATConv(256, 256, heads=4, concat=False, dropout=0.3, edge_dim=4 if edge else None).cuda().bfloat16().train(train)
     x = torch.randn(N, 256, device="cuda").bfloat16()
+    ea = torch.randn(ei.shape[1], 4, device="cuda").bfloat16() if edge else None      # the edge term of the logits (edge_bias)
     gout = torch.randn(N, 256, device="cuda").bfloat16()
     res = {}
     for mode in ("", "separate"):
@@ -411,7 +413,7 @@ def test_gatconv_softmax_inside_the_fused_kernel_equals_separate_kernel(train, m
         torch.manual_seed(11)
         xg = x.clone().requires_grad_(True)
         m.zero_grad(set_to_none=True)
-        out = m(xg, ei)
+        out = m(xg, ei, edge_attr=ea) if edge else m(xg, ei)
         out.backward(gout)
         res[mode] = (out.detach().float(), xg.grad.float(), m.att_src.grad.float().clone())
     scale = res["separate"][0].abs().max()
