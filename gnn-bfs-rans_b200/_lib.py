@@ -53,6 +53,7 @@ SIGNATURES = {
     "b2g_adam_workspace_bytes": (i64, []),
     "b2g_clip_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, vp, vp]),
     "b2g_gat_alpha": (i32, [vp, i64, vp, vp, vp, i64, i64, i32, f32, f32, u64, vp, vp, vp, vp]),
+    "b2g_linear_fwd_masked": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, i64, i32, i32, i32, vp, vp]),
     "b2g_gatw_gemm_sm": (i32, [vp, i64, vp, vp, vp, vp, i64, vp, f32, f32, u64, vp, vp, vp, i64, vp, vp, i64, i64, i64, i32, i32, i32, i32,
                                 i64, vp]),
     "b2g_gatw_gemm": (i32, [vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, i64, i64, i32, i32, i32, i32, i64, vp]),
@@ -111,6 +112,9 @@ def load():
         raise RuntimeError("b2g: libb2g.so version mismatch; rebuild it")
     _lib = lib
     return lib
+
+
+E_UNSUPPORTED = -5          # include/b2g.h B2G_E_UNSUPPORTED: "this build has no kernel for the request"
 
 
 def check(rc: int, what: str = ""):

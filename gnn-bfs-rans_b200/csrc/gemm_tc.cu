@@ -16,6 +16,7 @@
 // 64-column chunks).  The epilogue is instruction-bound with one warp per scheduler, hence eight warps
 // and a specialised chunk body per (row-scale, bias, ReLU) combination.
 #include <cstdlib>
+#include "rows.cuh"
 #include "tc_ptx.cuh"
 
 namespace b2g {
@@ -51,7 +52,7 @@ static_assert(TC_SMEM_RES + 1024 <= 232448 && TC_SMEM_STR + 1024 <= 232448, "sha
 // bf16 and park it in the warp's staging buffer (16-byte pieces XOR-swizzled by row: conflict-free).
 template <bool kRS, bool kBias, bool kRelu>
 __device__ __forceinline__ void epi_pack(const uint32_t (&r)[32], float rs, const float* __restrict__ bias, int cg0,
-                                         uint8_t* stg, int lane, int hlf) {
+                                         uint8_t* stg, int lane, int hlf, const uint4* mk4) {
 #pragma unroll
   for (int j = 0; j < 32; j += 8) {
     float v[8];
@@ -71,6 +72,12 @@ __device__ __forceinline__ void epi_pack(const uint32_t (&r)[32], float rs, cons
 #pragma unroll
       for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
     }
+    if (mk4) {                                   // warp-uniform: this row's 8 mask values (prefetched), zero where mask <= 0
+      float mk[8];
+      unpack_row16(mk4[j >> 3], mk, __nv_bfloat16());
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = mk[k] > 0.f ? v[k] : 0.f;
+    }
     Vec<__nv_bfloat16> o;
     o.from_float(v);
     *reinterpret_cast<uint4*>(stg + lane * TC_STG_PITCH + (((hlf * 4 + (j >> 3)) ^ (lane & 7)) << 4)) = o.v;
@@ -88,6 +95,8 @@ struct TcParams {
   int64_t ldaux;
   int act;
   int tma_store;   // full 64-column chunks leave through map_y (cp.async.bulk.tensor stores) instead of LDS + 128-byte row stores
+  const __nv_bfloat16* mask;   // [n, m_main] or NULL: Y = 0 where mask <= 0 (ReLU backward fused into the dgrad GEMM: mask = the
+  int64_t ldmask;              // ReLU's output), applied after row scale / bias / activation
 };
 
 // kPlan: 0 = streaming (X + W k-blocks through the ring), 1 = resident W block (k <= 256), 2 = streaming with TWO row tiles per
@@ -95,7 +104,9 @@ struct TcParams {
 // 1.7 MB) from L2 for every 128 rows: ncu on the k = 3336 dgrad showed 69 GB of DRAM reads at 3.9 TB/s with ~200 GB of L2 -> SM
 // traffic.  Plan 2 multiplies each W k-block with two X tiles into the two TMEM accumulators (no accumulator double buffering:
 // the epilogue of a pair is 3 us against a 40 us main loop), which halves the W traffic per row.
-template <int kPlan>
+// kMask: the ReLU-backward mask epilogue (b2g_linear_fwd_masked).  A separate instantiation: merely carrying the (unused) mask
+// code made the plain kernel 10 % slower (same box: 256 -> 256 1.79-1.86 ms against 1.62-1.67).
+template <int kPlan, bool kMask = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_y, const TcParams p) {
@@ -273,6 +284,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const int64_t row = row0 + lane;
       const bool row_ok = row < p.n;
       const float rs = (p.row_scale && row_ok) ? __ldg(p.row_scale + row) : 1.0f;
+      const __nv_bfloat16* mrow = (kMask && p.mask) ? p.mask + (row_ok ? row : 0) * p.ldmask : nullptr;   // rows >= n: any valid row
       const int col0 = ct * TC_BN;
       const int ncols = min(TC_BN, p.m - col0);
 #pragma unroll 1
@@ -287,6 +299,11 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t r2[2][32];
           tc_ld32_issue(taddr, r2[0]);                        // both halves in flight: one TMEM latency per chunk
           tc_ld32_issue(taddr + 32, r2[1]);
+          uint4 mkv[2][4];                                    // the row's 64 mask values, requested before anything waits: a load
+          if (kMask && mrow) {                                // per 8 columns inside epi_pack ran the epilogue at one L2 latency each
+#pragma unroll
+            for (int t8 = 0; t8 < 8; ++t8) mkv[t8 >> 2][t8 & 3] = __ldg(reinterpret_cast<const uint4*>(mrow + cg0 + t8 * 8));
+          }
           if (p.tma_store) {
             if (lane == 0) {                                  // the store that last read THIS buffer has finished reading
               if (NBUF == 2) tma_store_wait_read1(); else tma_store_wait_read();
@@ -298,14 +315,14 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           for (int hlf = 0; hlf < 2; ++hlf) {
             const uint32_t (&r)[32] = r2[hlf];
             switch (flags) {   // warp-uniform; each case is a straight-line body without per-element predicates
-              case 0: epi_pack<false, false, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
-              case 1: epi_pack<true, false, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
-              case 2: epi_pack<false, true, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
-              case 3: epi_pack<true, true, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
-              case 4: epi_pack<false, false, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
-              case 5: epi_pack<true, false, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
-              case 6: epi_pack<false, true, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
-              default: epi_pack<true, true, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf); break;
+              case 0: epi_pack<false, false, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf, (kMask && mrow) ? mkv[hlf] : nullptr); break;
+              case 1: epi_pack<true, false, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf, (kMask && mrow) ? mkv[hlf] : nullptr); break;
+              case 2: epi_pack<false, true, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf, (kMask && mrow) ? mkv[hlf] : nullptr); break;
+              case 3: epi_pack<true, true, false>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf, (kMask && mrow) ? mkv[hlf] : nullptr); break;
+              case 4: epi_pack<false, false, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf, (kMask && mrow) ? mkv[hlf] : nullptr); break;
+              case 5: epi_pack<true, false, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf, (kMask && mrow) ? mkv[hlf] : nullptr); break;
+              case 6: epi_pack<false, true, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf, (kMask && mrow) ? mkv[hlf] : nullptr); break;
+              default: epi_pack<true, true, true>(r, rs, p.bias, cg0 + hlf * 32, my_stg, lane, hlf, (kMask && mrow) ? mkv[hlf] : nullptr); break;
             }
           }
           if (p.tma_store) {
@@ -345,6 +362,7 @@ tc_linear_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                   if (p.row_scale) x *= rs;
                   if (p.bias) x += __ldg(p.bias + cg);
                   if (p.act == 1) x = fmaxf(x, 0.f);
+                  if (kMask && mrow && cg < p.m_main && !(__bfloat162float(mrow[cg]) > 0.f)) x = 0.f;
                   if (cg < p.m_main) p.Y[row * p.ldy + cg] = __float2bfloat16_rn(x);
                   else p.aux[row * p.ldaux + (cg - p.m_main)] = x;
                 }
@@ -910,7 +928,8 @@ static const int g_tma_store = [] { const char* e = getenv("B2G_TC_TMA_STORE"); 
 
 int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                   const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n, int m,
-                  int m_main, int k, int dt, int act, int reserve_sms, void* ws, cudaStream_t st) {
+                  int m_main, int k, int dt, int act, int reserve_sms, const void* mask, int64_t ldmask, void* ws, cudaStream_t st) {
+  if (mask && (dt != B2G_BF16 || !aligned16(mask) || (ldmask * 2) % 16 || m_main != m)) return B2G_E_UNSUPPORTED;
   if (dt == B2G_F32)
     return tc_linear_fwd_tf32x3(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, act, ws, st);
   if (dt != B2G_BF16) return B2G_E_UNSUPPORTED;
@@ -922,6 +941,7 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
     cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_STR);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_DUAL);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_RES);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
@@ -930,6 +950,7 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   TcParams p;
   p.n = n; p.m = m; p.m_main = m_main; p.k = k; p.bias = bias; p.row_scale = row_scale;
   p.Y = static_cast<__nv_bfloat16*>(Y); p.ldy = ldy; p.aux = aux; p.ldaux = ldaux; p.act = act;
+  p.mask = static_cast<const __nv_bfloat16*>(mask); p.ldmask = ldmask;
   CUtensorMap map_y = map_a;                                  // placeholder when the row-store epilogue is used
   p.tma_store = (g_tma_store && m_main >= 64 && (m_main % 8) == 0 && make_map(&map_y, Y, n, m_main, ldy, 32)) ? 1 : 0;
   const int64_t row_tiles = ceil_div(n, TC_BM), col_tiles = ceil_div(m, TC_BN);
@@ -939,7 +960,10 @@ int tc_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const 
   if (k <= TC_RES_KB_MAX * TC_BK && col_tiles <= sms) {
     int64_t per = sms / col_tiles;                            // CTAs per column group
     if (per > row_tiles) per = row_tiles;
-    tc_linear_kernel<1><<<(unsigned)(per * col_tiles), TC_THREADS, TC_SMEM_RES, st>>>(map_a, map_b, map_y, p);
+    if (mask) tc_linear_kernel<1, true><<<(unsigned)(per * col_tiles), TC_THREADS, TC_SMEM_RES, st>>>(map_a, map_b, map_y, p);
+    else tc_linear_kernel<1><<<(unsigned)(per * col_tiles), TC_THREADS, TC_SMEM_RES, st>>>(map_a, map_b, map_y, p);
+  } else if (mask) {
+    return B2G_E_UNSUPPORTED;                                 // the mask epilogue exists for the resident plan (k <= 256) only
   } else if (g_dual_plan && col_tiles == 1 && row_tiles >= 2 * (int64_t)sms) {
     tc_linear_kernel<2><<<(unsigned)sms, TC_THREADS, TC_SMEM_DUAL, st>>>(map_a, map_b, map_y, p);
   } else {

@@ -11,7 +11,7 @@ int simt_linear_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_
 // gemm_tc.cu
 bool tc_linear_supported(int64_t n, int m, int k, int dt, int which);
 int64_t tc_linear_ws_bytes(int64_t n, int m, int k, int dt, int which);
-int tc_linear_fwd(const void*, int64_t, const void*, int64_t, const float*, const float*, void*, int64_t, float*, int64_t, int64_t, int, int, int, int, int, int, void*, cudaStream_t);
+int tc_linear_fwd(const void*, int64_t, const void*, int64_t, const float*, const float*, void*, int64_t, float*, int64_t, int64_t, int, int, int, int, int, int, const void*, int64_t, void*, cudaStream_t);
 int64_t tc_wgrad_ws_bytes(int64_t n, int m, int k);
 int tc_linear_wgrad(const void*, int64_t, const void*, int64_t, float*, int64_t, int64_t, int, int, void*, cudaStream_t);
 }  // namespace b2g
@@ -53,12 +53,23 @@ int b2g_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const
   const bool tc = tc_linear_supported(n, m, k, dt, 0);
   if (impl == 2 && !tc) return B2G_E_UNSUPPORTED;
   if (tc && impl != 1) {
-    const int rc = tc_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, reserve, ws, st);
+    const int rc = tc_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, reserve, nullptr, 0, ws, st);
     // shapes the tensor-core kernels decline at launch time (fp32 aux split with k > 256, tensors TMA cannot map):
     // auto mode falls through to the exact-fp32 SIMT kernel instead of failing the request
     if (rc != B2G_E_UNSUPPORTED || impl == 2) return rc;
   }
   return simt_linear_fwd(X, ldx, W, ldw, bias, row_scale, Y, ldy, aux, ldaux, n, m, m_main, k, dt, act, st);
+}
+
+/* Y = (X W^T) where mask > 0, else 0 (bf16, tensor-core path only): the ReLU backward fused into the dgrad GEMM of the layer
+ * behind it — X = dY of that layer, W = its weight transposed ([k_out, m_in] row-major), mask = the ReLU's output [n, m]. */
+int b2g_linear_fwd_masked(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* mask, int64_t ldmask, void* Y,
+                          int64_t ldy, int64_t n, int m, int k, int dt, void* ws, void* stream) {
+  if (n < 0 || m <= 0 || k <= 0 || !dt_ok(dt)) return B2G_E_ARG;
+  if (n == 0) return B2G_OK;
+  if (!X || !W || !Y || !mask) return B2G_E_ARG;
+  if (dt != B2G_BF16 || !tc_linear_supported(n, m, k, dt, 0)) return B2G_E_UNSUPPORTED;
+  return tc_linear_fwd(X, ldx, W, ldw, nullptr, nullptr, Y, ldy, nullptr, 0, n, m, m, k, dt, 0, 0, mask, ldmask, ws, (cudaStream_t)stream);
 }
 
 int b2g_linear_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dX,

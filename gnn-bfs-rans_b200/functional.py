@@ -560,3 +560,39 @@ class TConvZFn(torch.autograd.Function):
 
 def linear(x, weight, bias=None, act: int = 0):
     return LinearFn.apply(x, weight, bias, act)
+
+
+class MLP2Fn(torch.autograd.Function):
+    """y = relu(x W1^T + b1) W2^T + b2 — the Linear-ReLU-Linear MLP of GINConv (gnn_model.py:70-75) as ONE autograd node, so that
+    the ReLU backward is the mask epilogue of the second Linear's dgrad GEMM (`b2g_linear_fwd_masked`) instead of a separate
+    pass over [N, C] (aten.threshold_backward: 10 GB of traffic at cfg4)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        h1, _ = ops.linear_fwd(x, w1, b1, act=1)
+        y, _ = ops.linear_fwd(h1, w2, b2)
+        ctx.save_for_backward(x, w1, w2, h1)
+        ctx.has_b = (b1 is not None, b2 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w1, w2, h1 = ctx.saved_tensors
+        g = g.contiguous()
+        gw1 = gb1 = gw2 = gb2 = gx = None
+        if ctx.needs_input_grad[3] or (ctx.has_b[1] and ctx.needs_input_grad[4]):
+            dw, db = ops.linear_wgrad(g, h1, want_bias=ctx.has_b[1])
+            gw2, gb2 = _cast_like(dw, w2), (db if ctx.has_b[1] else None)
+        gh = ops.linear_dgrad_masked(g, w2, h1)                 # (g W2) where h1 > 0
+        if gh is None:                                          # shapes / dtypes without the fused epilogue (fp32, SIMT)
+            gh = torch.ops.aten.threshold_backward(ops.linear_dgrad(g, w2), h1, 0.0)
+        if ctx.needs_input_grad[1] or (ctx.has_b[0] and ctx.needs_input_grad[2]):
+            dw, db = ops.linear_wgrad(gh, x, want_bias=ctx.has_b[0])
+            gw1, gb1 = _cast_like(dw, w1), (db if ctx.has_b[0] else None)
+        if ctx.needs_input_grad[0]:
+            gx = ops.linear_dgrad(gh, w1)
+        return gx, gw1, gb1, gw2, gb2
+
+
+def mlp2(x, w1, b1, w2, b2):
+    return MLP2Fn.apply(x, w1, b1, w2, b2)

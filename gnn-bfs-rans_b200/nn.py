@@ -280,6 +280,10 @@ class GINConv(MessagePassing):
         n = self.nn
         if (isinstance(n, tnn.Sequential) and len(n) == 3 and isinstance(n[0], tnn.Linear)
                 and isinstance(n[1], tnn.ReLU) and isinstance(n[2], tnn.Linear)):
+            import os
+            if (os.environ.get("B2G_GIN_MLP", "") != "split" and torch.is_grad_enabled()
+                    and (h.requires_grad or any(p_.requires_grad for p_ in n.parameters()))):
+                return Fn.mlp2(h, n[0].weight, n[0].bias, n[2].weight, n[2].bias)   # one node: ReLU backward in the dgrad epilogue
             h = Fn.linear(h, n[0].weight, n[0].bias, act=1)       # Linear + ReLU fused epilogue
             return Fn.linear(h, n[2].weight, n[2].bias)
         return n(h)

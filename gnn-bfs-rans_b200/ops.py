@@ -325,6 +325,29 @@ def linear_dgrad(dy, w, out=None):
     return dx
 
 
+def linear_dgrad_masked(dy, w, mask):
+    """dx = (dy @ w) where mask > 0, else 0: the ReLU backward fused into the dgrad GEMM's epilogue (bf16 tensor-core path);
+    returns None when the shape / dtype has no such kernel (the caller masks separately)."""
+    _cuda(dy, w, mask)
+    lib = _lib.load()
+    if dy.dtype != torch.bfloat16 or GEMM_IMPL == 1:
+        return None
+    dy, w, mask = _rows(dy), _rows(w), _rows(mask)
+    n, m = dy.shape
+    k = w.shape[1]
+    if lib.b2g_linear_impl(n, k, m, _dt(dy), 0) != 2:
+        return None
+    wt = (w if w.dtype == dy.dtype else w.to(dy.dtype)).t().contiguous()                 # [k, m]
+    dx = torch.empty((n, k), dtype=dy.dtype, device=dy.device)
+    ws = _ws(lib.b2g_linear_workspace_bytes(n, k, m, _dt(dy), 0), dy.device)
+    rc = lib.b2g_linear_fwd_masked(_p(dy), _ld(dy), _p(wt), _ld(wt), _p(mask), _ld(mask), _p(dx), _ld(dx), n, k, m, _dt(dy),
+                                   _p(ws), _stream())
+    if rc == _lib.E_UNSUPPORTED:
+        return None
+    _lib.check(rc, "linear_fwd_masked")
+    return dx
+
+
 def linear_wgrad(dy, x, want_bias=True):
     """dW[m,k] = dy.T @ x (fp32), db[m] = dy.sum(0) (fp32)."""
     _cuda(dy, x)

@@ -353,6 +353,11 @@ int b2g_linear_impl(int64_t n, int m, int k, int dt, int which);
 int b2g_linear_fwd(const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
                    const float* row_scale, void* Y, int64_t ldy, float* aux, int64_t ldaux, int64_t n,
                    int m, int m_main, int k, int dt, int act, int impl, void* ws, void* stream);
+/* Y[n,m] = sum_k X[n,k] W[m,k] where mask[n,m] > 0, else 0 (bf16, tcgen05 path; B2G_E_UNSUPPORTED otherwise): the ReLU backward
+ * (aten.threshold_backward) fused into the dgrad GEMM of the Linear behind the ReLU — X = that Linear's dY, W = its weight
+ * transposed, mask = the ReLU's output.  Used by the Linear-ReLU-Linear MLP of GINConv (gnn_model.py:70-75). */
+int b2g_linear_fwd_masked(const void* X, int64_t ldx, const void* W, int64_t ldw, const void* mask, int64_t ldmask, void* Y,
+                          int64_t ldy, int64_t n, int m, int k, int dt, void* ws, void* stream);
 int b2g_linear_dgrad(const void* dY, int64_t lddy, const void* W, int64_t ldw, void* dX,
                      int64_t lddx, int64_t n, int m, int k, int dt, int impl, void* ws,
                      void* stream);

@@ -118,3 +118,44 @@ def test_linear_large_row_counts_plans(n, k, m):
         ref = torch.relu(rs[r0:r0 + 8192].double()[:, None] * (xs @ w.double().T) + b.double())
         assert rel(y[r0:r0 + 8192], ref) < 2e-2, r0
     assert bool(torch.isfinite(y.float()).all())
+
+
+@pytest.mark.parametrize("n,k,m", [(4099, 256, 256), (700, 256, 128), (40000, 1024, 256), (130, 64, 40)])
+def test_dgrad_with_relu_mask_epilogue(n, k, m):
+    """b2g_linear_fwd_masked: dx [n, k] = (dy [n, m] W [m, k]) where mask > 0 — aten.threshold_backward fused into the dgrad GEMM
+    (bf16, tcgen05, reductions m <= 256: the resident-W plan)."""
+    from gnn_bfs_rans_b200 import ops
+    torch.manual_seed(n + m)
+    dy = torch.randn(n, m, device='cuda').bfloat16()
+    w = (torch.randn(m, k, device='cuda') / m ** 0.5).bfloat16()
+    mask = torch.relu(torch.randn(n, k, device='cuda')).bfloat16()
+    got = ops.linear_dgrad_masked(dy, w, mask)
+    assert got is not None
+    ref = (dy.double() @ w.double()) * (mask > 0)
+    assert rel(got, ref) < 2e-2
+    assert bool((got[mask <= 0] == 0).all())
+    assert ops.linear_dgrad_masked(dy.float(), w.float(), mask.float()) is None       # fp32: the caller masks separately
+    wide = torch.randn(512, 320, device='cuda').bfloat16()                            # reduction > 256: no fused epilogue either
+    assert ops.linear_dgrad_masked(wide, torch.randn(320, 64, device='cuda').bfloat16(), torch.ones(512, 64, device='cuda').bfloat16()) is None
+
+
+def test_gin_mlp_single_node_backward_equals_two_linears():
+    """GINConv's Linear-ReLU-Linear as one autograd node (functional.MLP2Fn) against the two LinearFn nodes + threshold_backward."""
+    from gnn_bfs_rans_b200 import functional as Fn
+    torch.manual_seed(5)
+    n = 5000
+    for dtype in (torch.bfloat16, torch.float32):
+        x = torch.randn(n, 256, device='cuda').to(dtype)
+        ps = [(torch.randn(256, 256, device='cuda') / 16).to(dtype), torch.randn(256, device='cuda').to(dtype),
+              (torch.randn(128, 256, device='cuda') / 16).to(dtype), torch.randn(128, device='cuda').to(dtype)]
+        gout = torch.randn(n, 128, device='cuda').to(dtype)
+        res = []
+        for fused in (True, False):
+            xs = x.clone().requires_grad_(True)
+            pp = [p.clone().requires_grad_(True) for p in ps]
+            y = Fn.mlp2(xs, *pp) if fused else Fn.linear(Fn.linear(xs, pp[0], pp[1], act=1), pp[2], pp[3])
+            y.backward(gout)
+            res.append([y.detach()] + [t.grad for t in [xs] + pp])
+        tol = 1e-5 if dtype == torch.float32 else 1e-2
+        for a_, b_ in zip(*res):
+            assert rel(a_, b_) < tol
