@@ -117,7 +117,10 @@ __device__ __forceinline__ void gf_gather(float (&acc)[GF_H][8], const char* xk,
   for (int t = 0; t < K; ++t) gf_fma(acc, wrow[t * 4], buf[t]);   // staged [entry][row]: the 4 rows of a warp read 64 contiguous bytes
 }
 
-template <bool kPair>
+// kSm: softmax inside (a.alpha == NULL); kEx: the TransformerConv epilogue terms (srow / bvh / addend) may be present.  Compile-time
+// so that the GATConv instantiation carries neither the other mode's prologue nor the extra epilogue code (the tcgen05 Linear
+// lost 10 % to an unused epilogue option; this kernel sits at its 80-register ceiling).
+template <bool kPair, bool kSm, bool kEx>
 __global__ void __launch_bounds__(GF_THREADS, 1)
 gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_o, const GfArgs a) {
   constexpr int W_STAGES = kPair ? GF_W_STAGES_PAIR : GF_W_STAGES;
@@ -156,7 +159,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (a.bvh) {                                                          // visible to the epilogue warps after the __syncthreads below
+  if (kEx && a.bvh) {                                                   // visible to the epilogue warps after the __syncthreads below
     __nv_bfloat16* sb = reinterpret_cast<__nv_bfloat16*>(smem_raw + (sbv - smem_base));
     for (int t = threadIdx.x; t < GF_H * GF_BN; t += GF_THREADS) {
       const int h = t / GF_BN, c = t - h * GF_BN;
@@ -270,7 +273,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       const uint32_t rend = c0 + rows;
       const uint32_t my_row = row0 + lane;                 // the accumulator row this lane holds
       float4 srow4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.srow && my_row < rend) srow4 = __ldg(reinterpret_cast<const float4*>(a.srow) + my_row);
+      if (kEx && a.srow && my_row < rend) srow4 = __ldg(reinterpret_cast<const float4*>(a.srow) + my_row);
       // a block whose 32 rows all belong to this chunk leaves as ONE TMA tile store from the swizzled staging buffer (as in
       // gemm_tc.cu); partial blocks (chunk ends) keep the row stores — the rows past `rend` belong to another chunk
       const bool blk_tma = a.tma_store && row0 + 32 <= rend;
@@ -284,7 +287,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 #pragma unroll
         for (int hlf = 0; hlf < 2; ++hlf) {
           uint4 adv[4];                                      // this row's 32 addend values, requested before the TMEM read waits
-          if (a.addend) {
+          if (kEx && a.addend) {
 #pragma unroll
             for (int k8 = 0; k8 < 4; ++k8) {
               adv[k8] = make_uint4(0u, 0u, 0u, 0u);
@@ -306,7 +309,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
               v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
               v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-            if (a.bvh) {                                   // + sum_h s_ih bv_h / H: 4 broadcast LDS.128 from shared memory
+            if (kEx && a.bvh) {                            // + sum_h s_ih bv_h / H: 4 broadcast LDS.128 from shared memory
               const uint8_t* sb = smem_raw + (sbv - smem_base) + cg * 2;
 #pragma unroll
               for (int h = 0; h < GF_H; ++h) {
@@ -317,7 +320,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
                 for (int k = 0; k < 8; ++k) v[k] += sh * f[k];
               }
             }
-            if (a.addend) {                                // + the skip projection of this row (prefetched above; zeros past the end)
+            if (kEx && a.addend) {                         // + the skip projection of this row (prefetched above; zeros past the end)
               float f[8];
               unpack_row16(adv[j >> 3], f, __nv_bfloat16());
 #pragma unroll
@@ -388,7 +391,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
         const int pos = b0[u] + (has ? p : 0);
         int c = 0, pi = pos;
         float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.alpha) {
+        if (!kSm) {
           if (has) {
             c = __ldg(a.col + pos);
             if (a.perm) pi = __ldg(a.perm + pos);
@@ -469,7 +472,7 @@ gatw_gemm_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
 #undef B2G_CASE
             default: break;
           }
-          for (int t = 8; t < mlen[u]; ++t) {                             // rows longer than 8 entries (cold on meshes)
+          for (int t = 8; !kSm && t < mlen[u]; ++t) {                     // rows longer than 8 entries (cold on meshes; never with kSm)
             const bool has = t < len[u];
             float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -709,8 +712,11 @@ static int gatw_launch(const void* x, int64_t ldx, const int32_t* rowptr, const 
   static bool attr_set[64] = {false};
   const int dev = current_device_slot();
   if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gatw_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gatw_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gatw_gemm_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gatw_gemm_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gatw_gemm_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gatw_gemm_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gatw_gemm_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GF_SMEM);
     if (e != cudaSuccess) return (int)e;
     attr_set[dev] = true;
   }
@@ -745,11 +751,15 @@ static int gatw_launch(const void* x, int64_t ldx, const int32_t* rowptr, const 
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, gatw_gemm_kernel<true>, map_w, map_o, a);
+    const cudaError_t e = sm ? cudaLaunchKernelEx(&cfg, gatw_gemm_kernel<true, true, false>, map_w, map_o, a)
+                             : cudaLaunchKernelEx(&cfg, gatw_gemm_kernel<true, false, true>, map_w, map_o, a);
     if (e != cudaSuccess) return (int)e;
   } else {
     const unsigned grid = a.ord.n_chunks < (uint32_t)B2G_NUM_SMS ? a.ord.n_chunks : (unsigned)B2G_NUM_SMS;
-    gatw_gemm_kernel<false><<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, map_o, a);
+    const bool ex = srow || bvh || addend;
+    if (sm) gatw_gemm_kernel<false, true, false><<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, map_o, a);
+    else if (ex) gatw_gemm_kernel<false, false, true><<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, map_o, a);
+    else gatw_gemm_kernel<false, false, false><<<grid, GF_THREADS, GF_SMEM, (cudaStream_t)stream>>>(map_w, map_o, a);
   }
   count_launch();
   return cuda_status();
